@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Headline benchmark: VQA pairs/sec of the fused eval-mode VQAModel.forward on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--impl reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE).  Workload = BASELINE.json
+configs[1]: batch 256 per GPU, 224x224 images, 20-token questions, 1000 answers, bf16 engine,
+seeded random-init weights, synthetic inputs.  The batch is sharded across ranks with no
+data-path collective (weak scaling); rank 0 broadcasts the packed weight arena once at load.
+
+Prints ONE JSON line (rank 0).  ``value`` times K forwards with inputs resident in HBM (fp32 NCHW,
+154 MB per batch > 126 MB L2, so no L2 flush is needed); ``e2e`` times the same through the predict
+path from pinned HOST buffers (uint8 HWC images + ids + mask H2D, top-5 D2H inside the timed
+region).  ``--impl reference`` times the reference's own CPU algorithm (the oracle port) on the
+host cores for the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FLOP_PER_PAIR = 3.849e9          # FlopCounterMode on the reference, L=20 (2*MAC)
+METRIC = "vqa_pairs_per_sec"
+WORKLOAD = "VQAModel.forward eval, 224x224 images, 20-token questions, 1000 answers (BASELINE configs[1])"
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_reference_run(steps: int, warmup: int, batch: int = 32):
+    """Oracle (CPU restatement of the reference algorithm) on the host cores: pairs/s."""
+    import torch
+    from oracle import vqa_oracle as O
+    from vqa_b200.model import VQAModel
+    from vqa_b200.synth import synth_batch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = VQAModel().eval().state_dict()
+    _, img, ids, mask = synth_batch(batch, 1234, full_length=True)
+    for _ in range(warmup):
+        O.vqa_forward(sd, img, ids, mask)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.vqa_forward(sd, img, ids, mask)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * steps / total, "ms_per_step": 1e3 * total / steps, "cores": torch.get_num_threads(),
+            "best": batch / min(times), "batch": batch}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    r = cpu_reference_run(min(steps, 8), min(warmup, 2))
+    sample = f"{min(steps, 8)} timed fp32 forwards of batch {r['batch']} (BASELINE configs[0]) on the host CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": min(steps, 8), "warmup": min(warmup, 2), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": r["batch"], "device": "host CPU"},
+            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from vqa_b200 import program as P
+    from vqa_b200.engine import Engine
+    from vqa_b200.model import VQAModel
+    from vqa_b200.runtime import launch_count
+    from vqa_b200.synth import synth_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, L, K, Wm = args.batch, 20, args.steps, args.warmup
+    torch.manual_seed(0)
+    model = VQAModel().eval().to(dev)
+    # weights: rank 0 packs, everyone receives the arena over NCCL/NVLink (one collective, at load only)
+    weights = P.build_weights(model.state_dict(), model.config, dev)
+    if world > 1:
+        if rank != 0:
+            weights.arena.tensor.zero_()
+        dist.broadcast(weights.arena.tensor, src=0)
+    engine = Engine(model, weights)
+    model._engine = engine
+
+    u8, img, ids, mask = synth_batch(B, 1234 + rank, full_length=True)
+    d_img, d_ids, d_mask = img.to(dev), ids.to(dev), mask.to(dev)
+    h_u8, h_ids, h_mask = u8.pin_memory(), ids.pin_memory(), mask.pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput
+    with torch.no_grad():
+        for _ in range(max(Wm, 3)):
+            model(d_img, d_ids, d_mask)
+        barrier()
+        n0 = launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            e0.record()
+            for _ in range(K):
+                logits, _ = model(d_img, d_ids, d_mask)
+            e1.record()
+            barrier()
+        launches = launch_count() - n0
+        ms = reduce_max(e0.elapsed_time(e1))
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end from host buffers through predict (uint8 HWC -> top-5)
+    with torch.no_grad():
+        def e2e_step():
+            a = h_u8.to(dev, non_blocking=True)
+            b = h_ids.to(dev, non_blocking=True)
+            c = h_mask.to(dev, non_blocking=True)
+            idx, pr = model.predict(a, b, c, top_k=5)
+            return idx.to("cpu", non_blocking=True), pr.to("cpu", non_blocking=True)
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(K):
+            out = e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = reduce_max(e0.elapsed_time(e1))
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    h2d = h_u8.numel() + h_ids.numel() * 8 + h_mask.numel() * 8
+    d2h = B * 5 * (8 + 4)
+
+    # ---- per-kernel timing pass (CUDA events around every op of the plan) for the roofline line
+    peaks = measured_peaks()
+    roof = None
+    per_kernel = {}
+    if rank == 0:
+        prog, plan = engine.plan_for(B, L, "nchw_f32", P.MASK_I64, False, 0)
+        logits = torch.empty(B, model.config["num_answers"], device=dev)
+        ext = [d_img.data_ptr(), d_ids.data_ptr(), d_mask.data_ptr(), logits.data_ptr(), 0, 0]
+        stream = torch.cuda.current_stream().cuda_stream
+        reps = 3
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(plan.n_ops + 1)] for _ in range(reps)]
+        for r_ in range(reps):
+            evs[r_][0].record()
+            for k in range(plan.n_ops):
+                plan.run(ext, stream, k, k + 1)
+                evs[r_][k + 1].record()
+        torch.cuda.synchronize()
+        op_ms = [statistics.median(evs[r_][k].elapsed_time(evs[r_][k + 1]) for r_ in range(reps))
+                 for k in range(plan.n_ops)]
+        gemm_ms = sum(t for k, t in enumerate(op_ms) if prog.ops[k].kind == "gemm")
+        total_ms = sum(op_ms)
+        for k, t in enumerate(op_ms):
+            nm = plan.kernel_name(k)
+            per_kernel[nm] = per_kernel.get(nm, 0.0) + t
+        # algorithmic FLOPs: all 3.849 GFLOP/pair are GEMM-shaped (conv + linear); attention cores ~1 %
+        achieved = FLOP_PER_PAIR * B / (gemm_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "gemm_tap_kernel (all conv + linear launches of one forward)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "gemm_ms_per_step": gemm_ms,
+                "all_kernels_ms_per_step": total_ms, "gemm_share_of_step": gemm_ms / total_ms,
+                "whole_forward_frac": (FLOP_PER_PAIR * B * K / (ms * 1e-3) / 1e12) / peak}
+        if args.dump_ops:
+            os.makedirs(os.path.dirname(args.dump_ops) or ".", exist_ok=True)
+            with open(args.dump_ops, "w") as f:
+                json.dump({"batch": B, "ops": [{"op": k, "name": prog.ops[k].name, "kernel": plan.kernel_name(k),
+                                                "ms": op_ms[k]} for k in range(plan.n_ops)],
+                           "per_kernel_ms": per_kernel}, f, indent=1)
+
+    # ---- host CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(steps=4, warmup=1)
+        cpu = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+               "sample": "4 timed fp32 oracle forwards of batch 32 (BASELINE configs[0]) on the host CPU"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "seq_len": L,
+                           "precision": "bf16 backbone operands / tf32 text+fusion+head, fp32 accumulate",
+                           "parallelism": f"batch-sharded x{world}, weights broadcast once",
+                           "l2": "inputs 154 MB/GPU (fp32 NCHW) exceed the 126 MB L2; no flush needed"},
+                "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / K, "path": "pinned uint8 HWC + ids + mask -> predict(top_k=5) -> host"},
+                "gpu_launches": int(launches), "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_agreement(args):
+    """Top-1 agreement of the engine with the fp32 oracle over N pairs (BASELINE: >= 99 % over 10k)."""
+    import torch
+    from oracle import vqa_oracle as O
+    from vqa_b200.model import VQAModel
+    from vqa_b200.synth import synth_batch
+    torch.manual_seed(0)
+    model = VQAModel().eval()
+    sd = model.state_dict()
+    model = model.cuda()
+    n = agree = 0
+    worst = 0.0
+    b = 0
+    while n < args.agreement:
+        _, img, ids, mask = synth_batch(250, 1234 + b)
+        with torch.no_grad():
+            got, _ = model(img.cuda(), ids.cuda(), mask.cuda())
+        want, _ = O.vqa_forward(sd, img, ids, mask)
+        got = got.cpu()
+        agree += int((got.argmax(1) == want.argmax(1)).sum())
+        worst = max(worst, float((got - want).abs().max() / want.abs().max()))
+        n += 250
+        b += 1
+    print(json.dumps({"pairs": n, "top1_agreement": agree / n, "max_abs_rel_logit_err": worst}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default="")
+    ap.add_argument("--agreement", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.agreement:
+        return run_agreement(args)
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+/*
+ * vqa_b200.h -- C ABI of libvqa_b200.so: the sm_100a engine behind the reference's
+ * VQAModel.forward / VQAInference.predict hot path.
+ *
+ * The reference (zeyadmohamedabdo/Visual-Question-Answering-VQA-system) is pure Python on
+ * PyTorch; it has no FFI of its own.  This header is therefore the boundary a maintainer
+ * would bind with ctypes from models/vqa_model.py:243-311 (VQAModel.forward) and
+ * api/inference.py:195-323 (predict / predict_batch); INTEGRATION.md shows the stub.
+ * Each op kind below names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C types only: device pointers as uint64_t, sizes as int32_t, cudaStream_t as void*.
+ *   - the caller owns every buffer (weights arena, workspace, inputs, outputs); the library
+ *     never allocates or frees device memory, never synchronises the device, and launches
+ *     only on the stream it is given, so a run can be captured in a CUDA graph.
+ *   - every entry point returns 0 on success or a negative VQA_E_* code; vqa_last_error()
+ *     returns a thread-local human-readable message.  Nothing aborts the process
+ *     (api/main.py:213-221 expects exceptions it can stringify).
+ *   - a "plan" is an immutable list of ops (kernel launches) with their tensor maps encoded
+ *     once; the Python host builds the list from the model's state_dict (program.py).
+ *   - a pointer field whose top bit is set is an external slot: (VQA_EXT_TAG | k) resolves to
+ *     ext[k] of vqa_plan_run (model inputs / outputs that change per call).
+ */
+#ifndef VQA_B200_H_
+#define VQA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQA_ABI_VERSION 3
+
+#define VQA_OK            0
+#define VQA_E_INVALID    -1   /* bad argument / unsupported shape */
+#define VQA_E_CUDA       -2   /* CUDA runtime or driver error (message has the detail) */
+#define VQA_E_ALIGN      -3   /* misaligned pointer or stride */
+#define VQA_E_UNSUPPORTED -4  /* device is not sm_100 */
+
+#define VQA_EXT_TAG   0x8000000000000000ull
+#define VQA_MAX_TAPS   16
+#define VQA_MAX_GROUPS 12
+#define VQA_OP_NI      144
+#define VQA_OP_NP     12
+#define VQA_OP_NF     4
+
+/* Op kinds.  Field layouts (indices into VqaOp.i / .p / .f) are listed in program.py
+ * (FIELDS) and mirrored by the *_I / *_P enums in csrc/ops.h; vqa_op_num_fields() lets the
+ * host verify both sides agree. */
+enum VqaOpKind {
+  VQA_OP_INGEST        = 1,  /* NCHW fp32 (models/vqa_model.py:243-258) or uint8 HWC + normalise
+                                (data/preprocess.py:117-121) -> phase-packed bf16 stem input */
+  VQA_OP_GEMM          = 2,  /* tap-shifted GEMM on tcgen05: every Conv2d+BN(+ReLU)(+residual)
+                                (models/cnn_backbone.py:164-197,349-352) and every nn.Linear */
+  VQA_OP_MAXPOOL       = 3,  /* MaxPool2d 3x3/2 p1 (models/cnn_backbone.py:353) */
+  VQA_OP_SE_SQUEEZE    = 4,  /* adaptive_avg_pool2d partial sums (models/attention_modules.py:116) */
+  VQA_OP_SE_EXCITE     = 5,  /* fc1-ReLU-fc2-sigmoid (models/attention_modules.py:123-126) */
+  VQA_OP_SPATIAL_MAP   = 6,  /* channel max/mean, 7x7 conv, sigmoid (models/attention_modules.py:223-240) */
+  VQA_OP_SCALE_RELAYOUT= 7,  /* x*scale[c]*map[pixel] (attention_modules.py:133-136,243) + layout for next stage */
+  VQA_OP_EMBED         = 8,  /* embedding*sqrt(D)+PE (models/text_encoder.py:504-512) */
+  VQA_OP_LAYERNORM     = 9,  /* nn.LayerNorm(256) (+ projector row compaction and position add, models/fusion.py:98-112) */
+  VQA_OP_SELF_ATTN     = 10, /* masked softmax(QK^T/sqrt(d))V (models/text_encoder.py:229-259) */
+  VQA_OP_CROSS_ATTN    = 11, /* softmax(QK^T/sqrt(d))V over 49 image tokens (models/cross_attention.py:164-197) */
+  VQA_OP_POOL_GATE_LN  = 12, /* masked mean pools, gate, output_norm (models/fusion.py:299-326) */
+  VQA_OP_SOFTMAX_TOPK  = 13, /* softmax + top-k (models/vqa_model.py:336-337, api/inference.py:231-234) */
+  VQA_OP_MASK_PREP     = 14, /* attention_mask (int64 | fp32 | absent) -> int32 */
+  VQA_OP_GRID_TO_NCHW  = 15, /* padded-flat bf16 grid -> NCHW fp32 (aux['image_features'], models/vqa_model.py:301-309) */
+  VQA_OP_KIND_MAX      = 16
+};
+
+typedef struct VqaOp {
+  int32_t  kind;
+  int32_t  pad_;
+  int32_t  i[VQA_OP_NI];
+  float    f[VQA_OP_NF];
+  uint64_t p[VQA_OP_NP];
+} VqaOp;
+
+typedef struct VqaPlan VqaPlan;
+
+/* library / device */
+int         vqa_abi_version(void);
+const char* vqa_last_error(void);
+int         vqa_device_check(int device);            /* 0 iff `device` is compute capability 10.x */
+int         vqa_op_num_fields(int kind, int* n_i, int* n_p, int* n_f);
+
+/* plans */
+int  vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** out);
+int  vqa_plan_run(const VqaPlan* plan, const uint64_t* ext, int32_t n_ext, void* stream);
+int  vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last,
+                        const uint64_t* ext, int32_t n_ext, void* stream);
+int  vqa_plan_num_launches(const VqaPlan* plan);      /* kernels one vqa_plan_run launches */
+int  vqa_plan_op_kernel_name(const VqaPlan* plan, int32_t op, char* buf, int32_t buflen);
+void vqa_plan_destroy(VqaPlan* plan);
+
+/* counters (process-wide): kernels launched by this library since load */
+uint64_t vqa_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_B200_H_ */

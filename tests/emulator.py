@@ -1,0 +1,306 @@
+"""CPU interpreter for vqa_b200.program op lists (TEST INFRASTRUCTURE).
+
+Executes the exact op list the CUDA library receives, on CPU tensors, with the same storage
+dtypes (bf16 activations, tf32-truncated GEMM operands).  It validates the layout and tap
+algebra of ``program.py`` against the oracle without a GPU, and on the GPU box it serves as
+the per-op expected value for the kernels in ``csrc/``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from vqa_b200 import program as P
+
+MEAN = torch.tensor([0.485, 0.456, 0.406])
+STD = torch.tensor([0.229, 0.224, 0.225])
+
+
+def trunc_tf32(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _t(ref, dtype, ext):
+    """Flat typed view of a Buf / external tensor."""
+    if ref is None:
+        return None
+    if isinstance(ref, P.ExtRef):
+        return ext[ref.slot]
+    return ref.arena.tensor[ref.offset:].view(dtype)
+
+
+def _grid_index(B, H, W, Pp, rpi):
+    n = torch.arange(B).view(B, 1, 1)
+    h = torch.arange(H).view(1, H, 1)
+    w = torch.arange(W).view(1, 1, W)
+    return (n * rpi + h * Pp + w).reshape(-1)  # [B*H*W] flat rows, NHW order
+
+
+class Emulator:
+    def __init__(self, prog: P.Program, tf32_truncate: bool = True):
+        self.prog = prog
+        self.tf32_truncate = tf32_truncate
+
+    def run(self, ext, first=0, last=None):
+        ops = self.prog.ops[first:last]
+        for op in ops:
+            getattr(self, "op_" + op.kind)(op, ext)
+
+    # ------------------------------------------------------------------ ops
+    def op_ingest(self, op, ext):
+        i = op.i
+        B, Pp, rows = i["B"], i["P"], i["rows"]
+        src = ext[op.p["src"].slot]
+        if i["mode"] == 0:
+            x = src.float().view(B, 3, 224, 224)
+        else:
+            x = src.view(B, 224, 224, 3).float().div(255.0)
+            x = ((x - MEAN) / STD).permute(0, 3, 1, 2)
+        dst = _t(op.p["dst"], torch.bfloat16, ext)[: rows * 16].view(rows, 16)
+        dst.zero_()
+        # [B,3,112,2,112,2] -> [B,112,112,ph,pw,c]
+        xp = x.reshape(B, 3, 112, 2, 112, 2).permute(0, 2, 4, 3, 5, 1)
+        packed = torch.zeros(B, 112, 112, 2, 2, 4)
+        packed[..., :3] = xp
+        idx = _grid_index(B, 112, 112, Pp, Pp * Pp)
+        dst[idx] = packed.reshape(-1, 16).to(torch.bfloat16)
+
+    def op_gemm(self, op, ext):
+        i = op.i
+        dt = torch.bfloat16 if i["dtype"] == P.DT_BF16 else torch.float32
+        chunk = 64 if i["dtype"] == P.DT_BF16 else 32
+        M, N, Npad, Ktot = i["M"], i["N"], i["Npad"], i["Ktot"]
+        amaps = []
+        for k in ("a0", "a1"):
+            ref = op.p.get(k)
+            if ref is None:
+                amaps.append(None)
+                continue
+            rows, cols, ld = i[k + "_rows"], i[k + "_cols"], i[k + "_ld"]
+            flat = _t(ref, dt, ext)
+            amaps.append(torch.as_strided(flat, (rows, cols), (ld, 1)))
+        Wt = _t(op.p["b"], dt, ext)[: Npad * Ktot].view(Npad, Ktot).float()
+        acc = torch.zeros(M, Npad)
+        m = torch.arange(M)
+        halo = i["halo"]
+        covered = 0
+        for g in range(i["ngroups"]):
+            A = amaps[i[f"g_map{g}"]]
+            delta, acol, nch = i[f"g_delta{g}"], i[f"g_acol{g}"], i[f"g_chunks{g}"]
+            ntaps, kbase, tap0 = i[f"g_ntaps{g}"], i[f"g_kbase{g}"], i[f"g_tap0{g}"]
+            kw = nch * chunk
+            for t in range(ntaps):
+                idx = m + delta - halo + i[f"tap_rel{tap0 + t}"]
+                ok = (idx >= 0) & (idx < A.shape[0])
+                a = torch.zeros(M, kw)
+                a[ok] = A[idx[ok], acol: acol + kw].float()
+                if i["dtype"] == P.DT_TF32 and self.tf32_truncate:
+                    a = trunc_tf32(a)
+                kcol = kbase + t * kw
+                acc += a @ Wt[:, kcol: kcol + kw].t()
+                covered += kw
+        assert covered == Ktot
+        acc = acc[:, :N]
+        if op.p.get("bias") is not None:
+            acc = acc + _t(op.p["bias"], torch.float32, ext)[:N]
+        if op.p.get("res") is not None:
+            rdt = torch.bfloat16 if i["res_dtype"] == P.OUT_BF16 else torch.float32
+            r = torch.as_strided(_t(op.p["res"], rdt, ext), (M, N), (i["ldr"], 1)).float()
+            acc = acc + r
+        if i["relu"]:
+            acc = acc.clamp_min(0)
+        if i["mask_en"]:
+            rem = m % i["mRPI"]
+            valid = ((rem // i["mP"]) < i["mH"]) & ((rem % i["mP"]) < i["mW"])
+            acc = torch.where(valid.view(-1, 1), acc, torch.zeros(()))
+        if i["round_tf32"]:
+            acc = P.round_tf32(acc)
+        odt = torch.bfloat16 if i["out_dtype"] == P.OUT_BF16 else torch.float32
+        out = torch.as_strided(_t(op.p["out"], odt, ext), (M, N), (i["ldo"], 1))
+        out.copy_(acc.to(odt))
+
+    def op_maxpool(self, op, ext):
+        i = op.i
+        B, C = i["B"], i["C"]
+        src = _t(op.p["src"], torch.bfloat16, ext)[: B * i["RPIin"] * C].view(B * i["RPIin"], C)
+        idx = _grid_index(B, i["Hin"], i["Win"], i["Pin"], i["RPIin"])
+        x = src[idx].float().view(B, i["Hin"], i["Win"], C).permute(0, 3, 1, 2)
+        y = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1).reshape(-1, C)
+        dst = _t(op.p["dst"], torch.bfloat16, ext)[: B * i["RPIout"] * C].view(B * i["RPIout"], C)
+        dst.zero_()
+        dst[_grid_index(B, i["Hout"], i["Wout"], i["Pout"], i["RPIout"])] = y.to(torch.bfloat16)
+
+    def _grid_nhwc(self, ref, ext, B, C, H, W, Pp, rpi):
+        src = _t(ref, torch.bfloat16, ext)[: B * rpi * C].view(B * rpi, C)
+        return src[_grid_index(B, H, W, Pp, rpi)].float().view(B, H, W, C)
+
+    def op_se_squeeze(self, op, ext):
+        i = op.i
+        x = self._grid_nhwc(op.p["src"], ext, i["B"], i["C"], i["H"], i["W"], i["P"], i["RPI"])
+        _t(op.p["sums"], torch.float32, ext)[: i["B"] * i["C"]].view(i["B"], i["C"]).copy_(x.sum(dim=(1, 2)))
+
+    def op_se_excite(self, op, ext):
+        i = op.i
+        B, C, R = i["B"], i["C"], i["R"]
+        mean = _t(op.p["sums"], torch.float32, ext)[: B * C].view(B, C) / i["HW"]
+        w1 = _t(op.p["w1"], torch.float32, ext)[: R * C].view(R, C)
+        w2 = _t(op.p["w2"], torch.float32, ext)[: R * C].view(C, R)
+        sc = torch.sigmoid(F.relu(mean @ w1.t()) @ w2.t())
+        _t(op.p["scale"], torch.float32, ext)[: B * C].view(B, C).copy_(sc)
+
+    def op_spatial_map(self, op, ext):
+        i = op.i
+        B, C, H, W, ks = i["B"], i["C"], i["H"], i["W"], i["ksize"]
+        x = self._grid_nhwc(op.p["src"], ext, B, C, H, W, i["P"], i["RPI"])
+        if op.p.get("scale") is not None:
+            x = x * _t(op.p["scale"], torch.float32, ext)[: B * C].view(B, 1, 1, C)
+        pooled = torch.stack([x.max(dim=3)[0], x.mean(dim=3)], dim=1)  # [B,2,H,W], max first
+        w = _t(op.p["wconv"], torch.float32, ext)[: 2 * ks * ks].view(1, 2, ks, ks)
+        att = torch.sigmoid(F.conv2d(pooled, w, None, padding=ks // 2))
+        _t(op.p["att"], torch.float32, ext)[: B * H * W].view(B, H * W).copy_(att.view(B, H * W))
+
+    def op_scale_relayout(self, op, ext):
+        i = op.i
+        B, C, H, W = i["B"], i["C"], i["H"], i["W"]
+        x = self._grid_nhwc(op.p["src"], ext, B, C, H, W, i["P"], i["RPI"])
+        if op.p.get("scale") is not None:
+            x = x * _t(op.p["scale"], torch.float32, ext)[: B * C].view(B, 1, 1, C)
+        if op.p.get("att") is not None:
+            x = x * _t(op.p["att"], torch.float32, ext)[: B * H * W].view(B, H, W, 1)
+        x = x.to(torch.bfloat16)
+        if i["mode"] == 0:
+            dst = _t(op.p["dst"], torch.bfloat16, ext)[: B * i["RPIo"] * C].view(B * i["RPIo"], C)
+            dst.zero_()
+            dst[_grid_index(B, H, W, i["Po"], i["RPIo"])] = x.reshape(-1, C)
+        else:
+            pr = i["phase_rows"]
+            dst = _t(op.p["dst"], torch.bfloat16, ext)[: 4 * pr * C].view(4, pr, C)
+            dst.zero_()
+            idx = _grid_index(B, H // 2, W // 2, i["Po"], i["RPIo"])
+            for ph in range(2):
+                for pw in range(2):
+                    dst[ph * 2 + pw][idx] = x[:, ph::2, pw::2, :].reshape(-1, C)
+
+    def op_grid_to_nchw(self, op, ext):
+        i = op.i
+        x = self._grid_nhwc(op.p["src"], ext, i["B"], i["C"], i["H"], i["W"], i["P"], i["RPI"])
+        n = i["B"] * i["C"] * i["H"] * i["W"]
+        _t(op.p["dst"], torch.float32, ext)[:n].view(i["B"], i["C"], i["H"], i["W"]).copy_(x.permute(0, 3, 1, 2))
+
+    def op_mask_prep(self, op, ext):
+        i = op.i
+        src = ext[op.p["src"].slot]
+        _t(op.p["dst"], torch.int32, ext)[: i["B"] * i["L"]].view(i["B"], i["L"]).copy_((src != 0).to(torch.int32))
+
+    def op_embed(self, op, ext):
+        i = op.i
+        B, L, D, V = i["B"], i["L"], i["D"], i["V"]
+        ids = ext[op.p["ids"].slot].view(B, L)
+        table = _t(op.p["table"], torch.float32, ext)[: V * D].view(V, D)
+        pe = _t(op.p["pe"], torch.float32, ext)
+        x = table[ids] + pe[: L * D].view(1, L, D)
+        _t(op.p["dst"], torch.float32, ext)[: B * L * D].view(B, L, D).copy_(x)
+
+    def op_layernorm(self, op, ext):
+        i = op.i
+        rows, D = i["rows"], i["D"]
+        g = _t(op.p["gamma"], torch.float32, ext)[:D]
+        b = _t(op.p["beta"], torch.float32, ext)[:D]
+        flat = _t(op.p["src"], torch.float32, ext)
+        if i["mode"] == 0:
+            x = torch.as_strided(flat, (rows, D), (i["ld_src"], 1))
+        else:
+            S = i["S"]
+            Bn = rows // (S * S)
+            idx = _grid_index(Bn, S, S, i["Pg"], i["RPIg"])
+            x = torch.as_strided(flat, (Bn * i["RPIg"], D), (i["ld_src"], 1))[idx]
+        y = F.layer_norm(x, (D,), g, b, op.f["eps"])
+        if i["mode"] == 1:
+            S = i["S"]
+            pos = _t(op.p["pos"], torch.float32, ext)[: S * S * D].view(1, S * S, D)
+            y = (y.view(-1, S * S, D) + pos).view(rows, D)
+        if i["round_tf32"]:
+            y = P.round_tf32(y)
+        _t(op.p["dst"], torch.float32, ext)[: rows * D].view(rows, D).copy_(y)
+
+    @staticmethod
+    def _attend(q, k, v, hd, key_mask=None):
+        s = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(hd)
+        if key_mask is not None:
+            s = s.masked_fill(key_mask.view(key_mask.shape[0], 1, 1, -1) == 0, float("-inf"))
+        w = F.softmax(s, dim=-1)
+        return torch.matmul(w, v), w
+
+    def op_self_attn(self, op, ext):
+        i = op.i
+        B, L, H, hd, ld = i["B"], i["L"], i["H"], i["hd"], i["ld_qkv"]
+        D = H * hd
+        qkv = _t(op.p["qkv"], torch.float32, ext)[: B * L * ld].view(B, L, ld)
+        q, k, v = (qkv[..., j * D:(j + 1) * D].reshape(B, L, H, hd).transpose(1, 2) for j in range(3))
+        mask = None
+        if op.p.get("mask") is not None:
+            mask = _t(op.p["mask"], torch.int32, ext)[: B * L].view(B, L)
+        ctx, _ = self._attend(q, k, v, hd, mask)
+        _t(op.p["out"], torch.float32, ext)[: B * L * D].view(B, L, D).copy_(ctx.transpose(1, 2).reshape(B, L, D))
+
+    def op_cross_attn(self, op, ext):
+        i = op.i
+        B, L, H, hd, T = i["B"], i["L"], i["H"], i["hd"], i["T"]
+        D = H * hd
+        q = torch.as_strided(_t(op.p["q"], torch.float32, ext), (B * L, D), (i["ld_q"], 1)).view(B, L, H, hd).transpose(1, 2)
+        kvf = _t(op.p["kv"], torch.float32, ext)
+        k = torch.as_strided(kvf[i["k_off"]:], (B * T, D), (i["ld_kv"], 1)).view(B, T, H, hd).transpose(1, 2)
+        v = torch.as_strided(kvf[i["v_off"]:], (B * T, D), (i["ld_kv"], 1)).view(B, T, H, hd).transpose(1, 2)
+        ctx, w = self._attend(q, k, v, hd)
+        _t(op.p["out"], torch.float32, ext)[: B * L * D].view(B, L, D).copy_(ctx.transpose(1, 2).reshape(B, L, D))
+        if op.p.get("weights") is not None:
+            _t(op.p["weights"], torch.float32, ext)[: B * H * L * T].view(B, H, L, T).copy_(w)
+
+    def op_pool_gate_ln(self, op, ext):
+        i = op.i
+        B, L, D = i["B"], i["L"], i["D"]
+        xa = _t(op.p["xatt"], torch.float32, ext)[: B * L * D].view(B, L, D)
+        tx = _t(op.p["text"], torch.float32, ext)[: B * L * D].view(B, L, D)
+        if op.p.get("mask") is not None:
+            m = _t(op.p["mask"], torch.int32, ext)[: B * L].view(B, L, 1).float()
+        else:
+            m = torch.ones(B, L, 1)
+        den = m.sum(dim=1).clamp(min=1)
+        ap = (xa * m).sum(dim=1) / den
+        tp = (tx * m).sum(dim=1) / den
+        if i["use_gate"]:
+            wg = _t(op.p["wg"], torch.float32, ext)[: D * 2 * D].view(D, 2 * D)
+            bg = _t(op.p["bg"], torch.float32, ext)[:D]
+            g = torch.sigmoid(torch.cat([ap, tp], dim=-1) @ wg.t() + bg)
+            fz = g * ap + (1 - g) * tp
+        else:
+            fz = ap + tp
+        fz = F.layer_norm(fz, (D,), _t(op.p["gamma"], torch.float32, ext)[:D],
+                          _t(op.p["beta"], torch.float32, ext)[:D], op.f["eps"])
+        for key, val in (("fused", fz), ("att_pooled", ap), ("txt_pooled", tp)):
+            _t(op.p[key], torch.float32, ext)[: B * D].view(B, D).copy_(val)
+
+    def op_softmax_topk(self, op, ext):
+        i = op.i
+        B, N, k = i["B"], i["N"], i["k"]
+        logits = torch.as_strided(ext[op.p["logits"].slot].view(-1), (B, N), (i["ld"], 1))
+        probs, idx = F.softmax(logits, dim=-1).topk(k, dim=-1)
+        ext[op.p["idx"].slot].view(B, k).copy_(idx)
+        ext[op.p["probs"].slot].view(B, k).copy_(probs)
+
+
+def run_program(prog: P.Program, images, ids, mask, top_k=0, tf32_truncate=True):
+    """Run a CPU-resident program; returns (logits, ext list)."""
+    B = prog.B
+    NA = prog.cfg["num_answers"]
+    ext = [None] * 6
+    ext[P.EXT["images"]] = images
+    ext[P.EXT["ids"]] = ids
+    ext[P.EXT["mask"]] = mask
+    ext[P.EXT["logits"]] = torch.zeros(B, NA)
+    ext[P.EXT["top_idx"]] = torch.zeros(B, max(top_k, 1), dtype=torch.int64)
+    ext[P.EXT["top_probs"]] = torch.zeros(B, max(top_k, 1))
+    Emulator(prog, tf32_truncate).run(ext)
+    return ext[P.EXT["logits"]], ext

@@ -1,0 +1,163 @@
+"""tcgen05 tap-shifted GEMM (VQA_OP_GEMM) through the C ABI against the CPU emulator.
+
+Ordered from the plainest configuration to the ones that rely on less-documented hardware
+behaviour (row-shifted UMMA descriptors inside a SWIZZLE_128B window, overlapping-row tensor
+maps), so that a failure in the latter does not hide the former.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vqa_b200 import program as P  # noqa: E402
+import gpu_util as G  # noqa: E402
+
+
+def _weights(device, name, n, k, dtype, seed, npad=None):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(n, k, generator=g) * (1.0 / k ** 0.5)
+    if dtype == torch.float32:
+        w = P.round_tf32(w)
+    if npad:
+        w = P._pad_rows(w, npad)
+    W = P.Weights(device)
+    W.add(name + ".w", w, dtype)
+    W.add(name + ".b", P._pad_rows(torch.randn(n, generator=g), npad or 1), torch.float32)
+    return W
+
+
+def _fill(ol, name, seed, scale=1.0):
+    b, dtype, shape = ol.named[name]
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.randn(*shape, generator=g) * scale)
+    if dtype == torch.float32:
+        t = P.round_tf32(t)
+    return t.to(dtype)
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (300, 128, 64), (1000, 192, 128), (517, 256, 256), (130, 512, 512)])
+@pytest.mark.parametrize("out_dtype", [P.OUT_BF16, P.OUT_F32])
+def test_plain_bf16_gemm(M, K, N, out_dtype):
+    def build(device):
+        W = _weights(device, "w", N, K, torch.bfloat16, 1).finalize()
+        ol = P.OpList(W, device)
+        a = ol._buf("a", torch.bfloat16, M, K)
+        o = ol._buf("o", torch.bfloat16 if out_dtype == P.OUT_BF16 else torch.float32, M, N)
+        ol.gemm("g", dtype=P.DT_BF16, M=M, N=N, a0=a, a0_shape=(M, K, K), groups=[(0, 0, 0, K // 64, [0])],
+                w="w.w", bias="w.b", out=o, ldo=N, out_dtype=out_dtype, relu=True)
+        ol.commit()
+        G.named(ol, "a").copy_(_fill(ol, "a", 2))
+        return ol
+    cpu, gpu, _, _ = G.run_pair(build)
+    tol = 2e-2 if out_dtype == P.OUT_BF16 else 2e-3
+    G.report(f"plain bf16 M{M} K{K} N{N}", G.named(gpu, "o"), G.named(cpu, "o"), atol=tol, rtol=1e-2)
+
+
+@pytest.mark.parametrize("M,K,N,ldo", [(256, 256, 256, 256), (100, 256, 768, 768), (77, 1024, 256, 256),
+                                      (256, 256, 1000, 1000), (5, 512, 37, 37)])
+def test_tf32_linear_with_residual(M, K, N, ldo):
+    def build(device):
+        W = _weights(device, "w", N, K, torch.float32, 3, npad=256).finalize()
+        ol = P.OpList(W, device)
+        a = ol._buf("a", torch.float32, M, K)
+        o = ol._buf("o", torch.float32, M, ldo)
+        ol.linear("lin", a, M, K, "w.w", "w.b", o, N, ldo=ldo, res=o)
+        ol.commit()
+        G.named(ol, "a").copy_(_fill(ol, "a", 4))
+        G.named(ol, "o").copy_(_fill(ol, "o", 5))
+        return ol
+    cpu, gpu, _, _ = G.run_pair(build)
+    G.report(f"tf32 M{M} K{K} N{N}", G.named(gpu, "o"), G.named(cpu, "o"), atol=2e-3, rtol=2e-3)
+
+
+def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, desc_mode=0, extra_ds=False):
+    g = P.Grid(B, H, Wd)
+    gen = torch.Generator().manual_seed(7)
+    k = 9 * cin + (cin if extra_ds else 0)
+    W = P.Weights(device)
+    W.add("c.w", torch.randn(cout, k, generator=gen) * (1.0 / k ** 0.5), torch.bfloat16)
+    W.add("c.b", torch.randn(cout, generator=gen), torch.float32)
+    W.finalize()
+    ol = P.OpList(W, device, window=window)
+    x = ol._buf("x", torch.bfloat16, g.rows, cin)
+    x1 = ol._buf("x1", torch.bfloat16, g.rows, cin)
+    o = ol._buf("o", torch.bfloat16, g.rows, cout)
+    groups, halo, mt_auto = ol._conv3x3_groups(g, cin // 64, cout)
+    if extra_ds:
+        groups = groups + [(1, 0, 0, cin // 64, [halo])]
+    ol.gemm("conv", dtype=P.DT_BF16, M=g.rows, N=cout, a0=x, a0_shape=(g.rows, cin, cin), groups=groups,
+            a1=x1 if extra_ds else None, a1_shape=(g.rows, cin, cin) if extra_ds else None,
+            w="c.w", bias="c.b", out=o, ldo=cout, out_dtype=P.OUT_BF16, relu=True,
+            res=x if residual else None, res_dtype=P.OUT_BF16 if residual else -1, ldr=cin, grid=g,
+            halo=halo, MT=mt or mt_auto)
+    ol.ops[-1].i["desc_mode"] = desc_mode
+    ol.commit()
+    # valid pixels random, shared pads zero (the layout invariant every producer keeps)
+    xv = torch.randn(g.rows, cin, generator=gen)
+    r = torch.arange(g.rows) % g.rpi
+    valid = ((r // g.P) < g.H) & ((r % g.P) < g.W)
+    xv[~valid] = 0
+    G.named(ol, "x").copy_(xv.to(torch.bfloat16))
+    x1v = torch.randn(g.rows, cin, generator=gen)
+    x1v[~valid] = 0
+    G.named(ol, "x1").copy_(x1v.to(torch.bfloat16))
+    return ol
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,residual", [(2, 8, 8, 64, 64, False), (3, 14, 14, 128, 128, True),
+                                                    (2, 7, 7, 256, 512, False)])
+def test_conv3x3_per_tap_loads(B, H, W, cin, cout, residual):
+    """window=False: every tap TMA-loads its own row-shifted A tile (negative / out-of-range rows zero-fill)."""
+    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, False, B, H, W, cin, cout, residual and cin == cout))
+    G.report(f"conv per-tap {B}x{H}x{W} {cin}->{cout}", G.named(gpu, "o"), G.named(cpu, "o"), atol=3e-2, rtol=2e-2)
+
+
+def test_conv3x3_matches_torch_conv2d():
+    """The padded-flat shift-GEMM is a real 3x3 convolution: compare with F.conv2d on the valid pixels."""
+    B, H, Wd, cin, cout = 2, 9, 11, 64, 64
+    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, False, B, H, Wd, cin, cout, False))
+    g = P.Grid(B, H, Wd)
+    import emulator as E
+    idx = E._grid_index(B, H, Wd, g.P, g.rpi)
+    x = G.named(cpu, "x")[idx].float().view(B, H, Wd, cin).permute(0, 3, 1, 2)
+    w = cpu.W.tensor("c.w").float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    want = torch.relu(torch.nn.functional.conv2d(x, w, cpu.W.tensor("c.b"), padding=1))
+    got = G.named(gpu, "o").cpu()[idx].float().view(B, H, Wd, cout).permute(0, 3, 1, 2)
+    G.report("conv vs F.conv2d", got, want, atol=3e-2, rtol=2e-2)
+    pads = torch.ones(g.rows, dtype=torch.bool)
+    pads[idx] = False
+    assert G.named(gpu, "o").cpu()[pads].abs().max() == 0  # shared zero padding is preserved
+
+
+def test_stem_overlapping_row_tensor_map():
+    """Stem trick: rows of 64 bf16 that start every 16 elements (overlapping global strides)."""
+    rows, guard = 1000, 32
+    def build(device):
+        W = _weights(device, "w", 64, 256, torch.bfloat16, 11).finalize()
+        ol = P.OpList(W, device)
+        a = ol._buf("a", torch.bfloat16, rows + guard, 16)
+        o = ol._buf("o", torch.float32, rows, 64)
+        taps = [(0, (ia - 2) * 30 - 2 + guard, 0, 1, [0]) for ia in range(4)]
+        ol.gemm("stem", dtype=P.DT_BF16, M=rows, N=64, a0=a, a0_shape=(rows + guard, 64, 16), groups=taps,
+                w="w.w", bias="w.b", out=o, ldo=64, out_dtype=P.OUT_F32)
+        ol.commit()
+        G.named(ol, "a").copy_(_fill(ol, "a", 12))
+        return ol
+    cpu, gpu, _, _ = G.run_pair(build)
+    G.report("stem overlapped map", G.named(gpu, "o"), G.named(cpu, "o"), atol=2e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("desc_mode", [0, 1])
+@pytest.mark.parametrize("B,H,W,cin,cout,mt", [(2, 8, 8, 64, 64, 1), (2, 56, 56, 64, 64, 1), (3, 14, 14, 128, 128, 2),
+                                              (4, 28, 28, 128, 128, 2), (2, 7, 7, 512, 512, 2)])
+def test_conv3x3_window(B, H, W, cin, cout, mt, desc_mode):
+    """window=True: one A window per K chunk, taps are row-shifted UMMA descriptors into it."""
+    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, True, B, H, W, cin, cout, cin == cout, mt=mt,
+                                                     desc_mode=desc_mode))
+    G.report(f"conv window desc_mode={desc_mode} {B}x{H}x{W} {cin}->{cout} MT{mt}", G.named(gpu, "o"),
+             G.named(cpu, "o"), atol=3e-2, rtol=2e-2)
+
+
+def test_conv3x3_window_with_shortcut_group():
+    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, True, 3, 14, 14, 128, 128, False, mt=2, extra_ds=True))
+    G.report("conv window + shortcut K group", G.named(gpu, "o"), G.named(cpu, "o"), atol=3e-2, rtol=2e-2)

@@ -1,0 +1,102 @@
+"""Every op of the real forward program, one at a time, against the CPU emulator.
+
+Before each op the GPU workspace is overwritten with the emulator's state, so each kernel sees
+bit-identical inputs and an error is attributed to exactly one launch (op index + name are in
+the assertion message).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import emulator as E  # noqa: E402
+from vqa_b200 import program as P  # noqa: E402
+from vqa_b200.model import VQAModel  # noqa: E402
+from vqa_b200.runtime import Plan  # noqa: E402
+from vqa_b200.synth import randomise_state, synth_batch  # noqa: E402
+
+OUTPUTS = {
+    "ingest": [("dst", torch.bfloat16)], "gemm": [("out", None)], "maxpool": [("dst", torch.bfloat16)],
+    "se_squeeze": [("sums", torch.float32)], "se_excite": [("scale", torch.float32)],
+    "spatial_map": [("att", torch.float32)], "scale_relayout": [("dst", torch.bfloat16)],
+    "embed": [("dst", torch.float32)], "layernorm": [("dst", torch.float32)],
+    "self_attn": [("out", torch.float32)], "cross_attn": [("out", torch.float32), ("weights", torch.float32)],
+    "pool_gate_ln": [("fused", torch.float32), ("att_pooled", torch.float32), ("txt_pooled", torch.float32)],
+    "softmax_topk": [("idx", torch.int64), ("probs", torch.float32)], "mask_prep": [("dst", torch.int32)],
+    "grid_to_nchw": [("dst", torch.float32)],
+}
+
+
+def _view(ref, dtype, ext):
+    if isinstance(ref, P.ExtRef):
+        return ext[ref.slot].reshape(-1)
+    return ref.arena.tensor[ref.offset: ref.offset + ref.nbytes].view(dtype)
+
+
+def _case(ctor, B, L, in_fmt, mask_kind, window=True, seed=0):
+    torch.manual_seed(seed)
+    model = VQAModel(**ctor).eval()
+    sd = randomise_state(model.state_dict(), 1)
+    u8, img, ids, mask = synth_batch(B, 1234, max_len=L, vocab=model.config["vocab_size"])
+    images = u8 if in_fmt == "hwc_u8" else img
+    code = {"i64": P.MASK_I64, "f32": P.MASK_F32, "none": P.MASK_NONE}[mask_kind]
+    m = {"i64": mask, "f32": mask.float(), "none": None}[mask_kind]
+    progs = {}
+    for dev in ("cpu", "cuda"):
+        W = P.build_weights(sd, model.config, dev)
+        progs[dev] = P.Program(W, model.config, B, L, in_fmt, code, want_aux=True, top_k=5, device=dev, window=window)
+    NA = model.config["num_answers"]
+    ext = [images, ids, m, torch.zeros(B, NA), torch.zeros(B, 5, dtype=torch.int64), torch.zeros(B, 5)]
+    return progs["cpu"], progs["cuda"], ext
+
+
+@pytest.mark.parametrize("ctor,B,L,in_fmt,mask_kind,window", [
+    ({}, 2, 20, "nchw_f32", "i64", True),
+    ({}, 3, 20, "hwc_u8", "f32", False),
+    (dict(use_se_attention=False, use_spatial_attention=False, use_gating=False, num_transformer_layers=1,
+          num_cross_layers=1, max_question_length=12, vocab_size=500, num_answers=37), 2, 12, "nchw_f32", "none", True),
+    (dict(use_spatial_attention=False, max_question_length=64, num_cross_layers=1, num_transformer_layers=1),
+     1, 64, "nchw_f32", "i64", True),
+])
+def test_each_op_against_emulator(ctor, B, L, in_fmt, mask_kind, window):
+    cpu, gpu, ext = _case(ctor, B, L, in_fmt, mask_kind, window)
+    ext_gpu = [None if t is None else t.cuda() for t in ext]
+    plan = Plan(gpu.ops, 0)
+    emu = E.Emulator(cpu)
+    stream = torch.cuda.current_stream().cuda_stream
+    failures = []
+    for k, op in enumerate(cpu.ops):
+        gpu.ws.tensor.copy_(cpu.ws.tensor)
+        for a, b in zip(ext_gpu, ext):
+            if a is not None:
+                a.copy_(b)
+        emu.run(ext, k, k + 1)
+        plan.run([0 if t is None else t.data_ptr() for t in ext_gpu], stream, k, k + 1)
+        torch.cuda.synchronize()
+        gop = gpu.ops[k]
+        for field, dtype in OUTPUTS[op.kind]:
+            ref_c, ref_g = op.p.get(field), gop.p.get(field)
+            if ref_c is None:
+                continue
+            if dtype is None:
+                dtype = torch.bfloat16 if op.i["out_dtype"] == P.OUT_BF16 else torch.float32
+            want = _view(ref_c, dtype, ext)
+            got = _view(ref_g, dtype, ext_gpu).cpu()
+            if dtype in (torch.int32, torch.int64):
+                ok = torch.equal(got, want)
+                msg = f"op {k} {op.name} ({plan.kernel_name(k)}) {field}: integer mismatch"
+            else:
+                g32, w32 = got.float(), want.float()
+                atol, rtol = (1e-2, 1.6e-2) if dtype == torch.bfloat16 else (2e-3, 2e-3)
+                if op.kind in ("se_squeeze",):
+                    atol = 1e-2
+                err = (g32 - w32).abs()
+                finite = torch.isfinite(g32).all()
+                ok = bool(finite) and bool((err <= atol + rtol * w32.abs()).all())
+                msg = (f"op {k} {op.name} ({plan.kernel_name(k)}) {field}: max_abs_err={err.max().item():.3e} "
+                       f"ref_absmax={w32.abs().max().item():.3e} bad={(err > atol + rtol * w32.abs()).sum().item()}"
+                       f"/{err.numel()} finite={bool(finite)}")
+            if not ok:
+                failures.append(msg)
+                print("FAIL", msg)
+    assert not failures, "\n".join(failures[:20])

@@ -1,0 +1,756 @@
+// Memory-bound and small kernels of the VQA forward path (everything that is not a GEMM).
+// Each launcher takes the generic VqaOp (fields in op_fields.h) with external pointers resolved.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// INGEST: images -> phase-packed stem input.  Row r of the 114x114 (pad 2) grid holds the 2x2 pixel
+// block (2a+ph, 2b+pw) x (R,G,B,0) as 16 bf16.  mode 0: fp32 NCHW already normalised
+// (models/vqa_model.py:243-258); mode 1: uint8 HWC, normalised here exactly like
+// ToTensor + Normalize (data/preprocess.py:117-121): (u8/255 - mean)/std in fp32.
+__global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ dst, int B, int mode, int P,
+                              int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int rpi = P * P;
+  const int n = r / rpi, rem = r - n * rpi;
+  const int a = rem / P, b = rem - a * P;
+  uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (a < 112 && b < 112) {
+    float v[2][2][4];
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) v[ph][pw][3] = 0.f;
+    if (mode == 0) {
+      const float* x = reinterpret_cast<const float*>(src);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const float2 q = *reinterpret_cast<const float2*>(
+              x + ((static_cast<size_t>(n) * 3 + c) * 224 + (2 * a + ph)) * 224 + 2 * b);
+          v[ph][0][c] = q.x;
+          v[ph][1][c] = q.y;
+        }
+    } else {
+      const unsigned char* x = reinterpret_cast<const unsigned char*>(src);
+      const float mean[3] = {0.485f, 0.456f, 0.406f};
+      const float stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        const unsigned char* px = x + ((static_cast<size_t>(n) * 224 + (2 * a + ph)) * 224 + 2 * b) * 3;
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float f = __fdiv_rn(static_cast<float>(px[pw * 3 + c]), 255.f);
+            v[ph][pw][c] = __fdiv_rn(__fsub_rn(f, mean[c]), stdv[c]);
+          }
+      }
+    }
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        w[(ph * 2 + pw) * 2 + 0] = pack_bf16x2(v[ph][pw][0], v[ph][pw][1]);
+        w[(ph * 2 + pw) * 2 + 1] = pack_bf16x2(v[ph][pw][2], v[ph][pw][3]);
+      }
+  }
+  dst[2 * static_cast<size_t>(r)] = make_uint4(w[0], w[1], w[2], w[3]);
+  dst[2 * static_cast<size_t>(r) + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MAXPOOL 3x3/2 p1 on padded-flat bf16 grids; one thread = one output row x 8 channels.
+__global__ void maxpool_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int C8, int Hin, int Win,
+                               int Pin, int RPIin, int Hout, int Wout, int Pout, int RPIout) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * RPIout * C8;
+  if (t >= total) return;
+  const int cg = static_cast<int>(t % C8);
+  const int r = static_cast<int>(t / C8);
+  const int n = r / RPIout, rem = r - n * RPIout;
+  const int i = rem / Pout, j = rem - i * Pout;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (i < Hout && j < Wout) {
+    __nv_bfloat162 m[4];
+    bool any = false;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int h = 2 * i + dh;
+      if (h < 0 || h >= Hin) continue;
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int w = 2 * j + dw;
+        if (w < 0 || w >= Win) continue;
+        const uint4 q = src[(static_cast<size_t>(n) * RPIin + h * Pin + w) * C8 + cg];
+        const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&q);
+        if (!any) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = v[k];
+          any = true;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], v[k]);
+        }
+      }
+    }
+    o = *reinterpret_cast<uint4*>(m);
+  }
+  dst[static_cast<size_t>(r) * C8 + cg] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SE squeeze: per-(image, channel) sum over the valid pixels of a padded-flat bf16 grid.
+__global__ void se_squeeze_kernel(const uint4* __restrict__ src, float* __restrict__ sums, int C8, int H, int W, int P,
+                                  int RPI) {
+  extern __shared__ float red[];  // [lanes][C8*8]
+  const int n = blockIdx.x;
+  const int lanes = blockDim.x / C8;
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (pl < lanes) {
+    for (int q = pl; q < H * W; q += lanes) {
+      const int h = q / W, w = q - h * W;
+      const uint4 v = src[(static_cast<size_t>(n) * RPI + h * P + w) * C8 + cg];
+      acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+      acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[(pl * C8 + cg) * 8 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * C8 * 8 + c];
+    sums[static_cast<size_t>(n) * C8 * 8 + c] = s;
+  }
+}
+
+// SE excite: scale = sigmoid(W2 relu(W1 mean)), no biases (models/attention_modules.py:84-85,116-126).
+__global__ void se_excite_kernel(const float* __restrict__ sums, const float* __restrict__ w1,
+                                 const float* __restrict__ w2, float* __restrict__ scale, int C, int R, float inv_hw) {
+  extern __shared__ float sm[];  // mean[C], hid[R]
+  float* mean = sm;
+  float* hid = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[static_cast<size_t>(n) * C + c] * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += w1[static_cast<size_t>(r) * C + c] * mean[c];
+    s = warp_sum(s);
+    if (lane == 0) hid[r] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += w2[static_cast<size_t>(c) * R + r] * hid[r];
+    scale[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-s));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spatial attention map: channel max / mean of (x*scale), 7x7 conv over [max, avg], sigmoid.
+__global__ void spatial_map_kernel(const uint4* __restrict__ src, const float* __restrict__ scale,
+                                   const float* __restrict__ wconv, float* __restrict__ att, int C8, int H, int W,
+                                   int P, int RPI, int ks) {
+  extern __shared__ float sm[];  // mx[H*W], av[H*W], sc[C]
+  const int HW = H * W, C = C8 * 8;
+  float* mx = sm;
+  float* av = sm + HW;
+  float* sc = sm + 2 * HW;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sc[c] = scale ? scale[static_cast<size_t>(n) * C + c] : 1.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int q = warp; q < HW; q += nw) {
+    const int h = q / W, w = q - h * W;
+    const uint4* row = src + (static_cast<size_t>(n) * RPI + h * P + w) * C8;
+    float m = -INFINITY, s = 0.f;
+    for (int o = lane; o < C8; o += 32) {
+      const uint4 v = row[o];
+      const float* k = sc + o * 8;
+      const float x[8] = {bf16lo(v.x) * k[0], bf16hi(v.x) * k[1], bf16lo(v.y) * k[2], bf16hi(v.y) * k[3],
+                          bf16lo(v.z) * k[4], bf16hi(v.z) * k[5], bf16lo(v.w) * k[6], bf16hi(v.w) * k[7]};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { m = fmaxf(m, x[j]); s += x[j]; }
+    }
+    m = warp_max(m);
+    s = warp_sum(s);
+    if (lane == 0) { mx[q] = m; av[q] = s / static_cast<float>(C); }
+  }
+  __syncthreads();
+  const int pad = ks / 2;
+  for (int q = threadIdx.x; q < HW; q += blockDim.x) {
+    const int h = q / W, w = q - h * W;
+    float s = 0.f;
+    for (int kh = 0; kh < ks; ++kh) {
+      const int hh = h + kh - pad;
+      if (hh < 0 || hh >= H) continue;
+      for (int kw = 0; kw < ks; ++kw) {
+        const int ww = w + kw - pad;
+        if (ww < 0 || ww >= W) continue;
+        s += wconv[kh * ks + kw] * mx[hh * W + ww] + wconv[ks * ks + kh * ks + kw] * av[hh * W + ww];
+      }
+    }
+    att[static_cast<size_t>(n) * HW + q] = 1.f / (1.f + expf(-s));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x*scale[c]*att[pixel] -> bf16, written either on the same grid (mode 0) or as the 4-phase split
+// the next stage's stride-2 convolutions read (mode 1).  One thread = one dst row x 8 channels.
+__global__ void scale_relayout_kernel(const uint4* __restrict__ src, const float* __restrict__ scale,
+                                      const float* __restrict__ att, uint4* __restrict__ dst, int B, int C8, int H,
+                                      int W, int P, int RPI, int mode, int Po, int RPIo, int phase_rows) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total_rows = mode ? 4LL * phase_rows : static_cast<long long>(B) * RPIo;
+  if (t >= total_rows * C8) return;
+  const int cg = static_cast<int>(t % C8);
+  const long long r = t / C8;
+  int ph = 0, pw = 0;
+  long long rr = r;
+  if (mode) {
+    const int phase = static_cast<int>(r / phase_rows);
+    rr = r - static_cast<long long>(phase) * phase_rows;
+    ph = phase >> 1;
+    pw = phase & 1;
+  }
+  const int n = static_cast<int>(rr / RPIo), rem = static_cast<int>(rr - static_cast<long long>(n) * RPIo);
+  const int i = rem / Po, j = rem - i * Po;
+  const int Ho = mode ? H / 2 : H, Wo = mode ? W / 2 : W;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (i < Ho && j < Wo) {
+    const int h = mode ? 2 * i + ph : i, w = mode ? 2 * j + pw : j;
+    const uint4 v = src[(static_cast<size_t>(n) * RPI + h * P + w) * C8 + cg];
+    const float a = att ? att[static_cast<size_t>(n) * H * W + h * W + w] : 1.f;
+    float k[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) k[q] = scale ? scale[static_cast<size_t>(n) * C8 * 8 + cg * 8 + q] : 1.f;
+    o.x = pack_bf16x2(bf16lo(v.x) * k[0] * a, bf16hi(v.x) * k[1] * a);
+    o.y = pack_bf16x2(bf16lo(v.y) * k[2] * a, bf16hi(v.y) * k[3] * a);
+    o.z = pack_bf16x2(bf16lo(v.z) * k[4] * a, bf16hi(v.z) * k[5] * a);
+    o.w = pack_bf16x2(bf16lo(v.w) * k[6] * a, bf16hi(v.w) * k[7] * a);
+  }
+  dst[static_cast<size_t>(r) * C8 + cg] = o;
+}
+
+__global__ void grid_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int B, int C,
+                                    int H, int W, int P, int RPI) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(B) * C * H * W) return;
+  const int w = static_cast<int>(t % W);
+  const int h = static_cast<int>((t / W) % H);
+  const int c = static_cast<int>((t / (static_cast<long long>(W) * H)) % C);
+  const int n = static_cast<int>(t / (static_cast<long long>(W) * H * C));
+  dst[t] = __bfloat162float(src[(static_cast<size_t>(n) * RPI + h * P + w) * C + c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void mask_prep_kernel(const void* __restrict__ src, int* __restrict__ dst, int n, int dtype) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int v = 1;
+  if (dtype == 1) v = reinterpret_cast<const long long*>(src)[t] != 0;
+  else if (dtype == 2) v = reinterpret_cast<const float*>(src)[t] != 0.f;
+  else if (dtype == 3) v = reinterpret_cast<const int*>(src)[t] != 0;
+  else if (dtype == 4) v = reinterpret_cast<const unsigned char*>(src)[t] != 0;
+  dst[t] = v;
+}
+
+// x = table[ids]*sqrt(D) (pre-scaled at load) + pe[l]   (models/text_encoder.py:504-512)
+__global__ void embed_kernel(const long long* __restrict__ ids, const float4* __restrict__ table,
+                             const float4* __restrict__ pe, float4* __restrict__ dst, int T, int L, int D4, int V) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T * D4) return;
+  const int tok = t / D4, d = t - tok * D4;
+  long long id = ids[tok];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const float4 e = table[static_cast<size_t>(id) * D4 + d];
+  const float4 p = pe[static_cast<size_t>(tok % L) * D4 + d];
+  dst[t] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+}
+
+// LayerNorm over D = 256, one warp per row (biased variance, eps inside the sqrt).  mode 1 is the
+// image projector's variant: source rows are the valid pixels of the 7x7 (+pad) grid and the
+// learned position embedding is added after the affine (models/fusion.py:98-112).
+__global__ void layernorm256_kernel(const float* __restrict__ src, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float* __restrict__ dst,
+                                    const float* __restrict__ pos, int rows, int ld, int mode, int rnd, int S, int Pg,
+                                    int RPIg, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  size_t srow = row;
+  int pix = 0;
+  if (mode == 1) {
+    const int n = row / (S * S);
+    pix = row - n * S * S;
+    srow = static_cast<size_t>(n) * RPIg + (pix / S) * Pg + (pix % S);
+  }
+  const float4* x4 = reinterpret_cast<const float4*>(src + srow * ld);
+  const float4 a = x4[lane], b = x4[32 + lane];
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  const float mean = warp_sum(s) * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] -= mean; q += v[k] * v[k]; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+  const float4 g0 = reinterpret_cast<const float4*>(gamma)[lane], g1 = reinterpret_cast<const float4*>(gamma)[32 + lane];
+  const float4 b0 = reinterpret_cast<const float4*>(beta)[lane], b1 = reinterpret_cast<const float4*>(beta)[32 + lane];
+  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float y[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = v[k] * rstd * g[k] + bb[k];
+  if (mode == 1 && pos) {
+    const float4 p0 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(pix) * 256)[lane];
+    const float4 p1 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(pix) * 256)[32 + lane];
+    y[0] += p0.x; y[1] += p0.y; y[2] += p0.z; y[3] += p0.w;
+    y[4] += p1.x; y[5] += p1.y; y[6] += p1.z; y[7] += p1.w;
+  }
+  if (rnd) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = round_tf32_rna(y[k]);
+  }
+  float4* o4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(row) * 256);
+  o4[lane] = make_float4(y[0], y[1], y[2], y[3]);
+  o4[32 + lane] = make_float4(y[4], y[5], y[6], y[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-attention core for one (sequence, head): thread l owns query row l (L <= 64, head_dim 32).
+// Keys with mask == 0 get -inf before the softmax; a fully masked row yields NaN exactly like the
+// reference (models/text_encoder.py:240-247).
+constexpr int kMaxL = 64;
+constexpr int kHd = 32;
+
+__global__ void self_attn_kernel(const float* __restrict__ qkv, const int* __restrict__ mask, float* __restrict__ out,
+                                 int L, int H, int ld) {
+  __shared__ float ks[kMaxL][kHd + 1];
+  __shared__ float vs[kMaxL][kHd + 1];
+  __shared__ int ms[kMaxL];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int D = H * kHd;
+  const float* base = qkv + static_cast<size_t>(b) * L * ld;
+  for (int t = threadIdx.x; t < L * kHd; t += blockDim.x) {
+    const int j = t / kHd, d = t - j * kHd;
+    ks[j][d] = base[static_cast<size_t>(j) * ld + D + h * kHd + d];
+    vs[j][d] = base[static_cast<size_t>(j) * ld + 2 * D + h * kHd + d];
+  }
+  for (int j = threadIdx.x; j < L; j += blockDim.x) ms[j] = mask ? mask[b * L + j] : 1;
+  __syncthreads();
+  const int l = threadIdx.x;
+  if (l >= L) return;
+  float q[kHd];
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) q[d] = base[static_cast<size_t>(l) * ld + h * kHd + d];
+  const float scale = rsqrtf(static_cast<float>(kHd));
+  float s[kMaxL];
+  float m = -INFINITY;
+#pragma unroll 4
+  for (int j = 0; j < kMaxL; ++j) {
+    if (j < L) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < kHd; ++d) a += q[d] * ks[j][d];
+      a = ms[j] ? a * scale : -INFINITY;
+      s[j] = a;
+      m = fmaxf(m, a);
+    }
+  }
+  float den = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < kMaxL; ++j)
+    if (j < L) { s[j] = expf(s[j] - m); den += s[j]; }
+  const float inv = 1.f / den;
+  float c[kHd];
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) c[d] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < kMaxL; ++j)
+    if (j < L) {
+      const float w = s[j] * inv;
+#pragma unroll
+      for (int d = 0; d < kHd; ++d) c[d] += w * vs[j][d];
+    }
+  float* o = out + (static_cast<size_t>(b) * L + l) * D + h * kHd;
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) o[d] = round_tf32_rna(c[d]);   // feeds the W_o GEMM as a tf32 operand
+}
+
+// Cross-attention core for one (pair, head): text queries over the T = 49 image tokens, no mask
+// (models/cross_attention.py:164-197 with key_value_mask=None, models/fusion.py:292-297).
+constexpr int kMaxT = 64;
+
+__global__ void cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
+                                  float* __restrict__ weights, int L, int H, int T, int ld_q, int ld_kv, int k_off,
+                                  int v_off) {
+  __shared__ float ks[kMaxT][kHd + 1];
+  __shared__ float vs[kMaxT][kHd + 1];
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int D = H * kHd;
+  const float* kvb = kv + static_cast<size_t>(b) * T * ld_kv;
+  for (int t = threadIdx.x; t < T * kHd; t += blockDim.x) {
+    const int j = t / kHd, d = t - j * kHd;
+    ks[j][d] = kvb[static_cast<size_t>(j) * ld_kv + k_off + h * kHd + d];
+    vs[j][d] = kvb[static_cast<size_t>(j) * ld_kv + v_off + h * kHd + d];
+  }
+  __syncthreads();
+  const int l = threadIdx.x;
+  if (l >= L) return;
+  const float* qr = q + (static_cast<size_t>(b) * L + l) * ld_q + h * kHd;
+  float qv[kHd];
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) qv[d] = qr[d];
+  const float scale = rsqrtf(static_cast<float>(kHd));
+  float s[kMaxT];
+  float m = -INFINITY;
+#pragma unroll 4
+  for (int j = 0; j < kMaxT; ++j)
+    if (j < T) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < kHd; ++d) a += qv[d] * ks[j][d];
+      a *= scale;
+      s[j] = a;
+      m = fmaxf(m, a);
+    }
+  float den = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < kMaxT; ++j)
+    if (j < T) { s[j] = expf(s[j] - m); den += s[j]; }
+  const float inv = 1.f / den;
+  float c[kHd];
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) c[d] = 0.f;
+  float* wrow = weights ? weights + ((static_cast<size_t>(b) * H + h) * L + l) * T : nullptr;
+#pragma unroll 4
+  for (int j = 0; j < kMaxT; ++j)
+    if (j < T) {
+      const float w = s[j] * inv;
+      if (wrow) wrow[j] = w;
+#pragma unroll
+      for (int d = 0; d < kHd; ++d) c[d] += w * vs[j][d];
+    }
+  float* o = out + (static_cast<size_t>(b) * L + l) * D + h * kHd;
+#pragma unroll
+  for (int d = 0; d < kHd; ++d) o[d] = round_tf32_rna(c[d]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fusion tail for one pair: masked mean pools of the cross-attended and text features
+// (denominator clamp(min=1)), gate g = sigmoid(W[att;txt]+b), g*att+(1-g)*txt (or the plain sum when
+// gating is disabled), output LayerNorm (models/fusion.py:299-326, :159-166).  D = 256 = blockDim.
+__global__ void pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text,
+                                    const int* __restrict__ mask, const float* __restrict__ wg,
+                                    const float* __restrict__ bg, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float* __restrict__ fused,
+                                    float* __restrict__ att_pooled, float* __restrict__ txt_pooled, int L,
+                                    int use_gate, float eps) {
+  constexpr int D = 256;
+  __shared__ float cat[2 * D];
+  __shared__ float gate[D];
+  __shared__ float red[16];
+  const int b = blockIdx.x, d = threadIdx.x;
+  float cnt = 0.f, sa = 0.f, st = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float m = mask ? static_cast<float>(mask[b * L + l]) : 1.f;
+    cnt += m;
+    sa += xatt[(static_cast<size_t>(b) * L + l) * D + d] * m;
+    st += text[(static_cast<size_t>(b) * L + l) * D + d] * m;
+  }
+  const float den = fmaxf(cnt, 1.f);
+  const float ap = sa / den, tp = st / den;
+  cat[d] = ap;
+  cat[D + d] = tp;
+  if (att_pooled) att_pooled[static_cast<size_t>(b) * D + d] = ap;
+  if (txt_pooled) txt_pooled[static_cast<size_t>(b) * D + d] = tp;
+  __syncthreads();
+  float f;
+  if (use_gate) {
+    const int warp = d >> 5, lane = d & 31;
+    for (int r = warp * 32; r < warp * 32 + 32; ++r) {
+      float s = 0.f;
+      const float* wr = wg + static_cast<size_t>(r) * 2 * D;
+      for (int k = lane; k < 2 * D; k += 32) s += wr[k] * cat[k];
+      s = warp_sum(s);
+      if (lane == 0) gate[r] = 1.f / (1.f + expf(-(s + bg[r])));
+    }
+    __syncthreads();
+    const float g = gate[d];
+    f = g * ap + (1.f - g) * tp;
+  } else {
+    f = ap + tp;
+  }
+  // block LayerNorm over 256 values (8 warps)
+  float s = warp_sum(f);
+  if ((d & 31) == 0) red[d >> 5] = s;
+  __syncthreads();
+  float mean = 0.f;
+  for (int w = 0; w < 8; ++w) mean += red[w];
+  mean *= (1.f / D);
+  const float c = f - mean;
+  float q = warp_sum(c * c);
+  __syncthreads();
+  if ((d & 31) == 0) red[8 + (d >> 5)] = q;
+  __syncthreads();
+  float var = 0.f;
+  for (int w = 0; w < 8; ++w) var += red[8 + w];
+  var *= (1.f / D);
+  fused[static_cast<size_t>(b) * D + d] = c * rsqrtf(var + eps) * gamma[d] + beta[d];
+}
+
+// softmax over N answers + top-k (k <= 16), ties broken towards the lower index like torch.topk on
+// distinct values (models/vqa_model.py:336-337, api/inference.py:231-234).
+__global__ void softmax_topk_kernel(const float* __restrict__ logits, long long* __restrict__ idx,
+                                    float* __restrict__ probs, int N, int k, int ld) {
+  extern __shared__ float sm[];  // vals[N], red[64]
+  float* vals = sm;
+  float* red = sm + N;
+  int* redi = reinterpret_cast<int*>(red + 32);
+  const int b = blockIdx.x, tid = threadIdx.x, nw = blockDim.x >> 5;
+  const float* row = logits + static_cast<size_t>(b) * ld;
+  float m = -INFINITY;
+  for (int i = tid; i < N; i += blockDim.x) { vals[i] = row[i]; m = fmaxf(m, vals[i]); }
+  m = warp_max(m);
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  m = -INFINITY;
+  for (int w = 0; w < nw; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) s += expf(vals[i] - m);
+  s = warp_sum(s);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < nw; ++w) s += red[w];
+  __syncthreads();
+  for (int t = 0; t < k; ++t) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < N; i += blockDim.x)
+      if (vals[i] > best || (vals[i] == best && i < bi)) { best = vals[i]; bi = i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float bb = red[0];
+      int ii = redi[0];
+      for (int w = 1; w < nw; ++w)
+        if (red[w] > bb || (red[w] == bb && redi[w] < ii)) { bb = red[w]; ii = redi[w]; }
+      idx[static_cast<size_t>(b) * k + t] = ii;
+      probs[static_cast<size_t>(b) * k + t] = expf(bb - m) / s;
+      vals[ii] = -INFINITY;
+    }
+    __syncthreads();
+  }
+}
+
+inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ================================================================================================
+// launchers
+#define PTR(T, k) reinterpret_cast<T>(vqa_resolve(op.p[k], ext, n_ext))
+
+int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st) {
+  const int32_t* I = op.i;
+  switch (op.kind) {
+    case VQA_OP_INGEST: {
+      const int rows = I[INGEST_I_rows];
+      VQA_REQUIRE(I[INGEST_I_HW] == 224 && I[INGEST_I_P] == 114, VQA_E_INVALID, "ingest: only 224x224 inputs");
+      const void* src = PTR(const void*, INGEST_P_src);
+      VQA_REQUIRE(src != nullptr, VQA_E_INVALID, "ingest: null images");
+      VQA_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 || I[INGEST_I_mode] == 1, VQA_E_ALIGN,
+                  "ingest: fp32 images must be 8-byte aligned");
+      ingest_kernel<<<blocks_for(rows, 256), 256, 0, st>>>(src, PTR(uint4*, INGEST_P_dst), I[INGEST_I_B],
+                                                            I[INGEST_I_mode], I[INGEST_I_P], rows);
+      VQA_LAUNCH_OK("ingest_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_MAXPOOL: {
+      const int C8 = I[MAXPOOL_I_C] / 8;
+      const long long total = static_cast<long long>(I[MAXPOOL_I_B]) * I[MAXPOOL_I_RPIout] * C8;
+      maxpool_kernel<<<blocks_for(total, 256), 256, 0, st>>>(
+          PTR(const uint4*, MAXPOOL_P_src), PTR(uint4*, MAXPOOL_P_dst), I[MAXPOOL_I_B], C8, I[MAXPOOL_I_Hin],
+          I[MAXPOOL_I_Win], I[MAXPOOL_I_Pin], I[MAXPOOL_I_RPIin], I[MAXPOOL_I_Hout], I[MAXPOOL_I_Wout],
+          I[MAXPOOL_I_Pout], I[MAXPOOL_I_RPIout]);
+      VQA_LAUNCH_OK("maxpool_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_SE_SQUEEZE: {
+      const int C8 = I[SE_SQUEEZE_I_C] / 8;
+      VQA_REQUIRE(C8 >= 1 && C8 <= 256, VQA_E_INVALID, "se_squeeze: C out of range");
+      const int threads = 256 >= C8 ? 256 / C8 * C8 : C8;
+      const size_t smem = static_cast<size_t>(threads) * 8 * sizeof(float);
+      se_squeeze_kernel<<<I[SE_SQUEEZE_I_B], threads, smem, st>>>(PTR(const uint4*, SE_SQUEEZE_P_src),
+                                                                  PTR(float*, SE_SQUEEZE_P_sums), C8, I[SE_SQUEEZE_I_H],
+                                                                  I[SE_SQUEEZE_I_W], I[SE_SQUEEZE_I_P],
+                                                                  I[SE_SQUEEZE_I_RPI]);
+      VQA_LAUNCH_OK("se_squeeze_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_SE_EXCITE: {
+      const int C = I[SE_EXCITE_I_C], R = I[SE_EXCITE_I_R];
+      se_excite_kernel<<<I[SE_EXCITE_I_B], 256, (C + R) * sizeof(float), st>>>(
+          PTR(const float*, SE_EXCITE_P_sums), PTR(const float*, SE_EXCITE_P_w1), PTR(const float*, SE_EXCITE_P_w2),
+          PTR(float*, SE_EXCITE_P_scale), C, R, 1.f / static_cast<float>(I[SE_EXCITE_I_HW]));
+      VQA_LAUNCH_OK("se_excite_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_SPATIAL_MAP: {
+      const int C = I[SPATIAL_MAP_I_C], HW = I[SPATIAL_MAP_I_H] * I[SPATIAL_MAP_I_W];
+      const size_t smem = (2 * HW + C) * sizeof(float);
+      VQA_REQUIRE(smem <= 48 * 1024, VQA_E_INVALID, "spatial_map: feature map too large");
+      spatial_map_kernel<<<I[SPATIAL_MAP_I_B], 256, smem, st>>>(
+          PTR(const uint4*, SPATIAL_MAP_P_src), PTR(const float*, SPATIAL_MAP_P_scale),
+          PTR(const float*, SPATIAL_MAP_P_wconv), PTR(float*, SPATIAL_MAP_P_att), C / 8, I[SPATIAL_MAP_I_H],
+          I[SPATIAL_MAP_I_W], I[SPATIAL_MAP_I_P], I[SPATIAL_MAP_I_RPI], I[SPATIAL_MAP_I_ksize]);
+      VQA_LAUNCH_OK("spatial_map_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_SCALE_RELAYOUT: {
+      const int C8 = I[SCALE_RELAYOUT_I_C] / 8, mode = I[SCALE_RELAYOUT_I_mode];
+      const long long rows = mode ? 4LL * I[SCALE_RELAYOUT_I_phase_rows]
+                                  : static_cast<long long>(I[SCALE_RELAYOUT_I_B]) * I[SCALE_RELAYOUT_I_RPIo];
+      scale_relayout_kernel<<<blocks_for(rows * C8, 256), 256, 0, st>>>(
+          PTR(const uint4*, SCALE_RELAYOUT_P_src), PTR(const float*, SCALE_RELAYOUT_P_scale),
+          PTR(const float*, SCALE_RELAYOUT_P_att), PTR(uint4*, SCALE_RELAYOUT_P_dst), I[SCALE_RELAYOUT_I_B], C8,
+          I[SCALE_RELAYOUT_I_H], I[SCALE_RELAYOUT_I_W], I[SCALE_RELAYOUT_I_P], I[SCALE_RELAYOUT_I_RPI], mode,
+          I[SCALE_RELAYOUT_I_Po], I[SCALE_RELAYOUT_I_RPIo], I[SCALE_RELAYOUT_I_phase_rows]);
+      VQA_LAUNCH_OK("scale_relayout_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_GRID_TO_NCHW: {
+      const long long total = static_cast<long long>(I[GRID_TO_NCHW_I_B]) * I[GRID_TO_NCHW_I_C] * I[GRID_TO_NCHW_I_H] *
+                              I[GRID_TO_NCHW_I_W];
+      grid_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(
+          PTR(const __nv_bfloat16*, GRID_TO_NCHW_P_src), PTR(float*, GRID_TO_NCHW_P_dst), I[GRID_TO_NCHW_I_B],
+          I[GRID_TO_NCHW_I_C], I[GRID_TO_NCHW_I_H], I[GRID_TO_NCHW_I_W], I[GRID_TO_NCHW_I_P], I[GRID_TO_NCHW_I_RPI]);
+      VQA_LAUNCH_OK("grid_to_nchw_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_MASK_PREP: {
+      const int n = I[MASK_PREP_I_B] * I[MASK_PREP_I_L];
+      const void* src = PTR(const void*, MASK_PREP_P_src);
+      VQA_REQUIRE(src != nullptr || I[MASK_PREP_I_dtype] == 0, VQA_E_INVALID, "mask_prep: null mask");
+      mask_prep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, PTR(int*, MASK_PREP_P_dst), n, I[MASK_PREP_I_dtype]);
+      VQA_LAUNCH_OK("mask_prep_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_EMBED: {
+      const int T = I[EMBED_I_B] * I[EMBED_I_L], D4 = I[EMBED_I_D] / 4;
+      const long long* ids = PTR(const long long*, EMBED_P_ids);
+      VQA_REQUIRE(ids != nullptr, VQA_E_INVALID, "embed: null token ids");
+      embed_kernel<<<blocks_for(static_cast<long long>(T) * D4, 256), 256, 0, st>>>(
+          ids, PTR(const float4*, EMBED_P_table), PTR(const float4*, EMBED_P_pe), PTR(float4*, EMBED_P_dst), T,
+          I[EMBED_I_L], D4, I[EMBED_I_V]);
+      VQA_LAUNCH_OK("embed_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_LAYERNORM: {
+      VQA_REQUIRE(I[LAYERNORM_I_D] == 256, VQA_E_INVALID, "layernorm: D must be 256");
+      const int rows = I[LAYERNORM_I_rows];
+      layernorm256_kernel<<<blocks_for(rows, 8), 256, 0, st>>>(
+          PTR(const float*, LAYERNORM_P_src), PTR(const float*, LAYERNORM_P_gamma), PTR(const float*, LAYERNORM_P_beta),
+          PTR(float*, LAYERNORM_P_dst), PTR(const float*, LAYERNORM_P_pos), rows, I[LAYERNORM_I_ld_src],
+          I[LAYERNORM_I_mode], I[LAYERNORM_I_round_tf32], I[LAYERNORM_I_S], I[LAYERNORM_I_Pg], I[LAYERNORM_I_RPIg],
+          op.f[LAYERNORM_F_eps]);
+      VQA_LAUNCH_OK("layernorm256_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_SELF_ATTN: {
+      const int L = I[SELF_ATTN_I_L];
+      VQA_REQUIRE(L >= 1 && L <= kMaxL && I[SELF_ATTN_I_hd] == kHd, VQA_E_INVALID, "self_attn: L<=64, head_dim=32");
+      self_attn_kernel<<<dim3(I[SELF_ATTN_I_B], I[SELF_ATTN_I_H]), 64, 0, st>>>(
+          PTR(const float*, SELF_ATTN_P_qkv), PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), L,
+          I[SELF_ATTN_I_H], I[SELF_ATTN_I_ld_qkv]);
+      VQA_LAUNCH_OK("self_attn_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_CROSS_ATTN: {
+      const int L = I[CROSS_ATTN_I_L], T = I[CROSS_ATTN_I_T];
+      VQA_REQUIRE(L >= 1 && L <= 64 && T >= 1 && T <= kMaxT && I[CROSS_ATTN_I_hd] == kHd, VQA_E_INVALID,
+                  "cross_attn: L<=64, T<=64, head_dim=32");
+      cross_attn_kernel<<<dim3(I[CROSS_ATTN_I_B], I[CROSS_ATTN_I_H]), 64, 0, st>>>(
+          PTR(const float*, CROSS_ATTN_P_q), PTR(const float*, CROSS_ATTN_P_kv), PTR(float*, CROSS_ATTN_P_out),
+          PTR(float*, CROSS_ATTN_P_weights), L, I[CROSS_ATTN_I_H], T, I[CROSS_ATTN_I_ld_q], I[CROSS_ATTN_I_ld_kv],
+          I[CROSS_ATTN_I_k_off], I[CROSS_ATTN_I_v_off]);
+      VQA_LAUNCH_OK("cross_attn_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_POOL_GATE_LN: {
+      VQA_REQUIRE(I[POOL_GATE_LN_I_D] == 256, VQA_E_INVALID, "pool_gate_ln: D must be 256");
+      pool_gate_ln_kernel<<<I[POOL_GATE_LN_I_B], 256, 0, st>>>(
+          PTR(const float*, POOL_GATE_LN_P_xatt), PTR(const float*, POOL_GATE_LN_P_text),
+          PTR(const int*, POOL_GATE_LN_P_mask), PTR(const float*, POOL_GATE_LN_P_wg), PTR(const float*, POOL_GATE_LN_P_bg),
+          PTR(const float*, POOL_GATE_LN_P_gamma), PTR(const float*, POOL_GATE_LN_P_beta),
+          PTR(float*, POOL_GATE_LN_P_fused), PTR(float*, POOL_GATE_LN_P_att_pooled),
+          PTR(float*, POOL_GATE_LN_P_txt_pooled), I[POOL_GATE_LN_I_L], I[POOL_GATE_LN_I_use_gate],
+          op.f[POOL_GATE_LN_F_eps]);
+      VQA_LAUNCH_OK("pool_gate_ln_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_SOFTMAX_TOPK: {
+      const int N = I[SOFTMAX_TOPK_I_N], k = I[SOFTMAX_TOPK_I_k];
+      VQA_REQUIRE(k >= 1 && k <= 16 && k <= N && N <= 10000, VQA_E_INVALID, "softmax_topk: 1<=k<=16, N<=10000");
+      softmax_topk_kernel<<<I[SOFTMAX_TOPK_I_B], 256, (N + 64) * sizeof(float), st>>>(
+          PTR(const float*, SOFTMAX_TOPK_P_logits), PTR(long long*, SOFTMAX_TOPK_P_idx),
+          PTR(float*, SOFTMAX_TOPK_P_probs), N, k, I[SOFTMAX_TOPK_I_ld]);
+      VQA_LAUNCH_OK("softmax_topk_kernel");
+      return VQA_OK;
+    }
+    default:
+      vqa_set_error("unknown op kind " + std::to_string(op.kind));
+      return VQA_E_INVALID;
+  }
+}
+
+const char* misc_kernel_name(int kind) {
+  switch (kind) {
+    case VQA_OP_INGEST: return "ingest_kernel";
+    case VQA_OP_MAXPOOL: return "maxpool_kernel";
+    case VQA_OP_SE_SQUEEZE: return "se_squeeze_kernel";
+    case VQA_OP_SE_EXCITE: return "se_excite_kernel";
+    case VQA_OP_SPATIAL_MAP: return "spatial_map_kernel";
+    case VQA_OP_SCALE_RELAYOUT: return "scale_relayout_kernel";
+    case VQA_OP_GRID_TO_NCHW: return "grid_to_nchw_kernel";
+    case VQA_OP_MASK_PREP: return "mask_prep_kernel";
+    case VQA_OP_EMBED: return "embed_kernel";
+    case VQA_OP_LAYERNORM: return "layernorm256_kernel";
+    case VQA_OP_SELF_ATTN: return "self_attn_kernel";
+    case VQA_OP_CROSS_ATTN: return "cross_attn_kernel";
+    case VQA_OP_POOL_GATE_LN: return "pool_gate_ln_kernel";
+    case VQA_OP_SOFTMAX_TOPK: return "softmax_topk_kernel";
+    default: return "?";
+  }
+}

@@ -1,0 +1,162 @@
+// C ABI of libvqa_b200.so: plans (immutable op lists with pre-encoded tensor maps), error
+// reporting and launch accounting.  See include/vqa_b200.h for the contract.
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+// implemented in gemm_tcgen05.cu / kernels_misc.cu
+int gemm_launch_bytes();
+int gemm_prepare(const VqaOp& op, void* storage);
+int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t stream);
+const char* gemm_kernel_name(const void* storage);
+int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st);
+const char* misc_kernel_name(int kind);
+
+namespace {
+thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+
+struct FieldCount { int ni, np, nf; };
+const FieldCount kFields[VQA_OP_KIND_MAX] = {
+    {0, 0, 0},
+    {INGEST_NI, INGEST_NP, INGEST_NF},
+    {GEMM_NI, GEMM_NP, GEMM_NF},
+    {MAXPOOL_NI, MAXPOOL_NP, MAXPOOL_NF},
+    {SE_SQUEEZE_NI, SE_SQUEEZE_NP, SE_SQUEEZE_NF},
+    {SE_EXCITE_NI, SE_EXCITE_NP, SE_EXCITE_NF},
+    {SPATIAL_MAP_NI, SPATIAL_MAP_NP, SPATIAL_MAP_NF},
+    {SCALE_RELAYOUT_NI, SCALE_RELAYOUT_NP, SCALE_RELAYOUT_NF},
+    {EMBED_NI, EMBED_NP, EMBED_NF},
+    {LAYERNORM_NI, LAYERNORM_NP, LAYERNORM_NF},
+    {SELF_ATTN_NI, SELF_ATTN_NP, SELF_ATTN_NF},
+    {CROSS_ATTN_NI, CROSS_ATTN_NP, CROSS_ATTN_NF},
+    {POOL_GATE_LN_NI, POOL_GATE_LN_NP, POOL_GATE_LN_NF},
+    {SOFTMAX_TOPK_NI, SOFTMAX_TOPK_NP, SOFTMAX_TOPK_NF},
+    {MASK_PREP_NI, MASK_PREP_NP, MASK_PREP_NF},
+    {GRID_TO_NCHW_NI, GRID_TO_NCHW_NP, GRID_TO_NCHW_NF},
+};
+static_assert(GEMM_NI <= VQA_OP_NI, "VqaOp.i too small for the gemm op");
+static_assert(POOL_GATE_LN_NP <= VQA_OP_NP, "VqaOp.p too small");
+}  // namespace
+
+void vqa_set_error(const std::string& msg) { g_error = msg; }
+void vqa_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct VqaPlan {
+  int device = 0;
+  std::vector<VqaOp> ops;
+  std::vector<void*> gemm;   // per op: prepared GemmLaunch (64-byte aligned) or nullptr
+  ~VqaPlan() {
+    for (void* g : gemm)
+      if (g) std::free(g);
+  }
+};
+
+extern "C" {
+
+int vqa_abi_version(void) { return VQA_ABI_VERSION; }
+
+const char* vqa_last_error(void) { return g_error.c_str(); }
+
+uint64_t vqa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vqa_device_check(int device) {
+  cudaDeviceProp prop;
+  VQA_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    vqa_set_error(std::string("device ") + prop.name + " is compute capability " + std::to_string(prop.major) + "." +
+                  std::to_string(prop.minor) + "; libvqa_b200 is built for sm_100a only");
+    return VQA_E_UNSUPPORTED;
+  }
+  return VQA_OK;
+}
+
+int vqa_op_num_fields(int kind, int* n_i, int* n_p, int* n_f) {
+  VQA_REQUIRE(kind >= 1 && kind < VQA_OP_KIND_MAX, VQA_E_INVALID, "unknown op kind");
+  if (n_i) *n_i = kFields[kind].ni;
+  if (n_p) *n_p = kFields[kind].np;
+  if (n_f) *n_f = kFields[kind].nf;
+  return VQA_OK;
+}
+
+int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** out) {
+  VQA_REQUIRE(ops != nullptr && out != nullptr && n_ops > 0, VQA_E_INVALID, "vqa_plan_create: null argument");
+  *out = nullptr;
+  int rc = vqa_device_check(device);
+  if (rc) return rc;
+  VQA_CUDA_OK(cudaSetDevice(device));
+  VqaPlan* plan = new (std::nothrow) VqaPlan();
+  VQA_REQUIRE(plan != nullptr, VQA_E_INVALID, "out of host memory");
+  plan->device = device;
+  plan->ops.assign(ops, ops + n_ops);
+  plan->gemm.assign(n_ops, nullptr);
+  for (int k = 0; k < n_ops; ++k) {
+    const VqaOp& op = plan->ops[k];
+    if (op.kind < 1 || op.kind >= VQA_OP_KIND_MAX) {
+      vqa_set_error("op " + std::to_string(k) + ": unknown kind " + std::to_string(op.kind));
+      delete plan;
+      return VQA_E_INVALID;
+    }
+    if (op.kind == VQA_OP_GEMM) {
+      void* st = nullptr;
+      const size_t bytes = (static_cast<size_t>(gemm_launch_bytes()) + 63) / 64 * 64;
+      if (posix_memalign(&st, 64, bytes) != 0) {
+        vqa_set_error("out of host memory");
+        delete plan;
+        return VQA_E_INVALID;
+      }
+      std::memset(st, 0, bytes);
+      plan->gemm[k] = st;
+      rc = gemm_prepare(op, st);
+      if (rc) {
+        vqa_set_error("op " + std::to_string(k) + ": " + g_error);
+        delete plan;
+        return rc;
+      }
+    }
+  }
+  *out = plan;
+  return VQA_OK;
+}
+
+int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const uint64_t* ext, int32_t n_ext,
+                       void* stream) {
+  VQA_REQUIRE(plan != nullptr, VQA_E_INVALID, "vqa_plan_run: null plan");
+  const int n = static_cast<int>(plan->ops.size());
+  VQA_REQUIRE(first >= 0 && last <= n && first <= last, VQA_E_INVALID, "vqa_plan_run: bad op range");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int k = first; k < last; ++k) {
+    const VqaOp& op = plan->ops[k];
+    int rc = (op.kind == VQA_OP_GEMM) ? gemm_run(plan->gemm[k], ext, n_ext, st) : run_misc_op(op, ext, n_ext, st);
+    if (rc) {
+      vqa_set_error("op " + std::to_string(k) + ": " + g_error);
+      return rc;
+    }
+  }
+  return VQA_OK;
+}
+
+int vqa_plan_run(const VqaPlan* plan, const uint64_t* ext, int32_t n_ext, void* stream) {
+  VQA_REQUIRE(plan != nullptr, VQA_E_INVALID, "vqa_plan_run: null plan");
+  return vqa_plan_run_range(plan, 0, static_cast<int32_t>(plan->ops.size()), ext, n_ext, stream);
+}
+
+int vqa_plan_num_launches(const VqaPlan* plan) { return plan ? static_cast<int>(plan->ops.size()) : 0; }
+
+int vqa_plan_op_kernel_name(const VqaPlan* plan, int32_t op, char* buf, int32_t buflen) {
+  VQA_REQUIRE(plan != nullptr && buf != nullptr && buflen > 0, VQA_E_INVALID, "null argument");
+  VQA_REQUIRE(op >= 0 && op < static_cast<int32_t>(plan->ops.size()), VQA_E_INVALID, "op index out of range");
+  const char* name = plan->ops[op].kind == VQA_OP_GEMM ? gemm_kernel_name(plan->gemm[op])
+                                                        : misc_kernel_name(plan->ops[op].kind);
+  std::strncpy(buf, name, static_cast<size_t>(buflen) - 1);
+  buf[buflen - 1] = 0;
+  return VQA_OK;
+}
+
+void vqa_plan_destroy(VqaPlan* plan) { delete plan; }
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""Engine: packed weights + per-shape plans behind ``VQAModel.forward``.
+
+One Engine belongs to one VQAModel on one CUDA device.  Weights are packed once
+(``program.build_weights``); a plan (workspace + op list + tensor maps) is built per
+(batch, length, input format, mask dtype, aux, top-k) and cached.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import program as P
+from .runtime import Plan, VqaError, lib
+
+
+class Engine:
+    def __init__(self, model, weights: Optional[P.Weights] = None):
+        p = next(model.parameters())
+        if p.device.type != "cuda":
+            raise VqaError("vqa_b200.VQAModel runs on CUDA (sm_100a) only: move the model with .cuda() "
+                           "(there is no CPU path)")
+        lib()  # fail early if the library is missing
+        self.device = p.device
+        self.cfg = dict(model.config)
+        with torch.no_grad():
+            self.weights = weights if weights is not None else P.build_weights(model.state_dict(), self.cfg, self.device)
+        self._plans: Dict[tuple, Tuple[P.Program, Plan]] = {}
+        self.window = True
+
+    # ------------------------------------------------------------------ plans
+    def plan_for(self, B: int, L: int, in_fmt: str, mask_dtype: int, want_aux: bool, top_k: int):
+        key = (B, L, in_fmt, mask_dtype, want_aux, top_k, self.window)
+        hit = self._plans.get(key)
+        if hit is None:
+            if L > self.cfg["max_question_length"]:
+                raise RuntimeError(f"sequence length {L} exceeds max_question_length "
+                                   f"{self.cfg['max_question_length']} (size of the positional-encoding buffer)")
+            prog = P.Program(self.weights, self.cfg, B, L, in_fmt, mask_dtype, want_aux, top_k, self.device,
+                             window=self.window)
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            hit = (prog, Plan(prog.ops, idx))
+            self._plans[key] = hit
+        return hit
+
+    @staticmethod
+    def _mask_code(mask: Optional[torch.Tensor]) -> int:
+        if mask is None:
+            return P.MASK_NONE
+        return {torch.int64: P.MASK_I64, torch.float32: P.MASK_F32, torch.int32: P.MASK_I32,
+                torch.bool: P.MASK_U8, torch.uint8: P.MASK_U8}.get(mask.dtype, -1)
+
+    # ------------------------------------------------------------------ execution
+    def run(self, images: torch.Tensor, token_ids: torch.Tensor, attention_mask: Optional[torch.Tensor],
+            want_aux: bool = False, top_k: int = 0):
+        """Launch the forward on the current stream.  Returns (logits, top_idx, top_probs, program)."""
+        if images.device != self.device or token_ids.device != self.device:
+            raise VqaError(f"inputs must live on {self.device} (got images on {images.device}, "
+                           f"ids on {token_ids.device})")
+        if images.dim() != 4:
+            raise ValueError("images must be [B,3,224,224] float32 (NCHW) or [B,224,224,3] uint8 (HWC)")
+        if images.dtype == torch.uint8:
+            in_fmt = "hwc_u8"
+            if tuple(images.shape[1:]) != (224, 224, 3):
+                raise ValueError("uint8 images must be [B,224,224,3]")
+        else:
+            in_fmt = "nchw_f32"
+            if tuple(images.shape[1:]) != (3, 224, 224):
+                raise ValueError("float images must be [B,3,224,224]")
+            if images.dtype != torch.float32:
+                images = images.float()
+        B, L = token_ids.shape
+        if images.shape[0] != B:
+            raise ValueError("images and token_ids disagree on the batch size")
+        images = images.contiguous()
+        ids = token_ids.contiguous()
+        if ids.dtype != torch.int64:
+            ids = ids.long()
+        mask = attention_mask
+        code = self._mask_code(mask)
+        if mask is not None:
+            if mask.device != self.device:
+                raise VqaError("attention_mask must live on the model's device")
+            if code < 0:
+                mask, code = mask.float(), P.MASK_F32
+            if tuple(mask.shape) != (B, L):
+                raise ValueError("attention_mask must be [B, L]")
+            mask = mask.contiguous()
+        prog, plan = self.plan_for(B, L, in_fmt, code, want_aux, top_k)
+        NA = self.cfg["num_answers"]
+        logits = torch.empty(B, NA, dtype=torch.float32, device=self.device)
+        top_idx = torch.empty(B, max(top_k, 1), dtype=torch.int64, device=self.device)
+        top_p = torch.empty(B, max(top_k, 1), dtype=torch.float32, device=self.device)
+        ext = [0] * len(P.EXT)
+        ext[P.EXT["images"]] = images.data_ptr()
+        ext[P.EXT["ids"]] = ids.data_ptr()
+        ext[P.EXT["mask"]] = mask.data_ptr() if mask is not None else 0
+        ext[P.EXT["logits"]] = logits.data_ptr()
+        ext[P.EXT["top_idx"]] = top_idx.data_ptr()
+        ext[P.EXT["top_probs"]] = top_p.data_ptr()
+        stream = torch.cuda.current_stream(self.device)
+        plan.run(ext, stream.cuda_stream)
+        for t in (images, ids, mask):  # keep inputs alive until the stream has consumed them
+            if t is not None:
+                t.record_stream(stream)
+        return logits, top_idx, top_p, prog
+
+    def forward(self, images, token_ids, attention_mask=None, return_aux=False):
+        logits, _, _, prog = self.run(images, token_ids, attention_mask, want_aux=return_aux)
+        if not return_aux:
+            return logits, None
+        B, L = token_ids.shape
+        D = self.cfg["embed_dim"]
+        aux = {
+            "image_features": prog.tensor("aux.image_features").clone(),
+            "text_features": prog.tensor("text_features").view(B, L, D).clone(),
+            "text_pooled": prog.tensor("text_pooled").clone(),
+            "fused": prog.tensor("fused").clone(),
+            "cross_attention_weights": [prog.tensor(n).clone() for n in prog.xattn_weights],
+            "image_projected": prog.tensor("image_projected").view(B, 49, D).clone(),
+            "attended_pooled": prog.tensor("attended_pooled").clone(),
+        }
+        return logits, aux
+
+    def predict(self, images, token_ids, attention_mask=None, top_k=5):
+        _, idx, probs, _ = self.run(images, token_ids, attention_mask, top_k=top_k)
+        return idx, probs

@@ -1,0 +1,126 @@
+"""ctypes binding of libvqa_b200.so (the C ABI in include/vqa_b200.h).
+
+Loading fails loudly when the library is missing: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Sequence
+
+from . import program as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvqa_b200.so")
+
+OP_NI, OP_NP, OP_NF = 144, 12, 4
+ABI_VERSION = 3
+
+
+class VqaOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad_", C.c_int32), ("i", C.c_int32 * OP_NI),
+                ("f", C.c_float * OP_NF), ("p", C.c_uint64 * OP_NP)]
+
+
+class VqaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library (built in-tree by ``python -m vqa_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VqaError(f"{LIB_PATH} is missing: build it with `python -m vqa_b200.build` "
+                       "(the engine has no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    L.vqa_abi_version.restype = C.c_int
+    L.vqa_last_error.restype = C.c_char_p
+    L.vqa_device_check.argtypes = [C.c_int]
+    L.vqa_op_num_fields.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.vqa_plan_create.argtypes = [C.POINTER(VqaOp), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.vqa_plan_run.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]
+    L.vqa_plan_run_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]
+    L.vqa_plan_num_launches.argtypes = [C.c_void_p]
+    L.vqa_plan_op_kernel_name.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
+    L.vqa_plan_destroy.argtypes = [C.c_void_p]
+    L.vqa_plan_destroy.restype = None
+    L.vqa_launch_count.restype = C.c_uint64
+    if L.vqa_abi_version() != ABI_VERSION:
+        raise VqaError(f"libvqa_b200.so ABI {L.vqa_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    for kind, code in P.KINDS.items():  # both sides of the op field tables must agree
+        ni, np_, nf = C.c_int(), C.c_int(), C.c_int()
+        check(L.vqa_op_num_fields(code, C.byref(ni), C.byref(np_), C.byref(nf)), L)
+        spec = P.FIELDS[kind]
+        if (ni.value, np_.value, nf.value) != (len(spec["i"]), len(spec["p"]), len(spec["f"])):
+            raise VqaError(f"op field table mismatch for {kind}; rebuild libvqa_b200.so")
+    _lib = L
+    return L
+
+
+def check(rc: int, L=None):
+    if rc != 0:
+        L = L or lib()
+        msg = L.vqa_last_error().decode("utf-8", "replace")
+        if rc == -4:
+            raise NotImplementedError(msg)
+        raise VqaError(f"libvqa_b200 error {rc}: {msg}")
+
+
+def pack_ops(ops: Sequence[P.Op]):
+    arr = (VqaOp * len(ops))()
+    for k, op in enumerate(ops):
+        spec = P.FIELDS[op.kind]
+        o = arr[k]
+        o.kind = P.KINDS[op.kind]
+        for j, name in enumerate(spec["i"]):
+            o.i[j] = int(op.i.get(name, 0))
+        for j, name in enumerate(spec["f"]):
+            o.f[j] = float(op.f.get(name, 0.0))
+        for j, name in enumerate(spec["p"]):
+            ref = op.p.get(name)
+            o.p[j] = 0 if ref is None else ref.addr()
+    return arr
+
+
+class Plan:
+    """Owns a VqaPlan handle; ``run`` launches every op on the given CUDA stream."""
+
+    def __init__(self, ops: Sequence[P.Op], device_index: int):
+        self._L = lib()
+        self._ops = pack_ops(ops)
+        self.n_ops = len(ops)
+        self.names = [op.name for op in ops]
+        h = C.c_void_p()
+        check(self._L.vqa_plan_create(self._ops, len(ops), device_index, C.byref(h)))
+        self._h = h
+
+    def run(self, ext: List[int], stream: int, first: int = 0, last: int = -1):
+        arr = (C.c_uint64 * len(ext))(*ext)
+        if first == 0 and last < 0:
+            check(self._L.vqa_plan_run(self._h, arr, len(ext), C.c_void_p(stream)))
+        else:
+            check(self._L.vqa_plan_run_range(self._h, first, self.n_ops if last < 0 else last, arr, len(ext),
+                                             C.c_void_p(stream)))
+
+    def kernel_name(self, op: int) -> str:
+        buf = C.create_string_buffer(128)
+        check(self._L.vqa_plan_op_kernel_name(self._h, op, buf, 128))
+        return buf.value.decode()
+
+    @property
+    def num_launches(self) -> int:
+        return self._L.vqa_plan_num_launches(self._h)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.vqa_plan_destroy(h)
+
+
+def launch_count() -> int:
+    return int(lib().vqa_launch_count())
