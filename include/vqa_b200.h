@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 3
+#define VQA_ABI_VERSION 4
 
 #define VQA_OK            0
 #define VQA_E_INVALID    -1   /* bad argument / unsupported shape */
@@ -71,7 +71,7 @@ enum VqaOpKind {
 
 typedef struct VqaOp {
   int32_t  kind;
-  int32_t  pad_;
+  int32_t  lane;            /* 0 = caller's stream; 1 = the plan's side stream (forked/joined per run) */
   int32_t  i[VQA_OP_NI];
   float    f[VQA_OP_NF];
   uint64_t p[VQA_OP_NP];

@@ -1,4 +1,4 @@
-// Tap-shifted GEMM on tcgen05 / TMEM fed by TMA  (VQA_OP_GEMM).
+// Tap-shifted GEMM on tcgen05 / TMEM fed by TMA  (VQA_OP_GEMM), persistent and warp-specialised.
 //
 // One kernel covers every Conv2d(+BN folded)(+ReLU)(+residual) of the backbone
 // (reference models/cnn_backbone.py:164-197, 349-352) and every nn.Linear of the text encoder,
@@ -9,30 +9,44 @@
 // window of A rows (tile rows + halo on both sides, SWIZZLE_128B) and the MMA thread issues one
 // UMMA set per tap whose A descriptor starts `rel` rows into that window -- a 3x3 convolution
 // re-uses each input row 9 times out of shared memory instead of re-fetching it from L2.
+// (Measured on B200: the UMMA SWIZZLE_128B pattern is a function of the absolute shared-memory
+// address, so a start address offset by whole 128-byte rows needs no base_offset correction.)
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue (TMEM -> registers
-// -> bias / residual / ReLU / pad-mask -> global).  Accumulators: MT sub-tiles of 128 x BN fp32 in
-// TMEM.  Pipelines: A-window ring and B (weight) ring, each with full/empty mbarriers.
+// CTA = 10 warps, one CTA per SM, looping over output tiles (static round-robin):
+//   warp 0      TMA producer: A-window ring + weight ring (or all weights resident when they fit)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma; tcgen05.commit frees ring slots
+//   warps 2..9  epilogue: TMEM -> registers -> bias / residual / ReLU / pad-mask -> global; two
+//               warps per TMEM lane quadrant, each taking half of the tile's columns
+// Accumulators are double-buffered in TMEM (when 2*MT*BN <= 512 columns) so the epilogue of tile
+// i overlaps the MMAs of tile i+1.
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kChunkBytes = 128;  // one SWIZZLE_128B row: 64 bf16 or 32 fp32 (tf32)
+constexpr int kMaxASlots = 8;
+constexpr int kMaxBSlots = 12;
 
 struct GemmParams {
   int M, N;
-  int MT;            // 128-row sub-tiles per CTA (1 or 2)
+  int MT;            // 128-row sub-tiles per CTA tile (1 or 2); mirrors the kernel's template MT
   int halo;          // window rows before/after the tile
   int box_rows;      // TMA box rows for A
   int nboxes;        // boxes per window (1 or 2)
   int a_slots, b_slots;
   int a_slot_bytes, b_slot_bytes;
+  int b_resident;    // all weight chunks of the N tile stay in shared memory for the CTA's lifetime
+  int k_chunks;      // Ktot / chunk_elems
+  int acc_stages;    // TMEM accumulator double buffering (1 or 2)
+  int m_tiles, n_tiles;
   int ngroups;
   int chunk_elems;   // 64 (bf16) / 32 (tf32)
   int is_tf32;
   uint32_t idesc;
-  int desc_mode;     // 0: base_offset field 0 (absolute-address swizzle); 1: base_offset=(addr>>7)&7
   int g_map[VQA_MAX_GROUPS], g_delta[VQA_MAX_GROUPS], g_acol[VQA_MAX_GROUPS], g_chunks[VQA_MAX_GROUPS];
   int g_ntaps[VQA_MAX_GROUPS], g_kbase[VQA_MAX_GROUPS], g_tap0[VQA_MAX_GROUPS];
   int tap_rel[VQA_MAX_TAPS];
@@ -44,13 +58,93 @@ struct GemmParams {
   int relu, round_tf32, mask_en, mP, mRPI, mH, mW;
 };
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, int desc_mode) {
-  uint64_t d = umma_desc_sw128(addr);
-  if (desc_mode == 1) d |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;
-  return d;
+// ---- epilogue helpers -----------------------------------------------------------------------
+// Residual prefetch for 32 columns of one row: bf16 -> 4 x uint4, fp32 -> 8 x uint4.
+struct ResRegs { uint4 q[8]; };
+
+__device__ __forceinline__ void res_prefetch(ResRegs& r, const GemmParams& p, int row, int col, bool row_ok) {
+  if (!p.res || !row_ok) return;
+  if (p.res_dtype == 0) {
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
+    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r.q[j] = reinterpret_cast<const uint4*>(src)[j];
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
+    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.q[j] = reinterpret_cast<const uint4*>(src)[j];
+    }
+  }
 }
 
-template <int BN>
+__device__ __forceinline__ void res_apply(float (&x)[32], const ResRegs& r, const GemmParams& p, int row, int col) {
+  if (!p.res) return;
+  if (p.res_dtype == 0) {
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
+    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {r.q[j].x, r.q[j].y, r.q[j].z, r.q[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          x[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+          x[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+        }
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (col + j < p.N) x[j] += __bfloat162float(src[j]);
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
+    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[4 * j] += __uint_as_float(r.q[j].x);
+        x[4 * j + 1] += __uint_as_float(r.q[j].y);
+        x[4 * j + 2] += __uint_as_float(r.q[j].z);
+        x[4 * j + 3] += __uint_as_float(r.q[j].w);
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (col + j < p.N) x[j] += src[j];
+    }
+  }
+}
+
+__device__ __forceinline__ void store_row32(const float (&x)[32], const GemmParams& p, int row, int col) {
+  if (p.out_dtype == 0) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q;
+        q.x = pack_bf16x2(x[8 * j], x[8 * j + 1]);
+        q.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+        q.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+        q.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+        reinterpret_cast<uint4*>(o)[j] = q;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (col + j < p.N) o[j] = __float2bfloat16_rn(x[j]);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (col + j < p.N) o[j] = x[j];
+    }
+  }
+}
+
+template <int BN, int MT, bool TF32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
@@ -61,18 +155,19 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128 * p.MT;
-  const int n0 = blockIdx.y * BN;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int b_region_slots = p.b_resident ? p.k_chunks : p.b_slots;
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.a_slots * p.a_slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.b_slots * p.b_slot_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + b_region_slots * p.b_slot_bytes);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + p.a_slots;
-  uint64_t* b_full = a_empty + p.a_slots;
-  uint64_t* b_empty = b_full + p.b_slots;
-  uint64_t* acc_full = b_empty + p.b_slots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* a_empty = a_full + kMaxASlots;
+  uint64_t* b_full = a_empty + kMaxASlots;     // b_full[0] doubles as the "all weights landed" barrier
+  uint64_t* b_empty = b_full + kMaxBSlots;
+  uint64_t* acc_full = b_empty + kMaxBSlots;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -81,12 +176,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < p.b_slots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
     mbar_fence_init();
   }
+  const uint32_t tmem_cols = static_cast<uint32_t>(BN * MT * p.acc_stages);
   if (warp == 2) {
-    tmem_alloc(tmem_slot, static_cast<uint32_t>(BN * p.MT));
+    tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -95,174 +191,203 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer (one elected lane) =====================
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    bool b_loaded = false;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.m_tiles) * 128 * MT;
+      const int n0 = (tile / p.m_tiles) * BN;
+      if (p.b_resident && !b_loaded) {   // n_tiles == 1 in this mode: load every weight chunk once
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[0], static_cast<uint32_t>(p.k_chunks * p.b_slot_bytes));
+          for (int q = 0; q < p.k_chunks; ++q)
+            tma_load_2d(smem_b + q * p.b_slot_bytes, &mapB, &b_full[0], q * p.chunk_elems, n0);
+        }
+        __syncwarp();
+        b_loaded = true;
+      }
       for (int g = 0; g < p.ngroups; ++g) {
         const CUtensorMap* mapA = p.g_map[g] ? &mapA1 : &mapA0;
         const int row0 = m0 + p.g_delta[g] - p.halo;
         for (int c = 0; c < p.g_chunks[g]; ++c) {
           mbar_wait(&a_empty[as], aph ^ 1u);
-          mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_slot_bytes));
-          uint8_t* dst = smem_a + as * p.a_slot_bytes;
-          const int x = p.g_acol[g] + c * p.chunk_elems;
-          for (int b = 0; b < p.nboxes; ++b)
-            tma_load_2d(dst + b * p.box_rows * kChunkBytes, mapA, &a_full[as], x, row0 + b * p.box_rows);
+          if (elect_one()) {
+            mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_slot_bytes));
+            uint8_t* dst = smem_a + as * p.a_slot_bytes;
+            const int x = p.g_acol[g] + c * p.chunk_elems;
+            for (int b = 0; b < p.nboxes; ++b)
+              tma_load_2d(dst + b * p.box_rows * kChunkBytes, mapA, &a_full[as], x, row0 + b * p.box_rows);
+          }
+          __syncwarp();
           if (++as == p.a_slots) { as = 0; aph ^= 1u; }
-          for (int t = 0; t < p.g_ntaps[g]; ++t) {
-            mbar_wait(&b_empty[bs], bph ^ 1u);
-            mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(p.b_slot_bytes));
-            const int kcol = p.g_kbase[g] + (t * p.g_chunks[g] + c) * p.chunk_elems;
-            tma_load_2d(smem_b + bs * p.b_slot_bytes, &mapB, &b_full[bs], kcol, n0);
-            if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+          if (!p.b_resident) {
+            for (int t = 0; t < p.g_ntaps[g]; ++t) {
+              mbar_wait(&b_empty[bs], bph ^ 1u);
+              if (elect_one()) {
+                mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(p.b_slot_bytes));
+                const int kcol = p.g_kbase[g] + (t * p.g_chunks[g] + c) * p.chunk_elems;
+                tma_load_2d(smem_b + bs * p.b_slot_bytes, &mapB, &b_full[bs], kcol, n0);
+              }
+              __syncwarp();
+              if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      uint32_t first = 1;  // first MMA of each accumulator overwrites, the rest accumulate
-      const uint32_t a_base0 = smem_u32(smem_a);
-      const uint32_t b_base0 = smem_u32(smem_b);
+    // ===================== MMA issuer (whole warp loops convergently, one elected lane issues) =====
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, accph = 0;
+    const uint32_t a_base0 = smem_u32(smem_a);
+    const uint32_t b_base0 = smem_u32(smem_b);
+    // descriptor high word is constant: SBO = 1024 B, version 1, SWIZZLE_128B (see umma_desc_sw128)
+    constexpr uint32_t kDescHi = static_cast<uint32_t>(umma_desc_sw128_hi());
+    bool b_ready = false;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], accph ^ 1u);   // epilogue has drained this accumulator stage
+      if (p.b_resident && !b_ready) {
+        mbar_wait(&b_full[0], 0);
+        b_ready = true;
+      }
+      tc_fence_after();
+      const uint32_t d_tile = tmem_base + acc * (BN * MT);
+      uint32_t fresh = 1;  // first MMA of each accumulator overwrites, the rest accumulate
       for (int g = 0; g < p.ngroups; ++g) {
-        for (int c = 0; c < p.g_chunks[g]; ++c) {
+        const int nchunks = p.g_chunks[g], ntaps = p.g_ntaps[g], tap0 = p.g_tap0[g];
+        const int q0 = p.g_kbase[g] / p.chunk_elems;
+        for (int c = 0; c < nchunks; ++c) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
           const uint32_t a_win = a_base0 + as * p.a_slot_bytes;
-          for (int t = 0; t < p.g_ntaps[g]; ++t) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint32_t b_tile = b_base0 + bs * p.b_slot_bytes;
-            const uint32_t a_tap = a_win + static_cast<uint32_t>(p.tap_rel[p.g_tap0[g] + t]) * kChunkBytes;
-            for (int sub = 0; sub < p.MT; ++sub) {
-              const uint32_t a_sub = a_tap + sub * 128 * kChunkBytes;
-              const uint32_t d_tmem = tmem_base + sub * BN;
+          for (int t = 0; t < ntaps; ++t) {
+            uint32_t b_tile;
+            if (p.b_resident) {
+              b_tile = b_base0 + (q0 + t * nchunks + c) * p.b_slot_bytes;
+            } else {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              b_tile = b_base0 + bs * p.b_slot_bytes;
+            }
+            const uint32_t a_lo = ((a_win + static_cast<uint32_t>(p.tap_rel[tap0 + t]) * kChunkBytes) & 0x3FFFFu) >> 4;
+            const uint32_t b_lo = (b_tile & 0x3FFFFu) >> 4;
+            if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 bytes) per 128-byte chunk
-                const uint64_t ad = make_desc(a_sub + k * 32, p.desc_mode);
-                const uint64_t bd = make_desc(b_tile + k * 32, p.desc_mode);
-                const uint32_t acc = (first && k == 0) ? 0u : 1u;
-                if (p.is_tf32) umma_tf32(d_tmem, ad, bd, p.idesc, acc);
-                else           umma_f16(d_tmem, ad, bd, p.idesc, acc);
+              for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 bytes) per 128-byte chunk; 32 B >> 4 = 2
+                  const uint64_t ad = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + sub * (128 * kChunkBytes / 16) + 2 * k);
+                  const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
+                  const uint32_t accum = (k == 0) ? (fresh ^ 1u) : 1u;
+                  if (TF32) umma_tf32(d_tile + sub * BN, ad, bd, p.idesc, accum);
+                  else      umma_f16(d_tile + sub * BN, ad, bd, p.idesc, accum);
+                }
               }
             }
-            first = 0;
-            umma_commit(&b_empty[bs]);   // weight slot is free once these MMAs retire
-            if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+            __syncwarp();
+            fresh = 0;
+            if (!p.b_resident) {
+              if (elect_one()) umma_commit(&b_empty[bs]);   // weight slot is free once these MMAs retire
+              __syncwarp();
+              if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
+            }
           }
-          umma_commit(&a_empty[as]);     // window slot is free once all its taps retire
+          if (elect_one()) umma_commit(&a_empty[as]);       // window slot is free once all its taps retire
+          __syncwarp();
           if (++as == p.a_slots) { as = 0; aph ^= 1u; }
         }
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
     }
   } else {
-    // ===================== epilogue warps (TMEM lane quadrant = warp % 4) =====================
-    const int quad = warp & 3;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const bool out_bf16 = p.out_dtype == 0;
-    for (int sub = 0; sub < p.MT; ++sub) {
-      const int row = m0 + sub * 128 + quad * 32 + lane;
-      bool row_ok = row < p.M;
-      bool pix_ok = true;
-      if (p.mask_en) {
-        const int rem = row % p.mRPI;
-        pix_ok = (rem / p.mP) < p.mH && (rem % p.mP) < p.mW;
-      }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sub * BN;
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;           // which half of the tile's columns
+    constexpr int kCols = BN / 2;       // columns per warp per sub-tile
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.m_tiles) * 128 * MT;
+      const int n0 = (tile / p.m_tiles) * BN;
+      const int row_first = m0 + quad * 32 + lane;
+      ResRegs rr;
+      res_prefetch(rr, p, row_first, n0 + half * kCols, row_first < p.M);
+      mbar_wait(&acc_full[acc], accph);
+      tc_fence_after();
+      for (int sub = 0; sub < MT; ++sub) {
+        const int row = m0 + sub * 128 + quad * 32 + lane;
+        const bool row_ok = row < p.M;
+        bool pix_ok = true;
+        if (p.mask_en) {
+          const int rem = row % p.mRPI;
+          pix_ok = (rem / p.mP) < p.mH && (rem % p.mP) < p.mW;
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (BN * MT) + sub * BN +
+                               half * kCols;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        const int col = n0 + c0;
-        if (col >= p.N) break;                      // warp-uniform
-        uint32_t v[16];
-        __syncwarp();                               // tcgen05.ld is warp-collective (.sync.aligned)
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (row_ok) {                               // rows past M only take part in the TMEM load
-        float x[16];
-        const bool full = col + 16 <= p.N;
+        for (int c0 = 0; c0 < kCols; c0 += 32) {
+          const int col = n0 + half * kCols + c0;
+          uint32_t v[32];
+          __syncwarp();                               // tcgen05.ld is warp-collective (.sync.aligned)
+          tmem_ld32(taddr + c0, v);
+          // prefetch the residual of the next chunk while the TMEM load is in flight
+          ResRegs rn;
+          {
+            int nrow = row, ncol = col + 32;
+            if (c0 + 32 >= kCols) { nrow = row + 128; ncol = n0 + half * kCols; }
+            const bool more = (c0 + 32 < kCols) || (sub + 1 < MT);
+            res_prefetch(rn, p, nrow, ncol, more && nrow < p.M && ncol < p.N);
+          }
+          tmem_ld_wait();
+          if (row_ok && col < p.N) {
+            float x[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-        if (p.bias) {
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+              if (col + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] += (full || col + j < p.N) ? __ldg(p.bias + col + j) : 0.f;
-        }
-        if (p.res) {
-          if (p.res_dtype == 0) {
-            const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
-            if (full && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
-              const uint4 q0 = *reinterpret_cast<const uint4*>(r);
-              const uint4 q1 = *reinterpret_cast<const uint4*>(r + 8);
-              const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                x[2 * j] += __uint_as_float(w[j] << 16);
-                x[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+                  x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col + j < p.N) x[j] += __ldg(p.bias + col + j);
               }
-            } else {
-              for (int j = 0; j < 16; ++j) if (col + j < p.N) x[j] += __bfloat162float(r[j]);
             }
-          } else {
-            const float* r = reinterpret_cast<const float*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
-            if (full && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+            res_apply(x, rr, p, row, col);
+            if (p.relu) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 q = *reinterpret_cast<const float4*>(r + 4 * j);
-                x[4 * j] += q.x; x[4 * j + 1] += q.y; x[4 * j + 2] += q.z; x[4 * j + 3] += q.w;
-              }
-            } else {
-              for (int j = 0; j < 16; ++j) if (col + j < p.N) x[j] += r[j];
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
             }
+            if (!pix_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = 0.f;   // keep the shared zero padding of the grid intact
+            }
+            if (p.round_tf32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = round_tf32_rna(x[j]);
+            }
+            store_row32(x, p, row, col);
           }
+          rr = rn;
         }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
-        }
-        if (!pix_ok) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = 0.f;   // keep the shared zero padding of the grid intact
-        }
-        if (p.round_tf32) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = round_tf32_rna(x[j]);
-        }
-        if (out_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
-          if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-            uint4 q0, q1;
-            q0.x = pack_bf16x2(x[0], x[1]);   q0.y = pack_bf16x2(x[2], x[3]);
-            q0.z = pack_bf16x2(x[4], x[5]);   q0.w = pack_bf16x2(x[6], x[7]);
-            q1.x = pack_bf16x2(x[8], x[9]);   q1.y = pack_bf16x2(x[10], x[11]);
-            q1.z = pack_bf16x2(x[12], x[13]); q1.w = pack_bf16x2(x[14], x[15]);
-            *reinterpret_cast<uint4*>(o) = q0;
-            *reinterpret_cast<uint4*>(o + 8) = q1;
-          } else {
-            for (int j = 0; j < 16; ++j) if (col + j < p.N) o[j] = __float2bfloat16_rn(x[j]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
-          if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(o + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 16; ++j) if (col + j < p.N) o[j] = x[j];
-          }
-        }
-        }  // row_ok
       }
+      // all TMEM reads of this warp are complete (wait::ld above): release the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(BN * p.MT));
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -317,21 +442,41 @@ uint32_t make_idesc(bool tf32, int n) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
+int num_sms(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  if (device >= 0 && device < 64) cached[device] = n;
+  return n;
+}
+
 }  // namespace
 
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+
+static GemmKernelFn pick_kernel(int bn, int mt, bool tf32) {
+#define VQA_PICK(BN_, MT_)                                                                    \
+  if (bn == BN_ && mt == MT_) return tf32 ? static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, true>) \
+                                          : static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, false>);
+  VQA_PICK(64, 1) VQA_PICK(64, 2) VQA_PICK(128, 1) VQA_PICK(128, 2) VQA_PICK(256, 1) VQA_PICK(256, 2)
+#undef VQA_PICK
+  return nullptr;
+}
+
 struct GemmLaunch {
+  GemmKernelFn fn;
   CUtensorMap mapA0, mapA1, mapB;
   GemmParams prm;
   dim3 grid;
   int bn;
   size_t smem;
-  bool ext_out, ext_res;
   uint64_t out_raw, res_raw;
 };
 
 int gemm_launch_bytes() { return static_cast<int>(sizeof(GemmLaunch)); }
 
-int gemm_prepare(const VqaOp& op, void* storage) {
+int gemm_prepare(const VqaOp& op, void* storage, int device) {
   GemmLaunch* L = new (storage) GemmLaunch();
   GemmParams& p = L->prm;
   const int32_t* I = op.i;
@@ -342,7 +487,7 @@ int gemm_prepare(const VqaOp& op, void* storage) {
   p.N = I[GEMM_I_N];
   p.MT = I[GEMM_I_MT];
   p.halo = I[GEMM_I_halo];
-  VQA_REQUIRE(p.MT == 1 || p.MT == 2, VQA_E_INVALID, "gemm: MT must be 1 or 2");
+  VQA_REQUIRE(p.MT == 1 || p.MT == 2, VQA_E_INVALID, "gemm: p.MT must be 1 or 2");
   VQA_REQUIRE(p.MT * bn <= 512, VQA_E_INVALID, "gemm: accumulators exceed 512 TMEM columns");
   VQA_REQUIRE(p.M > 0 && p.N > 0 && I[GEMM_I_Npad] % bn == 0 && I[GEMM_I_Npad] >= p.N, VQA_E_INVALID,
               "gemm: bad M/N/Npad");
@@ -352,7 +497,8 @@ int gemm_prepare(const VqaOp& op, void* storage) {
   p.chunk_elems = tf32 ? 32 : 64;
   p.is_tf32 = tf32 ? 1 : 0;
   p.idesc = make_idesc(tf32, bn);
-  p.desc_mode = I[GEMM_I_desc_mode];
+  VQA_REQUIRE(I[GEMM_I_Ktot] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: Ktot must be a multiple of the K chunk");
+  p.k_chunks = I[GEMM_I_Ktot] / p.chunk_elems;
   bool lockstep = p.halo == 0;
   long long kcover = 0;
   bool uses_a1 = false;
@@ -366,6 +512,7 @@ int gemm_prepare(const VqaOp& op, void* storage) {
     p.g_tap0[g] = I[GEMM_I_g_tap00 + g];
     VQA_REQUIRE(p.g_chunks[g] >= 1 && p.g_ntaps[g] >= 1 && p.g_tap0[g] + p.g_ntaps[g] <= VQA_MAX_TAPS,
                 VQA_E_INVALID, "gemm: bad group");
+    VQA_REQUIRE(p.g_kbase[g] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: group K base must be chunk aligned");
     if (p.g_ntaps[g] != 1) lockstep = false;
     uses_a1 |= p.g_map[g] != 0;
     kcover += static_cast<long long>(p.g_ntaps[g]) * p.g_chunks[g] * p.chunk_elems;
@@ -388,22 +535,32 @@ int gemm_prepare(const VqaOp& op, void* storage) {
   VQA_REQUIRE(p.box_rows <= 256, VQA_E_INVALID, "gemm: halo too large for a 2-box window");
   p.a_slot_bytes = win * kChunkBytes;
   p.b_slot_bytes = bn * kChunkBytes;
-  // pipeline depth from the shared-memory budget
-  int n_iters = 0;
-  for (int g = 0; g < p.ngroups; ++g) n_iters += p.g_chunks[g];
+  p.m_tiles = (p.M + 128 * p.MT - 1) / (128 * p.MT);
+  p.n_tiles = (p.N + bn - 1) / bn;        // only N tiles that contain real columns run
+  p.acc_stages = (2 * p.MT * bn <= 512) ? 2 : 1;
+
+  // shared-memory plan: one CTA per SM (persistent), ~210 KB of rings
   int budget = I[GEMM_I_smem_budget];
-  if (budget <= 0) budget = (lockstep && n_iters <= 16 && p.MT * bn <= 256) ? 100 * 1024 : 200 * 1024;
-  if (lockstep) {
+  if (budget <= 0) budget = 208 * 1024;
+  const long long b_all = static_cast<long long>(p.k_chunks) * p.b_slot_bytes;
+  p.b_resident = (p.n_tiles == 1 && b_all <= 96 * 1024 && b_all + 2LL * p.a_slot_bytes <= budget) ? 1 : 0;
+  if (p.b_resident) {
+    int s = static_cast<int>((budget - b_all) / p.a_slot_bytes);
+    p.a_slots = s < 2 ? 2 : (s > kMaxASlots ? kMaxASlots : s);
+    p.b_slots = 1;
+  } else if (lockstep) {
     int s = budget / (p.a_slot_bytes + p.b_slot_bytes);
-    s = s < 2 ? 2 : (s > 8 ? 8 : s);
+    s = s < 2 ? 2 : (s > kMaxASlots ? kMaxASlots : s);
     p.a_slots = p.b_slots = s;
   } else {
-    p.a_slots = 2;
-    int s = (budget - 2 * p.a_slot_bytes) / p.b_slot_bytes;
-    p.b_slots = s < 2 ? 2 : (s > 10 ? 10 : s);
+    // window mode: 3 windows in flight when they are cheap, the rest of the budget to the weight ring
+    p.a_slots = (3 * p.a_slot_bytes + 4 * p.b_slot_bytes <= budget) ? 3 : 2;
+    int s = (budget - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+    p.b_slots = s < 2 ? 2 : (s > kMaxBSlots ? kMaxBSlots : s);
   }
-  L->smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(p.b_slots) * p.b_slot_bytes +
-            8 * (2 * p.a_slots + 2 * p.b_slots + 1) + 16;
+  const long long b_bytes = p.b_resident ? b_all : static_cast<long long>(p.b_slots) * p.b_slot_bytes;
+  L->smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(b_bytes) +
+            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 4) + 16;
   VQA_REQUIRE(L->smem <= 227 * 1024, VQA_E_INVALID, "gemm: shared memory budget exceeded");
 
   // tensor maps (only for non-external operands: A and W always live in the arenas)
@@ -435,22 +592,21 @@ int gemm_prepare(const VqaOp& op, void* storage) {
   p.mH = I[GEMM_I_mH];
   p.mW = I[GEMM_I_mW];
   p.bias = reinterpret_cast<const float*>(op.p[GEMM_P_bias]);
+  VQA_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, VQA_E_ALIGN,
+              "gemm: bias must be 16-byte aligned");
   L->out_raw = op.p[GEMM_P_out];
   L->res_raw = op.p[GEMM_P_res];
   VQA_REQUIRE(L->out_raw != 0, VQA_E_INVALID, "gemm: null output");
   L->bn = bn;
-  L->grid = dim3((p.M + 128 * p.MT - 1) / (128 * p.MT), I[GEMM_I_Npad] / bn, 1);
-  // only N tiles that contain real columns need to run
-  L->grid.y = (p.N + bn - 1) / bn;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int sms = num_sms(device);
+  L->grid = dim3(tiles < sms ? tiles : sms, 1, 1);
 
-  auto set_attr = [&](const void* fn) -> int {
-    VQA_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    return VQA_OK;
-  };
-  if (bn == 64) rc = set_attr(reinterpret_cast<const void*>(&gemm_tap_kernel<64>));
-  else if (bn == 128) rc = set_attr(reinterpret_cast<const void*>(&gemm_tap_kernel<128>));
-  else rc = set_attr(reinterpret_cast<const void*>(&gemm_tap_kernel<256>));
-  return rc;
+  L->fn = pick_kernel(bn, p.MT, tf32);
+  VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT");
+  VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024));
+  return VQA_OK;
 }
 
 int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t stream) {
@@ -459,17 +615,14 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
   p.out = reinterpret_cast<void*>(vqa_resolve(L->out_raw, ext, n_ext));
   p.res = reinterpret_cast<const void*>(vqa_resolve(L->res_raw, ext, n_ext));
   VQA_REQUIRE(p.out != nullptr, VQA_E_INVALID, "gemm: unresolved external output");
-  if (L->bn == 64)
-    gemm_tap_kernel<64><<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, p);
-  else if (L->bn == 128)
-    gemm_tap_kernel<128><<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, p);
-  else
-    gemm_tap_kernel<256><<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, p);
+  L->fn<<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, p);
   VQA_LAUNCH_OK("gemm_tap_kernel");
   return VQA_OK;
 }
 
 const char* gemm_kernel_name(const void* storage) {
   const GemmLaunch* L = reinterpret_cast<const GemmLaunch*>(storage);
-  return L->bn == 64 ? "gemm_tap_kernel<64>" : (L->bn == 128 ? "gemm_tap_kernel<128>" : "gemm_tap_kernel<256>");
+  static thread_local char name[64];
+  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16");
+  return name;
 }

@@ -10,7 +10,7 @@
 
 // implemented in gemm_tcgen05.cu / kernels_misc.cu
 int gemm_launch_bytes();
-int gemm_prepare(const VqaOp& op, void* storage);
+int gemm_prepare(const VqaOp& op, void* storage, int device);
 int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t stream);
 const char* gemm_kernel_name(const void* storage);
 int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st);
@@ -50,9 +50,15 @@ struct VqaPlan {
   int device = 0;
   std::vector<VqaOp> ops;
   std::vector<void*> gemm;   // per op: prepared GemmLaunch (64-byte aligned) or nullptr
+  bool has_side = false;     // some op runs on lane 1
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
   ~VqaPlan() {
     for (void* g : gemm)
       if (g) std::free(g);
+    if (fork) cudaEventDestroy(fork);
+    if (join) cudaEventDestroy(join);
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -111,12 +117,22 @@ int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** o
       }
       std::memset(st, 0, bytes);
       plan->gemm[k] = st;
-      rc = gemm_prepare(op, st);
+      rc = gemm_prepare(op, st, device);
       if (rc) {
         vqa_set_error("op " + std::to_string(k) + ": " + g_error);
         delete plan;
         return rc;
       }
+    }
+  }
+  for (const VqaOp& op : plan->ops) plan->has_side |= op.lane == 1;
+  if (plan->has_side) {
+    if (cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&plan->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&plan->join, cudaEventDisableTiming) != cudaSuccess) {
+      vqa_set_error("could not create the side stream / events");
+      delete plan;
+      return VQA_E_CUDA;
     }
   }
   *out = plan;
@@ -129,13 +145,35 @@ int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const u
   const int n = static_cast<int>(plan->ops.size());
   VQA_REQUIRE(first >= 0 && last <= n && first <= last, VQA_E_INVALID, "vqa_plan_run: bad op range");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Whole-plan runs fork lane-1 ops (the text encoder, independent of the backbone) onto the side
+  // stream and join before the first lane-0 op that follows them; partial ranges run serially.
+  const bool two_lanes = plan->has_side && first == 0 && last == n;
+  bool forked = false, pending_join = false;
   for (int k = first; k < last; ++k) {
     const VqaOp& op = plan->ops[k];
-    int rc = (op.kind == VQA_OP_GEMM) ? gemm_run(plan->gemm[k], ext, n_ext, st) : run_misc_op(op, ext, n_ext, st);
+    cudaStream_t s = st;
+    if (two_lanes && op.lane == 1) {
+      if (!forked) {
+        VQA_CUDA_OK(cudaEventRecord(plan->fork, st));
+        VQA_CUDA_OK(cudaStreamWaitEvent(plan->side, plan->fork, 0));
+        forked = true;
+      }
+      s = plan->side;
+      pending_join = true;
+    } else if (two_lanes && pending_join && forked && k > 0 && plan->ops[k - 1].lane == 1) {
+      VQA_CUDA_OK(cudaEventRecord(plan->join, plan->side));
+      VQA_CUDA_OK(cudaStreamWaitEvent(st, plan->join, 0));
+      pending_join = false;
+    }
+    int rc = (op.kind == VQA_OP_GEMM) ? gemm_run(plan->gemm[k], ext, n_ext, s) : run_misc_op(op, ext, n_ext, s);
     if (rc) {
       vqa_set_error("op " + std::to_string(k) + ": " + g_error);
       return rc;
     }
+  }
+  if (pending_join) {   // plan ended on the side lane: the caller's stream must still observe it
+    VQA_CUDA_OK(cudaEventRecord(plan->join, plan->side));
+    VQA_CUDA_OK(cudaStreamWaitEvent(st, plan->join, 0));
   }
   return VQA_OK;
 }

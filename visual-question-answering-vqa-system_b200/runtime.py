@@ -14,11 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqa_b200.so")
 
 OP_NI, OP_NP, OP_NF = 144, 12, 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class VqaOp(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("pad_", C.c_int32), ("i", C.c_int32 * OP_NI),
+    _fields_ = [("kind", C.c_int32), ("lane", C.c_int32), ("i", C.c_int32 * OP_NI),
                 ("f", C.c_float * OP_NF), ("p", C.c_uint64 * OP_NP)]
 
 
@@ -77,6 +77,7 @@ def pack_ops(ops: Sequence[P.Op]):
         spec = P.FIELDS[op.kind]
         o = arr[k]
         o.kind = P.KINDS[op.kind]
+        o.lane = int(op.lane)
         for j, name in enumerate(spec["i"]):
             o.i[j] = int(op.i.get(name, 0))
         for j, name in enumerate(spec["f"]):
