@@ -54,14 +54,16 @@ def test_plain_bf16_gemm(M, K, N, out_dtype):
 
 
 @pytest.mark.parametrize("M,K,N,ldo", [(256, 256, 256, 256), (100, 256, 768, 768), (77, 1024, 256, 256),
-                                      (256, 256, 1000, 1000), (5, 512, 37, 37)])
-def test_tf32_linear_with_residual(M, K, N, ldo):
+                                      (256, 256, 1000, 1000), (5, 512, 37, 37), (1500, 256, 256, 256)])
+@pytest.mark.parametrize("max_ctas", [0, 2])
+def test_tf32_linear_with_residual(M, K, N, ldo, max_ctas):
     def build(device):
         W = _weights(device, "w", N, K, torch.float32, 3, npad=256).finalize()
         ol = P.OpList(W, device)
         a = ol._buf("a", torch.float32, M, K)
         o = ol._buf("o", torch.float32, M, ldo)
         ol.linear("lin", a, M, K, "w.w", "w.b", o, N, ldo=ldo, res=o)
+        ol.ops[-1].i["max_ctas"] = max_ctas
         ol.commit()
         G.named(ol, "a").copy_(_fill(ol, "a", 4))
         G.named(ol, "o").copy_(_fill(ol, "o", 5))
@@ -70,7 +72,7 @@ def test_tf32_linear_with_residual(M, K, N, ldo):
     G.report(f"tf32 M{M} K{K} N{N}", G.named(gpu, "o"), G.named(cpu, "o"), atol=2e-3, rtol=2e-3)
 
 
-def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, desc_mode=0, extra_ds=False):
+def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, max_ctas=0, extra_ds=False):
     g = P.Grid(B, H, Wd)
     gen = torch.Generator().manual_seed(7)
     k = 9 * cin + (cin if extra_ds else 0)
@@ -90,7 +92,7 @@ def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, desc_mode
             w="c.w", bias="c.b", out=o, ldo=cout, out_dtype=P.OUT_BF16, relu=True,
             res=x if residual else None, res_dtype=P.OUT_BF16 if residual else -1, ldr=cin, grid=g,
             halo=halo, MT=mt or mt_auto)
-    ol.ops[-1].i["desc_mode"] = desc_mode
+    ol.ops[-1].i["max_ctas"] = max_ctas
     ol.commit()
     # valid pixels random, shared pads zero (the layout invariant every producer keeps)
     xv = torch.randn(g.rows, cin, generator=gen)
@@ -106,9 +108,11 @@ def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, desc_mode
 
 @pytest.mark.parametrize("B,H,W,cin,cout,residual", [(2, 8, 8, 64, 64, False), (3, 14, 14, 128, 128, True),
                                                     (2, 7, 7, 256, 512, False)])
-def test_conv3x3_per_tap_loads(B, H, W, cin, cout, residual):
+@pytest.mark.parametrize("max_ctas", [0, 2])
+def test_conv3x3_per_tap_loads(B, H, W, cin, cout, residual, max_ctas):
     """window=False: every tap TMA-loads its own row-shifted A tile (negative / out-of-range rows zero-fill)."""
-    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, False, B, H, W, cin, cout, residual and cin == cout))
+    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, False, B, H, W, cin, cout, residual and cin == cout,
+                                                     max_ctas=max_ctas))
     G.report(f"conv per-tap {B}x{H}x{W} {cin}->{cout}", G.named(gpu, "o"), G.named(cpu, "o"), atol=3e-2, rtol=2e-2)
 
 
@@ -129,9 +133,10 @@ def test_conv3x3_matches_torch_conv2d():
     assert G.named(gpu, "o").cpu()[pads].abs().max() == 0  # shared zero padding is preserved
 
 
-def test_stem_overlapping_row_tensor_map():
+@pytest.mark.parametrize("max_ctas", [0, 1])
+def test_stem_overlapping_row_tensor_map(max_ctas):
     """Stem trick: rows of 64 bf16 that start every 16 elements (overlapping global strides)."""
-    rows, guard = 1000, 32
+    rows, guard = 3000, 32
     def build(device):
         W = _weights(device, "w", 64, 256, torch.bfloat16, 11).finalize()
         ol = P.OpList(W, device)
@@ -140,6 +145,7 @@ def test_stem_overlapping_row_tensor_map():
         taps = [(0, (ia - 2) * 30 - 2 + guard, 0, 1, [0]) for ia in range(4)]
         ol.gemm("stem", dtype=P.DT_BF16, M=rows, N=64, a0=a, a0_shape=(rows + guard, 64, 16), groups=taps,
                 w="w.w", bias="w.b", out=o, ldo=64, out_dtype=P.OUT_F32)
+        ol.ops[-1].i["max_ctas"] = max_ctas
         ol.commit()
         G.named(ol, "a").copy_(_fill(ol, "a", 12))
         return ol
@@ -149,15 +155,17 @@ def test_stem_overlapping_row_tensor_map():
 
 @pytest.mark.parametrize("B,H,W,cin,cout,mt", [(2, 8, 8, 64, 64, 1), (2, 56, 56, 64, 64, 1), (3, 14, 14, 128, 128, 2),
                                               (4, 28, 28, 128, 128, 2), (2, 7, 7, 512, 512, 2)])
-def test_conv3x3_window(B, H, W, cin, cout, mt, desc_mode=0):
+@pytest.mark.parametrize("max_ctas", [0, 3])
+def test_conv3x3_window(B, H, W, cin, cout, mt, max_ctas):
     """window=True: one A window per K chunk, taps are row-shifted UMMA descriptors into it.
 
-    Measured on B200 (round 1): with the descriptor base_offset field left 0 the row-shifted start
+    max_ctas=3 forces many tiles per persistent CTA (ring wrap-around, both MMA issuers, TMEM double
+    buffering).  Measured on B200 (round 1): with the descriptor base_offset field left 0 the row-shifted start
     address reads the TMA-written SWIZZLE_128B window correctly (the swizzle is a function of the
     absolute shared-memory address); setting base_offset=(addr>>7)&7 gives wrong results."""
     cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, True, B, H, W, cin, cout, cin == cout, mt=mt,
-                                                     desc_mode=desc_mode))
-    G.report(f"conv window desc_mode={desc_mode} {B}x{H}x{W} {cin}->{cout} MT{mt}", G.named(gpu, "o"),
+                                                     max_ctas=max_ctas))
+    G.report(f"conv window max_ctas={max_ctas} {B}x{H}x{W} {cin}->{cout} MT{mt}", G.named(gpu, "o"),
              G.named(cpu, "o"), atol=3e-2, rtol=2e-2)
 
 

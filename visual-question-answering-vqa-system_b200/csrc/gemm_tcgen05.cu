@@ -20,13 +20,14 @@
 // Accumulators are double-buffered in TMEM (when 2*MT*BN <= 512 columns) so the epilogue of tile
 // i overlaps the MMAs of tile i+1.
 #include <cstdio>
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kThreads = 32 * (2 + kEpiWarps);   // producer, MMA issuer, 8 epilogue warps
 constexpr int kChunkBytes = 128;  // one SWIZZLE_128B row: 64 bf16 or 32 fp32 (tf32)
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBSlots = 12;
@@ -42,6 +43,8 @@ struct GemmParams {
   int b_resident;    // all weight chunks of the N tile stay in shared memory for the CTA's lifetime
   int k_chunks;      // Ktot / chunk_elems
   int acc_stages;    // TMEM accumulator double buffering (1 or 2)
+  int win_per_tile;  // A windows one tile consumes (sum of chunks over groups)
+  int steps_per_tile;// weight tiles one tile consumes (sum of chunks*taps over groups)
   int m_tiles, n_tiles;
   int ngroups;
   int chunk_elems;   // 64 (bf16) / 32 (tf32)
@@ -56,95 +59,46 @@ struct GemmParams {
   const void* res;
   int ldo, ldr, out_dtype, res_dtype;
   int relu, round_tf32, mask_en, mP, mRPI, mH, mW;
+  long long* dbg;    // optional: 16 clock64() timestamps of CTA 0 (profiling aid, nullptr in production)
 };
 
+#define VQA_DBG(slot)                                                         \
+  do {                                                                        \
+    if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[slot] = clock64();       \
+  } while (0)
+
 // ---- epilogue helpers -----------------------------------------------------------------------
-// Residual prefetch for 32 columns of one row: bf16 -> 4 x uint4, fp32 -> 8 x uint4.
-struct ResRegs { uint4 q[8]; };
+// The accumulator comes out of TMEM one row per lane.  Writing rows straight to global memory
+// makes every 16-byte store of a warp touch 32 different 128-byte lines (measured: 14k cycles for
+// a 128x256 fp32 tile).  Each epilogue warp therefore transposes its 32x32 chunk through a
+// private, XOR-swizzled 4 KB shared-memory stage and does all global traffic (residual read,
+// output write) with 8 lanes per contiguous row segment.
+constexpr int kStageBytes = 32 * 128;   // 32 rows x 32 fp32 per epilogue warp
 
-__device__ __forceinline__ void res_prefetch(ResRegs& r, const GemmParams& p, int row, int col, bool row_ok) {
-  if (!p.res || !row_ok) return;
-  if (p.res_dtype == 0) {
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
-    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+__device__ __forceinline__ void stage_write(uint8_t* stage, int lane, const uint32_t (&v)[32]) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r.q[j] = reinterpret_cast<const uint4*>(src)[j];
-    }
+  for (int j = 0; j < 8; ++j) {
+    const uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = q;
+  }
+}
+__device__ __forceinline__ float4 stage_read(const uint8_t* stage, int row, int slot) {
+  return *reinterpret_cast<const float4*>(stage + row * 128 + ((slot ^ (row & 7)) << 4));
+}
+
+// EPI: 0 = bf16 out, no residual | 1 = bf16 out + bf16 residual | 2 = fp32 out, no residual | 3 = fp32 out + fp32 residual
+// mbarrier wait that also accumulates the cycles spent waiting (profiling aid, only when dbg is set)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
+  if (timed) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
   } else {
-    const float* src = reinterpret_cast<const float*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
-    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r.q[j] = reinterpret_cast<const uint4*>(src)[j];
-    }
+    mbar_wait(bar, parity);
   }
 }
 
-__device__ __forceinline__ void res_apply(float (&x)[32], const ResRegs& r, const GemmParams& p, int row, int col) {
-  if (!p.res) return;
-  if (p.res_dtype == 0) {
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
-    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t w[4] = {r.q[j].x, r.q[j].y, r.q[j].z, r.q[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          x[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
-          x[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
-        }
-      }
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (col + j < p.N) x[j] += __bfloat162float(src[j]);
-    }
-  } else {
-    const float* src = reinterpret_cast<const float*>(p.res) + static_cast<size_t>(row) * p.ldr + col;
-    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        x[4 * j] += __uint_as_float(r.q[j].x);
-        x[4 * j + 1] += __uint_as_float(r.q[j].y);
-        x[4 * j + 2] += __uint_as_float(r.q[j].z);
-        x[4 * j + 3] += __uint_as_float(r.q[j].w);
-      }
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (col + j < p.N) x[j] += src[j];
-    }
-  }
-}
-
-__device__ __forceinline__ void store_row32(const float (&x)[32], const GemmParams& p, int row, int col) {
-  if (p.out_dtype == 0) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
-    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 q;
-        q.x = pack_bf16x2(x[8 * j], x[8 * j + 1]);
-        q.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
-        q.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
-        q.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
-        reinterpret_cast<uint4*>(o)[j] = q;
-      }
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (col + j < p.N) o[j] = __float2bfloat16_rn(x[j]);
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
-    if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(o)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (col + j < p.N) o[j] = x[j];
-    }
-  }
-}
-
-template <int BN, int MT, bool TF32>
+template <int BN, int MT, bool TF32, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
@@ -167,8 +121,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint64_t* b_empty = b_full + kMaxBSlots;
   uint64_t* acc_full = b_empty + kMaxBSlots;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  uint32_t* s_rel = tmem_slot + 4;                                   // tap row offsets, pre-shifted for descriptors
+  uint8_t* smem_stage = reinterpret_cast<uint8_t*>(s_rel + VQA_MAX_TAPS);   // 16-byte aligned by construction
 
+  if (warp == 0) VQA_DBG(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
@@ -179,6 +136,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
     mbar_fence_init();
+    for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kChunkBytes / 16);
   }
   const uint32_t tmem_cols = static_cast<uint32_t>(BN * MT * p.acc_stages);
   if (warp == 2) {
@@ -189,12 +147,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) VQA_DBG(1);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     bool b_loaded = false;
+    const bool timed = p.dbg != nullptr && blockIdx.x == 0;
+    long long w_aempty = 0, w_bempty = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile % p.m_tiles) * 128 * MT;
       const int n0 = (tile / p.m_tiles) * BN;
@@ -211,7 +172,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const CUtensorMap* mapA = p.g_map[g] ? &mapA1 : &mapA0;
         const int row0 = m0 + p.g_delta[g] - p.halo;
         for (int c = 0; c < p.g_chunks[g]; ++c) {
-          mbar_wait(&a_empty[as], aph ^ 1u);
+          mbar_wait_t(&a_empty[as], aph ^ 1u, timed, w_aempty);
           if (elect_one()) {
             mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_slot_bytes));
             uint8_t* dst = smem_a + as * p.a_slot_bytes;
@@ -220,10 +181,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               tma_load_2d(dst + b * p.box_rows * kChunkBytes, mapA, &a_full[as], x, row0 + b * p.box_rows);
           }
           __syncwarp();
+          if (tile == blockIdx.x && g == 0 && c == 0) VQA_DBG(2);
           if (++as == p.a_slots) { as = 0; aph ^= 1u; }
           if (!p.b_resident) {
             for (int t = 0; t < p.g_ntaps[g]; ++t) {
-              mbar_wait(&b_empty[bs], bph ^ 1u);
+              mbar_wait_t(&b_empty[bs], bph ^ 1u, timed, w_bempty);
               if (elect_one()) {
                 mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(p.b_slot_bytes));
                 const int kcol = p.g_kbase[g] + (t * p.g_chunks[g] + c) * p.chunk_elems;
@@ -236,158 +198,303 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         }
       }
     }
+    if (timed && lane == 0) { p.dbg[16] = w_aempty; p.dbg[17] = w_bempty; }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp loops convergently, one elected lane issues) =====
-    int as = 0, bs = 0, acc = 0;
-    uint32_t aph = 0, bph = 0, accph = 0;
-    const uint32_t a_base0 = smem_u32(smem_a);
-    const uint32_t b_base0 = smem_u32(smem_b);
-    // descriptor high word is constant: SBO = 1024 B, version 1, SWIZZLE_128B (see umma_desc_sw128)
-    constexpr uint32_t kDescHi = static_cast<uint32_t>(umma_desc_sw128_hi());
-    bool b_ready = false;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&acc_empty[acc], accph ^ 1u);   // epilogue has drained this accumulator stage
-      if (p.b_resident && !b_ready) {
-        mbar_wait(&b_full[0], 0);
-        b_ready = true;
-      }
-      tc_fence_after();
-      const uint32_t d_tile = tmem_base + acc * (BN * MT);
-      uint32_t fresh = 1;  // first MMA of each accumulator overwrites, the rest accumulate
-      for (int g = 0; g < p.ngroups; ++g) {
-        const int nchunks = p.g_chunks[g], ntaps = p.g_ntaps[g], tap0 = p.g_tap0[g];
-        const int q0 = p.g_kbase[g] / p.chunk_elems;
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t a_win = a_base0 + as * p.a_slot_bytes;
-          for (int t = 0; t < ntaps; ++t) {
-            uint32_t b_tile;
-            if (p.b_resident) {
-              b_tile = b_base0 + (q0 + t * nchunks + c) * p.b_slot_bytes;
+    // ===================== MMA issuer: ONE elected thread runs the whole role =====================
+    // Inside an elect.sync region ptxas keeps descriptors in uniform registers and emits
+    // back-to-back UTCHMMA.  Measured on B200: the cost is the ~200-cycle per-step overhead of a
+    // single thread's dependent instruction chain (loop control, tap-table load, address math), not
+    // the MMA issue itself (splitting the K slices over two issuer threads changed nothing and made
+    // the accumulation order non-deterministic), so the common 9-tap window group is fully unrolled
+    // with its tap offsets held in registers and loop-invariant parameters hoisted by hand.
+    if (elect_one()) {
+      const int a_slots = p.a_slots, b_slots = p.b_slots, ngroups = p.ngroups, acc_stages = p.acc_stages;
+      const bool resident = p.b_resident != 0;
+      const uint32_t a_slot_lo = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
+      const uint32_t b_slot_lo = static_cast<uint32_t>(p.b_slot_bytes) >> 4;
+      const uint32_t a_base_lo = smem_u32(smem_a) >> 4;
+      const uint32_t b_base_lo = smem_u32(smem_b) >> 4;
+      const uint32_t idesc = p.idesc;
+      const int chunk_elems = p.chunk_elems;
+      constexpr uint64_t kDescHi = umma_desc_sw128_hi() << 32;
+      const bool timed = p.dbg != nullptr && blockIdx.x == 0;
+      long long w_accempty = 0, w_afull = 0, w_bfull = 0;
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, accph = 0;
+      uint32_t rel9[9];                      // group 0's tap offsets (3x3 window) in registers
+#pragma unroll
+      for (int t = 0; t < 9; ++t) rel9[t] = s_rel[t];
+      const bool g0_is_3x3 = p.g_ntaps[0] == 9 && p.g_tap0[0] == 0;
+      uint32_t d_tile = 0, fresh = 1;
+
+      // one (window, tap) step: 4*MT MMAs over the 128-byte K chunk
+      auto issue_step = [&](uint32_t a_lo, uint32_t b_lo) {
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 bytes); 32 B >> 4 = 2
+            const uint64_t ad = kDescHi | (a_lo + sub * (128 * kChunkBytes / 16) + 2 * k);
+            const uint64_t bd = kDescHi | (b_lo + 2 * k);
+            const uint32_t accum = (k == 0) ? (fresh ^ 1u) : 1u;
+            if (TF32) umma_tf32(d_tile + sub * BN, ad, bd, idesc, accum);
+            else      umma_f16(d_tile + sub * BN, ad, bd, idesc, accum);
+          }
+        }
+        fresh = 0;
+      };
+      // weight tile of this step: resident chunk q, or the next ring slot (wait / commit around the MMAs)
+      auto b_acquire = [&](uint32_t q) -> uint32_t {
+        if (resident) return b_base_lo + q * b_slot_lo;
+        mbar_wait_t(&b_full[bs], bph, timed, w_bfull);
+        tc_fence_after();
+        return b_base_lo + bs * b_slot_lo;
+      };
+      auto b_release = [&]() {
+        if (!resident) {
+          umma_commit(&b_empty[bs]);       // weight slot is free once these MMAs retire
+          if (++bs == b_slots) { bs = 0; bph ^= 1u; }
+        }
+      };
+
+      if (resident) mbar_wait(&b_full[0], 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait_t(&acc_empty[acc], accph ^ 1u, timed, w_accempty);   // epilogue has drained this accumulator stage
+        tc_fence_after();
+        d_tile = tmem_base + acc * (BN * MT);
+        fresh = 1;                           // first MMA of each accumulator overwrites, the rest accumulate
+        for (int g = 0; g < ngroups; ++g) {
+          const int nchunks = p.g_chunks[g], ntaps = p.g_ntaps[g];
+          const uint32_t q0 = static_cast<uint32_t>(p.g_kbase[g] / chunk_elems);
+          const bool unrolled9 = g == 0 && g0_is_3x3;
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait_t(&a_full[as], aph, timed, w_afull);
+            tc_fence_after();
+            if (tile == 0 && g == 0 && c == 0 && timed) p.dbg[3] = clock64();
+            const uint32_t a_win_lo = a_base_lo + as * a_slot_lo;
+            if (unrolled9) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const uint32_t b_lo = b_acquire(q0 + t * nchunks + c);
+                issue_step(a_win_lo + rel9[t], b_lo);
+                b_release();
+              }
             } else {
-              mbar_wait(&b_full[bs], bph);
-              tc_fence_after();
-              b_tile = b_base0 + bs * p.b_slot_bytes;
-            }
-            const uint32_t a_lo = ((a_win + static_cast<uint32_t>(p.tap_rel[tap0 + t]) * kChunkBytes) & 0x3FFFFu) >> 4;
-            const uint32_t b_lo = (b_tile & 0x3FFFFu) >> 4;
-            if (elect_one()) {
-#pragma unroll
-              for (int sub = 0; sub < MT; ++sub) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 bytes) per 128-byte chunk; 32 B >> 4 = 2
-                  const uint64_t ad = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo + sub * (128 * kChunkBytes / 16) + 2 * k);
-                  const uint64_t bd = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k);
-                  const uint32_t accum = (k == 0) ? (fresh ^ 1u) : 1u;
-                  if (TF32) umma_tf32(d_tile + sub * BN, ad, bd, p.idesc, accum);
-                  else      umma_f16(d_tile + sub * BN, ad, bd, p.idesc, accum);
-                }
+              const uint32_t* rel = s_rel + p.g_tap0[g];
+              for (int t = 0; t < ntaps; ++t) {
+                const uint32_t b_lo = b_acquire(q0 + t * nchunks + c);
+                issue_step(a_win_lo + rel[t], b_lo);
+                b_release();
               }
             }
-            __syncwarp();
-            fresh = 0;
-            if (!p.b_resident) {
-              if (elect_one()) umma_commit(&b_empty[bs]);   // weight slot is free once these MMAs retire
-              __syncwarp();
-              if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
-            }
+            umma_commit(&a_empty[as]);       // window slot is free once all its taps retire
+            if (++as == a_slots) { as = 0; aph ^= 1u; }
           }
-          if (elect_one()) umma_commit(&a_empty[as]);       // window slot is free once all its taps retire
-          __syncwarp();
-          if (++as == p.a_slots) { as = 0; aph ^= 1u; }
         }
+        umma_commit(&acc_full[acc]);
+        if (timed) {
+          if (tile == 0) p.dbg[4] = clock64();
+          if (tile + static_cast<int>(gridDim.x) >= total_tiles) p.dbg[9] = clock64();
+        }
+        if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
       }
-      if (elect_one()) umma_commit(&acc_full[acc]);
-      __syncwarp();
-      if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
+      if (timed) { p.dbg[18] = w_accempty; p.dbg[19] = w_afull; p.dbg[20] = w_bfull; }
     }
   } else {
     // ===================== epilogue warps =====================
+    constexpr bool kOutBf16 = EPI < 2;
+    constexpr bool kRes = (EPI & 1) != 0;
+    constexpr int kCols = BN / 2;       // columns per warp per sub-tile
+    constexpr int kChunks = kCols / 32; // 32-column chunks per warp per sub-tile (1, 2 or 4)
+    using OutT = typename std::conditional<kOutBf16, __nv_bfloat16, float>::type;
     const int ew = warp - 2;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int half = ew >> 2;           // which half of the tile's columns
-    constexpr int kCols = BN / 2;       // columns per warp per sub-tile
+    uint8_t* stage = smem_stage + ew * kStageBytes;
+    const int slot = lane & 7;          // coalesced domain: this lane owns columns 4*slot..4*slot+3 ...
+    const int rsub = lane >> 3;         // ... of rows 4*r + rsub, r = 0..7
+    // loop-invariant parameters in registers (the asm volatile barriers would otherwise force reloads)
+    const int N = p.N, M = p.M, ldo = p.ldo, ldr = p.ldr;
+    const bool relu = p.relu != 0, rnd = p.round_tf32 != 0, mask_en = p.mask_en != 0;
+    const int mRPI = p.mRPI, mP = p.mP, mH = p.mH, mW = p.mW;
+    OutT* const out = reinterpret_cast<OutT*>(p.out);
+    const OutT* const res = reinterpret_cast<const OutT*>(p.res);   // residual has the output's dtype
+    const float* const bias = p.bias;
+    const int m_tiles = p.m_tiles, acc_stages = p.acc_stages;
+    const bool aligned = ((ldo * static_cast<int>(sizeof(OutT))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                         (!kRes || (((ldr * static_cast<int>(sizeof(OutT))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)));
+
+    // residual of one 32x32 chunk in the coalesced domain (8 row segments of 4 columns per lane).
+    // The loads land in RAW registers and are converted at use: converting right after each load
+    // makes ptxas reuse one temporary and serialise the eight DRAM round trips.
+    using ResRaw = typename std::conditional<kOutBf16, uint2, float4>::type;
+    auto load_res = [&](ResRaw (&rr)[8], int row_base, int col) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = min(row_base + 4 * r + rsub, M - 1);   // clamp instead of predicating: rows >= M are never stored
+        rr[r] = *reinterpret_cast<const ResRaw*>(res + static_cast<size_t>(row) * ldr + col);
+      }
+    };
+    auto res_as_float4 = [&](const ResRaw& q) -> float4 {
+      if constexpr (kOutBf16) {
+        return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u),
+                           __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xFFFF0000u));
+      } else {
+        return q;
+      }
+    };
+
     int acc = 0;
     uint32_t accph = 0;
+    const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
+    long long w_accfull = 0;
+    ResRaw rres[8];
+    bool res_ready = false;   // rres already holds the residual of the upcoming chunk
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.m_tiles) * 128 * MT;
-      const int n0 = (tile / p.m_tiles) * BN;
-      const int row_first = m0 + quad * 32 + lane;
-      ResRegs rr;
-      res_prefetch(rr, p, row_first, n0 + half * kCols, row_first < p.M);
-      mbar_wait(&acc_full[acc], accph);
-      tc_fence_after();
+      const int m0 = (tile % m_tiles) * 128 * MT;
+      const int n0 = (tile / m_tiles) * BN;
+      const int colw = n0 + half * kCols;               // first column this warp owns
+      const bool fast = aligned && (colw + kCols <= N); // whole warp slice in range and vectorisable
+      // ---- work that does not need the accumulator: done while the MMAs are still running
+      uint32_t pix_mask[MT];
+#pragma unroll
       for (int sub = 0; sub < MT; ++sub) {
-        const int row = m0 + sub * 128 + quad * 32 + lane;
-        const bool row_ok = row < p.M;
-        bool pix_ok = true;
-        if (p.mask_en) {
-          const int rem = row % p.mRPI;
-          pix_ok = (rem / p.mP) < p.mH && (rem % p.mP) < p.mW;
+        bool pix = true;
+        if (mask_en) {
+          const int rem = (m0 + sub * 128 + quad * 32 + lane) % mRPI;
+          pix = (rem / mP) < mH && (rem % mP) < mW;
         }
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (BN * MT) + sub * BN +
-                               half * kCols;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kCols; c0 += 32) {
-          const int col = n0 + half * kCols + c0;
-          uint32_t v[32];
-          __syncwarp();                               // tcgen05.ld is warp-collective (.sync.aligned)
-          tmem_ld32(taddr + c0, v);
-          // prefetch the residual of the next chunk while the TMEM load is in flight
-          ResRegs rn;
-          {
-            int nrow = row, ncol = col + 32;
-            if (c0 + 32 >= kCols) { nrow = row + 128; ncol = n0 + half * kCols; }
-            const bool more = (c0 + 32 < kCols) || (sub + 1 < MT);
-            res_prefetch(rn, p, nrow, ncol, more && nrow < p.M && ncol < p.N);
+        pix_mask[sub] = __ballot_sync(0xffffffffu, pix);
+      }
+      float4 b4[kChunks];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = colw + 32 * c + 4 * slot;
+        b4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) {
+          if (fast) b4[c] = __ldg(reinterpret_cast<const float4*>(bias + col));
+          else {
+            b4[c].x = col < N ? __ldg(bias + col) : 0.f;
+            b4[c].y = col + 1 < N ? __ldg(bias + col + 1) : 0.f;
+            b4[c].z = col + 2 < N ? __ldg(bias + col + 2) : 0.f;
+            b4[c].w = col + 3 < N ? __ldg(bias + col + 3) : 0.f;
           }
-          tmem_ld_wait();
-          if (row_ok && col < p.N) {
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-            if (p.bias) {
-              if (col + 32 <= p.N) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
-                  x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col + j < p.N) x[j] += __ldg(p.bias + col + j);
-              }
-            }
-            res_apply(x, rr, p, row, col);
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-            }
-            if (!pix_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = 0.f;   // keep the shared zero padding of the grid intact
-            }
-            if (p.round_tf32) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = round_tf32_rna(x[j]);
-            }
-            store_row32(x, p, row, col);
-          }
-          rr = rn;
         }
       }
+      if (kRes && fast && !res_ready) load_res(rres, m0 + quad * 32, colw + 4 * slot);   // first tile only
+      // the tile after this one (its first chunk's residual is prefetched during this tile's last chunk)
+      const int ntile = tile + static_cast<int>(gridDim.x);
+      const int n_m0 = (ntile % m_tiles) * 128 * MT;
+      const int n_colw = (ntile / m_tiles) * BN + half * kCols;
+      const bool n_fast = ntile < total_tiles && aligned && (n_colw + kCols <= N);
+
+      mbar_wait_t(&acc_full[acc], accph, timed, w_accfull);
+      tc_fence_after();
+      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(5);
+#pragma unroll
+      for (int sub = 0; sub < MT; ++sub) {
+        const int row_base = m0 + sub * 128 + quad * 32;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (BN * MT) + sub * BN +
+                               half * kCols;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = colw + 32 * c;               // first column of this 32-wide chunk
+          if (col0 >= N) break;                         // warp-uniform
+          const int col = col0 + 4 * slot;              // this lane's 4 columns in the coalesced domain
+          uint32_t v[32];
+          __syncwarp();                                 // previous chunk's stage reads are done; ld is .sync.aligned
+          tmem_ld32(taddr + 32 * c, v);
+          // prefetch the next chunk's residual while the TMEM load is in flight
+          ResRaw rnext[8];
+          const bool has_next = (c + 1 < kChunks) || (sub + 1 < MT);
+          bool got_next = false;
+          if (kRes) {
+            if (has_next) {
+              if (fast) {
+                const int nsub = (c + 1 < kChunks) ? sub : sub + 1;
+                const int nc = (c + 1 < kChunks) ? c + 1 : 0;
+                load_res(rnext, m0 + nsub * 128 + quad * 32, colw + 32 * nc + 4 * slot);
+                got_next = true;
+              }
+            } else if (n_fast) {
+              load_res(rnext, n_m0 + quad * 32, n_colw + 4 * slot);
+              got_next = true;
+            }
+          }
+          tmem_ld_wait();
+          stage_write(stage, lane, v);
+          __syncwarp();
+          if (fast) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int lrow = 4 * r + rsub;
+              const int row = row_base + lrow;
+              float4 x = stage_read(stage, lrow, slot);
+              x.x += b4[c].x; x.y += b4[c].y; x.z += b4[c].z; x.w += b4[c].w;
+              if (kRes) { const float4 rv = res_as_float4(rres[r]); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+              if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+              if (!((pix_mask[sub] >> lrow) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);   // keep the grid's zero padding
+              if (rnd) {
+                x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w);
+              }
+              if (row < M) {
+                if constexpr (kOutBf16) {
+                  uint2 q;
+                  q.x = pack_bf16x2(x.x, x.y);
+                  q.y = pack_bf16x2(x.z, x.w);
+                  *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = q;
+                } else {
+                  *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ldo + col) = x;
+                }
+              }
+            }
+          } else {
+            // ragged / unaligned slice (N not a multiple of 32, odd leading dimensions): scalar, guarded
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) {
+              const int lrow = 4 * r + rsub;
+              const int row = row_base + lrow;
+              const float4 xs = stage_read(stage, lrow, slot);
+              const float xe[4] = {xs.x + b4[c].x, xs.y + b4[c].y, xs.z + b4[c].z, xs.w + b4[c].w};
+              if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (col + j < N) {
+                    float e = xe[j];
+                    if (kRes) e += static_cast<float>(res[static_cast<size_t>(row) * ldr + col + j]);
+                    if (relu) e = fmaxf(e, 0.f);
+                    if (!((pix_mask[sub] >> lrow) & 1u)) e = 0.f;
+                    if (rnd) e = round_tf32_rna(e);
+                    out[static_cast<size_t>(row) * ldo + col + j] = static_cast<OutT>(e);
+                  }
+                }
+              }
+            }
+          }
+          if (kRes) {
+            if (got_next) {
+#pragma unroll
+              for (int r = 0; r < 8; ++r) rres[r] = rnext[r];
+            }
+            res_ready = got_next;
+          }
+        }
+      }
+      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(13);
       // all TMEM reads of this warp are complete (wait::ld above): release the accumulator stage
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
+      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(6);
+      if (warp == 2 && tile + static_cast<int>(gridDim.x) >= total_tiles) VQA_DBG(7);
+      if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
     }
+    if (timed && lane == 0) p.dbg[21] = w_accfull;
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 0) VQA_DBG(8);
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -455,17 +562,25 @@ int num_sms(int device) {
 
 typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
 
-static GemmKernelFn pick_kernel(int bn, int mt, bool tf32) {
-#define VQA_PICK(BN_, MT_)                                                                    \
-  if (bn == BN_ && mt == MT_) return tf32 ? static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, true>) \
-                                          : static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, false>);
-  VQA_PICK(64, 1) VQA_PICK(64, 2) VQA_PICK(128, 1) VQA_PICK(128, 2) VQA_PICK(256, 1) VQA_PICK(256, 2)
+// Instantiated (BN, MT, operand type, epilogue) combinations: bf16 kernels with epilogues 0/1/2
+// (convolutions, image projector), tf32 kernels with MT = 1 and epilogues 2/3 (all nn.Linear layers).
+static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi) {
+#define VQA_PICK(BN_, MT_, TF_, EPI_) \
+  if (bn == BN_ && mt == MT_ && tf32 == TF_ && epi == EPI_) return static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, TF_, EPI_>);
+#define VQA_PICK_BF16(BN_, MT_) VQA_PICK(BN_, MT_, false, 0) VQA_PICK(BN_, MT_, false, 1) VQA_PICK(BN_, MT_, false, 2)
+#define VQA_PICK_TF32(BN_) VQA_PICK(BN_, 1, true, 2) VQA_PICK(BN_, 1, true, 3)
+  VQA_PICK_BF16(64, 1) VQA_PICK_BF16(64, 2) VQA_PICK_BF16(128, 1) VQA_PICK_BF16(128, 2)
+  VQA_PICK_BF16(256, 1) VQA_PICK_BF16(256, 2)
+  VQA_PICK_TF32(64) VQA_PICK_TF32(128) VQA_PICK_TF32(256)
+#undef VQA_PICK_TF32
+#undef VQA_PICK_BF16
 #undef VQA_PICK
   return nullptr;
 }
 
 struct GemmLaunch {
   GemmKernelFn fn;
+  int epi;
   CUtensorMap mapA0, mapA1, mapB;
   GemmParams prm;
   dim3 grid;
@@ -518,6 +633,11 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
     kcover += static_cast<long long>(p.g_ntaps[g]) * p.g_chunks[g] * p.chunk_elems;
   }
   VQA_REQUIRE(kcover == I[GEMM_I_Ktot], VQA_E_INVALID, "gemm: groups do not cover Ktot");
+  p.win_per_tile = p.steps_per_tile = 0;
+  for (int g = 0; g < p.ngroups; ++g) {
+    p.win_per_tile += p.g_chunks[g];
+    p.steps_per_tile += p.g_chunks[g] * p.g_ntaps[g];
+  }
   for (int t = 0; t < VQA_MAX_TAPS; ++t) {
     p.tap_rel[t] = I[GEMM_I_tap_rel0 + t];
     VQA_REQUIRE(t >= I[GEMM_I_ntaps] || (p.tap_rel[t] >= 0 && p.tap_rel[t] <= 2 * p.halo), VQA_E_INVALID,
@@ -541,7 +661,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
 
   // shared-memory plan: one CTA per SM (persistent), ~210 KB of rings
   int budget = I[GEMM_I_smem_budget];
-  if (budget <= 0) budget = 208 * 1024;
+  if (budget <= 0) budget = 190 * 1024;   // + 32 KB of epilogue staging + barriers stays under 227 KB
   const long long b_all = static_cast<long long>(p.k_chunks) * p.b_slot_bytes;
   p.b_resident = (p.n_tiles == 1 && b_all <= 96 * 1024 && b_all + 2LL * p.a_slot_bytes <= budget) ? 1 : 0;
   if (p.b_resident) {
@@ -560,7 +680,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   }
   const long long b_bytes = p.b_resident ? b_all : static_cast<long long>(p.b_slots) * p.b_slot_bytes;
   L->smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(b_bytes) +
-            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 4) + 16;
+            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 6) + 16 + 4 * VQA_MAX_TAPS + kEpiWarps * kStageBytes;
   VQA_REQUIRE(L->smem <= 227 * 1024, VQA_E_INVALID, "gemm: shared memory budget exceeded");
 
   // tensor maps (only for non-external operands: A and W always live in the arenas)
@@ -594,16 +714,21 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.bias = reinterpret_cast<const float*>(op.p[GEMM_P_bias]);
   VQA_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, VQA_E_ALIGN,
               "gemm: bias must be 16-byte aligned");
+  p.dbg = reinterpret_cast<long long*>(op.p[GEMM_P_dbg]);
   L->out_raw = op.p[GEMM_P_out];
   L->res_raw = op.p[GEMM_P_res];
   VQA_REQUIRE(L->out_raw != 0, VQA_E_INVALID, "gemm: null output");
   L->bn = bn;
   const int tiles = p.m_tiles * p.n_tiles;
-  const int sms = num_sms(device);
+  int sms = num_sms(device);
+  if (I[GEMM_I_max_ctas] > 0 && I[GEMM_I_max_ctas] < sms) sms = I[GEMM_I_max_ctas];   // tests: force many tiles per CTA
   L->grid = dim3(tiles < sms ? tiles : sms, 1, 1);
 
-  L->fn = pick_kernel(bn, p.MT, tf32);
-  VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT");
+  const bool has_res = op.p[GEMM_P_res] != 0;
+  VQA_REQUIRE(!has_res || p.res_dtype == p.out_dtype, VQA_E_INVALID, "gemm: the residual must have the output's dtype");
+  L->epi = (p.out_dtype == 0 ? 0 : 2) + (has_res ? 1 : 0);
+  L->fn = pick_kernel(bn, p.MT, tf32, L->epi);
+  VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT/dtype/epilogue");
   VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
   return VQA_OK;
@@ -623,6 +748,6 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
 const char* gemm_kernel_name(const void* storage) {
   const GemmLaunch* L = reinterpret_cast<const GemmLaunch*>(storage);
   static thread_local char name[64];
-  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16");
+  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16", L->epi);
   return name;
 }
