@@ -52,6 +52,7 @@ struct GemmParams {
   uint32_t idesc;
   int g_map[VQA_MAX_GROUPS], g_delta[VQA_MAX_GROUPS], g_acol[VQA_MAX_GROUPS], g_chunks[VQA_MAX_GROUPS];
   int g_ntaps[VQA_MAX_GROUPS], g_kbase[VQA_MAX_GROUPS], g_tap0[VQA_MAX_GROUPS];
+  int g_q0[VQA_MAX_GROUPS];   // g_kbase / chunk_elems (first weight chunk of the group)
   int tap_rel[VQA_MAX_TAPS];
   // epilogue
   void* out;
@@ -123,7 +124,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   uint32_t* s_rel = tmem_slot + 4;                                   // tap row offsets, pre-shifted for descriptors
-  uint8_t* smem_stage = reinterpret_cast<uint8_t*>(s_rel + VQA_MAX_TAPS);   // 16-byte aligned by construction
+  int4* s_grp = reinterpret_cast<int4*>(s_rel + VQA_MAX_TAPS);      // per group {chunks, taps, tap0, q0}
+  uint8_t* smem_stage = reinterpret_cast<uint8_t*>(s_grp + VQA_MAX_GROUPS);   // 16-byte aligned by construction
 
   if (warp == 0) VQA_DBG(0);
   if (warp == 0 && lane == 0) {
@@ -137,6 +139,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
     mbar_fence_init();
     for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kChunkBytes / 16);
+    for (int g = 0; g < VQA_MAX_GROUPS; ++g) s_grp[g] = make_int4(p.g_chunks[g], p.g_ntaps[g], p.g_tap0[g], p.g_q0[g]);
   }
   const uint32_t tmem_cols = static_cast<uint32_t>(BN * MT * p.acc_stages);
   if (warp == 2) {
@@ -215,7 +218,6 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const uint32_t a_base_lo = smem_u32(smem_a) >> 4;
       const uint32_t b_base_lo = smem_u32(smem_b) >> 4;
       const uint32_t idesc = p.idesc;
-      const int chunk_elems = p.chunk_elems;
       constexpr uint64_t kDescHi = umma_desc_sw128_hi() << 32;
       const bool timed = p.dbg != nullptr && blockIdx.x == 0;
       long long w_accempty = 0, w_afull = 0, w_bfull = 0;
@@ -263,8 +265,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         d_tile = tmem_base + acc * (BN * MT);
         fresh = 1;                           // first MMA of each accumulator overwrites, the rest accumulate
         for (int g = 0; g < ngroups; ++g) {
-          const int nchunks = p.g_chunks[g], ntaps = p.g_ntaps[g];
-          const uint32_t q0 = static_cast<uint32_t>(p.g_kbase[g] / chunk_elems);
+          const int4 grp = s_grp[g];
+          const int nchunks = grp.x, ntaps = grp.y;
+          const uint32_t q0 = static_cast<uint32_t>(grp.w);
           const bool unrolled9 = g == 0 && g0_is_3x3;
           for (int c = 0; c < nchunks; ++c) {
             mbar_wait_t(&a_full[as], aph, timed, w_afull);
@@ -279,7 +282,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 b_release();
               }
             } else {
-              const uint32_t* rel = s_rel + p.g_tap0[g];
+              const uint32_t* rel = s_rel + grp.z;
               for (int t = 0; t < ntaps; ++t) {
                 const uint32_t b_lo = b_acquire(q0 + t * nchunks + c);
                 issue_step(a_win_lo + rel[t], b_lo);
@@ -310,8 +313,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int half = ew >> 2;           // which half of the tile's columns
     uint8_t* stage = smem_stage + ew * kStageBytes;
-    const int slot = lane & 7;          // coalesced domain: this lane owns columns 4*slot..4*slot+3 ...
-    const int rsub = lane >> 3;         // ... of rows 4*r + rsub, r = 0..7
+    const int slot = lane & 3;          // coalesced domain: this lane owns columns 8*slot..8*slot+7 ...
+    const int rsub = lane >> 2;         // ... of rows 8*r + rsub, r = 0..3
     // loop-invariant parameters in registers (the asm volatile barriers would otherwise force reloads)
     const int N = p.N, M = p.M, ldo = p.ldo, ldr = p.ldr;
     const bool relu = p.relu != 0, rnd = p.round_tf32 != 0, mask_en = p.mask_en != 0;
@@ -326,20 +329,31 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // residual of one 32x32 chunk in the coalesced domain (8 row segments of 4 columns per lane).
     // The loads land in RAW registers and are converted at use: converting right after each load
     // makes ptxas reuse one temporary and serialise the eight DRAM round trips.
-    using ResRaw = typename std::conditional<kOutBf16, uint2, float4>::type;
-    auto load_res = [&](ResRaw (&rr)[8], int row_base, int col) {
+    struct F8 { float4 lo, hi; };
+    using ResRaw = typename std::conditional<kOutBf16, uint4, F8>::type;
+    auto load_res = [&](ResRaw (&rr)[4], int row_base, int col) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int row = min(row_base + 4 * r + rsub, M - 1);   // clamp instead of predicating: rows >= M are never stored
-        rr[r] = *reinterpret_cast<const ResRaw*>(res + static_cast<size_t>(row) * ldr + col);
+      for (int r = 0; r < 4; ++r) {
+        const int row = min(row_base + 8 * r + rsub, M - 1);   // clamp instead of predicating: rows >= M are never stored
+        if constexpr (kOutBf16) {
+          rr[r] = *reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * ldr + col);
+        } else {
+          rr[r].lo = *reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * ldr + col);
+          rr[r].hi = *reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * ldr + col + 4);
+        }
       }
     };
-    auto res_as_float4 = [&](const ResRaw& q) -> float4 {
+    auto res_add = [&](float (&x)[8], const ResRaw& q) {
       if constexpr (kOutBf16) {
-        return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u),
-                           __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xFFFF0000u));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          x[2 * k] += __uint_as_float(w[k] << 16);
+          x[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+        }
       } else {
-        return q;
+        x[0] += q.lo.x; x[1] += q.lo.y; x[2] += q.lo.z; x[3] += q.lo.w;
+        x[4] += q.hi.x; x[5] += q.hi.y; x[6] += q.hi.z; x[7] += q.hi.w;
       }
     };
 
@@ -347,9 +361,16 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     uint32_t accph = 0;
     const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
     long long w_accfull = 0;
-    ResRaw rres[8];
-    bool res_ready = false;   // rres already holds the residual of the upcoming chunk
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // Residual registers are double buffered (chunk j reads buffer j&1 and prefetches chunk j+1 -- the
+    // first chunk of the CTA's next tile after the last one -- into the other buffer).  Copying a
+    // prefetched buffer into a "current" one would stall on the outstanding loads, so the chunk loops
+    // are fully unrolled and the buffers are selected at compile time; with an odd number of chunks
+    // per tile (BN = 64, MT = 1) consecutive tiles swap the two buffers.
+    constexpr int kChunksPerTile = MT * kChunks;
+    ResRaw rbuf0[4], rbuf1[4];
+    bool res_ready = false;   // the first buffer already holds the residual of the upcoming tile's first chunk
+
+    auto epi_tile = [&](int tile, ResRaw (&bufA)[4], ResRaw (&bufB)[4]) {
       const int m0 = (tile % m_tiles) * 128 * MT;
       const int n0 = (tile / m_tiles) * BN;
       const int colw = n0 + half * kCols;               // first column this warp owns
@@ -365,22 +386,26 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         }
         pix_mask[sub] = __ballot_sync(0xffffffffu, pix);
       }
-      float4 b4[kChunks];
+      float b8[kChunks][8];
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
-        const int col = colw + 32 * c + 4 * slot;
-        b4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int col = colw + 32 * c + 8 * slot;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b8[c][k] = 0.f;
         if (bias) {
-          if (fast) b4[c] = __ldg(reinterpret_cast<const float4*>(bias + col));
-          else {
-            b4[c].x = col < N ? __ldg(bias + col) : 0.f;
-            b4[c].y = col + 1 < N ? __ldg(bias + col + 1) : 0.f;
-            b4[c].z = col + 2 < N ? __ldg(bias + col + 2) : 0.f;
-            b4[c].w = col + 3 < N ? __ldg(bias + col + 3) : 0.f;
+          if (fast) {
+            const float4 lo = __ldg(reinterpret_cast<const float4*>(bias + col));
+            const float4 hi = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+            b8[c][0] = lo.x; b8[c][1] = lo.y; b8[c][2] = lo.z; b8[c][3] = lo.w;
+            b8[c][4] = hi.x; b8[c][5] = hi.y; b8[c][6] = hi.z; b8[c][7] = hi.w;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b8[c][k] = col + k < N ? __ldg(bias + col + k) : 0.f;
           }
         }
       }
-      if (kRes && fast && !res_ready) load_res(rres, m0 + quad * 32, colw + 4 * slot);   // first tile only
+      if (kRes && fast && !res_ready) load_res(bufA, m0 + quad * 32, colw + 8 * slot);   // first tile only
+      res_ready = false;
       // the tile after this one (its first chunk's residual is prefetched during this tile's last chunk)
       const int ntile = tile + static_cast<int>(gridDim.x);
       const int n_m0 = (ntile % m_tiles) * 128 * MT;
@@ -397,86 +422,92 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                                half * kCols;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
+          const int j = sub * kChunks + c;              // compile-time chunk index within the tile
+          ResRaw (&rcur)[4] = (j & 1) ? bufB : bufA;
+          ResRaw (&rnxt)[4] = (j & 1) ? bufA : bufB;
           const int col0 = colw + 32 * c;               // first column of this 32-wide chunk
-          if (col0 >= N) break;                         // warp-uniform
-          const int col = col0 + 4 * slot;              // this lane's 4 columns in the coalesced domain
+          if (col0 < N) {                               // warp-uniform
+          const int col = col0 + 8 * slot;              // this lane's 8 columns in the coalesced domain
           uint32_t v[32];
           __syncwarp();                                 // previous chunk's stage reads are done; ld is .sync.aligned
           tmem_ld32(taddr + 32 * c, v);
           // prefetch the next chunk's residual while the TMEM load is in flight
-          ResRaw rnext[8];
-          const bool has_next = (c + 1 < kChunks) || (sub + 1 < MT);
-          bool got_next = false;
           if (kRes) {
-            if (has_next) {
+            if (j + 1 < kChunksPerTile) {
               if (fast) {
                 const int nsub = (c + 1 < kChunks) ? sub : sub + 1;
                 const int nc = (c + 1 < kChunks) ? c + 1 : 0;
-                load_res(rnext, m0 + nsub * 128 + quad * 32, colw + 32 * nc + 4 * slot);
-                got_next = true;
+                load_res(rnxt, m0 + nsub * 128 + quad * 32, colw + 32 * nc + 8 * slot);
               }
             } else if (n_fast) {
-              load_res(rnext, n_m0 + quad * 32, n_colw + 4 * slot);
-              got_next = true;
+              load_res(rnxt, n_m0 + quad * 32, n_colw + 8 * slot);
+              res_ready = true;
             }
           }
           tmem_ld_wait();
           stage_write(stage, lane, v);
           __syncwarp();
           if (fast) {
+            OutT* orow = out + static_cast<size_t>(row_base + rsub) * ldo + col;
+            const size_t ostep = static_cast<size_t>(8) * ldo;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const int lrow = 4 * r + rsub;
-              const int row = row_base + lrow;
-              float4 x = stage_read(stage, lrow, slot);
-              x.x += b4[c].x; x.y += b4[c].y; x.z += b4[c].z; x.w += b4[c].w;
-              if (kRes) { const float4 rv = res_as_float4(rres[r]); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
-              if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-              if (!((pix_mask[sub] >> lrow) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);   // keep the grid's zero padding
-              if (rnd) {
-                x.x = round_tf32_rna(x.x); x.y = round_tf32_rna(x.y); x.z = round_tf32_rna(x.z); x.w = round_tf32_rna(x.w);
+            for (int r = 0; r < 4; ++r) {
+              const int lrow = 8 * r + rsub;
+              const float4 lo = stage_read(stage, lrow, 2 * slot);
+              const float4 hi = stage_read(stage, lrow, 2 * slot + 1);
+              float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) x[k] += b8[c][k];
+              if (kRes) res_add(x, rcur[r]);
+              if (relu) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = fmaxf(x[k], 0.f);
               }
-              if (row < M) {
+              const bool keep = ((pix_mask[sub] >> lrow) & 1u) != 0;   // keep the grid's shared zero padding intact
+#pragma unroll
+              for (int k = 0; k < 8; ++k) x[k] = keep ? x[k] : 0.f;
+              if (TF32 && rnd) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = round_tf32_rna(x[k]);
+              }
+              if (row_base + lrow < M) {
                 if constexpr (kOutBf16) {
-                  uint2 q;
-                  q.x = pack_bf16x2(x.x, x.y);
-                  q.y = pack_bf16x2(x.z, x.w);
-                  *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * ldo + col) = q;
+                  uint4 q;
+                  q.x = pack_bf16x2(x[0], x[1]); q.y = pack_bf16x2(x[2], x[3]);
+                  q.z = pack_bf16x2(x[4], x[5]); q.w = pack_bf16x2(x[6], x[7]);
+                  *reinterpret_cast<uint4*>(orow) = q;
                 } else {
-                  *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ldo + col) = x;
+                  *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+                  *reinterpret_cast<float4*>(orow + 4) = make_float4(x[4], x[5], x[6], x[7]);
                 }
               }
+              orow += ostep;
             }
           } else {
             // ragged / unaligned slice (N not a multiple of 32, odd leading dimensions): scalar, guarded
 #pragma unroll 1
-            for (int r = 0; r < 8; ++r) {
-              const int lrow = 4 * r + rsub;
+            for (int r = 0; r < 4; ++r) {
+              const int lrow = 8 * r + rsub;
               const int row = row_base + lrow;
-              const float4 xs = stage_read(stage, lrow, slot);
-              const float xe[4] = {xs.x + b4[c].x, xs.y + b4[c].y, xs.z + b4[c].z, xs.w + b4[c].w};
+              const float4 lo = stage_read(stage, lrow, 2 * slot);
+              const float4 hi = stage_read(stage, lrow, 2 * slot + 1);
+              const float xe[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
               if (row < M) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (col + j < N) {
-                    float e = xe[j];
-                    if (kRes) e += static_cast<float>(res[static_cast<size_t>(row) * ldr + col + j]);
+                for (int jj = 0; jj < 8; ++jj) {
+                  if (col + jj < N) {
+                    float e = xe[jj] + b8[c][jj];
+                    if (kRes) e += static_cast<float>(res[static_cast<size_t>(row) * ldr + col + jj]);
                     if (relu) e = fmaxf(e, 0.f);
                     if (!((pix_mask[sub] >> lrow) & 1u)) e = 0.f;
-                    if (rnd) e = round_tf32_rna(e);
-                    out[static_cast<size_t>(row) * ldo + col + j] = static_cast<OutT>(e);
+                    if (TF32 && rnd) e = round_tf32_rna(e);
+                    out[static_cast<size_t>(row) * ldo + col + jj] = static_cast<OutT>(e);
                   }
                 }
               }
             }
           }
-          if (kRes) {
-            if (got_next) {
-#pragma unroll
-              for (int r = 0; r < 8; ++r) rres[r] = rnext[r];
-            }
-            res_ready = got_next;
-          }
+          }  // col0 < N
         }
       }
       if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(13);
@@ -487,6 +518,16 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(6);
       if (warp == 2 && tile + static_cast<int>(gridDim.x) >= total_tiles) VQA_DBG(7);
       if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
+    };
+
+    const int tstep = static_cast<int>(gridDim.x);
+    if constexpr (kChunksPerTile % 2 == 0) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += tstep) epi_tile(tile, rbuf0, rbuf1);
+    } else {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += 2 * tstep) {
+        epi_tile(tile, rbuf0, rbuf1);
+        if (tile + tstep < total_tiles) epi_tile(tile + tstep, rbuf1, rbuf0);
+      }
     }
     if (timed && lane == 0) p.dbg[21] = w_accfull;
   }
@@ -630,6 +671,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
     VQA_REQUIRE(p.g_kbase[g] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: group K base must be chunk aligned");
     if (p.g_ntaps[g] != 1) lockstep = false;
     uses_a1 |= p.g_map[g] != 0;
+    p.g_q0[g] = p.g_kbase[g] / p.chunk_elems;
     kcover += static_cast<long long>(p.g_ntaps[g]) * p.g_chunks[g] * p.chunk_elems;
   }
   VQA_REQUIRE(kcover == I[GEMM_I_Ktot], VQA_E_INVALID, "gemm: groups do not cover Ktot");
@@ -680,7 +722,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   }
   const long long b_bytes = p.b_resident ? b_all : static_cast<long long>(p.b_slots) * p.b_slot_bytes;
   L->smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(b_bytes) +
-            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 6) + 16 + 4 * VQA_MAX_TAPS + kEpiWarps * kStageBytes;
+            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 6) + 16 + 4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS + kEpiWarps * kStageBytes;
   VQA_REQUIRE(L->smem <= 227 * 1024, VQA_E_INVALID, "gemm: shared memory budget exceeded");
 
   // tensor maps (only for non-external operands: A and W always live in the arenas)
