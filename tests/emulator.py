@@ -70,7 +70,7 @@ class Emulator:
     def op_gemm(self, op, ext):
         i = op.i
         dt = torch.bfloat16 if i["dtype"] == P.DT_BF16 else torch.float32
-        chunk = 64 if i["dtype"] == P.DT_BF16 else 32
+        chunk = i.get("row_bytes", 128) // (2 if i["dtype"] == P.DT_BF16 else 4)
         M, N, Npad, Ktot = i["M"], i["N"], i["Npad"], i["Ktot"]
         amaps = []
         for k in ("a0", "a1"):
@@ -146,8 +146,8 @@ class Emulator:
         B, C, R = i["B"], i["C"], i["R"]
         mean = _t(op.p["sums"], torch.float32, ext)[: B * C].view(B, C) / i["HW"]
         w1 = _t(op.p["w1"], torch.float32, ext)[: R * C].view(R, C)
-        w2 = _t(op.p["w2"], torch.float32, ext)[: R * C].view(C, R)
-        sc = torch.sigmoid(F.relu(mean @ w1.t()) @ w2.t())
+        w2t = _t(op.p["w2"], torch.float32, ext)[: R * C].view(R, C)   # stored transposed
+        sc = torch.sigmoid(F.relu(mean @ w1.t()) @ w2t)
         _t(op.p["scale"], torch.float32, ext)[: B * C].view(B, C).copy_(sc)
 
     def op_spatial_map(self, op, ext):

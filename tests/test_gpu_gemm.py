@@ -172,3 +172,26 @@ def test_conv3x3_window(B, H, W, cin, cout, mt, max_ctas):
 def test_conv3x3_window_with_shortcut_group():
     cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, True, 3, 14, 14, 128, 128, False, mt=2, extra_ds=True))
     G.report("conv window + shortcut K group", G.named(gpu, "o"), G.named(cpu, "o"), atol=3e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("max_ctas", [0, 2])
+@pytest.mark.parametrize("mt", [1, 2])
+def test_stem_window_32_byte_rows(mt, max_ctas):
+    """Stem form: 32-byte rows (SWIZZLE_32B), one asymmetric window per tile, 16 row-shifted K=16 taps."""
+    Pw, rows = 30, 4000
+    def build(device):
+        W = _weights(device, "w", 64, 256, torch.bfloat16, 21).finalize()
+        ol = P.OpList(W, device)
+        a = ol._buf("a", torch.bfloat16, rows, 16)
+        o = ol._buf("o", torch.float32 if mt == 2 else torch.bfloat16, rows, 64)
+        lo, hi = 2 * Pw + 2, Pw + 1
+        rels = [lo + (ia - 2) * Pw + (ib - 2) for ia in range(4) for ib in range(4)]
+        ol.gemm("stem", dtype=P.DT_BF16, M=rows, N=64, a0=a, a0_shape=(rows, 16, 16), groups=[(0, 0, 0, 1, rels)],
+                w="w.w", bias="w.b", out=o, ldo=64, out_dtype=P.OUT_F32 if mt == 2 else P.OUT_BF16, relu=True,
+                halo=lo, halo_hi=hi, MT=mt, row_bytes=32)
+        ol.ops[-1].i["max_ctas"] = max_ctas
+        ol.commit()
+        G.named(ol, "a").copy_(_fill(ol, "a", 22))
+        return ol
+    cpu, gpu, _, _ = G.run_pair(build)
+    G.report(f"stem window row32 MT{mt} max_ctas={max_ctas}", G.named(gpu, "o"), G.named(cpu, "o"), atol=2e-2, rtol=1e-2)

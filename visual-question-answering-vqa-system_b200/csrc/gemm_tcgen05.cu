@@ -28,16 +28,18 @@ namespace {
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);   // producer, MMA issuer, 8 epilogue warps
-constexpr int kChunkBytes = 128;  // one SWIZZLE_128B row: 64 bf16 or 32 fp32 (tf32)
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBSlots = 12;
 
 struct GemmParams {
   int M, N;
   int MT;            // 128-row sub-tiles per CTA tile (1 or 2); mirrors the kernel's template MT
-  int halo;          // window rows before/after the tile
+  int halo;          // window rows before the tile (halo_hi rows after it)
   int box_rows;      // TMA box rows for A
-  int nboxes;        // boxes per window (1 or 2)
+  int nboxes;        // boxes per window (1..3)
+  int row_bytes;     // K-chunk width: 128 (SWIZZLE_128B, 4 MMAs per chunk) or 32 (SWIZZLE_32B, 1 MMA per chunk)
+  int a_tx_bytes;    // bytes one window load delivers (nboxes * box_rows * row_bytes)
+  uint32_t desc_hi;  // high word of the UMMA shared-memory descriptor (SBO, version, swizzle mode)
   int a_slots, b_slots;
   int a_slot_bytes, b_slot_bytes;
   int b_resident;    // all weight chunks of the N tile stay in shared memory for the CTA's lifetime
@@ -99,7 +101,8 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
   }
 }
 
-template <int BN, int MT, bool TF32, int EPI>
+// ROW32: K chunks are 32-byte rows (the stem) instead of 128-byte rows.
+template <int BN, int MT, bool TF32, int EPI, bool ROW32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
@@ -108,6 +111,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
+  constexpr int kRowBytes = ROW32 ? 32 : 128;   // bytes of one K chunk row
+  constexpr int kMmaPerChunk = kRowBytes / 32;  // UMMA K is 32 bytes (16 bf16 / 8 tf32)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -138,7 +143,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
     mbar_fence_init();
-    for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kChunkBytes / 16);
+    for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kRowBytes / 16);
     for (int g = 0; g < VQA_MAX_GROUPS; ++g) s_grp[g] = make_int4(p.g_chunks[g], p.g_ntaps[g], p.g_tap0[g], p.g_q0[g]);
   }
   const uint32_t tmem_cols = static_cast<uint32_t>(BN * MT * p.acc_stages);
@@ -177,11 +182,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         for (int c = 0; c < p.g_chunks[g]; ++c) {
           mbar_wait_t(&a_empty[as], aph ^ 1u, timed, w_aempty);
           if (elect_one()) {
-            mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_slot_bytes));
+            mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_tx_bytes));
             uint8_t* dst = smem_a + as * p.a_slot_bytes;
             const int x = p.g_acol[g] + c * p.chunk_elems;
             for (int b = 0; b < p.nboxes; ++b)
-              tma_load_2d(dst + b * p.box_rows * kChunkBytes, mapA, &a_full[as], x, row0 + b * p.box_rows);
+              tma_load_2d(dst + b * p.box_rows * kRowBytes, mapA, &a_full[as], x, row0 + b * p.box_rows);
           }
           __syncwarp();
           if (tile == blockIdx.x && g == 0 && c == 0) VQA_DBG(2);
@@ -218,24 +223,25 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const uint32_t a_base_lo = smem_u32(smem_a) >> 4;
       const uint32_t b_base_lo = smem_u32(smem_b) >> 4;
       const uint32_t idesc = p.idesc;
-      constexpr uint64_t kDescHi = umma_desc_sw128_hi() << 32;
+      const uint64_t kDescHi = static_cast<uint64_t>(p.desc_hi) << 32;
       const bool timed = p.dbg != nullptr && blockIdx.x == 0;
       long long w_accempty = 0, w_afull = 0, w_bfull = 0;
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
-      uint32_t rel9[9];                      // group 0's tap offsets (3x3 window) in registers
+      constexpr int kUnroll = ROW32 ? 16 : 9;   // taps of the unrolled window group (4x4 stem / 3x3 conv)
+      uint32_t relu_[kUnroll];                  // group 0's tap offsets in registers
 #pragma unroll
-      for (int t = 0; t < 9; ++t) rel9[t] = s_rel[t];
-      const bool g0_is_3x3 = p.g_ntaps[0] == 9 && p.g_tap0[0] == 0;
+      for (int t = 0; t < kUnroll; ++t) relu_[t] = s_rel[t];
+      const bool g0_unrolled = p.g_ntaps[0] == kUnroll && p.g_tap0[0] == 0;
       uint32_t d_tile = 0, fresh = 1;
 
-      // one (window, tap) step: 4*MT MMAs over the 128-byte K chunk
+      // one (window, tap) step: kMmaPerChunk*MT MMAs over the K chunk
       auto issue_step = [&](uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
         for (int sub = 0; sub < MT; ++sub) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 bytes); 32 B >> 4 = 2
-            const uint64_t ad = kDescHi | (a_lo + sub * (128 * kChunkBytes / 16) + 2 * k);
+          for (int k = 0; k < kMmaPerChunk; ++k) {   // K = 32 bytes per MMA; 32 B >> 4 = 2
+            const uint64_t ad = kDescHi | (a_lo + sub * (128 * kRowBytes / 16) + 2 * k);
             const uint64_t bd = kDescHi | (b_lo + 2 * k);
             const uint32_t accum = (k == 0) ? (fresh ^ 1u) : 1u;
             if (TF32) umma_tf32(d_tile + sub * BN, ad, bd, idesc, accum);
@@ -268,17 +274,17 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           const int4 grp = s_grp[g];
           const int nchunks = grp.x, ntaps = grp.y;
           const uint32_t q0 = static_cast<uint32_t>(grp.w);
-          const bool unrolled9 = g == 0 && g0_is_3x3;
+          const bool unrolled = g == 0 && g0_unrolled;
           for (int c = 0; c < nchunks; ++c) {
             mbar_wait_t(&a_full[as], aph, timed, w_afull);
             tc_fence_after();
             if (tile == 0 && g == 0 && c == 0 && timed) p.dbg[3] = clock64();
             const uint32_t a_win_lo = a_base_lo + as * a_slot_lo;
-            if (unrolled9) {
+            if (unrolled) {
 #pragma unroll
-              for (int t = 0; t < 9; ++t) {
+              for (int t = 0; t < kUnroll; ++t) {
                 const uint32_t b_lo = b_acquire(q0 + t * nchunks + c);
-                issue_step(a_win_lo + rel9[t], b_lo);
+                issue_step(a_win_lo + relu_[t], b_lo);
                 b_release();
               }
             } else {
@@ -556,8 +562,8 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D K-major tensor map: dim0 = cols (contiguous), dim1 = rows with stride ld elements;
-// box = {128 bytes, box_rows}, SWIZZLE_128B, out-of-range elements read as zero.
-int encode_2d(CUtensorMap* map, bool tf32, uint64_t base, int rows, int cols, int ld, int box_rows,
+// box = {row_bytes, box_rows}, SWIZZLE_128B / SWIZZLE_32B to match row_bytes, out-of-range elements read as zero.
+int encode_2d(CUtensorMap* map, bool tf32, uint64_t base, int rows, int cols, int ld, int box_rows, int row_bytes,
               const char* what) {
   EncodeTiledFn fn = get_encode_fn();
   VQA_REQUIRE(fn != nullptr, VQA_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
@@ -568,11 +574,11 @@ int encode_2d(CUtensorMap* map, bool tf32, uint64_t base, int rows, int cols, in
   VQA_REQUIRE(box_rows >= 1 && box_rows <= 256, VQA_E_INVALID, std::string(what) + ": box rows out of range");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkBytes / esz), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(row_bytes / esz), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                   reinterpret_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     vqa_set_error(std::string(what) + ": cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) +
@@ -605,9 +611,15 @@ typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 
 // Instantiated (BN, MT, operand type, epilogue) combinations: bf16 kernels with epilogues 0/1/2
 // (convolutions, image projector), tf32 kernels with MT = 1 and epilogues 2/3 (all nn.Linear layers).
-static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi) {
+static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_bytes) {
+  if (row_bytes == 32) {   // the stem: 32-byte rows, bf16, N = 64, ReLU epilogue without residual
+    if (bn == 64 && mt == 1 && !tf32 && epi == 0) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 1, false, 0, true>);
+    if (bn == 64 && mt == 2 && !tf32 && epi == 0) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 2, false, 0, true>);
+    if (bn == 64 && mt == 2 && !tf32 && epi == 2) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 2, false, 2, true>);
+    return nullptr;
+  }
 #define VQA_PICK(BN_, MT_, TF_, EPI_) \
-  if (bn == BN_ && mt == MT_ && tf32 == TF_ && epi == EPI_) return static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, TF_, EPI_>);
+  if (bn == BN_ && mt == MT_ && tf32 == TF_ && epi == EPI_) return static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, TF_, EPI_, false>);
 #define VQA_PICK_BF16(BN_, MT_) VQA_PICK(BN_, MT_, false, 0) VQA_PICK(BN_, MT_, false, 1) VQA_PICK(BN_, MT_, false, 2)
 #define VQA_PICK_TF32(BN_) VQA_PICK(BN_, 1, true, 2) VQA_PICK(BN_, 1, true, 3)
   VQA_PICK_BF16(64, 1) VQA_PICK_BF16(64, 2) VQA_PICK_BF16(128, 1) VQA_PICK_BF16(128, 2)
@@ -650,12 +662,19 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.ngroups = I[GEMM_I_ngroups];
   VQA_REQUIRE(p.ngroups >= 1 && p.ngroups <= VQA_MAX_GROUPS, VQA_E_INVALID, "gemm: bad group count");
   VQA_REQUIRE(I[GEMM_I_ntaps] >= 1 && I[GEMM_I_ntaps] <= VQA_MAX_TAPS, VQA_E_INVALID, "gemm: bad tap count");
-  p.chunk_elems = tf32 ? 32 : 64;
+  p.row_bytes = I[GEMM_I_row_bytes] > 0 ? I[GEMM_I_row_bytes] : 128;
+  VQA_REQUIRE(p.row_bytes == 128 || (p.row_bytes == 32 && !tf32), VQA_E_INVALID, "gemm: row_bytes must be 128 (or 32 for bf16)");
+  const int halo_hi = I[GEMM_I_halo_hi];
+  VQA_REQUIRE(p.halo >= 0 && halo_hi >= 0, VQA_E_INVALID, "gemm: negative halo");
+  p.chunk_elems = p.row_bytes / (tf32 ? 4 : 2);
   p.is_tf32 = tf32 ? 1 : 0;
+  // UMMA shared-memory descriptor high word: SBO (8 rows) >> 4 at [32,46), version 1 at [46,48),
+  // swizzle mode at [61,64): 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
+  p.desc_hi = static_cast<uint32_t>((8 * p.row_bytes) >> 4) | (1u << 14) | ((p.row_bytes == 128 ? 2u : 6u) << 29);
   p.idesc = make_idesc(tf32, bn);
   VQA_REQUIRE(I[GEMM_I_Ktot] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: Ktot must be a multiple of the K chunk");
   p.k_chunks = I[GEMM_I_Ktot] / p.chunk_elems;
-  bool lockstep = p.halo == 0;
+  bool lockstep = p.halo == 0 && halo_hi == 0;
   long long kcover = 0;
   bool uses_a1 = false;
   for (int g = 0; g < p.ngroups; ++g) {
@@ -682,21 +701,18 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   }
   for (int t = 0; t < VQA_MAX_TAPS; ++t) {
     p.tap_rel[t] = I[GEMM_I_tap_rel0 + t];
-    VQA_REQUIRE(t >= I[GEMM_I_ntaps] || (p.tap_rel[t] >= 0 && p.tap_rel[t] <= 2 * p.halo), VQA_E_INVALID,
+    VQA_REQUIRE(t >= I[GEMM_I_ntaps] || (p.tap_rel[t] >= 0 && p.tap_rel[t] <= p.halo + halo_hi), VQA_E_INVALID,
                 "gemm: tap offset outside the window");
   }
   // window geometry
-  int win = (128 * p.MT + 2 * p.halo + 7) / 8 * 8;
-  p.nboxes = 1;
-  p.box_rows = win;
-  if (win > 256) {
-    p.nboxes = 2;
-    p.box_rows = ((win + 1) / 2 + 7) / 8 * 8;
-    win = 2 * p.box_rows;
-  }
-  VQA_REQUIRE(p.box_rows <= 256, VQA_E_INVALID, "gemm: halo too large for a 2-box window");
-  p.a_slot_bytes = win * kChunkBytes;
-  p.b_slot_bytes = bn * kChunkBytes;
+  const int win = 128 * p.MT + p.halo + halo_hi;
+  p.nboxes = (win + 255) / 256;
+  VQA_REQUIRE(p.nboxes <= 3, VQA_E_INVALID, "gemm: halo too large for a 3-box window");
+  p.box_rows = ((win + p.nboxes - 1) / p.nboxes + 7) / 8 * 8;    // 8-row groups keep every box swizzle-aligned
+  p.a_tx_bytes = p.nboxes * p.box_rows * p.row_bytes;
+  p.a_slot_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
+  p.b_slot_bytes = bn * p.row_bytes;
+  VQA_REQUIRE(p.b_slot_bytes % 1024 == 0, VQA_E_INVALID, "gemm: weight tile must be a multiple of 1024 bytes");
   p.m_tiles = (p.M + 128 * p.MT - 1) / (128 * p.MT);
   p.n_tiles = (p.N + bn - 1) / bn;        // only N tiles that contain real columns run
   p.acc_stages = (2 * p.MT * bn <= 512) ? 2 : 1;
@@ -729,17 +745,17 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   VQA_REQUIRE(!(op.p[GEMM_P_a0] & VQA_EXT_TAG) && !(op.p[GEMM_P_b] & VQA_EXT_TAG) && !(op.p[GEMM_P_a1] & VQA_EXT_TAG),
               VQA_E_INVALID, "gemm: A/B operands must be arena buffers");
   int rc = encode_2d(&L->mapA0, tf32, op.p[GEMM_P_a0], I[GEMM_I_a0_rows], I[GEMM_I_a0_cols], I[GEMM_I_a0_ld],
-                     p.box_rows, "gemm A0");
+                     p.box_rows, p.row_bytes, "gemm A0");
   if (rc) return rc;
   if (uses_a1) {
     VQA_REQUIRE(op.p[GEMM_P_a1] != 0, VQA_E_INVALID, "gemm: group references A1 but it is null");
     rc = encode_2d(&L->mapA1, tf32, op.p[GEMM_P_a1], I[GEMM_I_a1_rows], I[GEMM_I_a1_cols], I[GEMM_I_a1_ld],
-                   p.box_rows, "gemm A1");
+                   p.box_rows, p.row_bytes, "gemm A1");
     if (rc) return rc;
   } else {
     L->mapA1 = L->mapA0;
   }
-  rc = encode_2d(&L->mapB, tf32, op.p[GEMM_P_b], I[GEMM_I_Npad], I[GEMM_I_Ktot], I[GEMM_I_Ktot], bn, "gemm B");
+  rc = encode_2d(&L->mapB, tf32, op.p[GEMM_P_b], I[GEMM_I_Npad], I[GEMM_I_Ktot], I[GEMM_I_Ktot], bn, p.row_bytes, "gemm B");
   if (rc) return rc;
 
   p.ldo = I[GEMM_I_ldo];
@@ -769,7 +785,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   const bool has_res = op.p[GEMM_P_res] != 0;
   VQA_REQUIRE(!has_res || p.res_dtype == p.out_dtype, VQA_E_INVALID, "gemm: the residual must have the output's dtype");
   L->epi = (p.out_dtype == 0 ? 0 : 2) + (has_res ? 1 : 0);
-  L->fn = pick_kernel(bn, p.MT, tf32, L->epi);
+  L->fn = pick_kernel(bn, p.MT, tf32, L->epi, p.row_bytes);
   VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT/dtype/epilogue");
   VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
@@ -790,6 +806,7 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
 const char* gemm_kernel_name(const void* storage) {
   const GemmLaunch* L = reinterpret_cast<const GemmLaunch*>(storage);
   static thread_local char name[64];
-  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16", L->epi);
+  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d%s>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16", L->epi,
+           L->prm.row_bytes == 32 ? ",row32" : "");
   return name;
 }

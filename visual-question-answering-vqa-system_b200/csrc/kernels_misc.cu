@@ -160,9 +160,9 @@ __global__ void se_excite_kernel(const float* __restrict__ sums, const float* __
     if (lane == 0) hid[r] = fmaxf(s, 0.f);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // w2 is stored transposed [R][C]: coalesced over c
     float s = 0.f;
-    for (int r = 0; r < R; ++r) s += w2[static_cast<size_t>(c) * R + r] * hid[r];
+    for (int r = 0; r < R; ++r) s += w2[static_cast<size_t>(r) * C + c] * hid[r];
     scale[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-s));
   }
 }
@@ -340,186 +340,180 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Self-attention core for one (sequence, head): thread l owns query row l (L <= 64, head_dim 32).
-// Keys with mask == 0 get -inf before the softmax; a fully masked row yields NaN exactly like the
-// reference (models/text_encoder.py:240-247).
-constexpr int kMaxL = 64;
+// Attention core, one WARP per (pair, head): softmax(Q K^T / sqrt(32) [+ key mask]) V with head_dim 32,
+// up to 64 queries and up to 64 keys.  Self-attention (models/text_encoder.py:229-259; keys with
+// mask == 0 get -inf, a fully masked row yields NaN exactly like the reference) and
+// cross-attention over the 49 image tokens (models/cross_attention.py:164-197, no mask) share it.
+//   scores:  lane j owns key rows j and j+32 in registers; the query row is broadcast from shared memory
+//   softmax: warp-shuffle max / sum in fp32
+//   P V:     lane d owns output dim d; probabilities are broadcast by shuffle, V rows read from shared memory
 constexpr int kHd = 32;
+constexpr int kAttnWarps = 4;
 
-__global__ void self_attn_kernel(const float* __restrict__ qkv, const int* __restrict__ mask, float* __restrict__ out,
-                                 int L, int H, int ld) {
-  __shared__ float ks[kMaxL][kHd + 1];
-  __shared__ float vs[kMaxL][kHd + 1];
-  __shared__ int ms[kMaxL];
-  const int b = blockIdx.x, h = blockIdx.y;
-  const int D = H * kHd;
-  const float* base = qkv + static_cast<size_t>(b) * L * ld;
-  for (int t = threadIdx.x; t < L * kHd; t += blockDim.x) {
-    const int j = t / kHd, d = t - j * kHd;
-    ks[j][d] = base[static_cast<size_t>(j) * ld + D + h * kHd + d];
-    vs[j][d] = base[static_cast<size_t>(j) * ld + 2 * D + h * kHd + d];
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_warp_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                 const int* __restrict__ mask, float* __restrict__ out, float* __restrict__ weights, int n_units,
+                 int H, int L, int T, int ld_q, int ld_kv) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * kAttnWarps + warp;     // (pair, head)
+  if (unit >= n_units) return;
+  const int b = unit / H, h = unit - b * H;
+  float* qs = sm + warp * (64 + 64) * kHd;             // [L][32] query rows
+  float* vs = qs + 64 * kHd;                           // [T][32] value rows
+  const float* qb = q + static_cast<size_t>(b) * L * ld_q + h * kHd;
+  const float* kb = k + static_cast<size_t>(b) * T * ld_kv + h * kHd;
+  const float* vb = v + static_cast<size_t>(b) * T * ld_kv + h * kHd;
+  // stage Q and V (8 lanes cover one 128-byte row: coalesced)
+  for (int t = lane; t < L * 8; t += 32) {
+    const int r = t >> 3, c4 = t & 7;
+    reinterpret_cast<float4*>(qs)[r * 8 + c4] = *reinterpret_cast<const float4*>(qb + static_cast<size_t>(r) * ld_q + c4 * 4);
   }
-  for (int j = threadIdx.x; j < L; j += blockDim.x) ms[j] = mask ? mask[b * L + j] : 1;
-  __syncthreads();
-  const int l = threadIdx.x;
-  if (l >= L) return;
-  float q[kHd];
+  for (int t = lane; t < T * 8; t += 32) {
+    const int r = t >> 3, c4 = t & 7;
+    reinterpret_cast<float4*>(vs)[r * 8 + c4] = *reinterpret_cast<const float4*>(vb + static_cast<size_t>(r) * ld_kv + c4 * 4);
+  }
+  // this lane's key rows in registers
+  float k0[kHd], k1[kHd];
+  const bool has0 = lane < T, has1 = lane + 32 < T;
 #pragma unroll
-  for (int d = 0; d < kHd; ++d) q[d] = base[static_cast<size_t>(l) * ld + h * kHd + d];
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (has0) a = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(lane) * ld_kv + c4 * 4);
+    if (has1) c = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(lane + 32) * ld_kv + c4 * 4);
+    k0[4 * c4] = a.x; k0[4 * c4 + 1] = a.y; k0[4 * c4 + 2] = a.z; k0[4 * c4 + 3] = a.w;
+    k1[4 * c4] = c.x; k1[4 * c4 + 1] = c.y; k1[4 * c4 + 2] = c.z; k1[4 * c4 + 3] = c.w;
+  }
+  bool m0 = has0, m1 = has1;   // key participates
+  if (mask) {
+    if (has0) m0 = mask[b * T + lane] != 0;
+    if (has1) m1 = mask[b * T + lane + 32] != 0;
+  }
+  __syncwarp();
   const float scale = rsqrtf(static_cast<float>(kHd));
-  float s[kMaxL];
-  float m = -INFINITY;
-#pragma unroll 4
-  for (int j = 0; j < kMaxL; ++j) {
-    if (j < L) {
-      float a = 0.f;
+  for (int l = 0; l < L; ++l) {
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < kHd; ++d) a += q[d] * ks[j][d];
-      a = ms[j] ? a * scale : -INFINITY;
-      s[j] = a;
-      m = fmaxf(m, a);
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 qq = reinterpret_cast<const float4*>(qs)[l * 8 + c4];   // broadcast read
+      s0 += qq.x * k0[4 * c4] + qq.y * k0[4 * c4 + 1] + qq.z * k0[4 * c4 + 2] + qq.w * k0[4 * c4 + 3];
+      s1 += qq.x * k1[4 * c4] + qq.y * k1[4 * c4 + 1] + qq.z * k1[4 * c4 + 2] + qq.w * k1[4 * c4 + 3];
     }
+    s0 = m0 ? s0 * scale : -INFINITY;
+    s1 = m1 ? s1 * scale : -INFINITY;
+    const float mx = warp_max(fmaxf(s0, s1));
+    // exp(-inf - -inf) = NaN reproduces the reference for a fully masked row; padding lanes never contribute
+    float p0 = has0 ? expf(s0 - mx) : 0.f;
+    float p1 = has1 ? expf(s1 - mx) : 0.f;
+    const float inv = 1.f / warp_sum(p0 + p1);
+    p0 *= inv;
+    p1 *= inv;
+    if (weights) {
+      float* wrow = weights + ((static_cast<size_t>(b) * H + h) * L + l) * T;
+      if (has0) wrow[lane] = p0;
+      if (has1) wrow[lane + 32] = p1;
+    }
+    float acc = 0.f;
+    for (int j = 0; j < T && j < 32; ++j) acc += __shfl_sync(0xffffffffu, p0, j) * vs[j * kHd + lane];
+    for (int j = 32; j < T; ++j) acc += __shfl_sync(0xffffffffu, p1, j - 32) * vs[j * kHd + lane];
+    out[(static_cast<size_t>(b) * L + l) * (H * kHd) + h * kHd + lane] = round_tf32_rna(acc);   // tf32 operand of W_o
   }
-  float den = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < kMaxL; ++j)
-    if (j < L) { s[j] = expf(s[j] - m); den += s[j]; }
-  const float inv = 1.f / den;
-  float c[kHd];
-#pragma unroll
-  for (int d = 0; d < kHd; ++d) c[d] = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < kMaxL; ++j)
-    if (j < L) {
-      const float w = s[j] * inv;
-#pragma unroll
-      for (int d = 0; d < kHd; ++d) c[d] += w * vs[j][d];
-    }
-  float* o = out + (static_cast<size_t>(b) * L + l) * D + h * kHd;
-#pragma unroll
-  for (int d = 0; d < kHd; ++d) o[d] = round_tf32_rna(c[d]);   // feeds the W_o GEMM as a tf32 operand
-}
-
-// Cross-attention core for one (pair, head): text queries over the T = 49 image tokens, no mask
-// (models/cross_attention.py:164-197 with key_value_mask=None, models/fusion.py:292-297).
-constexpr int kMaxT = 64;
-
-__global__ void cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
-                                  float* __restrict__ weights, int L, int H, int T, int ld_q, int ld_kv, int k_off,
-                                  int v_off) {
-  __shared__ float ks[kMaxT][kHd + 1];
-  __shared__ float vs[kMaxT][kHd + 1];
-  const int b = blockIdx.x, h = blockIdx.y;
-  const int D = H * kHd;
-  const float* kvb = kv + static_cast<size_t>(b) * T * ld_kv;
-  for (int t = threadIdx.x; t < T * kHd; t += blockDim.x) {
-    const int j = t / kHd, d = t - j * kHd;
-    ks[j][d] = kvb[static_cast<size_t>(j) * ld_kv + k_off + h * kHd + d];
-    vs[j][d] = kvb[static_cast<size_t>(j) * ld_kv + v_off + h * kHd + d];
-  }
-  __syncthreads();
-  const int l = threadIdx.x;
-  if (l >= L) return;
-  const float* qr = q + (static_cast<size_t>(b) * L + l) * ld_q + h * kHd;
-  float qv[kHd];
-#pragma unroll
-  for (int d = 0; d < kHd; ++d) qv[d] = qr[d];
-  const float scale = rsqrtf(static_cast<float>(kHd));
-  float s[kMaxT];
-  float m = -INFINITY;
-#pragma unroll 4
-  for (int j = 0; j < kMaxT; ++j)
-    if (j < T) {
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < kHd; ++d) a += qv[d] * ks[j][d];
-      a *= scale;
-      s[j] = a;
-      m = fmaxf(m, a);
-    }
-  float den = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < kMaxT; ++j)
-    if (j < T) { s[j] = expf(s[j] - m); den += s[j]; }
-  const float inv = 1.f / den;
-  float c[kHd];
-#pragma unroll
-  for (int d = 0; d < kHd; ++d) c[d] = 0.f;
-  float* wrow = weights ? weights + ((static_cast<size_t>(b) * H + h) * L + l) * T : nullptr;
-#pragma unroll 4
-  for (int j = 0; j < kMaxT; ++j)
-    if (j < T) {
-      const float w = s[j] * inv;
-      if (wrow) wrow[j] = w;
-#pragma unroll
-      for (int d = 0; d < kHd; ++d) c[d] += w * vs[j][d];
-    }
-  float* o = out + (static_cast<size_t>(b) * L + l) * D + h * kHd;
-#pragma unroll
-  for (int d = 0; d < kHd; ++d) o[d] = round_tf32_rna(c[d]);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fusion tail for one pair: masked mean pools of the cross-attended and text features
+// Fusion tail, kTailRows pairs per CTA: masked mean pools of the cross-attended and text features
 // (denominator clamp(min=1)), gate g = sigmoid(W[att;txt]+b), g*att+(1-g)*txt (or the plain sum when
 // gating is disabled), output LayerNorm (models/fusion.py:299-326, :159-166).  D = 256 = blockDim.
-__global__ void pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text,
-                                    const int* __restrict__ mask, const float* __restrict__ wg,
-                                    const float* __restrict__ bg, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, float* __restrict__ fused,
-                                    float* __restrict__ att_pooled, float* __restrict__ txt_pooled, int L,
-                                    int use_gate, float eps) {
+// The 512 KB gate matrix is read once per CTA and applied to all of its pairs.
+constexpr int kTailRows = 4;
+
+__global__ void __launch_bounds__(256)
+pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text, const int* __restrict__ mask,
+                    const float* __restrict__ wg, const float* __restrict__ bg, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ fused, float* __restrict__ att_pooled,
+                    float* __restrict__ txt_pooled, int B, int L, int use_gate, float eps) {
   constexpr int D = 256;
-  __shared__ float cat[2 * D];
-  __shared__ float gate[D];
-  __shared__ float red[16];
-  const int b = blockIdx.x, d = threadIdx.x;
-  float cnt = 0.f, sa = 0.f, st = 0.f;
-  for (int l = 0; l < L; ++l) {
-    const float m = mask ? static_cast<float>(mask[b * L + l]) : 1.f;
-    cnt += m;
-    sa += xatt[(static_cast<size_t>(b) * L + l) * D + d] * m;
-    st += text[(static_cast<size_t>(b) * L + l) * D + d] * m;
+  __shared__ float cat[kTailRows][2 * D];
+  __shared__ float gate[kTailRows][D];
+  __shared__ float red[kTailRows][16];
+  const int b0 = blockIdx.x * kTailRows, d = threadIdx.x;
+  const int warp = d >> 5, lane = d & 31;
+  float ap[kTailRows], tp[kTailRows];
+#pragma unroll
+  for (int i = 0; i < kTailRows; ++i) {
+    const int b = b0 + i;
+    float cnt = 0.f, sa = 0.f, st = 0.f;
+    if (b < B) {
+      for (int l = 0; l < L; ++l) {
+        const float m = mask ? static_cast<float>(mask[b * L + l]) : 1.f;
+        cnt += m;
+        sa += xatt[(static_cast<size_t>(b) * L + l) * D + d] * m;
+        st += text[(static_cast<size_t>(b) * L + l) * D + d] * m;
+      }
+    }
+    const float den = fmaxf(cnt, 1.f);
+    ap[i] = sa / den;
+    tp[i] = st / den;
+    cat[i][d] = ap[i];
+    cat[i][D + d] = tp[i];
+    if (b < B) {
+      if (att_pooled) att_pooled[static_cast<size_t>(b) * D + d] = ap[i];
+      if (txt_pooled) txt_pooled[static_cast<size_t>(b) * D + d] = tp[i];
+    }
   }
-  const float den = fmaxf(cnt, 1.f);
-  const float ap = sa / den, tp = st / den;
-  cat[d] = ap;
-  cat[D + d] = tp;
-  if (att_pooled) att_pooled[static_cast<size_t>(b) * D + d] = ap;
-  if (txt_pooled) txt_pooled[static_cast<size_t>(b) * D + d] = tp;
   __syncthreads();
-  float f;
+  float f[kTailRows];
   if (use_gate) {
-    const int warp = d >> 5, lane = d & 31;
-    for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-      float s = 0.f;
+    for (int r = warp * 32; r < warp * 32 + 32; ++r) {      // 8 warps x 32 gate rows
       const float* wr = wg + static_cast<size_t>(r) * 2 * D;
-      for (int k = lane; k < 2 * D; k += 32) s += wr[k] * cat[k];
-      s = warp_sum(s);
-      if (lane == 0) gate[r] = 1.f / (1.f + expf(-(s + bg[r])));
+      float s[kTailRows];
+#pragma unroll
+      for (int i = 0; i < kTailRows; ++i) s[i] = 0.f;
+      for (int k = lane; k < 2 * D; k += 32) {
+        const float w = wr[k];
+#pragma unroll
+        for (int i = 0; i < kTailRows; ++i) s[i] += w * cat[i][k];
+      }
+#pragma unroll
+      for (int i = 0; i < kTailRows; ++i) {
+        const float t = warp_sum(s[i]);
+        if (lane == 0) gate[i][r] = 1.f / (1.f + expf(-(t + bg[r])));
+      }
     }
     __syncthreads();
-    const float g = gate[d];
-    f = g * ap + (1.f - g) * tp;
+#pragma unroll
+    for (int i = 0; i < kTailRows; ++i) {
+      const float g = gate[i][d];
+      f[i] = g * ap[i] + (1.f - g) * tp[i];
+    }
   } else {
-    f = ap + tp;
+#pragma unroll
+    for (int i = 0; i < kTailRows; ++i) f[i] = ap[i] + tp[i];
   }
-  // block LayerNorm over 256 values (8 warps)
-  float s = warp_sum(f);
-  if ((d & 31) == 0) red[d >> 5] = s;
+  // block LayerNorm over 256 values (8 warps), all rows at once
+#pragma unroll
+  for (int i = 0; i < kTailRows; ++i) {
+    const float s = warp_sum(f[i]);
+    if (lane == 0) red[i][warp] = s;
+  }
   __syncthreads();
-  float mean = 0.f;
-  for (int w = 0; w < 8; ++w) mean += red[w];
-  mean *= (1.f / D);
-  const float c = f - mean;
-  float q = warp_sum(c * c);
+  float c[kTailRows];
+#pragma unroll
+  for (int i = 0; i < kTailRows; ++i) {
+    float mean = 0.f;
+    for (int w = 0; w < 8; ++w) mean += red[i][w];
+    c[i] = f[i] - mean * (1.f / D);
+    const float q = warp_sum(c[i] * c[i]);
+    if (lane == 0) red[i][8 + warp] = q;
+  }
   __syncthreads();
-  if ((d & 31) == 0) red[8 + (d >> 5)] = q;
-  __syncthreads();
-  float var = 0.f;
-  for (int w = 0; w < 8; ++w) var += red[8 + w];
-  var *= (1.f / D);
-  fused[static_cast<size_t>(b) * D + d] = c * rsqrtf(var + eps) * gamma[d] + beta[d];
+#pragma unroll
+  for (int i = 0; i < kTailRows; ++i) {
+    float var = 0.f;
+    for (int w = 0; w < 8; ++w) var += red[i][8 + w];
+    var *= (1.f / D);
+    if (b0 + i < B) fused[static_cast<size_t>(b0 + i) * D + d] = c[i] * rsqrtf(var + eps) * gamma[d] + beta[d];
+  }
 }
 
 // softmax over N answers + top-k (k <= 16), ties broken towards the lower index like torch.topk on
@@ -689,33 +683,53 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       return VQA_OK;
     }
     case VQA_OP_SELF_ATTN: {
-      const int L = I[SELF_ATTN_I_L];
-      VQA_REQUIRE(L >= 1 && L <= kMaxL && I[SELF_ATTN_I_hd] == kHd, VQA_E_INVALID, "self_attn: L<=64, head_dim=32");
-      self_attn_kernel<<<dim3(I[SELF_ATTN_I_B], I[SELF_ATTN_I_H]), 64, 0, st>>>(
-          PTR(const float*, SELF_ATTN_P_qkv), PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), L,
-          I[SELF_ATTN_I_H], I[SELF_ATTN_I_ld_qkv]);
-      VQA_LAUNCH_OK("self_attn_kernel");
+      const int L = I[SELF_ATTN_I_L], H = I[SELF_ATTN_I_H], B = I[SELF_ATTN_I_B];
+      VQA_REQUIRE(L >= 1 && L <= 64 && I[SELF_ATTN_I_hd] == kHd, VQA_E_INVALID, "self_attn: L<=64, head_dim=32");
+      const float* qkv = PTR(const float*, SELF_ATTN_P_qkv);
+      const int D = H * kHd, ld = I[SELF_ATTN_I_ld_qkv];
+      VQA_REQUIRE(ld % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, VQA_E_ALIGN, "self_attn: qkv alignment");
+      const size_t smem = static_cast<size_t>(kAttnWarps) * 128 * kHd * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
+        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_warp_kernel),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+      }
+      attn_warp_kernel<<<blocks_for(static_cast<long long>(B) * H, kAttnWarps), kAttnWarps * 32, smem, st>>>(
+          qkv, qkv + D, qkv + 2 * D, PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), nullptr, B * H, H,
+          L, L, ld, ld);
+      VQA_LAUNCH_OK("attn_warp_kernel");
       return VQA_OK;
     }
     case VQA_OP_CROSS_ATTN: {
-      const int L = I[CROSS_ATTN_I_L], T = I[CROSS_ATTN_I_T];
-      VQA_REQUIRE(L >= 1 && L <= 64 && T >= 1 && T <= kMaxT && I[CROSS_ATTN_I_hd] == kHd, VQA_E_INVALID,
+      const int L = I[CROSS_ATTN_I_L], T = I[CROSS_ATTN_I_T], H = I[CROSS_ATTN_I_H], B = I[CROSS_ATTN_I_B];
+      VQA_REQUIRE(L >= 1 && L <= 64 && T >= 1 && T <= 64 && I[CROSS_ATTN_I_hd] == kHd, VQA_E_INVALID,
                   "cross_attn: L<=64, T<=64, head_dim=32");
-      cross_attn_kernel<<<dim3(I[CROSS_ATTN_I_B], I[CROSS_ATTN_I_H]), 64, 0, st>>>(
-          PTR(const float*, CROSS_ATTN_P_q), PTR(const float*, CROSS_ATTN_P_kv), PTR(float*, CROSS_ATTN_P_out),
-          PTR(float*, CROSS_ATTN_P_weights), L, I[CROSS_ATTN_I_H], T, I[CROSS_ATTN_I_ld_q], I[CROSS_ATTN_I_ld_kv],
-          I[CROSS_ATTN_I_k_off], I[CROSS_ATTN_I_v_off]);
-      VQA_LAUNCH_OK("cross_attn_kernel");
+      const float* kv = PTR(const float*, CROSS_ATTN_P_kv);
+      VQA_REQUIRE(I[CROSS_ATTN_I_ld_q] % 4 == 0 && I[CROSS_ATTN_I_ld_kv] % 4 == 0 && I[CROSS_ATTN_I_k_off] % 4 == 0 &&
+                      I[CROSS_ATTN_I_v_off] % 4 == 0, VQA_E_ALIGN, "cross_attn: leading dimensions must be multiples of 4");
+      const size_t smem = static_cast<size_t>(kAttnWarps) * 128 * kHd * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
+        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_warp_kernel),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+      }
+      attn_warp_kernel<<<blocks_for(static_cast<long long>(B) * H, kAttnWarps), kAttnWarps * 32, smem, st>>>(
+          PTR(const float*, CROSS_ATTN_P_q), kv + I[CROSS_ATTN_I_k_off], kv + I[CROSS_ATTN_I_v_off], nullptr,
+          PTR(float*, CROSS_ATTN_P_out), PTR(float*, CROSS_ATTN_P_weights), B * H, H, L, T, I[CROSS_ATTN_I_ld_q],
+          I[CROSS_ATTN_I_ld_kv]);
+      VQA_LAUNCH_OK("attn_warp_kernel");
       return VQA_OK;
     }
     case VQA_OP_POOL_GATE_LN: {
       VQA_REQUIRE(I[POOL_GATE_LN_I_D] == 256, VQA_E_INVALID, "pool_gate_ln: D must be 256");
-      pool_gate_ln_kernel<<<I[POOL_GATE_LN_I_B], 256, 0, st>>>(
+      pool_gate_ln_kernel<<<(I[POOL_GATE_LN_I_B] + kTailRows - 1) / kTailRows, 256, 0, st>>>(
           PTR(const float*, POOL_GATE_LN_P_xatt), PTR(const float*, POOL_GATE_LN_P_text),
           PTR(const int*, POOL_GATE_LN_P_mask), PTR(const float*, POOL_GATE_LN_P_wg), PTR(const float*, POOL_GATE_LN_P_bg),
           PTR(const float*, POOL_GATE_LN_P_gamma), PTR(const float*, POOL_GATE_LN_P_beta),
           PTR(float*, POOL_GATE_LN_P_fused), PTR(float*, POOL_GATE_LN_P_att_pooled),
-          PTR(float*, POOL_GATE_LN_P_txt_pooled), I[POOL_GATE_LN_I_L], I[POOL_GATE_LN_I_use_gate],
+          PTR(float*, POOL_GATE_LN_P_txt_pooled), I[POOL_GATE_LN_I_B], I[POOL_GATE_LN_I_L], I[POOL_GATE_LN_I_use_gate],
           op.f[POOL_GATE_LN_F_eps]);
       VQA_LAUNCH_OK("pool_gate_ln_kernel");
       return VQA_OK;
@@ -747,8 +761,8 @@ const char* misc_kernel_name(int kind) {
     case VQA_OP_MASK_PREP: return "mask_prep_kernel";
     case VQA_OP_EMBED: return "embed_kernel";
     case VQA_OP_LAYERNORM: return "layernorm256_kernel";
-    case VQA_OP_SELF_ATTN: return "self_attn_kernel";
-    case VQA_OP_CROSS_ATTN: return "cross_attn_kernel";
+    case VQA_OP_SELF_ATTN: return "attn_warp_kernel(self)";
+    case VQA_OP_CROSS_ATTN: return "attn_warp_kernel(cross)";
     case VQA_OP_POOL_GATE_LN: return "pool_gate_ln_kernel";
     case VQA_OP_SOFTMAX_TOPK: return "softmax_topk_kernel";
     default: return "?";
