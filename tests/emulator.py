@@ -138,13 +138,18 @@ class Emulator:
 
     def op_se_squeeze(self, op, ext):
         i = op.i
-        x = self._grid_nhwc(op.p["src"], ext, i["B"], i["C"], i["H"], i["W"], i["P"], i["RPI"])
-        _t(op.p["sums"], torch.float32, ext)[: i["B"] * i["C"]].view(i["B"], i["C"]).copy_(x.sum(dim=(1, 2)))
+        B, C, H, W, S = i["B"], i["C"], i["H"], i["W"], i["S"]
+        x = self._grid_nhwc(op.p["src"], ext, B, C, H, W, i["P"], i["RPI"]).reshape(B, H * W, C)
+        per = (H * W + S - 1) // S
+        part = torch.zeros(B, S, C)
+        for k in range(S):   # slice partial sums, added in slice order by se_excite
+            part[:, k] = x[:, k * per: (k + 1) * per].sum(dim=1)
+        _t(op.p["sums"], torch.float32, ext)[: B * S * C].view(B, S, C).copy_(part)
 
     def op_se_excite(self, op, ext):
         i = op.i
-        B, C, R = i["B"], i["C"], i["R"]
-        mean = _t(op.p["sums"], torch.float32, ext)[: B * C].view(B, C) / i["HW"]
+        B, C, R, S = i["B"], i["C"], i["R"], i["S"]
+        mean = _t(op.p["sums"], torch.float32, ext)[: B * S * C].view(B, S, C).sum(dim=1) / i["HW"]
         w1 = _t(op.p["w1"], torch.float32, ext)[: R * C].view(R, C)
         w2t = _t(op.p["w2"], torch.float32, ext)[: R * C].view(R, C)   # stored transposed
         sc = torch.sigmoid(F.relu(mean @ w1.t()) @ w2t)

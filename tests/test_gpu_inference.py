@@ -1,0 +1,66 @@
+"""VQAInference (predict API) on the GPU: result schema, parity with the oracle, batching, CUDA graph."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+pytestmark = pytest.mark.gpu
+
+from conftest import REPO  # noqa: E402
+
+sys.path.insert(0, REPO)
+from oracle import vqa_oracle as O  # noqa: E402
+from vqa_b200 import VQAInference  # noqa: E402
+from vqa_b200.synth import synth_images_u8  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def engine():
+    torch.manual_seed(0)
+    inf = VQAInference()
+    inf.load()
+    return inf
+
+
+def _oracle_topk(inf, u8, question, k):
+    sd = {n: t.detach().cpu() for n, t in inf.model.state_dict().items()}
+    ids, mask = inf.preprocess_question(question)
+    logits, _ = O.vqa_forward(sd, O.preprocess_u8(u8.unsqueeze(0)), ids, mask)
+    return O.predict_topk(logits, k)
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_predict_schema_and_parity(engine, graph):
+    engine.use_cuda_graph = graph
+    u8 = synth_images_u8(1, 7)[0]
+    q = "What COLOR is this, really?!  don't know"
+    out = engine.predict(Image.fromarray(u8.numpy(), "RGB"), q, top_k=5)
+    assert set(out) == {"question", "answers", "top_answer", "confidence"} and out["question"] == q
+    assert len(out["answers"]) == 5 and set(out["answers"][0]) == {"answer", "probability", "index"}
+    idx, probs = _oracle_topk(engine, u8, q, 5)
+    assert out["answers"][0]["index"] == int(idx[0, 0])
+    assert out["top_answer"] == f"answer_{int(idx[0, 0])}" and out["confidence"] == out["answers"][0]["probability"]
+    np.testing.assert_allclose([a["probability"] for a in out["answers"]], probs[0].numpy(), rtol=2e-2, atol=1e-5)
+    ids, mask = engine.preprocess_question(q)
+    assert ids.tolist()[0][:9] == [2, 4, 7, 5, 6, 1, 1, 1, 3] and int(mask.sum()) == 9   # default 13-word tokenizer
+
+
+def test_predict_batch_and_resize(engine):
+    engine.use_cuda_graph = True
+    imgs = [Image.fromarray(synth_images_u8(1, 10 + i)[0].numpy(), "RGB") for i in range(3)]
+    imgs[1] = imgs[1].resize((320, 200))   # goes through the PIL antialiased bilinear resize
+    qs = ["what is this", "how many are there", "where is what type"]
+    res = engine.predict_batch(imgs, qs, top_k=3)
+    assert [r["question"] for r in res] == qs and all(len(r["answers"]) == 3 for r in res)
+    for im, q, r in zip(imgs, qs, res):
+        u8 = engine.preprocess_image_u8(im)
+        idx, _ = _oracle_topk(engine, u8, q, 3)
+        assert r["answers"][0]["index"] == int(idx[0, 0])
+    single = engine.predict(imgs[0], qs[0], top_k=3)
+    assert single["answers"][0]["index"] == res[0]["answers"][0]["index"]
+    with pytest.raises(ValueError):
+        engine.predict_batch(imgs, qs[:2])
+    info = engine.get_model_info()
+    assert info["num_answers"] == 1000 and info["vocab_size"] == 13 and info["parameters"]["total"] == 19310316

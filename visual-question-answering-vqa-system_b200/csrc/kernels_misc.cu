@@ -118,15 +118,20 @@ __global__ void maxpool_kernel(const uint4* __restrict__ src, uint4* __restrict_
 
 // ------------------------------------------------------------------------------------------------
 // SE squeeze: per-(image, channel) sum over the valid pixels of a padded-flat bf16 grid.
+// grid = (B, S): every CTA reduces one slice of the image's pixels into sums[n][slice][c]; se_excite adds the
+// S partials in a fixed order, so the result is deterministic (no atomics).
 __global__ void se_squeeze_kernel(const uint4* __restrict__ src, float* __restrict__ sums, int C8, int H, int W, int P,
                                   int RPI) {
   extern __shared__ float red[];  // [lanes][C8*8]
   const int n = blockIdx.x;
   const int lanes = blockDim.x / C8;
   const int cg = threadIdx.x % C8, pl = threadIdx.x / C8;
+  const int HW = H * W;
+  const int per = (HW + gridDim.y - 1) / gridDim.y;
+  const int q0 = blockIdx.y * per, q1 = min(HW, q0 + per);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (pl < lanes) {
-    for (int q = pl; q < H * W; q += lanes) {
+    for (int q = q0 + pl; q < q1; q += lanes) {
       const int h = q / W, w = q - h * W;
       const uint4 v = src[(static_cast<size_t>(n) * RPI + h * P + w) * C8 + cg];
       acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
@@ -139,18 +144,23 @@ __global__ void se_squeeze_kernel(const uint4* __restrict__ src, float* __restri
   for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) {
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += red[l * C8 * 8 + c];
-    sums[static_cast<size_t>(n) * C8 * 8 + c] = s;
+    sums[(static_cast<size_t>(n) * gridDim.y + blockIdx.y) * C8 * 8 + c] = s;
   }
 }
 
 // SE excite: scale = sigmoid(W2 relu(W1 mean)), no biases (models/attention_modules.py:84-85,116-126).
 __global__ void se_excite_kernel(const float* __restrict__ sums, const float* __restrict__ w1,
-                                 const float* __restrict__ w2, float* __restrict__ scale, int C, int R, float inv_hw) {
+                                 const float* __restrict__ w2, float* __restrict__ scale, int C, int R, int S,
+                                 float inv_hw) {
   extern __shared__ float sm[];  // mean[C], hid[R]
   float* mean = sm;
   float* hid = sm + C;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[static_cast<size_t>(n) * C + c] * inv_hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < S; ++k) t += sums[(static_cast<size_t>(n) * S + k) * C + c];   // fixed order: deterministic
+    mean[c] = t * inv_hw;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int r = warp; r < R; r += nw) {
@@ -425,7 +435,7 @@ attn_warp_kernel(const float* __restrict__ q, const float* __restrict__ k, const
 // (denominator clamp(min=1)), gate g = sigmoid(W[att;txt]+b), g*att+(1-g)*txt (or the plain sum when
 // gating is disabled), output LayerNorm (models/fusion.py:299-326, :159-166).  D = 256 = blockDim.
 // The 512 KB gate matrix is read once per CTA and applied to all of its pairs.
-constexpr int kTailRows = 4;
+constexpr int kTailRows = 1;   // 1 measured fastest at batch 256 (4 halves the L2 traffic but leaves SMs idle)
 
 __global__ void __launch_bounds__(256)
 pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text, const int* __restrict__ mask,
@@ -606,7 +616,9 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(C8 >= 1 && C8 <= 256, VQA_E_INVALID, "se_squeeze: C out of range");
       const int threads = 256 >= C8 ? 256 / C8 * C8 : C8;
       const size_t smem = static_cast<size_t>(threads) * 8 * sizeof(float);
-      se_squeeze_kernel<<<I[SE_SQUEEZE_I_B], threads, smem, st>>>(PTR(const uint4*, SE_SQUEEZE_P_src),
+      const int slices = I[SE_SQUEEZE_I_S];
+      VQA_REQUIRE(slices >= 1 && slices <= 64, VQA_E_INVALID, "se_squeeze: bad slice count");
+      se_squeeze_kernel<<<dim3(I[SE_SQUEEZE_I_B], slices), threads, smem, st>>>(PTR(const uint4*, SE_SQUEEZE_P_src),
                                                                   PTR(float*, SE_SQUEEZE_P_sums), C8, I[SE_SQUEEZE_I_H],
                                                                   I[SE_SQUEEZE_I_W], I[SE_SQUEEZE_I_P],
                                                                   I[SE_SQUEEZE_I_RPI]);
@@ -617,7 +629,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int C = I[SE_EXCITE_I_C], R = I[SE_EXCITE_I_R];
       se_excite_kernel<<<I[SE_EXCITE_I_B], 256, (C + R) * sizeof(float), st>>>(
           PTR(const float*, SE_EXCITE_P_sums), PTR(const float*, SE_EXCITE_P_w1), PTR(const float*, SE_EXCITE_P_w2),
-          PTR(float*, SE_EXCITE_P_scale), C, R, 1.f / static_cast<float>(I[SE_EXCITE_I_HW]));
+          PTR(float*, SE_EXCITE_P_scale), C, R, I[SE_EXCITE_I_S], 1.f / static_cast<float>(I[SE_EXCITE_I_HW]));
       VQA_LAUNCH_OK("se_excite_kernel");
       return VQA_OK;
     }

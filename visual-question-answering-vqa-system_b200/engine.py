@@ -100,9 +100,10 @@ class Engine:
         ext[P.EXT["top_probs"]] = top_p.data_ptr()
         stream = torch.cuda.current_stream(self.device)
         plan.run(ext, stream.cuda_stream)
-        for t in (images, ids, mask):  # keep inputs alive until the stream has consumed them
-            if t is not None:
-                t.record_stream(stream)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in (images, ids, mask):  # keep inputs alive until the stream has consumed them
+                if t is not None:
+                    t.record_stream(stream)
         return logits, top_idx, top_p, prog
 
     def forward(self, images, token_ids, attention_mask=None, return_aux=False):

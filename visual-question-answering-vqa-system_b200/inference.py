@@ -1,0 +1,228 @@
+"""``VQAInference``: the reference's predict API on the sm_100a engine.
+
+Boundary #2 of SURVEY.md section 8b.  Same constructor, lazy ``load()`` with the same
+fall-backs (random default model / 13-word default tokenizer / ``answer_{i}`` vocabulary when
+the files do not exist), same method names and result schema as ``api/inference.py:36-358``:
+
+    predict(image, question, top_k=5) -> {'question', 'answers': [{'answer','probability','index'}],
+                                          'top_answer', 'confidence'}
+
+What changes underneath: the image stays uint8 after PIL decode/resize and is normalised by
+the ingest kernel on the GPU (one 150 KB host-to-device copy instead of a 602 KB fp32 one); the
+forward, softmax and top-k run as one plan launch; the result comes back in a single
+device-to-host copy instead of 2*k ``.item()`` synchronisations.  For a fixed batch size the
+whole launch sequence is captured once in a CUDA graph and replayed (batch-1 latency path).
+"""
+from __future__ import annotations
+
+import os
+from io import BytesIO
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+from PIL import Image
+
+from .model import VQAModel, load_vqa_model
+from .synth import IMAGENET_MEAN, IMAGENET_STD
+from .text import AnswerVocabulary, Tokenizer
+
+# Defaults of the reference's config singletons (utils/config.py:73-134,225) that the predict
+# path reads; the reference's PathConfig (which creates directories on import) is not mirrored.
+DEFAULT_QUESTION_VOCAB_SIZE = 10000
+DEFAULT_NUM_ANSWERS = 1000
+DEFAULT_MAX_QUESTION_LENGTH = 20
+DEFAULT_IMAGE_SIZE = 224
+DEFAULT_TOP_K = 5
+_REF_BASE = "d:/cnn"   # the reference hard-codes Windows paths under this prefix (utils/config.py:27-44)
+DEFAULT_CHECKPOINT = _REF_BASE + "/checkpoints/best_model.pt"
+DEFAULT_QUESTION_VOCAB = _REF_BASE + "/data/question_vocab.json"
+DEFAULT_ANSWER_VOCAB = _REF_BASE + "/data/vocab.json"
+
+ImageLike = Union[str, bytes, Image.Image]
+
+
+def get_device() -> str:
+    """The engine has no CPU path: CUDA or a loud failure at load()."""
+    return "cuda"
+
+
+class VQAInference:
+    def __init__(self, checkpoint_path: Optional[str] = None, device: Optional[str] = None,
+                 question_vocab_path: Optional[str] = None, answer_vocab_path: Optional[str] = None,
+                 use_cuda_graph: bool = True):
+        self.device = device or get_device()
+        self.checkpoint_path = checkpoint_path or DEFAULT_CHECKPOINT
+        self.question_vocab_path = question_vocab_path or DEFAULT_QUESTION_VOCAB
+        self.answer_vocab_path = answer_vocab_path or DEFAULT_ANSWER_VOCAB
+        self.model: Optional[VQAModel] = None
+        self.tokenizer: Optional[Tokenizer] = None
+        self.answer_vocab: Optional[AnswerVocabulary] = None
+        self.transform = None
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[Tuple[int, int], dict] = {}
+        self._is_loaded = False
+
+    # ------------------------------------------------------------------ loading
+    def load(self):
+        if self._is_loaded:
+            return
+        if not str(self.device).startswith("cuda"):
+            raise RuntimeError("vqa_b200.VQAInference needs a CUDA device (sm_100a); there is no CPU path")
+        if os.path.exists(self.checkpoint_path):
+            self.model = load_vqa_model(self.checkpoint_path, self.device)
+        else:
+            self.model = VQAModel(vocab_size=DEFAULT_QUESTION_VOCAB_SIZE,
+                                  num_answers=DEFAULT_NUM_ANSWERS).to(self.device)
+        self.model.eval()
+        if os.path.exists(self.question_vocab_path):
+            self.tokenizer = Tokenizer()
+            self.tokenizer.load(self.question_vocab_path)
+        else:
+            self.tokenizer = Tokenizer(max_length=DEFAULT_MAX_QUESTION_LENGTH)
+            self.tokenizer.build_vocab(["what is this", "what color", "how many", "is there", "where is",
+                                        "what type"], min_freq=1)
+        if os.path.exists(self.answer_vocab_path):
+            self.answer_vocab = AnswerVocabulary()
+            self.answer_vocab.load(self.answer_vocab_path)
+        else:
+            self.answer_vocab = AnswerVocabulary(num_answers=DEFAULT_NUM_ANSWERS)
+            for i in range(DEFAULT_NUM_ANSWERS):
+                self.answer_vocab.idx2answer[i] = f"answer_{i}"
+        self.transform = self.preprocess_image
+        self._is_loaded = True
+
+    # ------------------------------------------------------------------ preprocessing
+    @staticmethod
+    def _open(image: ImageLike) -> Image.Image:
+        if isinstance(image, str):
+            pil = Image.open(image)
+        elif isinstance(image, (bytes, bytearray)):
+            pil = Image.open(BytesIO(image))
+        else:
+            pil = image
+        if pil.mode != "RGB":
+            pil = pil.convert("RGB")
+        return pil
+
+    def preprocess_image_u8(self, image: ImageLike) -> torch.Tensor:
+        """Decode + resize to 224x224 exactly like the reference's transform does for PIL inputs
+        (torchvision Resize -> PIL antialiased bilinear, data/preprocess.py:117-121), but stop at
+        uint8 HWC [224,224,3]: /255 and mean/std normalisation happen in the GPU ingest kernel."""
+        pil = self._open(image)
+        size = DEFAULT_IMAGE_SIZE
+        if pil.size != (size, size):
+            pil = pil.resize((size, size), Image.BILINEAR)
+        return torch.frombuffer(bytearray(pil.tobytes()), dtype=torch.uint8).view(size, size, 3)
+
+    def preprocess_image(self, image: ImageLike) -> torch.Tensor:
+        """Reference-compatible output: normalised float32 [1,3,224,224] on the CPU."""
+        u8 = self.preprocess_image_u8(image)
+        x = u8.to(torch.float32).div(255.0).permute(2, 0, 1)
+        mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
+        std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
+        return ((x - mean) / std).unsqueeze(0)
+
+    def preprocess_question(self, question: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        ids, mask = self.tokenizer.encode(question, add_special_tokens=True, padding=True, truncation=True)
+        return torch.tensor([ids], dtype=torch.long), torch.tensor([mask], dtype=torch.long)
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, u8: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, top_k: int):
+        """u8 [B,224,224,3], ids/mask [B,L] on the host -> (top_idx [B,k], top_probs [B,k]) on the host."""
+        B, L = ids.shape
+        k = min(top_k, self.model.num_answers)
+        if not self.use_cuda_graph:
+            with torch.no_grad():
+                idx, probs = self.model.predict(u8.to(self.device, non_blocking=True),
+                                                ids.to(self.device, non_blocking=True),
+                                                mask.to(self.device, non_blocking=True), top_k=k)
+            return idx.cpu(), probs.cpu()
+        key = (B, L, k)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(B, L, k)
+            self._graphs[key] = g
+        g["h_u8"].copy_(u8)
+        g["h_ids"].copy_(ids)
+        g["h_mask"].copy_(mask)
+        g["graph"].replay()
+        torch.cuda.current_stream().synchronize()
+        return g["h_idx"].clone(), g["h_probs"].clone()
+
+    def _capture(self, B: int, L: int, k: int) -> dict:
+        """Static pinned/device buffers + one CUDA graph: H2D copies, the plan's launches, D2H copies."""
+        dev = torch.device(self.device)
+        g = {
+            "h_u8": torch.empty(B, 224, 224, 3, dtype=torch.uint8).pin_memory(),
+            "h_ids": torch.empty(B, L, dtype=torch.long).pin_memory(),
+            "h_mask": torch.empty(B, L, dtype=torch.long).pin_memory(),
+            "h_idx": torch.empty(B, k, dtype=torch.long).pin_memory(),
+            "h_probs": torch.empty(B, k, dtype=torch.float32).pin_memory(),
+            "d_u8": torch.zeros(B, 224, 224, 3, dtype=torch.uint8, device=dev),
+            "d_ids": torch.zeros(B, L, dtype=torch.long, device=dev),
+            "d_mask": torch.ones(B, L, dtype=torch.long, device=dev),
+        }
+        engine = self.model.engine()
+        with torch.no_grad():
+            for _ in range(2):   # warm up: builds the plan, loads kernels
+                engine.predict(g["d_u8"], g["d_ids"], g["d_mask"], k)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["d_u8"].copy_(g["h_u8"], non_blocking=True)
+                g["d_ids"].copy_(g["h_ids"], non_blocking=True)
+                g["d_mask"].copy_(g["h_mask"], non_blocking=True)
+                idx, probs = engine.predict(g["d_u8"], g["d_ids"], g["d_mask"], k)
+                g["h_idx"].copy_(idx, non_blocking=True)
+                g["h_probs"].copy_(probs, non_blocking=True)
+        g["graph"] = graph
+        g["keep"] = (idx, probs)
+        return g
+
+    def _format(self, question: str, idx_row, prob_row) -> Dict:
+        answers = []
+        for i, p in zip(idx_row, prob_row):
+            i = int(i)
+            answers.append({"answer": self.answer_vocab.decode(i), "probability": float(p), "index": i})
+        return {"question": question, "answers": answers, "top_answer": answers[0]["answer"],
+                "confidence": answers[0]["probability"]}
+
+    @torch.no_grad()
+    def predict(self, image: ImageLike, question: str, top_k: int = DEFAULT_TOP_K) -> Dict:
+        if not self._is_loaded:
+            self.load()
+        u8 = self.preprocess_image_u8(image).unsqueeze(0)
+        ids, mask = self.preprocess_question(question)
+        idx, probs = self._run(u8, ids, mask, top_k)
+        return self._format(question, idx[0].tolist(), probs[0].tolist())
+
+    @torch.no_grad()
+    def predict_batch(self, images: List[ImageLike], questions: List[str], top_k: int = DEFAULT_TOP_K) -> List[Dict]:
+        if len(images) != len(questions):
+            raise ValueError("Number of images must match number of questions")
+        if not self._is_loaded:
+            self.load()
+        u8 = torch.stack([self.preprocess_image_u8(im) for im in images], dim=0)
+        pairs = [self.preprocess_question(q) for q in questions]
+        ids = torch.cat([p[0] for p in pairs], dim=0)
+        mask = torch.cat([p[1] for p in pairs], dim=0)
+        idx, probs = self._run(u8, ids, mask, top_k)
+        return [self._format(q, idx[b].tolist(), probs[b].tolist()) for b, q in enumerate(questions)]
+
+    def get_model_info(self) -> Dict:
+        if not self._is_loaded:
+            self.load()
+        return {"device": str(self.device), "vocab_size": self.tokenizer.vocab_size,
+                "num_answers": self.answer_vocab.num_answers, "parameters": self.model.get_num_parameters(),
+                "config": self.model.config}
+
+
+_inference_instance: Optional[VQAInference] = None
+
+
+def get_inference_engine() -> VQAInference:
+    global _inference_instance
+    if _inference_instance is None:
+        _inference_instance = VQAInference()
+        _inference_instance.load()
+    return _inference_instance
