@@ -199,15 +199,18 @@ def run_b200(args):
     inf = VQAInference(device=str(dev))
     inf.model, inf._is_loaded = model, True      # same weights as the device-resident leg
     with torch.no_grad():
-        for _ in range(3):
-            inf._run(h_u8, h_ids, h_mask, 5)
+        for _ in inf.predict_tensors_pipelined([(h_u8, h_ids, h_mask)] * 3, 5):
+            pass
         barrier()
-        e0.record()
-        for _ in range(K):
-            out = inf._run(h_u8, h_ids, h_mask, 5)
-        e1.record()
+        t0 = time.perf_counter()                      # host clock: copies and compute run on the API's own streams
+        n_out = 0
+        for top_idx, top_probs in inf.predict_tensors_pipelined([(h_u8, h_ids, h_mask)] * K, 5):
+            n_out += top_idx.shape[0]
+        torch.cuda.synchronize()
+        ms_local = (time.perf_counter() - t0) * 1e3
         barrier()
-        ms_e2e = reduce_max(e0.elapsed_time(e1))
+        assert n_out == B * K
+        ms_e2e = reduce_max(ms_local)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
     h2d = h_u8.numel() + h_ids.numel() * 8 + h_mask.numel() * 8
     d2h = B * 5 * (8 + 4)
@@ -293,7 +296,9 @@ def run_b200(args):
                 "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K,
-                        "path": "pinned uint8 HWC + ids + mask -> H2D -> normalise+forward+top-5 (CUDA graph) -> D2H"},
+                        "path": "VQAInference.predict_tensors_pipelined: pinned uint8 HWC + ids + mask -> H2D (copy "
+                                "stream, double buffered) -> normalise+forward+top-5 -> D2H; every step copies its own "
+                                "inputs and results; timed on the host clock around all K steps"},
                 "latency_batch1": latency,
                 "gpu_launches": int(launches), "clocks": clocks.summary()}
         print(json.dumps(line), flush=True)

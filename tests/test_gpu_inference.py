@@ -64,3 +64,17 @@ def test_predict_batch_and_resize(engine):
         engine.predict_batch(imgs, qs[:2])
     info = engine.get_model_info()
     assert info["num_answers"] == 1000 and info["vocab_size"] == 13 and info["parameters"]["total"] == 19310316
+
+
+def test_pipelined_throughput_path_matches_single_calls(engine):
+    from vqa_b200.synth import synth_batch
+    batches = []
+    for i in range(5):
+        u8, _, ids, mask = synth_batch(6, 50 + i)
+        batches.append((u8.pin_memory(), ids.pin_memory(), mask.pin_memory()))
+    outs = list(engine.predict_tensors_pipelined(batches, top_k=4))
+    assert len(outs) == 5
+    engine.use_cuda_graph = False
+    for (u8, ids, mask), (idx, probs) in zip(batches, outs):
+        ridx, rprobs = engine._run(u8, ids, mask, 4)
+        assert torch.equal(idx, ridx) and torch.equal(probs, rprobs)

@@ -1,0 +1,55 @@
+"""The op program (layout + tap algebra + weight folding) against the oracle, on the CPU emulator.
+This is the check that let the layout design be validated before any GPU time was spent."""
+import sys
+
+import pytest
+import torch
+
+from conftest import REPO
+
+sys.path.insert(0, REPO)
+import emulator as E  # noqa: E402
+from oracle import vqa_oracle as O  # noqa: E402
+from vqa_b200 import program as P  # noqa: E402
+from vqa_b200.model import VQAModel  # noqa: E402
+from vqa_b200.synth import randomise_state, synth_batch  # noqa: E402
+
+ABL = dict(use_se_attention=False, use_spatial_attention=False, use_gating=False, num_transformer_layers=1,
+           num_cross_layers=1, max_question_length=12, vocab_size=500, num_answers=37)
+
+
+@pytest.mark.parametrize("ctor,B,L,fmt,mk,window", [
+    ({}, 2, 20, "nchw_f32", "i64", True), ({}, 1, 20, "hwc_u8", "f32", False), (ABL, 2, 12, "nchw_f32", "none", True)])
+def test_program_matches_oracle(ctor, B, L, fmt, mk, window):
+    torch.manual_seed(0)
+    model = VQAModel(**ctor).eval()
+    sd = randomise_state(model.state_dict(), 1)
+    u8, img, ids, mask = synth_batch(B, 1234, max_len=L, vocab=model.config["vocab_size"])
+    W = P.build_weights(sd, model.config, "cpu")
+    code = {"i64": P.MASK_I64, "f32": P.MASK_F32, "none": P.MASK_NONE}[mk]
+    m = {"i64": mask, "f32": mask.float(), "none": None}[mk]
+    prog = P.Program(W, model.config, B, L, fmt, code, want_aux=True, top_k=5, device="cpu", window=window)
+    logits, ext = E.run_program(prog, u8 if fmt == "hwc_u8" else img, ids, m, top_k=5)
+    want, aux = O.vqa_forward(sd, img, ids, m, return_aux=True)
+    assert float((logits - want).abs().max() / want.abs().max()) < 1e-2
+    feat = prog.tensor("aux.image_features")
+    assert float((feat - aux["image_features"]).abs().max() / aux["image_features"].abs().max()) < 3e-2
+    assert torch.equal(ext[P.EXT["top_idx"]][:, 0], want.argmax(1))
+    kinds = [op.kind for op in prog.ops]
+    assert kinds.count("gemm") >= 30 and kinds[0] == "ingest"
+    assert all(op.lane in (0, 1) for op in prog.ops) and any(op.lane == 1 for op in prog.ops)
+
+
+def test_weight_folding_is_exact_in_fp32():
+    """BN fold + shortcut-as-extra-K reproduce conv->BN (+downsample->BN) exactly up to fp32 rounding."""
+    torch.manual_seed(3)
+    model = VQAModel().eval()
+    sd = randomise_state(model.state_dict(), 2)
+    q = "image_encoder.stage2.blocks.0"
+    w2, b2 = P._fold_bn(sd, q + ".conv2.weight", q + ".bn2")
+    x = torch.randn(1, 128, 6, 6)
+    want = O._bn(sd, q + ".bn2", torch.nn.functional.conv2d(x, sd[q + ".conv2.weight"], padding=1))
+    got = torch.nn.functional.conv2d(x, w2, b2, padding=1)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    m = P._stem_matrix(torch.arange(64 * 3 * 49, dtype=torch.float32).view(64, 3, 7, 7))
+    assert m.shape == (64, 256) and int((m != 0).sum()) == 64 * 147 - 1   # every tap placed once (one weight is 0)

@@ -179,6 +179,60 @@ class VQAInference:
         g["keep"] = (idx, probs)
         return g
 
+    @torch.no_grad()
+    def predict_tensors_pipelined(self, batches, top_k: int = DEFAULT_TOP_K):
+        """Throughput path: iterate over host batches ``(u8 [B,224,224,3], ids [B,L], mask [B,L])`` (ideally
+        pinned) and yield ``(top_idx, top_probs)`` host tensors in order.  The host-to-device copy of batch
+        i+1 runs on a copy stream while batch i computes (inputs are double buffered; the engine's
+        workspace is shared because compute is serialised on one stream), and each result comes back in
+        one small device-to-host copy."""
+        if not self._is_loaded:
+            self.load()
+        dev = torch.device(self.device)
+        copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        k = min(top_k, self.model.num_answers)
+        engine = self.model.engine()
+        slots = [None, None]
+        pending = []   # (done_event, h_idx, h_probs)
+
+        def drain(n_keep):
+            while len(pending) > n_keep:
+                ev, hi, hp = pending.pop(0)
+                ev.synchronize()
+                yield hi.clone(), hp.clone()
+
+        for i, (u8, ids, mask) in enumerate(batches):
+            B, L = ids.shape
+            sl = slots[i & 1]
+            if sl is None or sl["shape"] != (B, L):
+                sl = {"shape": (B, L),
+                      "d_u8": torch.empty(B, 224, 224, 3, dtype=torch.uint8, device=dev),
+                      "d_ids": torch.empty(B, L, dtype=torch.long, device=dev),
+                      "d_mask": torch.empty(B, L, dtype=torch.long, device=dev),
+                      "h_idx": torch.empty(B, k, dtype=torch.long).pin_memory(),
+                      "h_probs": torch.empty(B, k, dtype=torch.float32).pin_memory(),
+                      "copied": torch.cuda.Event(), "free": None}
+                slots[i & 1] = sl
+            with torch.cuda.stream(copy_s):
+                if sl["free"] is not None:
+                    copy_s.wait_event(sl["free"])          # the forward that last read this slot has finished
+                sl["d_u8"].copy_(u8, non_blocking=True)
+                sl["d_ids"].copy_(ids, non_blocking=True)
+                sl["d_mask"].copy_(mask, non_blocking=True)
+                sl["copied"].record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(sl["copied"])
+                idx, probs = engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k)
+                sl["free"] = torch.cuda.Event()
+                sl["free"].record(comp_s)
+                sl["h_idx"].copy_(idx, non_blocking=True)
+                sl["h_probs"].copy_(probs, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(comp_s)
+            pending.append((done, sl["h_idx"], sl["h_probs"]))
+            yield from drain(1)                             # keep one batch in flight behind the current one
+        yield from drain(0)
+
     def _format(self, question: str, idx_row, prob_row) -> Dict:
         answers = []
         for i, p in zip(idx_row, prob_row):
