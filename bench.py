@@ -198,6 +198,18 @@ def run_b200(args):
     from vqa_b200.inference import VQAInference
     inf = VQAInference(device=str(dev))
     inf.model, inf._is_loaded = model, True      # same weights as the device-resident leg
+    # raw pinned H2D bandwidth of this box (explains the e2e number: 38.6 MB of uint8 pixels per 256-pair step)
+    d_probe = torch.empty_like(h_u8, device=dev)
+    d_probe.copy_(h_u8, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        d_probe.copy_(h_u8, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 5 * h_u8.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del d_probe
     with torch.no_grad():
         for _ in inf.predict_tensors_pipelined([(h_u8, h_ids, h_mask)] * 3, 5):
             pass
@@ -295,7 +307,7 @@ def run_b200(args):
                            "l2": "inputs 154 MB/GPU (fp32 NCHW) exceed the 126 MB L2; no flush needed"},
                 "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / K,
+                        "ms_per_step": ms_e2e / K, "h2d_pinned_copy_gbps": h2d_gbps,
                         "path": "VQAInference.predict_tensors_pipelined: pinned uint8 HWC + ids + mask -> H2D (copy "
                                 "stream, double buffered) -> normalise+forward+top-5 -> D2H; every step copies its own "
                                 "inputs and results; timed on the host clock around all K steps"},

@@ -64,6 +64,8 @@ class Emulator:
         xp = x.reshape(B, 3, 112, 2, 112, 2).permute(0, 2, 4, 3, 5, 1)
         packed = torch.zeros(B, 112, 112, 2, 2, 4)
         packed[..., :3] = xp
+        if i.get("ones"):
+            packed[..., 0, :, 3] = 1.0   # bias columns of the fused stem (phases (0,0) and (0,1))
         idx = _grid_index(B, 112, 112, Pp, Pp * Pp)
         dst[idx] = packed.reshape(-1, 16).to(torch.bfloat16)
 
@@ -118,6 +120,16 @@ class Emulator:
         if i["round_tf32"]:
             acc = P.round_tf32(acc)
         odt = torch.bfloat16 if i["out_dtype"] == P.OUT_BF16 else torch.float32
+        if i.get("pool"):
+            # fused 3x3/2 max-pool of the (bf16-rounded) conv map, written to the pooled padded grid
+            B, H, W_ = i["n_imgs"], i["mH"], i["mW"]
+            conv = acc.to(odt)[_grid_index(B, H, W_, i["mP"], i["mRPI"])].float().view(B, H, W_, N)
+            y = F.max_pool2d(conv.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).reshape(-1, N)
+            rows_o = B * i["pool_rpio"]
+            dst = _t(op.p["out"], odt, ext)[: rows_o * N].view(rows_o, N)
+            dst.zero_()
+            dst[_grid_index(B, i["pool_Ho"], i["pool_Wo"], i["pool_Po"], i["pool_rpio"])] = y.to(odt)
+            return
         out = torch.as_strided(_t(op.p["out"], odt, ext), (M, N), (i["ldo"], 1))
         out.copy_(acc.to(odt))
 

@@ -195,3 +195,29 @@ def test_stem_window_32_byte_rows(mt, max_ctas):
         return ol
     cpu, gpu, _, _ = G.run_pair(build)
     G.report(f"stem window row32 MT{mt} max_ctas={max_ctas}", G.named(gpu, "o"), G.named(cpu, "o"), atol=2e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("max_ctas", [0, 3])
+@pytest.mark.parametrize("B,HW", [(2, 20), (3, 112)])
+def test_stem_window_fused_maxpool(B, HW, max_ctas):
+    """Stem conv + ReLU + 3x3/2 max-pool in one kernel: a tile is 3 conv rows of one image (strided M tiling,
+    MT=3), pooled in shared memory into one row of the pooled padded grid."""
+    g0, g1 = P.Grid(B, HW, HW, pad=2), P.Grid(B, HW // 2, HW // 2)
+    def build(device):
+        W = _weights(device, "w", 64, 256, torch.bfloat16, 31).finalize()
+        ol = P.OpList(W, device)
+        a = ol._buf("a", torch.bfloat16, g0.rows, 16)
+        o = ol._buf("o", torch.bfloat16, g1.rows, 64)
+        lo, hi = 2 * g0.P + 2, g0.P + 1
+        rels = [lo + (ia - 2) * g0.P + (ib - 2) for ia in range(4) for ib in range(4)]
+        ol.gemm("stem", dtype=P.DT_BF16, M=g0.rows, N=64, a0=a, a0_shape=(g0.rows, 16, 16), groups=[(0, 0, 0, 1, rels)],
+                w="w.w", bias="w.b", out=o, ldo=64, out_dtype=P.OUT_BF16, relu=True, grid=g0,
+                halo=lo, halo_hi=hi, MT=3, row_bytes=32, pool_to=g1)
+        ol.ops[-1].i["max_ctas"] = max_ctas
+        ol.commit()
+        G.named(ol, "a").copy_(_fill(ol, "a", 32))
+        G.named(ol, "o").fill_(7.0)      # pad rows/columns must be overwritten with zeros
+        return ol
+    cpu, gpu, _, _ = G.run_pair(build)
+    G.report(f"stem + fused max-pool B{B} {HW}x{HW} max_ctas={max_ctas}", G.named(gpu, "o"), G.named(cpu, "o"),
+             atol=2e-2, rtol=1e-2)

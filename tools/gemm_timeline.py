@@ -35,7 +35,8 @@ print("op name: setup | first_tma | first_a_full | tile0_mma_issued | tile0_acc_
 for k in gemms:
     t = prog.tensor(f"dbg{k}").cpu().tolist()
     d = [x - t[0] for x in t]
-    tiles = (prog.ops[k].i["M"] + 128 * prog.ops[k].i["MT"] - 1) // (128 * prog.ops[k].i["MT"])
+    oi = prog.ops[k].i
+    tiles = oi["tiles_per_img"] * oi["n_imgs"] if oi.get("tiles_per_img") else (oi["M"] + 128 * oi["MT"] - 1) // (128 * oi["MT"])
     print(f"{k:3d} {prog.ops[k].name:14s} setup {d[1]:5d} tma0 {d[2]:5d} a_full0 {d[3]:6d} mma0_issued {d[4]:6d} acc_seen0 {d[5]:6d} "
           f"epi0_done {d[6]:6d} last_mma {d[9]:7d} last_epi {d[7]:7d} exit {d[8]:7d} | waits: prod a_empty {t[16]:7d} b_empty {t[17]:7d} "
           f"| mma acc_empty {t[18]:7d} a_full {t[19]:7d} b_full {t[20]:7d} | epi(w2) acc_full {t[21]:7d} | m_tiles {tiles}")

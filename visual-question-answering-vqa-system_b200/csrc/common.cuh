@@ -206,6 +206,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// max(x, 0) rounded to bf16 (RN) in one instruction per pair
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 #endif  // __CUDACC__
 
 // ----------------------------------------------------------------------------- host-side op access

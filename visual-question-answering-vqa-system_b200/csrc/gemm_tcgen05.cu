@@ -62,8 +62,19 @@ struct GemmParams {
   const void* res;
   int ldo, ldr, out_dtype, res_dtype;
   int relu, round_tf32, mask_en, mP, mRPI, mH, mW;
+  // strided M tiling (fused stem + max-pool): tile t starts at (t / tiles_per_img) * img_rows +
+  // (t % tiles_per_img) * tile_stride + tile_row0 instead of t * 128 * MT  (tiles_per_img = 0: linear)
+  int tiles_per_img, tile_stride, tile_row0, img_rows;
+  // fused 3x3/2 max-pool epilogue (EPI 4): conv grid pitch / width, pooled grid geometry
+  int pool_P, pool_W, pool_Wo, pool_Ho, pool_Po, pool_rpio;
   long long* dbg;    // optional: 16 clock64() timestamps of CTA 0 (profiling aid, nullptr in production)
 };
+
+__device__ __forceinline__ int tile_m0(const GemmParams& p, int tile_m, int mt) {
+  if (p.tiles_per_img == 0) return tile_m * 128 * mt;
+  const int img = tile_m / p.tiles_per_img;
+  return img * p.img_rows + (tile_m - img * p.tiles_per_img) * p.tile_stride + p.tile_row0;
+}
 
 #define VQA_DBG(slot)                                                         \
   do {                                                                        \
@@ -146,7 +157,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kRowBytes / 16);
     for (int g = 0; g < VQA_MAX_GROUPS; ++g) s_grp[g] = make_int4(p.g_chunks[g], p.g_ntaps[g], p.g_tap0[g], p.g_q0[g]);
   }
-  const uint32_t tmem_cols = static_cast<uint32_t>(BN * MT * p.acc_stages);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(BN * MT * p.acc_stages)) tmem_cols <<= 1;   // power of two >= 32
   if (warp == 2) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
@@ -165,7 +177,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const bool timed = p.dbg != nullptr && blockIdx.x == 0;
     long long w_aempty = 0, w_bempty = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.m_tiles) * 128 * MT;
+      const int m0 = tile_m0(p, tile % p.m_tiles, MT);
       const int n0 = (tile / p.m_tiles) * BN;
       if (p.b_resident && !b_loaded) {   // n_tiles == 1 in this mode: load every weight chunk once
         if (elect_one()) {
@@ -308,6 +320,103 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
       if (timed) { p.dbg[18] = w_accempty; p.dbg[19] = w_afull; p.dbg[20] = w_bfull; }
     }
+  } else if constexpr (EPI == 4) {
+    // ===================== epilogue warps, fused ReLU + 3x3/2 max-pool (the stem) =====================
+    // The tile is 3 consecutive conv rows (2i'-1, 2i', 2i'+1; 342 of the 384 accumulator rows) of one
+    // image: every warp converts its TMEM block to bf16 (+bias, ReLU) into a swizzled
+    // shared-memory conv tile, the 8 epilogue warps synchronise on a named barrier, then pool the
+    // tile into pooled row i' (57 entries incl. the zero pad column) and write it -- the un-pooled
+    // 112x112x64 map (1.6 MB per image) never goes to HBM.  Reference: models/cnn_backbone.py:349-354.
+    static_assert(EPI != 4 || (BN == 64 && MT == 3), "pool epilogue is specialised for the stem");
+    const int ew = warp - 2;
+    const int quad = warp & 3, half = ew >> 2;
+    const int tid = threadIdx.x - 64;                  // 0..255 within the epilogue warps
+    uint8_t* ct = smem_stage;                          // conv tile: 384 rows x 128 B (64 bf16), 16-byte chunks XOR-swizzled by row
+    const float* const bias = p.bias;
+    const int acc_stages = p.acc_stages;
+    const int cP = p.pool_P, Wo = p.pool_Wo, Ho = p.pool_Ho, Po = p.pool_Po, rpio = p.pool_rpio, tpi = p.tiles_per_img;
+    uint4* const out = reinterpret_cast<uint4*>(p.out);
+    const bool has_bias = bias != nullptr;             // the VQA stem folds its bias into K (ingest writes a 1 column)
+    int acc = 0;
+    uint32_t accph = 0;
+    const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
+    long long w_accfull = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int img = tile / tpi, ip = tile - img * tpi;       // image, pooled row
+      mbar_wait_t(&acc_full[acc], accph, timed, w_accfull);
+      tc_fence_after();
+      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(5);
+      // No pad masking here: the pooling pass below only reads in-image conv positions.
+      uint32_t v[MT][32];
+      __syncwarp();
+#pragma unroll
+      for (int sub = 0; sub < MT; ++sub)
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (BN * MT) + sub * BN + half * 32, v[sub]);
+      tmem_ld_wait();
+      if (has_bias) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + half * 32) + k);
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub) {
+            v[sub][4 * k] = __float_as_uint(__uint_as_float(v[sub][4 * k]) + bq.x);
+            v[sub][4 * k + 1] = __float_as_uint(__uint_as_float(v[sub][4 * k + 1]) + bq.y);
+            v[sub][4 * k + 2] = __float_as_uint(__uint_as_float(v[sub][4 * k + 2]) + bq.z);
+            v[sub][4 * k + 3] = __float_as_uint(__uint_as_float(v[sub][4 * k + 3]) + bq.w);
+          }
+        }
+      }
+#pragma unroll
+      for (int sub = 0; sub < MT; ++sub) {
+        const int rl = sub * 128 + quad * 32 + lane;     // row within the conv tile
+        uint8_t* dst = ct + rl * 128;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            w[k] = pack_relu_bf16x2(__uint_as_float(v[sub][8 * c4 + 2 * k]), __uint_as_float(v[sub][8 * c4 + 2 * k + 1]));
+          *reinterpret_cast<uint4*>(dst + (((half * 4 + c4) ^ (rl & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);         // TMEM stage drained: the next tile's MMAs may start
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // conv tile complete (epilogue warps only)
+      // ---- pooling pass: item = (pooled column j', channel octet cg)
+      const size_t orow = static_cast<size_t>(img) * rpio + static_cast<size_t>(ip) * Po;
+      for (int item = tid; item < Po * 8; item += 256) {
+        const int jp = item >> 3, cg = item & 7;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (jp < Wo) {
+          __nv_bfloat162 m[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = __float2bfloat162_rn(0.f);   // post-ReLU values are >= 0
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            if (r == 0 && ip == 0) continue;                 // conv row -1 is padding (row 2i'+1 <= H-1 always holds)
+#pragma unroll
+            for (int dc = -1; dc <= 1; ++dc) {
+              const int c = 2 * jp + dc;
+              if (c < 0) continue;                           // column -1 is padding (c <= W-1 always holds)
+              const int rl = r * cP + c;
+              const uint4 q = *reinterpret_cast<const uint4*>(ct + rl * 128 + ((cg ^ (rl & 7)) << 4));
+              const __nv_bfloat162* qv = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], qv[k]);
+            }
+          }
+          o = *reinterpret_cast<uint4*>(m);
+        }
+        out[(orow + jp) * 8 + cg] = o;
+        if (ip == Ho - 1) out[(orow + Po + jp) * 8 + cg] = make_uint4(0u, 0u, 0u, 0u);   // the image's zero pad row
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // pooling done: the conv tile may be overwritten
+      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(6);
+      if (warp == 2 && tile + static_cast<int>(gridDim.x) >= total_tiles) VQA_DBG(7);
+      if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
+    }
+    if (timed && lane == 0) p.dbg[21] = w_accfull;
   } else {
     // ===================== epilogue warps =====================
     constexpr bool kOutBf16 = EPI < 2;
@@ -377,7 +486,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     bool res_ready = false;   // the first buffer already holds the residual of the upcoming tile's first chunk
 
     auto epi_tile = [&](int tile, ResRaw (&bufA)[4], ResRaw (&bufB)[4]) {
-      const int m0 = (tile % m_tiles) * 128 * MT;
+      const int m0 = tile_m0(p, tile % m_tiles, MT);
       const int n0 = (tile / m_tiles) * BN;
       const int colw = n0 + half * kCols;               // first column this warp owns
       const bool fast = aligned && (colw + kCols <= N); // whole warp slice in range and vectorisable
@@ -616,6 +725,7 @@ static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_byte
     if (bn == 64 && mt == 1 && !tf32 && epi == 0) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 1, false, 0, true>);
     if (bn == 64 && mt == 2 && !tf32 && epi == 0) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 2, false, 0, true>);
     if (bn == 64 && mt == 2 && !tf32 && epi == 2) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 2, false, 2, true>);
+    if (bn == 64 && mt == 3 && !tf32 && epi == 4) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 3, false, 4, true>);
     return nullptr;
   }
 #define VQA_PICK(BN_, MT_, TF_, EPI_) \
@@ -655,7 +765,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.N = I[GEMM_I_N];
   p.MT = I[GEMM_I_MT];
   p.halo = I[GEMM_I_halo];
-  VQA_REQUIRE(p.MT == 1 || p.MT == 2, VQA_E_INVALID, "gemm: p.MT must be 1 or 2");
+  VQA_REQUIRE(p.MT >= 1 && p.MT <= 3, VQA_E_INVALID, "gemm: MT must be 1, 2 or 3");
   VQA_REQUIRE(p.MT * bn <= 512, VQA_E_INVALID, "gemm: accumulators exceed 512 TMEM columns");
   VQA_REQUIRE(p.M > 0 && p.N > 0 && I[GEMM_I_Npad] % bn == 0 && I[GEMM_I_Npad] >= p.N, VQA_E_INVALID,
               "gemm: bad M/N/Npad");
@@ -714,12 +824,31 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.b_slot_bytes = bn * p.row_bytes;
   VQA_REQUIRE(p.b_slot_bytes % 1024 == 0, VQA_E_INVALID, "gemm: weight tile must be a multiple of 1024 bytes");
   p.m_tiles = (p.M + 128 * p.MT - 1) / (128 * p.MT);
+  p.tiles_per_img = I[GEMM_I_tiles_per_img];
+  p.tile_stride = I[GEMM_I_tile_stride];
+  p.tile_row0 = I[GEMM_I_tile_row0];
+  p.img_rows = I[GEMM_I_img_rows];
+  const bool pool = I[GEMM_I_pool] != 0;
+  if (p.tiles_per_img > 0) {
+    VQA_REQUIRE(p.img_rows > 0 && p.tile_stride > 0 && I[GEMM_I_n_imgs] > 0, VQA_E_INVALID, "gemm: bad strided tiling");
+    p.m_tiles = p.tiles_per_img * I[GEMM_I_n_imgs];
+  }
+  p.pool_P = I[GEMM_I_pool_P]; p.pool_W = I[GEMM_I_pool_W]; p.pool_Wo = I[GEMM_I_pool_Wo]; p.pool_Ho = I[GEMM_I_pool_Ho];
+  p.pool_Po = I[GEMM_I_pool_Po]; p.pool_rpio = I[GEMM_I_pool_rpio];
+  if (pool) {
+    VQA_REQUIRE(p.MT == 3 && bn == 64 && p.row_bytes == 32 && p.tiles_per_img == p.pool_Ho && 3 * p.pool_P <= 384 &&
+                    p.pool_Wo * 2 == p.pool_W && p.pool_Po >= p.pool_Wo + 1 && p.tile_stride == 2 * p.pool_P &&
+                    p.tile_row0 == -p.pool_P, VQA_E_INVALID,
+                "gemm: the fused max-pool epilogue needs 3 conv rows per tile (MT=3, BN=64, 32-byte rows)");
+  }
   p.n_tiles = (p.N + bn - 1) / bn;        // only N tiles that contain real columns run
   p.acc_stages = (2 * p.MT * bn <= 512) ? 2 : 1;
 
   // shared-memory plan: one CTA per SM (persistent), ~210 KB of rings
   int budget = I[GEMM_I_smem_budget];
   if (budget <= 0) budget = 190 * 1024;   // + 32 KB of epilogue staging + barriers stays under 227 KB
+  const int stage_bytes = pool ? 384 * 128 : kEpiWarps * kStageBytes;   // pool mode: the bf16 conv tile lives there
+  budget -= stage_bytes - kEpiWarps * kStageBytes;
   const long long b_all = static_cast<long long>(p.k_chunks) * p.b_slot_bytes;
   p.b_resident = (p.n_tiles == 1 && b_all <= 96 * 1024 && b_all + 2LL * p.a_slot_bytes <= budget) ? 1 : 0;
   if (p.b_resident) {
@@ -738,7 +867,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   }
   const long long b_bytes = p.b_resident ? b_all : static_cast<long long>(p.b_slots) * p.b_slot_bytes;
   L->smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(b_bytes) +
-            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 6) + 16 + 4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS + kEpiWarps * kStageBytes;
+            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 6) + 16 + 4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS + stage_bytes;
   VQA_REQUIRE(L->smem <= 227 * 1024, VQA_E_INVALID, "gemm: shared memory budget exceeded");
 
   // tensor maps (only for non-external operands: A and W always live in the arenas)
@@ -785,6 +914,11 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   const bool has_res = op.p[GEMM_P_res] != 0;
   VQA_REQUIRE(!has_res || p.res_dtype == p.out_dtype, VQA_E_INVALID, "gemm: the residual must have the output's dtype");
   L->epi = (p.out_dtype == 0 ? 0 : 2) + (has_res ? 1 : 0);
+  if (pool) {
+    VQA_REQUIRE(!has_res && p.out_dtype == 0 && (op.p[GEMM_P_out] & VQA_EXT_TAG) == 0, VQA_E_INVALID,
+                "gemm: the pooled output is a bf16 arena buffer without residual");
+    L->epi = 4;
+  }
   L->fn = pick_kernel(bn, p.MT, tf32, L->epi, p.row_bytes);
   VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT/dtype/epilogue");
   VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -23,8 +23,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // block (2a+ph, 2b+pw) x (R,G,B,0) as 16 bf16.  mode 0: fp32 NCHW already normalised
 // (models/vqa_model.py:243-258); mode 1: uint8 HWC, normalised here exactly like
 // ToTensor + Normalize (data/preprocess.py:117-121): (u8/255 - mean)/std in fp32.
+// ones = 1: the two spare slots (phase (0,0) and (0,1), channel 3) of every in-image block hold 1.0 so that
+// the stem GEMM adds its bias through two K columns (bias_hi + bias_lo) instead of in the epilogue.
 __global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ dst, int B, int mode, int P,
-                              int rows) {
+                              int rows, int ones) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int rpi = P * P;
@@ -36,7 +38,7 @@ __global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ 
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
-      for (int pw = 0; pw < 2; ++pw) v[ph][pw][3] = 0.f;
+      for (int pw = 0; pw < 2; ++pw) v[ph][pw][3] = (ones && ph == 0) ? 1.f : 0.f;
     if (mode == 0) {
       const float* x = reinterpret_cast<const float*>(src);
 #pragma unroll
@@ -597,7 +599,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 || I[INGEST_I_mode] == 1, VQA_E_ALIGN,
                   "ingest: fp32 images must be 8-byte aligned");
       ingest_kernel<<<blocks_for(rows, 256), 256, 0, st>>>(src, PTR(uint4*, INGEST_P_dst), I[INGEST_I_B],
-                                                            I[INGEST_I_mode], I[INGEST_I_P], rows);
+                                                            I[INGEST_I_mode], I[INGEST_I_P], rows, I[INGEST_I_ones]);
       VQA_LAUNCH_OK("ingest_kernel");
       return VQA_OK;
     }

@@ -42,11 +42,12 @@ _GROUPS = [f"g_{k}{g}" for k in ("map", "delta", "acol", "chunks", "ntaps", "kba
 _TAPS = [f"tap_rel{t}" for t in range(MAX_TAPS)]
 
 FIELDS: Dict[str, Dict[str, List[str]]] = {
-    "ingest": {"i": ["B", "mode", "HW", "P", "rows"], "p": ["src", "dst"], "f": []},
+    "ingest": {"i": ["B", "mode", "HW", "P", "rows", "ones"], "p": ["src", "dst"], "f": []},
     "gemm": {"i": ["dtype", "M", "N", "Npad", "Ktot", "BN", "MT", "halo", "a0_rows", "a0_cols", "a0_ld",
                    "a1_rows", "a1_cols", "a1_ld", "ngroups", "ntaps", "out_dtype", "ldo", "res_dtype", "ldr",
                    "relu", "round_tf32", "mask_en", "mP", "mRPI", "mH", "mW", "smem_budget", "max_ctas", "row_bytes",
-                   "halo_hi"]
+                   "halo_hi", "tiles_per_img", "tile_stride", "tile_row0", "img_rows", "n_imgs", "pool", "pool_P",
+                   "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio"]
                   + _GROUPS + _TAPS,
              "p": ["a0", "a1", "b", "out", "bias", "res", "dbg"], "f": []},
     "maxpool": {"i": ["B", "C", "Hin", "Win", "Pin", "RPIin", "Hout", "Wout", "Pout", "RPIout"],
@@ -266,6 +267,13 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
     w, b = _fold_bn(sd, "image_encoder.stem.0.weight", "image_encoder.stem.1")
     W.add("stem.w", _stem_matrix(w), bf)
     W.add("stem.b", b, f32)
+    # bias folded into K: ingest(ones=1) stores 1.0 in the spare channel of phases (0,0) and (0,1) of every
+    # in-image block; the centre tap's weights there carry the bias as a bf16 hi + lo pair (error ~2^-17)
+    mb = _stem_matrix(w).view(-1, 4, 4, 2, 2, 4).clone()
+    hi = b.to(bf).float()
+    mb[:, 2, 2, 0, 0, 3] = hi
+    mb[:, 2, 2, 0, 1, 3] = (b - hi).to(bf).float()
+    W.add("stem.wb", mb.reshape(-1, 256), bf)
     for s in (1, 2, 3, 4):
         p = f"image_encoder.stage{s}"
         blk = 0
@@ -365,6 +373,7 @@ class OpList:
         self.W = weights
         self.window = window
         self.stem_window = window
+        self.fuse_pool = window
         self.ws = Arena(device if device is not None else weights.arena.device)
         self.ops: List[Op] = []
         self.named: Dict[str, Tuple[Buf, torch.dtype, Tuple[int, ...]]] = {}
@@ -396,7 +405,7 @@ class OpList:
     def gemm(self, name, *, dtype, M, N, a0, a0_shape, groups, w, bias, out, ldo, out_dtype,
              a1=None, a1_shape=None, res=None, res_dtype=-1, ldr=0, relu=False, rnd=False,
              grid: Optional[Grid] = None, halo: int = 0, MT: int = 1, row_bytes: int = 128,
-             halo_hi: Optional[int] = None):
+             halo_hi: Optional[int] = None, pool_to: Optional[Grid] = None):
         """Tap-shifted GEMM.  ``groups``: list of (map, row_delta, a_col, n_chunks, [tap_rel...]).
 
         For K-chunk c of group g the kernel loads ONE window of A rows
@@ -426,6 +435,12 @@ class OpList:
                  mask_en=int(grid is not None), mP=grid.P if grid else 1, mRPI=grid.rpi if grid else 1,
                  mH=grid.H if grid else 1, mW=grid.W if grid else 1, smem_budget=0, max_ctas=0,
                  row_bytes=row_bytes, halo_hi=halo_hi)
+        if pool_to is not None:
+            # fused 3x3/2 max-pool epilogue: tile t = (image, pooled row i') covers conv rows 2i'-1 .. 2i'+1
+            assert grid is not None and MT == 3 and 3 * grid.P <= 384 and pool_to.H * 2 == grid.H
+            i.update(tiles_per_img=pool_to.H, tile_stride=2 * grid.P, tile_row0=-grid.P, img_rows=grid.rpi,
+                     n_imgs=grid.B, pool=1, pool_P=grid.P, pool_W=grid.W, pool_Wo=pool_to.W, pool_Ho=pool_to.H,
+                     pool_Po=pool_to.P, pool_rpio=pool_to.rpi)
         kbase = tap0 = 0
         for g, (mp, delta, acol, nch, rels) in enumerate(groups):
             assert all(0 <= r <= halo + halo_hi for r in rels), (name, rels, halo, halo_hi)
@@ -492,8 +507,25 @@ class Program(OpList):
         GUARD = 32   # zero phase-pixels in front of the data (only the overlapping-row variant needs them)
         s0g = self._buf("stem_in", bf, g0.rows + GUARD, 16)
         s0 = Buf(s0g.arena, s0g.offset + GUARD * 32, g0.rows * 32, "stem_in.data")
-        self._op("ingest", "ingest", dict(B=B, mode=0 if self.in_fmt == "nchw_f32" else 1, HW=224, P=g0.P, rows=g0.rows),
+        fused = self.stem_window and self.fuse_pool
+        self._op("ingest", "ingest", dict(B=B, mode=0 if self.in_fmt == "nchw_f32" else 1, HW=224, P=g0.P, rows=g0.rows,
+                                          ones=int(fused)),
                  dict(src=ExtRef(EXT["images"]), dst=s0))
+        g = Grid(B, 56, 56)
+        x = self._buf("s1.in", bf, g.rows, 64)
+        if fused:
+            lo, hi = 2 * g0.P + 2, g0.P + 1
+            rels = [lo + (ia - 2) * g0.P + (ib - 2) for ia in range(4) for ib in range(4)]
+            self.gemm("stem.conv+pool", dtype=DT_BF16, M=g0.rows, N=64, a0=s0, a0_shape=(g0.rows, 16, 16),
+                      groups=[(0, 0, 0, 1, rels)], w="stem.wb", bias=None, out=x, ldo=64, out_dtype=OUT_BF16,
+                      relu=True, grid=g0, halo=lo, halo_hi=hi, MT=3, row_bytes=32, pool_to=g)
+        else:
+            self._stem_unfused(g0, s0, s0g, GUARD, g, x)
+        self._build_rest(g, x)
+
+    def _stem_unfused(self, g0, s0, s0g, GUARD, g, x):
+        B = self.B
+        bf = torch.bfloat16
         s1 = self._buf("stem_out", bf, g0.rows, 64)
         if self.stem_window:
             # 32-byte rows (one phase-pixel = 16 packed bf16), SWIZZLE_32B: ONE window of phase-pixels per
@@ -512,10 +544,12 @@ class Program(OpList):
             taps = [(0, (ia - 2) * g0.P - 2 + GUARD, 0, 1, [0]) for ia in range(4)]
             self.gemm("stem.conv", dtype=DT_BF16, M=g0.rows, N=64, a0=s0g, a0_shape=(g0.rows + GUARD, 64, 16), groups=taps,
                       w="stem.w", bias="stem.b", out=s1, ldo=64, out_dtype=OUT_BF16, relu=True, grid=g0)
-        g = Grid(B, 56, 56)
-        x = self._buf("s1.in", bf, g.rows, 64)
         self._op("maxpool", "stem.pool", dict(B=B, C=64, Hin=112, Win=112, Pin=g0.P, RPIin=g0.rpi,
                                               Hout=56, Wout=56, Pout=g.P, RPIout=g.rpi), dict(src=s1, dst=x))
+
+    def _build_rest(self, g, x):
+        B, L, W, cfg = self.B, self.L, self.W, self.cfg
+        bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
         cin = 64
         x_is_phase = False
         phase_rows = 0
