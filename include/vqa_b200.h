@@ -66,7 +66,8 @@ enum VqaOpKind {
   VQA_OP_SOFTMAX_TOPK  = 13, /* softmax + top-k (models/vqa_model.py:336-337, api/inference.py:231-234) */
   VQA_OP_MASK_PREP     = 14, /* attention_mask (int64 | fp32 | absent) -> int32 */
   VQA_OP_GRID_TO_NCHW  = 15, /* padded-flat bf16 grid -> NCHW fp32 (aux['image_features'], models/vqa_model.py:301-309) */
-  VQA_OP_KIND_MAX      = 16
+  VQA_OP_COPY_ROWS     = 16, /* fp32 [rows, cols] copy between leading dimensions (logits whose num_answers is not a multiple of 4) */
+  VQA_OP_KIND_MAX      = 17
 };
 
 typedef struct VqaOp {

@@ -206,6 +206,11 @@ class Emulator:
         n = i["B"] * i["C"] * i["H"] * i["W"]
         _t(op.p["dst"], torch.float32, ext)[:n].view(i["B"], i["C"], i["H"], i["W"]).copy_(x.permute(0, 3, 1, 2))
 
+    def op_copy_rows(self, op, ext):
+        i = op.i
+        src = torch.as_strided(_t(op.p["src"], torch.float32, ext), (i["rows"], i["cols"]), (i["ld_src"], 1))
+        torch.as_strided(_t(op.p["dst"], torch.float32, ext), (i["rows"], i["cols"]), (i["ld_dst"], 1)).copy_(src)
+
     def op_mask_prep(self, op, ext):
         i = op.i
         src = ext[op.p["src"].slot]

@@ -23,7 +23,7 @@ OUTPUTS = {
     "self_attn": [("out", torch.float32)], "cross_attn": [("out", torch.float32), ("weights", torch.float32)],
     "pool_gate_ln": [("fused", torch.float32), ("att_pooled", torch.float32), ("txt_pooled", torch.float32)],
     "softmax_topk": [("idx", torch.int64), ("probs", torch.float32)], "mask_prep": [("dst", torch.int32)],
-    "grid_to_nchw": [("dst", torch.float32)],
+    "grid_to_nchw": [("dst", torch.float32)], "copy_rows": [("dst", torch.float32)],
 }
 
 

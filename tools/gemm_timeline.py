@@ -39,4 +39,5 @@ for k in gemms:
     tiles = oi["tiles_per_img"] * oi["n_imgs"] if oi.get("tiles_per_img") else (oi["M"] + 128 * oi["MT"] - 1) // (128 * oi["MT"])
     print(f"{k:3d} {prog.ops[k].name:14s} setup {d[1]:5d} tma0 {d[2]:5d} a_full0 {d[3]:6d} mma0_issued {d[4]:6d} acc_seen0 {d[5]:6d} "
           f"epi0_done {d[6]:6d} last_mma {d[9]:7d} last_epi {d[7]:7d} exit {d[8]:7d} | waits: prod a_empty {t[16]:7d} b_empty {t[17]:7d} "
-          f"| mma acc_empty {t[18]:7d} a_full {t[19]:7d} b_full {t[20]:7d} | epi(w2) acc_full {t[21]:7d} | m_tiles {tiles}")
+          f"| mma acc_empty {t[18]:7d} a_full {t[19]:7d} b_full {t[20]:7d} | epi(w2) acc_full {t[21]:7d} | m_tiles {tiles} "
+          f"| wall {(t[23] - t[22]) / 1e3:7.1f} us sm_clk {d[8] / max(t[23] - t[22], 1) * 1e3:6.0f} MHz")

@@ -81,23 +81,20 @@ __device__ __forceinline__ int tile_m0(const GemmParams& p, int tile_m, int mt) 
     if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[slot] = clock64();       \
   } while (0)
 
-// ---- epilogue helpers -----------------------------------------------------------------------
+// ---- epilogue --------------------------------------------------------------------------------
 // The accumulator comes out of TMEM one row per lane.  Writing rows straight to global memory
 // makes every 16-byte store of a warp touch 32 different 128-byte lines (measured: 14k cycles for
-// a 128x256 fp32 tile).  Each epilogue warp therefore transposes its 32x32 chunk through a
-// private, XOR-swizzled 4 KB shared-memory stage and does all global traffic (residual read,
-// output write) with 8 lanes per contiguous row segment.
-constexpr int kStageBytes = 32 * 128;   // 32 rows x 32 fp32 per epilogue warp
+// a 128x256 fp32 tile), so all global traffic of the epilogue goes through TMA instead: each
+// epilogue warp finishes its 32x32 chunk in the row-per-lane domain (bias from a shared-memory
+// table, residual from a TMA-loaded box, ReLU / pad mask / rounding), writes the result as a
+// swizzled box into its private staging slot and one lane issues a TMA store, which also clips
+// the M and N edges.  The residual box of the NEXT chunk is in flight while the current one is
+// processed.  Slots are 32 rows x 64 B (bf16, SWIZZLE_64B) or 32 rows x 128 B (fp32, SWIZZLE_128B).
+constexpr int kBiasTable = 1024;        // floats: bias of every N tile of the launch
+constexpr int kPoolTileBytes = 384 * 128;
 
-__device__ __forceinline__ void stage_write(uint8_t* stage, int lane, const uint32_t (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = q;
-  }
-}
-__device__ __forceinline__ float4 stage_read(const uint8_t* stage, int row, int slot) {
-  return *reinterpret_cast<const float4*>(stage + row * 128 + ((slot ^ (row & 7)) << 4));
+__host__ __device__ constexpr int epi_stage_bytes(int epi) {
+  return epi == 4 ? kPoolTileBytes : kEpiWarps * ((epi < 2 ? 2048 : 4096) * ((epi & 1) ? 2 : 1));
 }
 
 // EPI: 0 = bf16 out, no residual | 1 = bf16 out + bf16 residual | 2 = fp32 out, no residual | 3 = fp32 out + fp32 residual
@@ -116,7 +113,8 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
 template <int BN, int MT, bool TF32, int EPI, bool ROW32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
+                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window.
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -131,28 +129,38 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.a_slots * p.a_slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + b_region_slots * p.b_slot_bytes);
+  uint8_t* smem_stage = smem_b + b_region_slots * p.b_slot_bytes;     // 1024-byte aligned (slots are 1 KB multiples)
+  float* s_bias = reinterpret_cast<float*>(smem_stage + epi_stage_bytes(EPI));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kBiasTable);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxASlots;
   uint64_t* b_full = a_empty + kMaxASlots;     // b_full[0] doubles as the "all weights landed" barrier
   uint64_t* b_empty = b_full + kMaxBSlots;
   uint64_t* acc_full = b_empty + kMaxBSlots;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  uint64_t* res_bar = acc_empty + 2;           // one per epilogue warp: "residual box landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
   uint32_t* s_rel = tmem_slot + 4;                                   // tap row offsets, pre-shifted for descriptors
   int4* s_grp = reinterpret_cast<int4*>(s_rel + VQA_MAX_TAPS);      // per group {chunks, taps, tap0, q0}
-  uint8_t* smem_stage = reinterpret_cast<uint8_t*>(s_grp + VQA_MAX_GROUPS);   // 16-byte aligned by construction
 
   if (warp == 0) VQA_DBG(0);
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    p.dbg[22] = static_cast<long long>(ns);
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
+    if (EPI != 4) tma_prefetch_desc(&mapOut);
+    if (EPI & 1) tma_prefetch_desc(&mapRes);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+    for (int s = 0; s < kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
     mbar_fence_init();
     for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kRowBytes / 16);
     for (int g = 0; g < VQA_MAX_GROUPS; ++g) s_grp[g] = make_int4(p.g_chunks[g], p.g_ntaps[g], p.g_tap0[g], p.g_q0[g]);
@@ -421,208 +429,161 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== epilogue warps =====================
     constexpr bool kOutBf16 = EPI < 2;
     constexpr bool kRes = (EPI & 1) != 0;
-    constexpr int kCols = BN / 2;       // columns per warp per sub-tile
+    constexpr int kCols = BN / 2;       // columns per epilogue warp (two warps share a lane quadrant)
     constexpr int kChunks = kCols / 32; // 32-column chunks per warp per sub-tile (1, 2 or 4)
-    using OutT = typename std::conditional<kOutBf16, __nv_bfloat16, float>::type;
+    constexpr int kRowB = kOutBf16 ? 64 : 128;          // bytes of one chunk row in the staging slot
+    constexpr int kUnits = kRowB / 16;                  // 16-byte units per row (4 / 8)
+    constexpr int kSlotBytes = 32 * kRowB;
     const int ew = warp - 2;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int half = ew >> 2;           // which half of the tile's columns
-    uint8_t* stage = smem_stage + ew * kStageBytes;
-    const int slot = lane & 3;          // coalesced domain: this lane owns columns 8*slot..8*slot+7 ...
-    const int rsub = lane >> 2;         // ... of rows 8*r + rsub, r = 0..3
+    uint8_t* const out_slot = smem_stage + ew * ((kRes ? 2 : 1) * kSlotBytes);
+    uint8_t* const res_slot = out_slot + kSlotBytes;
+    uint64_t* const my_res_bar = &res_bar[ew];
+    // this lane's row inside a slot: 16-byte unit u lives at row_off + ((u ^ swz) << 4)
+    const uint32_t swz = kOutBf16 ? ((lane >> 1) & 3) : (lane & 7);
+    uint8_t* const out_row = out_slot + lane * kRowB;
+    const uint8_t* const res_row = res_slot + lane * kRowB;
     // loop-invariant parameters in registers (the asm volatile barriers would otherwise force reloads)
-    const int N = p.N, M = p.M, ldo = p.ldo, ldr = p.ldr;
+    const int N = p.N;
     const bool relu = p.relu != 0, rnd = p.round_tf32 != 0, mask_en = p.mask_en != 0;
     const int mRPI = p.mRPI, mP = p.mP, mH = p.mH, mW = p.mW;
-    OutT* const out = reinterpret_cast<OutT*>(p.out);
-    const OutT* const res = reinterpret_cast<const OutT*>(p.res);   // residual has the output's dtype
-    const float* const bias = p.bias;
     const int m_tiles = p.m_tiles, acc_stages = p.acc_stages;
-    const bool aligned = ((ldo * static_cast<int>(sizeof(OutT))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
-                         (!kRes || (((ldr * static_cast<int>(sizeof(OutT))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)));
-
-    // residual of one 32x32 chunk in the coalesced domain (8 row segments of 4 columns per lane).
-    // The loads land in RAW registers and are converted at use: converting right after each load
-    // makes ptxas reuse one temporary and serialise the eight DRAM round trips.
-    struct F8 { float4 lo, hi; };
-    using ResRaw = typename std::conditional<kOutBf16, uint4, F8>::type;
-    auto load_res = [&](ResRaw (&rr)[4], int row_base, int col) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int row = min(row_base + 8 * r + rsub, M - 1);   // clamp instead of predicating: rows >= M are never stored
-        if constexpr (kOutBf16) {
-          rr[r] = *reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * ldr + col);
-        } else {
-          rr[r].lo = *reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * ldr + col);
-          rr[r].hi = *reinterpret_cast<const float4*>(res + static_cast<size_t>(row) * ldr + col + 4);
-        }
-      }
-    };
-    auto res_add = [&](float (&x)[8], const ResRaw& q) {
-      if constexpr (kOutBf16) {
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          x[2 * k] += __uint_as_float(w[k] << 16);
-          x[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
-        }
-      } else {
-        x[0] += q.lo.x; x[1] += q.lo.y; x[2] += q.lo.z; x[3] += q.lo.w;
-        x[4] += q.hi.x; x[5] += q.hi.y; x[6] += q.hi.z; x[7] += q.hi.w;
-      }
-    };
+    const bool has_bias = p.bias != nullptr;
+    {   // bias of all N tiles -> shared memory (zero beyond N), read back as warp-wide broadcasts
+      const int nb = min(p.n_tiles * BN, kBiasTable);
+      for (int i = threadIdx.x - 64; i < nb; i += 32 * kEpiWarps) s_bias[i] = (has_bias && i < N) ? __ldg(p.bias + i) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
 
     int acc = 0;
-    uint32_t accph = 0;
+    uint32_t accph = 0, resph = 0;
     const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
     long long w_accfull = 0;
-    // Residual registers are double buffered (chunk j reads buffer j&1 and prefetches chunk j+1 -- the
-    // first chunk of the CTA's next tile after the last one -- into the other buffer).  Copying a
-    // prefetched buffer into a "current" one would stall on the outstanding loads, so the chunk loops
-    // are fully unrolled and the buffers are selected at compile time; with an odd number of chunks
-    // per tile (BN = 64, MT = 1) consecutive tiles swap the two buffers.
-    constexpr int kChunksPerTile = MT * kChunks;
-    ResRaw rbuf0[4], rbuf1[4];
-    bool res_ready = false;   // the first buffer already holds the residual of the upcoming tile's first chunk
+    const int tstep = static_cast<int>(gridDim.x);
 
-    auto epi_tile = [&](int tile, ResRaw (&bufA)[4], ResRaw (&bufB)[4]) {
+    auto issue_res = [&](int row0, int col0) {          // lane 0 only
+      mbar_expect_tx(my_res_bar, kSlotBytes);
+      tma_load_2d(res_slot, &mapRes, my_res_bar, col0, row0);
+    };
+    if (kRes && lane == 0 && static_cast<int>(blockIdx.x) < total_tiles) {
+      const int t0 = blockIdx.x;
+      issue_res(tile_m0(p, t0 % m_tiles, MT) + quad * 32, (t0 / m_tiles) * BN + half * kCols);
+    }
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += tstep) {
       const int m0 = tile_m0(p, tile % m_tiles, MT);
       const int n0 = (tile / m_tiles) * BN;
       const int colw = n0 + half * kCols;               // first column this warp owns
-      const bool fast = aligned && (colw + kCols <= N); // whole warp slice in range and vectorisable
       // ---- work that does not need the accumulator: done while the MMAs are still running
-      uint32_t pix_mask[MT];
+      bool pix[MT];
 #pragma unroll
       for (int sub = 0; sub < MT; ++sub) {
-        bool pix = true;
+        pix[sub] = true;
         if (mask_en) {
           const int rem = (m0 + sub * 128 + quad * 32 + lane) % mRPI;
-          pix = (rem / mP) < mH && (rem % mP) < mW;
-        }
-        pix_mask[sub] = __ballot_sync(0xffffffffu, pix);
-      }
-      float b8[kChunks][8];
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int col = colw + 32 * c + 8 * slot;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) b8[c][k] = 0.f;
-        if (bias) {
-          if (fast) {
-            const float4 lo = __ldg(reinterpret_cast<const float4*>(bias + col));
-            const float4 hi = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-            b8[c][0] = lo.x; b8[c][1] = lo.y; b8[c][2] = lo.z; b8[c][3] = lo.w;
-            b8[c][4] = hi.x; b8[c][5] = hi.y; b8[c][6] = hi.z; b8[c][7] = hi.w;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) b8[c][k] = col + k < N ? __ldg(bias + col + k) : 0.f;
-          }
+          pix[sub] = (rem / mP) < mH && (rem % mP) < mW;
         }
       }
-      if (kRes && fast && !res_ready) load_res(bufA, m0 + quad * 32, colw + 8 * slot);   // first tile only
-      res_ready = false;
-      // the tile after this one (its first chunk's residual is prefetched during this tile's last chunk)
-      const int ntile = tile + static_cast<int>(gridDim.x);
-      const int n_m0 = (ntile % m_tiles) * 128 * MT;
-      const int n_colw = (ntile / m_tiles) * BN + half * kCols;
-      const bool n_fast = ntile < total_tiles && aligned && (n_colw + kCols <= N);
+      const int ntile = tile + tstep;                   // the residual of its first chunk is prefetched at the end
+      const bool has_ntile = ntile < total_tiles;
+      const int n_row0 = tile_m0(p, ntile % m_tiles, MT) + quad * 32;
+      const int n_col0 = (ntile / m_tiles) * BN + half * kCols;
 
       mbar_wait_t(&acc_full[acc], accph, timed, w_accfull);
       tc_fence_after();
       if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(5);
 #pragma unroll
       for (int sub = 0; sub < MT; ++sub) {
-        const int row_base = m0 + sub * 128 + quad * 32;
+        const int row0 = m0 + sub * 128 + quad * 32;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (BN * MT) + sub * BN +
                                half * kCols;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
-          const int j = sub * kChunks + c;              // compile-time chunk index within the tile
-          ResRaw (&rcur)[4] = (j & 1) ? bufB : bufA;
-          ResRaw (&rnxt)[4] = (j & 1) ? bufA : bufB;
-          const int col0 = colw + 32 * c;               // first column of this 32-wide chunk
-          if (col0 < N) {                               // warp-uniform
-          const int col = col0 + 8 * slot;              // this lane's 8 columns in the coalesced domain
+          const int col0 = colw + 32 * c;               // first column of this 32-wide chunk (warp-uniform)
+          if (!kRes && col0 >= N) continue;             // chunk entirely beyond N (the residual chain never skips)
           uint32_t v[32];
-          __syncwarp();                                 // previous chunk's stage reads are done; ld is .sync.aligned
+          __syncwarp();                                 // tcgen05.ld is .sync.aligned
           tmem_ld32(taddr + 32 * c, v);
-          // prefetch the next chunk's residual while the TMEM load is in flight
-          if (kRes) {
-            if (j + 1 < kChunksPerTile) {
-              if (fast) {
-                const int nsub = (c + 1 < kChunks) ? sub : sub + 1;
-                const int nc = (c + 1 < kChunks) ? c + 1 : 0;
-                load_res(rnxt, m0 + nsub * 128 + quad * 32, colw + 32 * nc + 8 * slot);
-              }
-            } else if (n_fast) {
-              load_res(rnxt, n_m0 + quad * 32, n_colw + 8 * slot);
-              res_ready = true;
-            }
-          }
+          const float* bsrc = s_bias + col0;            // table covers every N tile of the launch
+          if (kRes) mbar_wait(my_res_bar, resph);       // this chunk's residual box has landed
           tmem_ld_wait();
-          stage_write(stage, lane, v);
-          __syncwarp();
-          if (fast) {
-            OutT* orow = out + static_cast<size_t>(row_base + rsub) * ldo + col;
-            const size_t ostep = static_cast<size_t>(8) * ldo;
+          float x[32];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const int lrow = 8 * r + rsub;
-              const float4 lo = stage_read(stage, lrow, 2 * slot);
-              const float4 hi = stage_read(stage, lrow, 2 * slot + 1);
-              float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
+          if (has_bias) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) x[k] += b8[c][k];
-              if (kRes) res_add(x, rcur[r]);
-              if (relu) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = fmaxf(x[k], 0.f);
-              }
-              const bool keep = ((pix_mask[sub] >> lrow) & 1u) != 0;   // keep the grid's shared zero padding intact
-#pragma unroll
-              for (int k = 0; k < 8; ++k) x[k] = keep ? x[k] : 0.f;
-              if (TF32 && rnd) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = round_tf32_rna(x[k]);
-              }
-              if (row_base + lrow < M) {
-                if constexpr (kOutBf16) {
-                  uint4 q;
-                  q.x = pack_bf16x2(x[0], x[1]); q.y = pack_bf16x2(x[2], x[3]);
-                  q.z = pack_bf16x2(x[4], x[5]); q.w = pack_bf16x2(x[6], x[7]);
-                  *reinterpret_cast<uint4*>(orow) = q;
-                } else {
-                  *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
-                  *reinterpret_cast<float4*>(orow + 4) = make_float4(x[4], x[5], x[6], x[7]);
-                }
-              }
-              orow += ostep;
-            }
-          } else {
-            // ragged / unaligned slice (N not a multiple of 32, odd leading dimensions): scalar, guarded
-#pragma unroll 1
-            for (int r = 0; r < 4; ++r) {
-              const int lrow = 8 * r + rsub;
-              const int row = row_base + lrow;
-              const float4 lo = stage_read(stage, lrow, 2 * slot);
-              const float4 hi = stage_read(stage, lrow, 2 * slot + 1);
-              const float xe[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-              if (row < M) {
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  if (col + jj < N) {
-                    float e = xe[jj] + b8[c][jj];
-                    if (kRes) e += static_cast<float>(res[static_cast<size_t>(row) * ldr + col + jj]);
-                    if (relu) e = fmaxf(e, 0.f);
-                    if (!((pix_mask[sub] >> lrow) & 1u)) e = 0.f;
-                    if (TF32 && rnd) e = round_tf32_rna(e);
-                    out[static_cast<size_t>(row) * ldo + col + jj] = static_cast<OutT>(e);
-                  }
-                }
-              }
+            for (int k = 0; k < 8; ++k) {
+              const float4 bq = *reinterpret_cast<const float4*>(bsrc + 4 * k);   // same address in every lane: broadcast
+              x[4 * k] += bq.x; x[4 * k + 1] += bq.y; x[4 * k + 2] += bq.z; x[4 * k + 3] += bq.w;
             }
           }
-          }  // col0 < N
+          if constexpr (kRes) {
+            resph ^= 1u;
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u) {
+              const uint4 q = *reinterpret_cast<const uint4*>(res_row + ((u ^ swz) << 4));
+              if constexpr (kOutBf16) {
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  x[8 * u + 2 * k] += __uint_as_float(w[k] << 16);
+                  x[8 * u + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+                }
+              } else {
+                x[4 * u] += __uint_as_float(q.x); x[4 * u + 1] += __uint_as_float(q.y);
+                x[4 * u + 2] += __uint_as_float(q.z); x[4 * u + 3] += __uint_as_float(q.w);
+              }
+            }
+            __syncwarp();                               // every lane has consumed the residual slot
+            if (lane == 0) {                            // prefetch the next chunk's residual box
+              const bool last = (sub == MT - 1) && (c == kChunks - 1);
+              if (!last) issue_res(m0 + ((c + 1 < kChunks) ? sub : sub + 1) * 128 + quad * 32,
+                                   colw + 32 * ((c + 1 < kChunks) ? c + 1 : 0));
+              else if (has_ntile) issue_res(n_row0, n_col0);
+            }
+          }
+          if (lane == 0) bulk_wait_read0();             // the previous chunk's TMA store has drained the out slot
+          __syncwarp();
+          if constexpr (kOutBf16) {
+            uint32_t w[16];
+            if (relu) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) w[k] = pack_relu_bf16x2(x[2 * k], x[2 * k + 1]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) w[k] = pack_bf16x2(x[2 * k], x[2 * k + 1]);
+            }
+            if (!pix[sub]) {                            // keep the grid's shared zero padding intact
+#pragma unroll
+              for (int k = 0; k < 16; ++k) w[k] = 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u)
+              *reinterpret_cast<uint4*>(out_row + ((u ^ swz) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+          } else {
+            if (relu) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) x[k] = fmaxf(x[k], 0.f);
+            }
+            if (!pix[sub]) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) x[k] = 0.f;
+            }
+            if (TF32 && rnd) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) x[k] = round_tf32_rna(x[k]);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnits; ++u)
+              *reinterpret_cast<float4*>(out_row + ((u ^ swz) << 4)) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+          }
+          fence_proxy_async();                          // staging writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapOut, out_slot, col0, row0);
+            bulk_commit();
+          }
         }
       }
       if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(13);
@@ -631,19 +592,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(6);
-      if (warp == 2 && tile + static_cast<int>(gridDim.x) >= total_tiles) VQA_DBG(7);
+      if (warp == 2 && tile + tstep >= total_tiles) VQA_DBG(7);
       if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
-    };
-
-    const int tstep = static_cast<int>(gridDim.x);
-    if constexpr (kChunksPerTile % 2 == 0) {
-      for (int tile = blockIdx.x; tile < total_tiles; tile += tstep) epi_tile(tile, rbuf0, rbuf1);
-    } else {
-      for (int tile = blockIdx.x; tile < total_tiles; tile += 2 * tstep) {
-        epi_tile(tile, rbuf0, rbuf1);
-        if (tile + tstep < total_tiles) epi_tile(tile + tstep, rbuf1, rbuf0);
-      }
     }
+    if (lane == 0) bulk_wait_all();                     // outstanding TMA stores complete before the CTA exits
     if (timed && lane == 0) p.dbg[21] = w_accfull;
   }
 
@@ -651,6 +603,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
   if (warp == 0) VQA_DBG(8);
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    p.dbg[23] = static_cast<long long>(ns);
+  }
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -698,6 +655,34 @@ int encode_2d(CUtensorMap* map, bool tf32, uint64_t base, int rows, int cols, in
   return VQA_OK;
 }
 
+// Epilogue tensor map over the output (or residual) matrix: 32 x 32 element boxes, SWIZZLE_64B for bf16
+// (64-byte box rows) / SWIZZLE_128B for fp32 (128-byte box rows), matching the staging slots of the kernel.
+int encode_box32(CUtensorMap* map, bool f32, uint64_t base, int rows, int cols, int ld, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  VQA_REQUIRE(fn != nullptr, VQA_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int esz = f32 ? 4 : 2;
+  VQA_REQUIRE(base != 0 && (base & 15) == 0, VQA_E_ALIGN, std::string(what) + ": base must be 16-byte aligned");
+  VQA_REQUIRE((static_cast<long long>(ld) * esz) % 16 == 0 && ld >= cols, VQA_E_ALIGN,
+              std::string(what) + ": leading dimension must be >= N and a multiple of 16 bytes");
+  // measured on B200: a TMA store clips the N edge in whole 16-byte granules, so a ragged last granule
+  // would overwrite up to 3 elements of padding
+  VQA_REQUIRE((static_cast<long long>(cols) * esz) % 16 == 0, VQA_E_ALIGN,
+              std::string(what) + ": N must be a multiple of 16 bytes (4 fp32 / 8 bf16 columns)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  reinterpret_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vqa_set_error(std::string(what) + ": cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return VQA_E_CUDA;
+  }
+  return VQA_OK;
+}
+
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format f32 [4,6)=1,
 // a/b format [7,10)/[10,13) (1 = bf16, 2 = tf32), K-major A and B, N>>3 at [17,23), M>>4 at [24,29).
 uint32_t make_idesc(bool tf32, int n) {
@@ -716,7 +701,8 @@ int num_sms(int device) {
 
 }  // namespace
 
-typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const GemmParams);
 
 // Instantiated (BN, MT, operand type, epilogue) combinations: bf16 kernels with epilogues 0/1/2
 // (convolutions, image projector), tf32 kernels with MT = 1 and epilogues 2/3 (all nn.Linear layers).
@@ -744,7 +730,8 @@ static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_byte
 struct GemmLaunch {
   GemmKernelFn fn;
   int epi;
-  CUtensorMap mapA0, mapA1, mapB;
+  CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes;
+  bool out_external;    // the output is a caller tensor (logits): its map is encoded per run
   GemmParams prm;
   dim3 grid;
   int bn;
@@ -844,11 +831,19 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.n_tiles = (p.N + bn - 1) / bn;        // only N tiles that contain real columns run
   p.acc_stages = (2 * p.MT * bn <= 512) ? 2 : 1;
 
-  // shared-memory plan: one CTA per SM (persistent), ~210 KB of rings
+  const bool has_res = op.p[GEMM_P_res] != 0;
+  p.out_dtype = I[GEMM_I_out_dtype];
+  p.res_dtype = I[GEMM_I_res_dtype];
+  VQA_REQUIRE(!has_res || p.res_dtype == p.out_dtype, VQA_E_INVALID, "gemm: the residual must have the output's dtype");
+  L->epi = pool ? 4 : (p.out_dtype == 0 ? 0 : 2) + (has_res ? 1 : 0);
+  VQA_REQUIRE(p.n_tiles * bn <= kBiasTable, VQA_E_INVALID, "gemm: N exceeds the epilogue's bias table");
+
+  // shared-memory plan: one CTA per SM (persistent): rings + epilogue staging + bias table + barriers <= 227 KB
+  const int stage_bytes = epi_stage_bytes(L->epi);
+  const int fixed_bytes = 1024 + stage_bytes + 4 * kBiasTable + 8 * (2 * kMaxASlots + 2 * kMaxBSlots + 4 + kEpiWarps) + 16 +
+                          4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS;
   int budget = I[GEMM_I_smem_budget];
-  if (budget <= 0) budget = 190 * 1024;   // + 32 KB of epilogue staging + barriers stays under 227 KB
-  const int stage_bytes = pool ? 384 * 128 : kEpiWarps * kStageBytes;   // pool mode: the bf16 conv tile lives there
-  budget -= stage_bytes - kEpiWarps * kStageBytes;
+  if (budget <= 0 || budget > 227 * 1024 - fixed_bytes) budget = 227 * 1024 - fixed_bytes;
   const long long b_all = static_cast<long long>(p.k_chunks) * p.b_slot_bytes;
   p.b_resident = (p.n_tiles == 1 && b_all <= 96 * 1024 && b_all + 2LL * p.a_slot_bytes <= budget) ? 1 : 0;
   if (p.b_resident) {
@@ -866,8 +861,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
     p.b_slots = s < 2 ? 2 : (s > kMaxBSlots ? kMaxBSlots : s);
   }
   const long long b_bytes = p.b_resident ? b_all : static_cast<long long>(p.b_slots) * p.b_slot_bytes;
-  L->smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(b_bytes) +
-            8 * (2 * kMaxASlots + 2 * kMaxBSlots + 6) + 16 + 4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS + stage_bytes;
+  L->smem = static_cast<size_t>(fixed_bytes) + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(b_bytes);
   VQA_REQUIRE(L->smem <= 227 * 1024, VQA_E_INVALID, "gemm: shared memory budget exceeded");
 
   // tensor maps (only for non-external operands: A and W always live in the arenas)
@@ -889,8 +883,6 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
 
   p.ldo = I[GEMM_I_ldo];
   p.ldr = I[GEMM_I_ldr];
-  p.out_dtype = I[GEMM_I_out_dtype];
-  p.res_dtype = I[GEMM_I_res_dtype];
   p.relu = I[GEMM_I_relu];
   p.round_tf32 = I[GEMM_I_round_tf32];
   p.mask_en = I[GEMM_I_mask_en];
@@ -911,13 +903,22 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   if (I[GEMM_I_max_ctas] > 0 && I[GEMM_I_max_ctas] < sms) sms = I[GEMM_I_max_ctas];   // tests: force many tiles per CTA
   L->grid = dim3(tiles < sms ? tiles : sms, 1, 1);
 
-  const bool has_res = op.p[GEMM_P_res] != 0;
-  VQA_REQUIRE(!has_res || p.res_dtype == p.out_dtype, VQA_E_INVALID, "gemm: the residual must have the output's dtype");
-  L->epi = (p.out_dtype == 0 ? 0 : 2) + (has_res ? 1 : 0);
+  L->out_external = (L->out_raw & VQA_EXT_TAG) != 0;
+  L->mapOut = L->mapA0;
+  L->mapRes = L->mapA0;
   if (pool) {
-    VQA_REQUIRE(!has_res && p.out_dtype == 0 && (op.p[GEMM_P_out] & VQA_EXT_TAG) == 0, VQA_E_INVALID,
+    VQA_REQUIRE(!has_res && p.out_dtype == 0 && !L->out_external, VQA_E_INVALID,
                 "gemm: the pooled output is a bf16 arena buffer without residual");
-    L->epi = 4;
+  } else {
+    if (!L->out_external) {
+      rc = encode_box32(&L->mapOut, p.out_dtype != 0, L->out_raw, p.M, p.N, p.ldo, "gemm output");
+      if (rc) return rc;
+    }
+    if (has_res) {
+      VQA_REQUIRE(!(L->res_raw & VQA_EXT_TAG), VQA_E_INVALID, "gemm: the residual must be an arena buffer");
+      rc = encode_box32(&L->mapRes, p.res_dtype != 0, L->res_raw, p.M, p.N, p.ldr, "gemm residual");
+      if (rc) return rc;
+    }
   }
   L->fn = pick_kernel(bn, p.MT, tf32, L->epi, p.row_bytes);
   VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT/dtype/epilogue");
@@ -932,7 +933,14 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
   p.out = reinterpret_cast<void*>(vqa_resolve(L->out_raw, ext, n_ext));
   p.res = reinterpret_cast<const void*>(vqa_resolve(L->res_raw, ext, n_ext));
   VQA_REQUIRE(p.out != nullptr, VQA_E_INVALID, "gemm: unresolved external output");
-  L->fn<<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, p);
+  if (L->out_external) {   // caller-owned output: encode its store map for this call (host-only work, graph-capturable)
+    CUtensorMap mo;
+    int rc = encode_box32(&mo, p.out_dtype != 0, reinterpret_cast<uint64_t>(p.out), p.M, p.N, p.ldo, "gemm output");
+    if (rc) return rc;
+    L->fn<<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, mo, L->mapRes, p);
+  } else {
+    L->fn<<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, L->mapOut, L->mapRes, p);
+  }
   VQA_LAUNCH_OK("gemm_tap_kernel");
   return VQA_OK;
 }

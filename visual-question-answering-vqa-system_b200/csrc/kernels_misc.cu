@@ -228,6 +228,16 @@ __global__ void spatial_map_kernel(const uint4* __restrict__ src, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// COPY_ROWS: dst[r, c] = src[r, c] between two leading dimensions (un-padding of the logits).
+__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int ld_src,
+                                 int ld_dst) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(t / cols), c = static_cast<int>(t - static_cast<long long>(r) * cols);
+  dst[static_cast<size_t>(r) * ld_dst + c] = src[static_cast<size_t>(r) * ld_src + c];
+}
+
+// ------------------------------------------------------------------------------------------------
 // x*scale[c]*att[pixel] -> bf16, written either on the same grid (mode 0) or as the 4-phase split
 // the next stage's stride-2 convolutions read (mode 1).  One thread = one dst row x 8 channels.
 __global__ void scale_relayout_kernel(const uint4* __restrict__ src, const float* __restrict__ scale,
@@ -667,6 +677,14 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_LAUNCH_OK("grid_to_nchw_kernel");
       return VQA_OK;
     }
+    case VQA_OP_COPY_ROWS: {
+      const long long total = static_cast<long long>(I[COPY_ROWS_I_rows]) * I[COPY_ROWS_I_cols];
+      copy_rows_kernel<<<blocks_for(total, 256), 256, 0, st>>>(PTR(const float*, COPY_ROWS_P_src), PTR(float*, COPY_ROWS_P_dst),
+                                                               I[COPY_ROWS_I_rows], I[COPY_ROWS_I_cols],
+                                                               I[COPY_ROWS_I_ld_src], I[COPY_ROWS_I_ld_dst]);
+      VQA_LAUNCH_OK("copy_rows_kernel");
+      return VQA_OK;
+    }
     case VQA_OP_MASK_PREP: {
       const int n = I[MASK_PREP_I_B] * I[MASK_PREP_I_L];
       const void* src = PTR(const void*, MASK_PREP_P_src);
@@ -773,6 +791,7 @@ const char* misc_kernel_name(int kind) {
     case VQA_OP_SCALE_RELAYOUT: return "scale_relayout_kernel";
     case VQA_OP_GRID_TO_NCHW: return "grid_to_nchw_kernel";
     case VQA_OP_MASK_PREP: return "mask_prep_kernel";
+    case VQA_OP_COPY_ROWS: return "copy_rows_kernel";
     case VQA_OP_EMBED: return "embed_kernel";
     case VQA_OP_LAYERNORM: return "layernorm256_kernel";
     case VQA_OP_SELF_ATTN: return "attn_warp_kernel(self)";

@@ -38,6 +38,7 @@ const FieldCount kFields[VQA_OP_KIND_MAX] = {
     {SOFTMAX_TOPK_NI, SOFTMAX_TOPK_NP, SOFTMAX_TOPK_NF},
     {MASK_PREP_NI, MASK_PREP_NP, MASK_PREP_NF},
     {GRID_TO_NCHW_NI, GRID_TO_NCHW_NP, GRID_TO_NCHW_NF},
+    {COPY_ROWS_NI, COPY_ROWS_NP, COPY_ROWS_NF},
 };
 static_assert(GEMM_NI <= VQA_OP_NI, "VqaOp.i too small for the gemm op");
 static_assert(POOL_GATE_LN_NP <= VQA_OP_NP, "VqaOp.p too small");

@@ -35,6 +35,7 @@ KINDS = {
     "ingest": 1, "gemm": 2, "maxpool": 3, "se_squeeze": 4, "se_excite": 5, "spatial_map": 6,
     "scale_relayout": 7, "embed": 8, "layernorm": 9, "self_attn": 10, "cross_attn": 11,
     "pool_gate_ln": 12, "softmax_topk": 13, "mask_prep": 14, "grid_to_nchw": 15,
+    "copy_rows": 16,
 }
 
 _GROUPS = [f"g_{k}{g}" for k in ("map", "delta", "acol", "chunks", "ntaps", "kbase", "tap0")
@@ -70,6 +71,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
     "softmax_topk": {"i": ["B", "N", "k", "ld"], "p": ["logits", "idx", "probs"], "f": []},
     "mask_prep": {"i": ["B", "L", "dtype"], "p": ["src", "dst"], "f": []},
     "grid_to_nchw": {"i": ["B", "C", "H", "W", "P", "RPI"], "p": ["src", "dst"], "f": []},
+    "copy_rows": {"i": ["rows", "cols", "ld_src", "ld_dst"], "p": ["src", "dst"], "f": []},
 }
 
 DT_BF16, DT_TF32 = 0, 1          # gemm operand dtype
@@ -719,7 +721,16 @@ class Program(OpList):
         h1 = self._buf("head.h1", f32, B, D)
         self.linear("head0", fused, B, D, "head0.w", "head0.b", h0, 2 * D, relu=True, rnd=True)
         self.linear("head1", h0, B, 2 * D, "head1.w", "head1.b", h1, D, relu=True, rnd=True)
-        self.linear("head2", h1, B, D, "head2.w", "head2.b", ExtRef(EXT["logits"]), NA, ldo=NA)
+        if NA % 4 == 0:
+            self.linear("head2", h1, B, D, "head2.w", "head2.b", ExtRef(EXT["logits"]), NA, ldo=NA)
+        else:
+            # the GEMM epilogue stores through TMA (16-byte row pitch and N granules): an odd num_answers goes
+            # through a padded scratch matrix (the padded weight rows / bias entries are zero)
+            nap = (NA + 3) // 4 * 4
+            lg = self._buf("head.logits_padded", f32, B, nap)
+            self.linear("head2", h1, B, D, "head2.w", "head2.b", lg, nap, ldo=nap)
+            self._op("copy_rows", "head2.unpad", dict(rows=B, cols=NA, ld_src=nap, ld_dst=NA),
+                     dict(src=lg, dst=ExtRef(EXT["logits"])))
         if self.top_k:
             self._op("softmax_topk", "topk", dict(B=B, N=NA, k=self.top_k, ld=NA),
                      dict(logits=ExtRef(EXT["logits"]), idx=ExtRef(EXT["top_idx"]), probs=ExtRef(EXT["top_probs"])))
