@@ -176,6 +176,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) VQA_DBG(1);
+  // Programmatic dependent launch: the next kernel of the stream may start its own prologue now; this one
+  // has done everything that does not depend on its predecessors (barriers, TMEM, descriptor prefetch).
+  if (warp == 1) pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -196,6 +199,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         __syncwarp();
         b_loaded = true;
       }
+      if (tile == static_cast<int>(blockIdx.x)) pdl_wait();   // weights are constants; the activations are not
       for (int g = 0; g < p.ngroups; ++g) {
         const CUtensorMap* mapA = p.g_map[g] ? &mapA1 : &mapA0;
         const int row0 = m0 + p.g_delta[g] - p.halo;
@@ -345,6 +349,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int cP = p.pool_P, Wo = p.pool_Wo, Ho = p.pool_Ho, Po = p.pool_Po, rpio = p.pool_rpio, tpi = p.tiles_per_img;
     uint4* const out = reinterpret_cast<uint4*>(p.out);
     const bool has_bias = bias != nullptr;             // the VQA stem folds its bias into K (ingest writes a 1 column)
+    pdl_wait();                                        // the output buffer may still be read by a predecessor
     int acc = 0;
     uint32_t accph = 0;
     const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
@@ -455,6 +460,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       for (int i = threadIdx.x - 64; i < nb; i += 32 * kEpiWarps) s_bias[i] = (has_bias && i < N) ? __ldg(p.bias + i) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    pdl_wait();   // residual loads / output stores below touch buffers of the preceding kernels
 
     int acc = 0;
     uint32_t accph = 0, resph = 0;
@@ -937,9 +943,10 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
     CUtensorMap mo;
     int rc = encode_box32(&mo, p.out_dtype != 0, reinterpret_cast<uint64_t>(p.out), p.M, p.N, p.ldo, "gemm output");
     if (rc) return rc;
-    L->fn<<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, mo, L->mapRes, p);
+    VQA_CUDA_OK(vqa_launch(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->mapA0, L->mapA1, L->mapB, mo, L->mapRes, p));
   } else {
-    L->fn<<<L->grid, kThreads, L->smem, stream>>>(L->mapA0, L->mapA1, L->mapB, L->mapOut, L->mapRes, p);
+    VQA_CUDA_OK(vqa_launch(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->mapA0, L->mapA1, L->mapB, L->mapOut,
+                           L->mapRes, p));
   }
   VQA_LAUNCH_OK("gemm_tap_kernel");
   return VQA_OK;

@@ -27,6 +27,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // the stem GEMM adds its bias through two K columns (bias_hi + bias_lo) instead of in the epilogue.
 __global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ dst, int B, int mode, int P,
                               int rows, int ones) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int rpi = P * P;
@@ -82,6 +84,8 @@ __global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ 
 // MAXPOOL 3x3/2 p1 on padded-flat bf16 grids; one thread = one output row x 8 channels.
 __global__ void maxpool_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int C8, int Hin, int Win,
                                int Pin, int RPIin, int Hout, int Wout, int Pout, int RPIout) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * RPIout * C8;
   if (t >= total) return;
@@ -124,6 +128,8 @@ __global__ void maxpool_kernel(const uint4* __restrict__ src, uint4* __restrict_
 // S partials in a fixed order, so the result is deterministic (no atomics).
 __global__ void se_squeeze_kernel(const uint4* __restrict__ src, float* __restrict__ sums, int C8, int H, int W, int P,
                                   int RPI) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [lanes][C8*8]
   const int n = blockIdx.x;
   const int lanes = blockDim.x / C8;
@@ -154,6 +160,8 @@ __global__ void se_squeeze_kernel(const uint4* __restrict__ src, float* __restri
 __global__ void se_excite_kernel(const float* __restrict__ sums, const float* __restrict__ w1,
                                  const float* __restrict__ w2, float* __restrict__ scale, int C, int R, int S,
                                  float inv_hw) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // mean[C], hid[R]
   float* mean = sm;
   float* hid = sm + C;
@@ -184,6 +192,8 @@ __global__ void se_excite_kernel(const float* __restrict__ sums, const float* __
 __global__ void spatial_map_kernel(const uint4* __restrict__ src, const float* __restrict__ scale,
                                    const float* __restrict__ wconv, float* __restrict__ att, int C8, int H, int W,
                                    int P, int RPI, int ks) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // mx[H*W], av[H*W], sc[C]
   const int HW = H * W, C = C8 * 8;
   float* mx = sm;
@@ -231,6 +241,8 @@ __global__ void spatial_map_kernel(const uint4* __restrict__ src, const float* _
 // COPY_ROWS: dst[r, c] = src[r, c] between two leading dimensions (un-padding of the logits).
 __global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int ld_src,
                                  int ld_dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(t / cols), c = static_cast<int>(t - static_cast<long long>(r) * cols);
@@ -243,6 +255,8 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, float* __restric
 __global__ void scale_relayout_kernel(const uint4* __restrict__ src, const float* __restrict__ scale,
                                       const float* __restrict__ att, uint4* __restrict__ dst, int B, int C8, int H,
                                       int W, int P, int RPI, int mode, int Po, int RPIo, int phase_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total_rows = mode ? 4LL * phase_rows : static_cast<long long>(B) * RPIo;
   if (t >= total_rows * C8) return;
@@ -277,6 +291,8 @@ __global__ void scale_relayout_kernel(const uint4* __restrict__ src, const float
 
 __global__ void grid_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int B, int C,
                                     int H, int W, int P, int RPI) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(B) * C * H * W) return;
   const int w = static_cast<int>(t % W);
@@ -288,6 +304,8 @@ __global__ void grid_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
 
 // ------------------------------------------------------------------------------------------------
 __global__ void mask_prep_kernel(const void* __restrict__ src, int* __restrict__ dst, int n, int dtype) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   int v = 1;
@@ -301,6 +319,8 @@ __global__ void mask_prep_kernel(const void* __restrict__ src, int* __restrict__
 // x = table[ids]*sqrt(D) (pre-scaled at load) + pe[l]   (models/text_encoder.py:504-512)
 __global__ void embed_kernel(const long long* __restrict__ ids, const float4* __restrict__ table,
                              const float4* __restrict__ pe, float4* __restrict__ dst, int T, int L, int D4, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T * D4) return;
   const int tok = t / D4, d = t - tok * D4;
@@ -318,6 +338,8 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
                                     const float* __restrict__ beta, float* __restrict__ dst,
                                     const float* __restrict__ pos, int rows, int ld, int mode, int rnd, int S, int Pg,
                                     int RPIg, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -376,6 +398,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_warp_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                  const int* __restrict__ mask, float* __restrict__ out, float* __restrict__ weights, int n_units,
                  int H, int L, int T, int ld_q, int ld_kv) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * kAttnWarps + warp;     // (pair, head)
@@ -454,6 +478,8 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
                     const float* __restrict__ wg, const float* __restrict__ bg, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float* __restrict__ fused, float* __restrict__ att_pooled,
                     float* __restrict__ txt_pooled, int B, int L, int use_gate, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = 256;
   __shared__ float cat[kTailRows][2 * D];
   __shared__ float gate[kTailRows][D];
@@ -542,6 +568,8 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
 // distinct values (models/vqa_model.py:336-337, api/inference.py:231-234).
 __global__ void softmax_topk_kernel(const float* __restrict__ logits, long long* __restrict__ idx,
                                     float* __restrict__ probs, int N, int k, int ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // vals[N], red[64]
   float* vals = sm;
   float* red = sm + N;
@@ -608,18 +636,18 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(src != nullptr, VQA_E_INVALID, "ingest: null images");
       VQA_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 || I[INGEST_I_mode] == 1, VQA_E_ALIGN,
                   "ingest: fp32 images must be 8-byte aligned");
-      ingest_kernel<<<blocks_for(rows, 256), 256, 0, st>>>(src, PTR(uint4*, INGEST_P_dst), I[INGEST_I_B],
-                                                            I[INGEST_I_mode], I[INGEST_I_P], rows, I[INGEST_I_ones]);
+      VQA_CUDA_OK(vqa_launch(ingest_kernel, dim3(blocks_for(rows, 256)), dim3(256), 0, st, src, PTR(uint4*, INGEST_P_dst), I[INGEST_I_B],
+                                                            I[INGEST_I_mode], I[INGEST_I_P], rows, I[INGEST_I_ones]));
       VQA_LAUNCH_OK("ingest_kernel");
       return VQA_OK;
     }
     case VQA_OP_MAXPOOL: {
       const int C8 = I[MAXPOOL_I_C] / 8;
       const long long total = static_cast<long long>(I[MAXPOOL_I_B]) * I[MAXPOOL_I_RPIout] * C8;
-      maxpool_kernel<<<blocks_for(total, 256), 256, 0, st>>>(
+      VQA_CUDA_OK(vqa_launch(maxpool_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, 
           PTR(const uint4*, MAXPOOL_P_src), PTR(uint4*, MAXPOOL_P_dst), I[MAXPOOL_I_B], C8, I[MAXPOOL_I_Hin],
           I[MAXPOOL_I_Win], I[MAXPOOL_I_Pin], I[MAXPOOL_I_RPIin], I[MAXPOOL_I_Hout], I[MAXPOOL_I_Wout],
-          I[MAXPOOL_I_Pout], I[MAXPOOL_I_RPIout]);
+          I[MAXPOOL_I_Pout], I[MAXPOOL_I_RPIout]));
       VQA_LAUNCH_OK("maxpool_kernel");
       return VQA_OK;
     }
@@ -630,18 +658,18 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const size_t smem = static_cast<size_t>(threads) * 8 * sizeof(float);
       const int slices = I[SE_SQUEEZE_I_S];
       VQA_REQUIRE(slices >= 1 && slices <= 64, VQA_E_INVALID, "se_squeeze: bad slice count");
-      se_squeeze_kernel<<<dim3(I[SE_SQUEEZE_I_B], slices), threads, smem, st>>>(PTR(const uint4*, SE_SQUEEZE_P_src),
+      VQA_CUDA_OK(vqa_launch(se_squeeze_kernel, dim3(dim3(I[SE_SQUEEZE_I_B], slices)), dim3(threads), smem, st, PTR(const uint4*, SE_SQUEEZE_P_src),
                                                                   PTR(float*, SE_SQUEEZE_P_sums), C8, I[SE_SQUEEZE_I_H],
                                                                   I[SE_SQUEEZE_I_W], I[SE_SQUEEZE_I_P],
-                                                                  I[SE_SQUEEZE_I_RPI]);
+                                                                  I[SE_SQUEEZE_I_RPI]));
       VQA_LAUNCH_OK("se_squeeze_kernel");
       return VQA_OK;
     }
     case VQA_OP_SE_EXCITE: {
       const int C = I[SE_EXCITE_I_C], R = I[SE_EXCITE_I_R];
-      se_excite_kernel<<<I[SE_EXCITE_I_B], 256, (C + R) * sizeof(float), st>>>(
+      VQA_CUDA_OK(vqa_launch(se_excite_kernel, dim3(I[SE_EXCITE_I_B]), dim3(256), (C + R) * sizeof(float), st, 
           PTR(const float*, SE_EXCITE_P_sums), PTR(const float*, SE_EXCITE_P_w1), PTR(const float*, SE_EXCITE_P_w2),
-          PTR(float*, SE_EXCITE_P_scale), C, R, I[SE_EXCITE_I_S], 1.f / static_cast<float>(I[SE_EXCITE_I_HW]));
+          PTR(float*, SE_EXCITE_P_scale), C, R, I[SE_EXCITE_I_S], 1.f / static_cast<float>(I[SE_EXCITE_I_HW])));
       VQA_LAUNCH_OK("se_excite_kernel");
       return VQA_OK;
     }
@@ -649,10 +677,10 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int C = I[SPATIAL_MAP_I_C], HW = I[SPATIAL_MAP_I_H] * I[SPATIAL_MAP_I_W];
       const size_t smem = (2 * HW + C) * sizeof(float);
       VQA_REQUIRE(smem <= 48 * 1024, VQA_E_INVALID, "spatial_map: feature map too large");
-      spatial_map_kernel<<<I[SPATIAL_MAP_I_B], 256, smem, st>>>(
+      VQA_CUDA_OK(vqa_launch(spatial_map_kernel, dim3(I[SPATIAL_MAP_I_B]), dim3(256), smem, st, 
           PTR(const uint4*, SPATIAL_MAP_P_src), PTR(const float*, SPATIAL_MAP_P_scale),
           PTR(const float*, SPATIAL_MAP_P_wconv), PTR(float*, SPATIAL_MAP_P_att), C / 8, I[SPATIAL_MAP_I_H],
-          I[SPATIAL_MAP_I_W], I[SPATIAL_MAP_I_P], I[SPATIAL_MAP_I_RPI], I[SPATIAL_MAP_I_ksize]);
+          I[SPATIAL_MAP_I_W], I[SPATIAL_MAP_I_P], I[SPATIAL_MAP_I_RPI], I[SPATIAL_MAP_I_ksize]));
       VQA_LAUNCH_OK("spatial_map_kernel");
       return VQA_OK;
     }
@@ -660,28 +688,28 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int C8 = I[SCALE_RELAYOUT_I_C] / 8, mode = I[SCALE_RELAYOUT_I_mode];
       const long long rows = mode ? 4LL * I[SCALE_RELAYOUT_I_phase_rows]
                                   : static_cast<long long>(I[SCALE_RELAYOUT_I_B]) * I[SCALE_RELAYOUT_I_RPIo];
-      scale_relayout_kernel<<<blocks_for(rows * C8, 256), 256, 0, st>>>(
+      VQA_CUDA_OK(vqa_launch(scale_relayout_kernel, dim3(blocks_for(rows * C8, 256)), dim3(256), 0, st, 
           PTR(const uint4*, SCALE_RELAYOUT_P_src), PTR(const float*, SCALE_RELAYOUT_P_scale),
           PTR(const float*, SCALE_RELAYOUT_P_att), PTR(uint4*, SCALE_RELAYOUT_P_dst), I[SCALE_RELAYOUT_I_B], C8,
           I[SCALE_RELAYOUT_I_H], I[SCALE_RELAYOUT_I_W], I[SCALE_RELAYOUT_I_P], I[SCALE_RELAYOUT_I_RPI], mode,
-          I[SCALE_RELAYOUT_I_Po], I[SCALE_RELAYOUT_I_RPIo], I[SCALE_RELAYOUT_I_phase_rows]);
+          I[SCALE_RELAYOUT_I_Po], I[SCALE_RELAYOUT_I_RPIo], I[SCALE_RELAYOUT_I_phase_rows]));
       VQA_LAUNCH_OK("scale_relayout_kernel");
       return VQA_OK;
     }
     case VQA_OP_GRID_TO_NCHW: {
       const long long total = static_cast<long long>(I[GRID_TO_NCHW_I_B]) * I[GRID_TO_NCHW_I_C] * I[GRID_TO_NCHW_I_H] *
                               I[GRID_TO_NCHW_I_W];
-      grid_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, st>>>(
+      VQA_CUDA_OK(vqa_launch(grid_to_nchw_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, 
           PTR(const __nv_bfloat16*, GRID_TO_NCHW_P_src), PTR(float*, GRID_TO_NCHW_P_dst), I[GRID_TO_NCHW_I_B],
-          I[GRID_TO_NCHW_I_C], I[GRID_TO_NCHW_I_H], I[GRID_TO_NCHW_I_W], I[GRID_TO_NCHW_I_P], I[GRID_TO_NCHW_I_RPI]);
+          I[GRID_TO_NCHW_I_C], I[GRID_TO_NCHW_I_H], I[GRID_TO_NCHW_I_W], I[GRID_TO_NCHW_I_P], I[GRID_TO_NCHW_I_RPI]));
       VQA_LAUNCH_OK("grid_to_nchw_kernel");
       return VQA_OK;
     }
     case VQA_OP_COPY_ROWS: {
       const long long total = static_cast<long long>(I[COPY_ROWS_I_rows]) * I[COPY_ROWS_I_cols];
-      copy_rows_kernel<<<blocks_for(total, 256), 256, 0, st>>>(PTR(const float*, COPY_ROWS_P_src), PTR(float*, COPY_ROWS_P_dst),
+      VQA_CUDA_OK(vqa_launch(copy_rows_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, PTR(const float*, COPY_ROWS_P_src), PTR(float*, COPY_ROWS_P_dst),
                                                                I[COPY_ROWS_I_rows], I[COPY_ROWS_I_cols],
-                                                               I[COPY_ROWS_I_ld_src], I[COPY_ROWS_I_ld_dst]);
+                                                               I[COPY_ROWS_I_ld_src], I[COPY_ROWS_I_ld_dst]));
       VQA_LAUNCH_OK("copy_rows_kernel");
       return VQA_OK;
     }
@@ -689,7 +717,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int n = I[MASK_PREP_I_B] * I[MASK_PREP_I_L];
       const void* src = PTR(const void*, MASK_PREP_P_src);
       VQA_REQUIRE(src != nullptr || I[MASK_PREP_I_dtype] == 0, VQA_E_INVALID, "mask_prep: null mask");
-      mask_prep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, PTR(int*, MASK_PREP_P_dst), n, I[MASK_PREP_I_dtype]);
+      VQA_CUDA_OK(vqa_launch(mask_prep_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, PTR(int*, MASK_PREP_P_dst), n, I[MASK_PREP_I_dtype]));
       VQA_LAUNCH_OK("mask_prep_kernel");
       return VQA_OK;
     }
@@ -697,20 +725,20 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int T = I[EMBED_I_B] * I[EMBED_I_L], D4 = I[EMBED_I_D] / 4;
       const long long* ids = PTR(const long long*, EMBED_P_ids);
       VQA_REQUIRE(ids != nullptr, VQA_E_INVALID, "embed: null token ids");
-      embed_kernel<<<blocks_for(static_cast<long long>(T) * D4, 256), 256, 0, st>>>(
+      VQA_CUDA_OK(vqa_launch(embed_kernel, dim3(blocks_for(static_cast<long long>(T) * D4, 256)), dim3(256), 0, st, 
           ids, PTR(const float4*, EMBED_P_table), PTR(const float4*, EMBED_P_pe), PTR(float4*, EMBED_P_dst), T,
-          I[EMBED_I_L], D4, I[EMBED_I_V]);
+          I[EMBED_I_L], D4, I[EMBED_I_V]));
       VQA_LAUNCH_OK("embed_kernel");
       return VQA_OK;
     }
     case VQA_OP_LAYERNORM: {
       VQA_REQUIRE(I[LAYERNORM_I_D] == 256, VQA_E_INVALID, "layernorm: D must be 256");
       const int rows = I[LAYERNORM_I_rows];
-      layernorm256_kernel<<<blocks_for(rows, 8), 256, 0, st>>>(
+      VQA_CUDA_OK(vqa_launch(layernorm256_kernel, dim3(blocks_for(rows, 8)), dim3(256), 0, st, 
           PTR(const float*, LAYERNORM_P_src), PTR(const float*, LAYERNORM_P_gamma), PTR(const float*, LAYERNORM_P_beta),
           PTR(float*, LAYERNORM_P_dst), PTR(const float*, LAYERNORM_P_pos), rows, I[LAYERNORM_I_ld_src],
           I[LAYERNORM_I_mode], I[LAYERNORM_I_round_tf32], I[LAYERNORM_I_S], I[LAYERNORM_I_Pg], I[LAYERNORM_I_RPIg],
-          op.f[LAYERNORM_F_eps]);
+          op.f[LAYERNORM_F_eps]));
       VQA_LAUNCH_OK("layernorm256_kernel");
       return VQA_OK;
     }
@@ -727,9 +755,9 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_set = true;
       }
-      attn_warp_kernel<<<blocks_for(static_cast<long long>(B) * H, kAttnWarps), kAttnWarps * 32, smem, st>>>(
+      VQA_CUDA_OK(vqa_launch(attn_warp_kernel, dim3(blocks_for(static_cast<long long>(B) * H, kAttnWarps)), dim3(kAttnWarps * 32), smem, st, 
           qkv, qkv + D, qkv + 2 * D, PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), nullptr, B * H, H,
-          L, L, ld, ld);
+          L, L, ld, ld));
       VQA_LAUNCH_OK("attn_warp_kernel");
       return VQA_OK;
     }
@@ -747,31 +775,31 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_set = true;
       }
-      attn_warp_kernel<<<blocks_for(static_cast<long long>(B) * H, kAttnWarps), kAttnWarps * 32, smem, st>>>(
+      VQA_CUDA_OK(vqa_launch(attn_warp_kernel, dim3(blocks_for(static_cast<long long>(B) * H, kAttnWarps)), dim3(kAttnWarps * 32), smem, st, 
           PTR(const float*, CROSS_ATTN_P_q), kv + I[CROSS_ATTN_I_k_off], kv + I[CROSS_ATTN_I_v_off], nullptr,
           PTR(float*, CROSS_ATTN_P_out), PTR(float*, CROSS_ATTN_P_weights), B * H, H, L, T, I[CROSS_ATTN_I_ld_q],
-          I[CROSS_ATTN_I_ld_kv]);
+          I[CROSS_ATTN_I_ld_kv]));
       VQA_LAUNCH_OK("attn_warp_kernel");
       return VQA_OK;
     }
     case VQA_OP_POOL_GATE_LN: {
       VQA_REQUIRE(I[POOL_GATE_LN_I_D] == 256, VQA_E_INVALID, "pool_gate_ln: D must be 256");
-      pool_gate_ln_kernel<<<(I[POOL_GATE_LN_I_B] + kTailRows - 1) / kTailRows, 256, 0, st>>>(
+      VQA_CUDA_OK(vqa_launch(pool_gate_ln_kernel, dim3((I[POOL_GATE_LN_I_B] + kTailRows - 1) / kTailRows), dim3(256), 0, st, 
           PTR(const float*, POOL_GATE_LN_P_xatt), PTR(const float*, POOL_GATE_LN_P_text),
           PTR(const int*, POOL_GATE_LN_P_mask), PTR(const float*, POOL_GATE_LN_P_wg), PTR(const float*, POOL_GATE_LN_P_bg),
           PTR(const float*, POOL_GATE_LN_P_gamma), PTR(const float*, POOL_GATE_LN_P_beta),
           PTR(float*, POOL_GATE_LN_P_fused), PTR(float*, POOL_GATE_LN_P_att_pooled),
           PTR(float*, POOL_GATE_LN_P_txt_pooled), I[POOL_GATE_LN_I_B], I[POOL_GATE_LN_I_L], I[POOL_GATE_LN_I_use_gate],
-          op.f[POOL_GATE_LN_F_eps]);
+          op.f[POOL_GATE_LN_F_eps]));
       VQA_LAUNCH_OK("pool_gate_ln_kernel");
       return VQA_OK;
     }
     case VQA_OP_SOFTMAX_TOPK: {
       const int N = I[SOFTMAX_TOPK_I_N], k = I[SOFTMAX_TOPK_I_k];
       VQA_REQUIRE(k >= 1 && k <= 16 && k <= N && N <= 10000, VQA_E_INVALID, "softmax_topk: 1<=k<=16, N<=10000");
-      softmax_topk_kernel<<<I[SOFTMAX_TOPK_I_B], 256, (N + 64) * sizeof(float), st>>>(
+      VQA_CUDA_OK(vqa_launch(softmax_topk_kernel, dim3(I[SOFTMAX_TOPK_I_B]), dim3(256), (N + 64) * sizeof(float), st, 
           PTR(const float*, SOFTMAX_TOPK_P_logits), PTR(long long*, SOFTMAX_TOPK_P_idx),
-          PTR(float*, SOFTMAX_TOPK_P_probs), N, k, I[SOFTMAX_TOPK_I_ld]);
+          PTR(float*, SOFTMAX_TOPK_P_probs), N, k, I[SOFTMAX_TOPK_I_ld]));
       VQA_LAUNCH_OK("softmax_topk_kernel");
       return VQA_OK;
     }

@@ -45,6 +45,11 @@ static_assert(POOL_GATE_LN_NP <= VQA_OP_NP, "VqaOp.p too small");
 }  // namespace
 
 void vqa_set_error(const std::string& msg) { g_error = msg; }
+bool vqa_pdl_enabled() {
+  static const bool on = std::getenv("VQA_NO_PDL") == nullptr;
+  return on;
+}
+
 void vqa_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct VqaPlan {
