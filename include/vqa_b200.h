@@ -67,7 +67,8 @@ enum VqaOpKind {
   VQA_OP_MASK_PREP     = 14, /* attention_mask (int64 | fp32 | absent) -> int32 */
   VQA_OP_GRID_TO_NCHW  = 15, /* padded-flat bf16 grid -> NCHW fp32 (aux['image_features'], models/vqa_model.py:301-309) */
   VQA_OP_COPY_ROWS     = 16, /* fp32 [rows, cols] copy between leading dimensions (logits whose num_answers is not a multiple of 4) */
-  VQA_OP_KIND_MAX      = 17
+  VQA_OP_STAGE_TAIL    = 17, /* fused stage tail: SE squeeze+excite, spatial attention, scale, relayout (attention_modules.py:91-136,198-243) */
+  VQA_OP_KIND_MAX      = 18
 };
 
 typedef struct VqaOp {

@@ -206,6 +206,43 @@ class Emulator:
         n = i["B"] * i["C"] * i["H"] * i["W"]
         _t(op.p["dst"], torch.float32, ext)[:n].view(i["B"], i["C"], i["H"], i["W"]).copy_(x.permute(0, 3, 1, 2))
 
+    def op_stage_tail(self, op, ext):
+        i = op.i
+        B, C, H, W = i["B"], i["C"], i["H"], i["W"]
+        x = self._grid_nhwc(op.p["src"], ext, B, C, H, W, i["P"], i["RPI"])          # [B,H,W,C] fp32 (bf16 values)
+        sc = torch.ones(B, C)
+        if op.p.get("w1") is not None:
+            R = i["R"]
+            mean = x.reshape(B, H * W, C).sum(dim=1) / (H * W)
+            w1 = _t(op.p["w1"], torch.float32, ext)[: R * C].view(R, C)
+            w2t = _t(op.p["w2"], torch.float32, ext)[: R * C].view(R, C)
+            sc = torch.sigmoid(F.relu(mean @ w1.t()) @ w2t)
+            if op.p.get("scale") is not None:
+                _t(op.p["scale"], torch.float32, ext)[: B * C].view(B, C).copy_(sc)
+        xs = x * sc.view(B, 1, 1, C)
+        att = torch.ones(B, H, W)
+        if op.p.get("wconv") is not None:
+            ks = i["ks"]
+            pooled = torch.stack([xs.max(dim=3)[0], xs.mean(dim=3)], dim=1)
+            w = _t(op.p["wconv"], torch.float32, ext)[: 2 * ks * ks].view(1, 2, ks, ks)
+            att = torch.sigmoid(F.conv2d(pooled, w, None, padding=ks // 2)).view(B, H, W)
+            if op.p.get("att") is not None:
+                _t(op.p["att"], torch.float32, ext)[: B * H * W].view(B, H * W).copy_(att.view(B, H * W))
+        y = (x * sc.view(B, 1, 1, C) * att.view(B, H, W, 1)).to(torch.bfloat16)
+        Po, RPIo = i["Po"], i["RPIo"]
+        if i["mode"]:
+            pr = i["phase_rows"]
+            dst = _t(op.p["dst"], torch.bfloat16, ext)[: 4 * pr * C].view(4, pr, C)
+            dst.zero_()
+            idx = _grid_index(B, H // 2, W // 2, Po, RPIo)
+            for ph in range(2):
+                for pw in range(2):
+                    dst[ph * 2 + pw][idx] = y[:, ph::2, pw::2, :].reshape(-1, C)
+        else:
+            dst = _t(op.p["dst"], torch.bfloat16, ext)[: B * RPIo * C].view(B * RPIo, C)
+            dst.zero_()
+            dst[_grid_index(B, H, W, Po, RPIo)] = y.reshape(-1, C)
+
     def op_copy_rows(self, op, ext):
         i = op.i
         src = torch.as_strided(_t(op.p["src"], torch.float32, ext), (i["rows"], i["cols"]), (i["ld_src"], 1))

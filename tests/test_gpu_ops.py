@@ -24,6 +24,7 @@ OUTPUTS = {
     "pool_gate_ln": [("fused", torch.float32), ("att_pooled", torch.float32), ("txt_pooled", torch.float32)],
     "softmax_topk": [("idx", torch.int64), ("probs", torch.float32)], "mask_prep": [("dst", torch.int32)],
     "grid_to_nchw": [("dst", torch.float32)], "copy_rows": [("dst", torch.float32)],
+    "stage_tail": [("dst", torch.bfloat16), ("scale", torch.float32), ("att", torch.float32)],
 }
 
 

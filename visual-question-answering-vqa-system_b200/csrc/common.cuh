@@ -50,6 +50,36 @@ void vqa_count_launch();
 // ----------------------------------------------------------------------------- device PTX wrappers
 #ifdef __CUDACC__
 
+bool vqa_pdl_enabled();
+
+// Launch with a thread-block-cluster dimension (plus the programmatic-dependent-launch attribute).
+template <typename... KArgs, typename... Args>
+inline cudaError_t vqa_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (vqa_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 bool vqa_pdl_enabled();   // plan.cu: false when VQA_NO_PDL is set in the environment (debugging aid)
 
 // Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait below).

@@ -238,6 +238,207 @@ __global__ void spatial_map_kernel(const uint4* __restrict__ src, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// STAGE_TAIL: everything between a stage's last convolution and the next stage's first one, in ONE pass
+// over the feature map: SE squeeze -> excite -> (spatial attention map) -> x*scale*att -> bf16, written on
+// the same grid (mode 0) or as the 4-phase split the next stage's stride-2 convolutions read (mode 1)
+// (models/attention_modules.py:91-136, :198-243, :422-425; models/cnn_backbone.py:267-279).
+// A cluster of CS CTAs owns one image: each CTA stages H/CS pixel rows in shared memory (the map is read
+// from L2/HBM exactly once), reduces its channel sums, the cluster exchanges the CS partial sums through
+// distributed shared memory (added in rank order: deterministic), every CTA runs the tiny excite MLP,
+// and the scaled rows go straight from shared memory to their destination.  Spatial attention needs the
+// whole image's [max, mean] maps for its 7x7 convolution and therefore runs with CS = 1 (stages 3, 4).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank) {
+  uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(local)), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+constexpr int kTailThreads = 256;
+
+struct StageTailParams {
+  const uint4* src;
+  const float *w1, *w2, *wconv;
+  uint4* dst;
+  float *scale_out, *att_out;
+  int C8, H, W, P, RPI, R, ks, mode, Po, RPIo, phase_rows, CS;
+};
+
+__global__ void __launch_bounds__(kTailThreads)
+stage_tail_kernel(const StageTailParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t tail_smem[];
+  const int C8 = p.C8, C = C8 * 8, W = p.W, CS = p.CS;
+  const int rows_l = p.H / CS;                          // pixel rows of this CTA
+  const int NP = rows_l * W;                            // pixels of this CTA
+  const int n = blockIdx.x / CS;
+  const int rank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int h0 = rank * rows_l;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lanes = kTailThreads / C8;                  // pixel lanes (C8 divides 256)
+  const int cg = tid % C8, pl = tid / C8;
+  uint4* tile = reinterpret_cast<uint4*>(tail_smem);                       // [NP][C8]
+  float* red = reinterpret_cast<float*>(tile + static_cast<size_t>(NP) * C8);   // [lanes][C]; later mx/av maps
+  float* part = red + lanes * C;                        // [C] this CTA's channel sums (read by the cluster)
+  float* sc = part + C;                                 // [C] SE scale
+  float* hid = sc + C;                                  // [R]
+  float* att = hid + 64;                                // [NP] spatial attention (CS == 1)
+  const bool use_se = p.w1 != nullptr;
+
+  // ---- 1. stage the rows, accumulate channel sums on the way
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8;
+  for (int q0 = pl; q0 < NP; q0 += 4 * lanes) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * lanes;
+      if (q < NP) {
+        const int hl = q / W, w = q - hl * W;
+        v[u] = img[(static_cast<size_t>(h0 + hl) * p.P + w) * C8 + cg];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * lanes;
+      if (q < NP) {
+        tile[static_cast<size_t>(q) * C8 + cg] = v[u];
+        acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x); acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
+        acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z); acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
+      }
+    }
+  }
+  if (use_se) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[pl * C + cg * 8 + k] = acc[k];
+    __syncthreads();
+    for (int c = tid; c < C; c += kTailThreads) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += red[l * C + c];
+      part[c] = t;
+    }
+    // ---- 2. cluster-wide channel sums (rank order) -> mean
+    if (CS > 1) cluster_sync_all(); else __syncthreads();
+    const float inv_hw = 1.f / static_cast<float>(p.H * W);
+    float* mean = red;                                  // red is free again
+    for (int c = tid; c < C; c += kTailThreads) {
+      float t = 0.f;
+      if (CS > 1) {
+        for (int r = 0; r < CS; ++r) t += ld_dsmem_f32(part + c, static_cast<uint32_t>(r));
+      } else {
+        t = part[c];
+      }
+      mean[c] = t * inv_hw;
+    }
+    __syncthreads();
+    // ---- 3. excite: scale = sigmoid(W2 relu(W1 mean)), no biases
+    for (int r = warp; r < p.R; r += kTailThreads / 32) {
+      float t = 0.f;
+      for (int c = lane; c < C; c += 32) t += p.w1[static_cast<size_t>(r) * C + c] * mean[c];
+      t = warp_sum(t);
+      if (lane == 0) hid[r] = fmaxf(t, 0.f);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kTailThreads) {       // w2 is stored transposed [R][C]: coalesced over c
+      float t = 0.f;
+      for (int r = 0; r < p.R; ++r) t += p.w2[static_cast<size_t>(r) * C + c] * hid[r];
+      const float sg = 1.f / (1.f + expf(-t));
+      sc[c] = sg;
+      if (p.scale_out && rank == 0) p.scale_out[static_cast<size_t>(n) * C + c] = sg;
+    }
+  } else {
+    for (int c = tid; c < C; c += kTailThreads) sc[c] = 1.f;
+  }
+  __syncthreads();
+
+  // ---- 4. spatial attention (CS == 1): channel max / mean of x*scale, ks x ks conv over [max, avg], sigmoid
+  const bool use_sp = p.wconv != nullptr;
+  if (use_sp) {
+    float* mx = red;                                    // [NP]
+    float* av = red + NP;                               // [NP]  (2*NP <= lanes*C floats, checked on the host)
+    for (int q = warp; q < NP; q += kTailThreads / 32) {
+      float m = -INFINITY, t = 0.f;
+      for (int o = lane; o < C8; o += 32) {
+        const uint4 v = tile[static_cast<size_t>(q) * C8 + o];
+        const float* k = sc + o * 8;
+        const float x[8] = {bf16lo(v.x) * k[0], bf16hi(v.x) * k[1], bf16lo(v.y) * k[2], bf16hi(v.y) * k[3],
+                            bf16lo(v.z) * k[4], bf16hi(v.z) * k[5], bf16lo(v.w) * k[6], bf16hi(v.w) * k[7]};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m = fmaxf(m, x[j]); t += x[j]; }
+      }
+      m = warp_max(m);
+      t = warp_sum(t);
+      if (lane == 0) { mx[q] = m; av[q] = t / static_cast<float>(C); }
+    }
+    __syncthreads();
+    const int ks = p.ks, pad = ks / 2, H = p.H;
+    for (int q = tid; q < NP; q += kTailThreads) {
+      const int h = q / W, w = q - h * W;
+      float t = 0.f;
+      for (int kh = 0; kh < ks; ++kh) {
+        const int hh = h + kh - pad;
+        if (hh < 0 || hh >= H) continue;
+        for (int kw = 0; kw < ks; ++kw) {
+          const int ww = w + kw - pad;
+          if (ww < 0 || ww >= W) continue;
+          t += p.wconv[kh * ks + kw] * mx[hh * W + ww] + p.wconv[ks * ks + kh * ks + kw] * av[hh * W + ww];
+        }
+      }
+      const float a = 1.f / (1.f + expf(-t));
+      att[q] = a;
+      if (p.att_out) p.att_out[static_cast<size_t>(n) * NP + q] = a;
+    }
+    __syncthreads();
+  }
+
+  // ---- 5. apply and write (plus the destination grid's zero padding that belongs to these rows)
+  float k[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k[j] = sc[cg * 8 + j];
+  const int Po = p.Po;
+  const int rows_o = p.RPIo / Po;                       // destination rows per image incl. padding
+  for (int q = pl; q < NP; q += lanes) {
+    const int hl = q / W, w = q - hl * W, h = h0 + hl;
+    const uint4 v = tile[static_cast<size_t>(q) * C8 + cg];
+    const float a = use_sp ? att[q] : 1.f;
+    uint4 o;
+    o.x = pack_bf16x2(bf16lo(v.x) * k[0] * a, bf16hi(v.x) * k[1] * a);
+    o.y = pack_bf16x2(bf16lo(v.y) * k[2] * a, bf16hi(v.y) * k[3] * a);
+    o.z = pack_bf16x2(bf16lo(v.z) * k[4] * a, bf16hi(v.z) * k[5] * a);
+    o.w = pack_bf16x2(bf16lo(v.w) * k[6] * a, bf16hi(v.w) * k[7] * a);
+    size_t row;
+    if (p.mode) row = static_cast<size_t>((h & 1) * 2 + (w & 1)) * p.phase_rows + static_cast<size_t>(n) * p.RPIo + (h >> 1) * Po + (w >> 1);
+    else row = static_cast<size_t>(n) * p.RPIo + h * Po + w;
+    p.dst[row * C8 + cg] = o;
+  }
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const int Ho = p.mode ? p.H / 2 : p.H, Wo = p.mode ? W / 2 : W, nph = p.mode ? 4 : 1;
+  const int i0 = p.mode ? h0 / 2 : h0, i1 = p.mode ? (h0 + rows_l) / 2 : h0 + rows_l;
+  const int padw = Po - Wo;                             // pad columns per destination row
+  for (int ph = 0; ph < nph; ++ph) {
+    uint4* base = p.dst + (static_cast<size_t>(ph) * p.phase_rows + static_cast<size_t>(n) * p.RPIo) * C8;
+    for (int t = tid; t < (i1 - i0) * padw * C8; t += kTailThreads) {      // pad columns of this CTA's rows
+      const int c = t % C8, e = t / C8, i = i0 + e / padw, j = Wo + e % padw;
+      base[(static_cast<size_t>(i) * Po + j) * C8 + c] = z;
+    }
+    if (rank == CS - 1) {                                                   // pad rows below the image
+      for (int t = tid; t < (rows_o - Ho) * Po * C8; t += kTailThreads) base[static_cast<size_t>(Ho) * Po * C8 + t] = z;
+    }
+  }
+  if (CS > 1) cluster_sync_all();                       // peers may still be reading this CTA's partial sums
+}
+
+// ------------------------------------------------------------------------------------------------
 // COPY_ROWS: dst[r, c] = src[r, c] between two leading dimensions (un-padding of the logits).
 __global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int ld_src,
                                  int ld_dst) {
@@ -384,18 +585,23 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Attention core, one WARP per (pair, head): softmax(Q K^T / sqrt(32) [+ key mask]) V with head_dim 32,
-// up to 64 queries and up to 64 keys.  Self-attention (models/text_encoder.py:229-259; keys with
-// mask == 0 get -inf, a fully masked row yields NaN exactly like the reference) and
-// cross-attention over the 49 image tokens (models/cross_attention.py:164-197, no mask) share it.
-//   scores:  lane j owns key rows j and j+32 in registers; the query row is broadcast from shared memory
-//   softmax: warp-shuffle max / sum in fp32
-//   P V:     lane d owns output dim d; probabilities are broadcast by shuffle, V rows read from shared memory
+// Attention core, one WARP per (pair, head), one LANE per query: softmax(Q K^T / sqrt(32) [+ key mask]) V
+// with head_dim 32, up to 64 queries (two passes of 32) and up to TMAX keys.  Self-attention
+// (models/text_encoder.py:229-259; keys with mask == 0 get -inf, a fully masked row yields NaN exactly
+// like the reference) and cross-attention over the 49 image tokens
+// (models/cross_attention.py:164-197, no mask) share it.
+//   K and V rows of the head are staged in shared memory (coalesced) and read back as warp-wide
+//   broadcasts; each lane keeps its query row, its TMAX scores and its 32 output dims in registers,
+//   so there is no cross-lane reduction at all (the previous lane-per-key version spent its time in
+//   shuffles: 39 us for 2048 heads of 20x20).
 constexpr int kHd = 32;
 constexpr int kAttnWarps = 4;
 
+__host__ __device__ constexpr int attn_warp_floats(int T) { return 2 * T * kHd + 64; }
+
+template <int TMAX>
 __global__ void __launch_bounds__(kAttnWarps * 32)
-attn_warp_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+attn_lane_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                  const int* __restrict__ mask, float* __restrict__ out, float* __restrict__ weights, int n_units,
                  int H, int L, int T, int ld_q, int ld_kv) {
   pdl_launch_dependents();
@@ -405,65 +611,106 @@ attn_warp_kernel(const float* __restrict__ q, const float* __restrict__ k, const
   const int unit = blockIdx.x * kAttnWarps + warp;     // (pair, head)
   if (unit >= n_units) return;
   const int b = unit / H, h = unit - b * H;
-  float* qs = sm + warp * (64 + 64) * kHd;             // [L][32] query rows
-  float* vs = qs + 64 * kHd;                           // [T][32] value rows
+  float* ks = sm + warp * attn_warp_floats(T);         // [T][32] key rows
+  float* vs = ks + T * kHd;                            // [T][32] value rows
+  float* mb = vs + T * kHd;                            // [T] additive key mask: 0 or -inf
   const float* qb = q + static_cast<size_t>(b) * L * ld_q + h * kHd;
   const float* kb = k + static_cast<size_t>(b) * T * ld_kv + h * kHd;
   const float* vb = v + static_cast<size_t>(b) * T * ld_kv + h * kHd;
-  // stage Q and V (8 lanes cover one 128-byte row: coalesced)
-  for (int t = lane; t < L * 8; t += 32) {
+  for (int t = lane; t < T * 8; t += 32) {             // 8 lanes cover one 128-byte row: coalesced
     const int r = t >> 3, c4 = t & 7;
-    reinterpret_cast<float4*>(qs)[r * 8 + c4] = *reinterpret_cast<const float4*>(qb + static_cast<size_t>(r) * ld_q + c4 * 4);
-  }
-  for (int t = lane; t < T * 8; t += 32) {
-    const int r = t >> 3, c4 = t & 7;
+    reinterpret_cast<float4*>(ks)[r * 8 + c4] = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(r) * ld_kv + c4 * 4);
     reinterpret_cast<float4*>(vs)[r * 8 + c4] = *reinterpret_cast<const float4*>(vb + static_cast<size_t>(r) * ld_kv + c4 * 4);
   }
-  // this lane's key rows in registers
-  float k0[kHd], k1[kHd];
-  const bool has0 = lane < T, has1 = lane + 32 < T;
-#pragma unroll
-  for (int c4 = 0; c4 < 8; ++c4) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-    if (has0) a = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(lane) * ld_kv + c4 * 4);
-    if (has1) c = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(lane + 32) * ld_kv + c4 * 4);
-    k0[4 * c4] = a.x; k0[4 * c4 + 1] = a.y; k0[4 * c4 + 2] = a.z; k0[4 * c4 + 3] = a.w;
-    k1[4 * c4] = c.x; k1[4 * c4 + 1] = c.y; k1[4 * c4 + 2] = c.z; k1[4 * c4 + 3] = c.w;
-  }
-  bool m0 = has0, m1 = has1;   // key participates
-  if (mask) {
-    if (has0) m0 = mask[b * T + lane] != 0;
-    if (has1) m1 = mask[b * T + lane + 32] != 0;
-  }
+  for (int j = lane; j < T; j += 32) mb[j] = (mask == nullptr || mask[b * T + j] != 0) ? 0.f : -INFINITY;
   __syncwarp();
   const float scale = rsqrtf(static_cast<float>(kHd));
-  for (int l = 0; l < L; ++l) {
-    float s0 = 0.f, s1 = 0.f;
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + lane;
+    const bool act = l < L;
+    float qr[kHd];
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 qq = reinterpret_cast<const float4*>(qs)[l * 8 + c4];   // broadcast read
-      s0 += qq.x * k0[4 * c4] + qq.y * k0[4 * c4 + 1] + qq.z * k0[4 * c4 + 2] + qq.w * k0[4 * c4 + 3];
-      s1 += qq.x * k1[4 * c4] + qq.y * k1[4 * c4 + 1] + qq.z * k1[4 * c4 + 2] + qq.w * k1[4 * c4 + 3];
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act) a = *reinterpret_cast<const float4*>(qb + static_cast<size_t>(l) * ld_q + c4 * 4);
+      qr[4 * c4] = a.x; qr[4 * c4 + 1] = a.y; qr[4 * c4 + 2] = a.z; qr[4 * c4 + 3] = a.w;
     }
-    s0 = m0 ? s0 * scale : -INFINITY;
-    s1 = m1 ? s1 * scale : -INFINITY;
-    const float mx = warp_max(fmaxf(s0, s1));
-    // exp(-inf - -inf) = NaN reproduces the reference for a fully masked row; padding lanes never contribute
-    float p0 = has0 ? expf(s0 - mx) : 0.f;
-    float p1 = has1 ? expf(s1 - mx) : 0.f;
-    const float inv = 1.f / warp_sum(p0 + p1);
-    p0 *= inv;
-    p1 *= inv;
-    if (weights) {
-      float* wrow = weights + ((static_cast<size_t>(b) * H + h) * L + l) * T;
-      if (has0) wrow[lane] = p0;
-      if (has1) wrow[lane + 32] = p1;
+    float s[TMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TMAX; ++j) {
+      s[j] = -INFINITY;
+      if (j < T) {                                     // warp-uniform
+        float d = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 kk = reinterpret_cast<const float4*>(ks)[j * 8 + c4];   // broadcast read
+          d += qr[4 * c4] * kk.x + qr[4 * c4 + 1] * kk.y + qr[4 * c4 + 2] * kk.z + qr[4 * c4 + 3] * kk.w;
+        }
+        s[j] = d * scale + mb[j];
+        mx = fmaxf(mx, s[j]);
+      }
     }
-    float acc = 0.f;
-    for (int j = 0; j < T && j < 32; ++j) acc += __shfl_sync(0xffffffffu, p0, j) * vs[j * kHd + lane];
-    for (int j = 32; j < T; ++j) acc += __shfl_sync(0xffffffffu, p1, j - 32) * vs[j * kHd + lane];
-    out[(static_cast<size_t>(b) * L + l) * (H * kHd) + h * kHd + lane] = round_tf32_rna(acc);   // tf32 operand of W_o
+    // exp(-inf - -inf) = NaN reproduces the reference for a fully masked row
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < TMAX; ++j) {
+      if (j < T) {
+        s[j] = expf(s[j] - mx);
+        sum += s[j];
+      }
+    }
+    const float inv = 1.f / sum;
+    float o[kHd];
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TMAX; ++j) {
+      if (j < T) {
+        const float pj = s[j] * inv;
+        s[j] = pj;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 vv = reinterpret_cast<const float4*>(vs)[j * 8 + c4];   // broadcast read
+          o[4 * c4] += pj * vv.x; o[4 * c4 + 1] += pj * vv.y; o[4 * c4 + 2] += pj * vv.z; o[4 * c4 + 3] += pj * vv.w;
+        }
+      }
+    }
+    if (act) {
+      float* orow = out + (static_cast<size_t>(b) * L + l) * (H * kHd) + h * kHd;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4)                   // tf32 operand of W_o
+        *reinterpret_cast<float4*>(orow + 4 * c4) = make_float4(round_tf32_rna(o[4 * c4]), round_tf32_rna(o[4 * c4 + 1]),
+                                                                round_tf32_rna(o[4 * c4 + 2]), round_tf32_rna(o[4 * c4 + 3]));
+      if (weights) {
+        float* wrow = weights + ((static_cast<size_t>(b) * H + h) * L + l) * T;
+#pragma unroll
+        for (int j = 0; j < TMAX; ++j)
+          if (j < T) wrow[j] = s[j];
+      }
+    }
   }
+}
+
+typedef void (*AttnFn)(const float*, const float*, const float*, const int*, float*, float*, int, int, int, int, int, int);
+
+static int launch_attn(const float* q, const float* k, const float* v, const int* mask, float* out, float* weights, int B,
+                       int H, int L, int T, int ld_q, int ld_kv, cudaStream_t st) {
+  AttnFn fn = T <= 32 ? static_cast<AttnFn>(&attn_lane_kernel<32>) : static_cast<AttnFn>(&attn_lane_kernel<64>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int worst = kAttnWarps * attn_warp_floats(64) * static_cast<int>(sizeof(float));
+    VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_lane_kernel<32>),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, worst));
+    VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_lane_kernel<64>),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, worst));
+    attr_set = true;
+  }
+  const size_t smem = static_cast<size_t>(kAttnWarps) * attn_warp_floats(T) * sizeof(float);
+  VQA_CUDA_OK(vqa_launch(fn, dim3((B * H + kAttnWarps - 1) / kAttnWarps), dim3(kAttnWarps * 32), smem, st, q, k, v, mask, out,
+                         weights, B * H, H, L, T, ld_q, ld_kv));
+  VQA_LAUNCH_OK("attn_lane_kernel");
+  return VQA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,6 +952,40 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_LAUNCH_OK("grid_to_nchw_kernel");
       return VQA_OK;
     }
+    case VQA_OP_STAGE_TAIL: {
+      StageTailParams q;
+      q.src = PTR(const uint4*, STAGE_TAIL_P_src);
+      q.w1 = PTR(const float*, STAGE_TAIL_P_w1);
+      q.w2 = PTR(const float*, STAGE_TAIL_P_w2);
+      q.wconv = PTR(const float*, STAGE_TAIL_P_wconv);
+      q.dst = PTR(uint4*, STAGE_TAIL_P_dst);
+      q.scale_out = PTR(float*, STAGE_TAIL_P_scale);
+      q.att_out = PTR(float*, STAGE_TAIL_P_att);
+      const int C = I[STAGE_TAIL_I_C];
+      q.C8 = C / 8; q.H = I[STAGE_TAIL_I_H]; q.W = I[STAGE_TAIL_I_W]; q.P = I[STAGE_TAIL_I_P]; q.RPI = I[STAGE_TAIL_I_RPI];
+      q.R = I[STAGE_TAIL_I_R]; q.ks = I[STAGE_TAIL_I_ks]; q.mode = I[STAGE_TAIL_I_mode]; q.Po = I[STAGE_TAIL_I_Po];
+      q.RPIo = I[STAGE_TAIL_I_RPIo]; q.phase_rows = I[STAGE_TAIL_I_phase_rows]; q.CS = I[STAGE_TAIL_I_CS];
+      VQA_REQUIRE(C % 8 == 0 && q.C8 >= 1 && kTailThreads % q.C8 == 0, VQA_E_INVALID, "stage_tail: C/8 must divide 256");
+      VQA_REQUIRE(q.CS == 1 || q.CS == 2 || q.CS == 4 || q.CS == 8, VQA_E_INVALID, "stage_tail: cluster size must be 1, 2, 4 or 8");
+      VQA_REQUIRE(q.H % q.CS == 0 && (!q.mode || (q.H / q.CS) % 2 == 0) && (!q.mode || q.W % 2 == 0), VQA_E_INVALID,
+                  "stage_tail: rows per CTA must be whole (and even for the phase split)");
+      VQA_REQUIRE(q.wconv == nullptr || q.CS == 1, VQA_E_INVALID, "stage_tail: spatial attention needs the whole image (CS = 1)");
+      VQA_REQUIRE(q.R <= 64 && (q.w1 == nullptr) == (q.w2 == nullptr), VQA_E_INVALID, "stage_tail: bad SE weights");
+      VQA_REQUIRE(q.Po > 0 && q.RPIo % q.Po == 0, VQA_E_INVALID, "stage_tail: bad destination grid");
+      const int NP = q.H / q.CS * q.W, lanes = kTailThreads / q.C8;
+      VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= lanes * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
+      const size_t smem = static_cast<size_t>(NP) * C * 2 + sizeof(float) * (static_cast<size_t>(lanes) * C + 2 * C + 64 + NP);
+      VQA_REQUIRE(smem <= 227 * 1024, VQA_E_INVALID, "stage_tail: rows per CTA exceed shared memory (raise CS)");
+      static size_t attr_smem = 0;
+      if (smem > attr_smem) {
+        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&stage_tail_kernel),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_smem = 227 * 1024;
+      }
+      VQA_CUDA_OK(vqa_launch_cluster(stage_tail_kernel, dim3(I[STAGE_TAIL_I_B] * q.CS), dim3(kTailThreads), smem, st, q.CS, q));
+      VQA_LAUNCH_OK("stage_tail_kernel");
+      return VQA_OK;
+    }
     case VQA_OP_COPY_ROWS: {
       const long long total = static_cast<long long>(I[COPY_ROWS_I_rows]) * I[COPY_ROWS_I_cols];
       VQA_CUDA_OK(vqa_launch(copy_rows_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, PTR(const float*, COPY_ROWS_P_src), PTR(float*, COPY_ROWS_P_dst),
@@ -748,18 +1029,9 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const float* qkv = PTR(const float*, SELF_ATTN_P_qkv);
       const int D = H * kHd, ld = I[SELF_ATTN_I_ld_qkv];
       VQA_REQUIRE(ld % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, VQA_E_ALIGN, "self_attn: qkv alignment");
-      const size_t smem = static_cast<size_t>(kAttnWarps) * 128 * kHd * sizeof(float);
-      static bool attr_set = false;
-      if (!attr_set) {
-        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_warp_kernel),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
-      }
-      VQA_CUDA_OK(vqa_launch(attn_warp_kernel, dim3(blocks_for(static_cast<long long>(B) * H, kAttnWarps)), dim3(kAttnWarps * 32), smem, st, 
-          qkv, qkv + D, qkv + 2 * D, PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), nullptr, B * H, H,
-          L, L, ld, ld));
-      VQA_LAUNCH_OK("attn_warp_kernel");
-      return VQA_OK;
+      VQA_REQUIRE((reinterpret_cast<uintptr_t>(PTR(float*, SELF_ATTN_P_out)) & 15) == 0, VQA_E_ALIGN, "self_attn: out alignment");
+      return launch_attn(qkv, qkv + D, qkv + 2 * D, PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), nullptr, B,
+                         H, L, L, ld, ld, st);
     }
     case VQA_OP_CROSS_ATTN: {
       const int L = I[CROSS_ATTN_I_L], T = I[CROSS_ATTN_I_T], H = I[CROSS_ATTN_I_H], B = I[CROSS_ATTN_I_B];
@@ -768,19 +1040,9 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const float* kv = PTR(const float*, CROSS_ATTN_P_kv);
       VQA_REQUIRE(I[CROSS_ATTN_I_ld_q] % 4 == 0 && I[CROSS_ATTN_I_ld_kv] % 4 == 0 && I[CROSS_ATTN_I_k_off] % 4 == 0 &&
                       I[CROSS_ATTN_I_v_off] % 4 == 0, VQA_E_ALIGN, "cross_attn: leading dimensions must be multiples of 4");
-      const size_t smem = static_cast<size_t>(kAttnWarps) * 128 * kHd * sizeof(float);
-      static bool attr_set = false;
-      if (!attr_set) {
-        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_warp_kernel),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
-      }
-      VQA_CUDA_OK(vqa_launch(attn_warp_kernel, dim3(blocks_for(static_cast<long long>(B) * H, kAttnWarps)), dim3(kAttnWarps * 32), smem, st, 
-          PTR(const float*, CROSS_ATTN_P_q), kv + I[CROSS_ATTN_I_k_off], kv + I[CROSS_ATTN_I_v_off], nullptr,
-          PTR(float*, CROSS_ATTN_P_out), PTR(float*, CROSS_ATTN_P_weights), B * H, H, L, T, I[CROSS_ATTN_I_ld_q],
-          I[CROSS_ATTN_I_ld_kv]));
-      VQA_LAUNCH_OK("attn_warp_kernel");
-      return VQA_OK;
+      return launch_attn(PTR(const float*, CROSS_ATTN_P_q), kv + I[CROSS_ATTN_I_k_off], kv + I[CROSS_ATTN_I_v_off], nullptr,
+                         PTR(float*, CROSS_ATTN_P_out), PTR(float*, CROSS_ATTN_P_weights), B, H, L, T, I[CROSS_ATTN_I_ld_q],
+                         I[CROSS_ATTN_I_ld_kv], st);
     }
     case VQA_OP_POOL_GATE_LN: {
       VQA_REQUIRE(I[POOL_GATE_LN_I_D] == 256, VQA_E_INVALID, "pool_gate_ln: D must be 256");
@@ -820,10 +1082,11 @@ const char* misc_kernel_name(int kind) {
     case VQA_OP_GRID_TO_NCHW: return "grid_to_nchw_kernel";
     case VQA_OP_MASK_PREP: return "mask_prep_kernel";
     case VQA_OP_COPY_ROWS: return "copy_rows_kernel";
+    case VQA_OP_STAGE_TAIL: return "stage_tail_kernel";
     case VQA_OP_EMBED: return "embed_kernel";
     case VQA_OP_LAYERNORM: return "layernorm256_kernel";
-    case VQA_OP_SELF_ATTN: return "attn_warp_kernel(self)";
-    case VQA_OP_CROSS_ATTN: return "attn_warp_kernel(cross)";
+    case VQA_OP_SELF_ATTN: return "attn_lane_kernel(self)";
+    case VQA_OP_CROSS_ATTN: return "attn_lane_kernel(cross)";
     case VQA_OP_POOL_GATE_LN: return "pool_gate_ln_kernel";
     case VQA_OP_SOFTMAX_TOPK: return "softmax_topk_kernel";
     default: return "?";

@@ -35,7 +35,7 @@ KINDS = {
     "ingest": 1, "gemm": 2, "maxpool": 3, "se_squeeze": 4, "se_excite": 5, "spatial_map": 6,
     "scale_relayout": 7, "embed": 8, "layernorm": 9, "self_attn": 10, "cross_attn": 11,
     "pool_gate_ln": 12, "softmax_topk": 13, "mask_prep": 14, "grid_to_nchw": 15,
-    "copy_rows": 16,
+    "copy_rows": 16, "stage_tail": 17,
 }
 
 _GROUPS = [f"g_{k}{g}" for k in ("map", "delta", "acol", "chunks", "ntaps", "kbase", "tap0")
@@ -72,6 +72,8 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
     "mask_prep": {"i": ["B", "L", "dtype"], "p": ["src", "dst"], "f": []},
     "grid_to_nchw": {"i": ["B", "C", "H", "W", "P", "RPI"], "p": ["src", "dst"], "f": []},
     "copy_rows": {"i": ["rows", "cols", "ld_src", "ld_dst"], "p": ["src", "dst"], "f": []},
+    "stage_tail": {"i": ["B", "C", "H", "W", "P", "RPI", "R", "ks", "mode", "Po", "RPIo", "phase_rows", "CS"],
+                   "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att"], "f": []},
 }
 
 DT_BF16, DT_TF32 = 0, 1          # gemm operand dtype
@@ -376,6 +378,7 @@ class OpList:
         self.window = window
         self.stem_window = window
         self.fuse_pool = window
+        self.fused_tail = window
         self.ws = Arena(device if device is not None else weights.arena.device)
         self.ops: List[Op] = []
         self.named: Dict[str, Tuple[Buf, torch.dtype, Tuple[int, ...]]] = {}
@@ -549,6 +552,33 @@ class Program(OpList):
         self._op("maxpool", "stem.pool", dict(B=B, C=64, Hin=112, Win=112, Pin=g0.P, RPIin=g0.rpi,
                                               Hout=56, Wout=56, Pout=g.P, RPIout=g.rpi), dict(src=s1, dst=x))
 
+    def _stage_tail(self, s, x, g, cout, has_se, has_sp):
+        """One fused kernel per stage: SE squeeze/excite, spatial attention, scaling and the relayout."""
+        B, W = self.B, self.W
+        bf, f32 = torch.bfloat16, torch.float32
+        scale = self._buf(f"s{s}.se.scale", f32, B, cout) if has_se else None
+        att = self._buf(f"s{s}.spatial.att", f32, B, g.H * g.W) if has_sp else None
+        ks = int(round(math.sqrt(W.items[f"s{s}.spatial.w"][2][1]))) if has_sp else 0
+        r = W.items[f"s{s}.se.w1"][2][0] if has_se else 0
+        if s < 4:
+            gn = Grid(B, g.H // 2, g.W // 2)
+            nxt = self._buf(f"s{s + 1}.in", bf, 4 * gn.rows, cout)
+            mode, Po, RPIo, prow, out = 1, gn.P, gn.rpi, gn.rows, (nxt, True, gn.rows)
+        else:
+            nxt = self._buf("features", bf, g.rows, cout)
+            mode, Po, RPIo, prow, out = 0, g.P, g.rpi, g.rows, (nxt, False, 0)
+        # cluster size: rows per CTA small enough for two CTAs per SM (<= ~100 KB of pixels), whole image with spatial
+        cs = 1
+        if not has_sp:
+            while (g.H // cs) * g.W * cout * 2 > 104 * 1024 and cs < 8 and (g.H // (2 * cs)) % 2 == 0 and g.H % (2 * cs) == 0:
+                cs *= 2
+        self._op("stage_tail", f"s{s}.tail",
+                 dict(B=B, C=cout, H=g.H, W=g.W, P=g.P, RPI=g.rpi, R=r, ks=ks, mode=mode, Po=Po, RPIo=RPIo,
+                      phase_rows=prow, CS=cs),
+                 dict(src=x, w1=W.buf(f"s{s}.se.w1") if has_se else None, w2=W.buf(f"s{s}.se.w2") if has_se else None,
+                      wconv=W.buf(f"s{s}.spatial.w") if has_sp else None, dst=nxt, scale=scale, att=att))
+        return out
+
     def _build_rest(self, g, x):
         B, L, W, cfg = self.B, self.L, self.W, self.cfg
         bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
@@ -598,8 +628,12 @@ class Program(OpList):
                               res=x, res_dtype=OUT_BF16, ldr=cin, grid=g, halo=halo2, MT=mt2)
                 x, cin, x_is_phase = o, cout, False
             # ---- stage attention + relayout for the next stage
+            has_se, has_sp = f"s{s}.se.w1" in W, f"s{s}.spatial.w" in W
+            if self.fused_tail and (s < 4 or has_se or has_sp):
+                x, x_is_phase, phase_rows = self._stage_tail(s, x, g, cout, has_se, has_sp)
+                continue
             scale = att = None
-            if f"s{s}.se.w1" in W:
+            if has_se:
                 hw = g.H * g.W
                 S = 8 if hw >= 2048 else (4 if hw >= 512 else (2 if hw >= 128 else 1))   # pixel slices per image
                 sums = self._buf(f"s{s}.se.sums", f32, B, S, cout)
@@ -609,7 +643,7 @@ class Program(OpList):
                 r = W.items[f"s{s}.se.w1"][2][0]
                 self._op("se_excite", f"s{s}.se.excite", dict(B=B, C=cout, R=r, HW=g.H * g.W, S=S),
                          dict(sums=sums, w1=W.buf(f"s{s}.se.w1"), w2=W.buf(f"s{s}.se.w2"), scale=scale))
-            if f"s{s}.spatial.w" in W:
+            if has_sp:
                 att = self._buf(f"s{s}.spatial.att", f32, B, g.H * g.W)
                 ks = int(round(math.sqrt(W.items[f"s{s}.spatial.w"][2][1])))
                 self._op("spatial_map", f"s{s}.spatial.map", dict(B=B, C=cout, H=g.H, W=g.W, P=g.P, RPI=g.rpi, ksize=ks),
