@@ -320,26 +320,31 @@ class Emulator:
     def op_pool_gate_ln(self, op, ext):
         i = op.i
         B, L, D = i["B"], i["L"], i["D"]
-        xa = _t(op.p["xatt"], torch.float32, ext)[: B * L * D].view(B, L, D)
-        tx = _t(op.p["text"], torch.float32, ext)[: B * L * D].view(B, L, D)
-        if op.p.get("mask") is not None:
-            m = _t(op.p["mask"], torch.int32, ext)[: B * L].view(B, L, 1).float()
-        else:
-            m = torch.ones(B, L, 1)
-        den = m.sum(dim=1).clamp(min=1)
-        ap = (xa * m).sum(dim=1) / den
-        tp = (tx * m).sum(dim=1) / den
-        if i["use_gate"]:
-            wg = _t(op.p["wg"], torch.float32, ext)[: D * 2 * D].view(D, 2 * D)
-            bg = _t(op.p["bg"], torch.float32, ext)[:D]
-            g = torch.sigmoid(torch.cat([ap, tp], dim=-1) @ wg.t() + bg)
-            fz = g * ap + (1 - g) * tp
-        else:
+        phase = i.get("phase", 0)
+        buf = lambda key, n: _t(op.p[key], torch.float32, ext)[:n]
+        if phase != 2:
+            xa = buf("xatt", B * L * D).view(B, L, D)
+            tx = buf("text", B * L * D).view(B, L, D)
+            if op.p.get("mask") is not None:
+                m = _t(op.p["mask"], torch.int32, ext)[: B * L].view(B, L, 1).float()
+            else:
+                m = torch.ones(B, L, 1)
+            den = m.sum(dim=1).clamp(min=1)
+            ap = (xa * m).sum(dim=1) / den
+            tp = (tx * m).sum(dim=1) / den
+            buf("att_pooled", B * D).view(B, D).copy_(ap)
+            buf("txt_pooled", B * D).view(B, D).copy_(tp)
+            if phase == 1:      # pools only; [att;txt] as the tf32 A operand of the gate GEMM
+                buf("cat", B * 2 * D).view(B, 2 * D).copy_(P.round_tf32(torch.cat([ap, tp], dim=-1)))
+                return
+            assert not i["use_gate"]
             fz = ap + tp
-        fz = F.layer_norm(fz, (D,), _t(op.p["gamma"], torch.float32, ext)[:D],
-                          _t(op.p["beta"], torch.float32, ext)[:D], op.f["eps"])
-        for key, val in (("fused", fz), ("att_pooled", ap), ("txt_pooled", tp)):
-            _t(op.p[key], torch.float32, ext)[: B * D].view(B, D).copy_(val)
+        else:                   # gate pre-activation comes from the GEMM
+            ap, tp = buf("att_pooled", B * D).view(B, D), buf("txt_pooled", B * D).view(B, D)
+            g = torch.sigmoid(buf("pre", B * D).view(B, D))
+            fz = g * ap + (1 - g) * tp
+        fz = F.layer_norm(fz, (D,), buf("gamma", D), buf("beta", D), op.f["eps"])
+        buf("fused", B * D).view(B, D).copy_(fz)
 
     def op_softmax_topk(self, op, ext):
         i = op.i

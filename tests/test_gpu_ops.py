@@ -21,7 +21,8 @@ OUTPUTS = {
     "spatial_map": [("att", torch.float32)], "scale_relayout": [("dst", torch.bfloat16)],
     "embed": [("dst", torch.float32)], "layernorm": [("dst", torch.float32)],
     "self_attn": [("out", torch.float32)], "cross_attn": [("out", torch.float32), ("weights", torch.float32)],
-    "pool_gate_ln": [("fused", torch.float32), ("att_pooled", torch.float32), ("txt_pooled", torch.float32)],
+    "pool_gate_ln": [("fused", torch.float32), ("att_pooled", torch.float32), ("txt_pooled", torch.float32),
+                     ("cat", torch.float32)],
     "softmax_topk": [("idx", torch.int64), ("probs", torch.float32)], "mask_prep": [("dst", torch.int32)],
     "grid_to_nchw": [("dst", torch.float32)], "copy_rows": [("dst", torch.float32)],
     "stage_tail": [("dst", torch.bfloat16), ("scale", torch.float32), ("att", torch.float32)],

@@ -1,5 +1,7 @@
 // Memory-bound and small kernels of the VQA forward path (everything that is not a GEMM).
 // Each launcher takes the generic VqaOp (fields in op_fields.h) with external pointers resolved.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -293,15 +295,17 @@ stage_tail_kernel(const StageTailParams p) {
   float* sc = part + C;                                 // [C] SE scale
   float* hid = sc + C;                                  // [R]
   float* att = hid + 64;                                // [NP] spatial attention (CS == 1)
+  float* wc = att + NP;                                 // [2*ks*ks] spatial conv weights
   const bool use_se = p.w1 != nullptr;
 
   // ---- 1. stage the rows, accumulate channel sums on the way
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8;
-  for (int q0 = pl; q0 < NP; q0 += 4 * lanes) {
-    uint4 v[4];
+  constexpr int kLd = 8;                                // independent 16-byte loads in flight per thread
+  for (int q0 = pl; q0 < NP; q0 += kLd * lanes) {
+    uint4 v[kLd];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kLd; ++u) {
       const int q = q0 + u * lanes;
       if (q < NP) {
         const int hl = q / W, w = q - hl * W;
@@ -309,7 +313,7 @@ stage_tail_kernel(const StageTailParams p) {
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kLd; ++u) {
       const int q = q0 + u * lanes;
       if (q < NP) {
         tile[static_cast<size_t>(q) * C8 + cg] = v[u];
@@ -342,16 +346,28 @@ stage_tail_kernel(const StageTailParams p) {
     }
     __syncthreads();
     // ---- 3. excite: scale = sigmoid(W2 relu(W1 mean)), no biases
-    for (int r = warp; r < p.R; r += kTailThreads / 32) {
+    // 8 lanes per hidden unit, every lane's loads independent (one L2 round trip instead of a chain)
+    for (int r0 = 0; r0 < p.R; r0 += kTailThreads / 8) {
+      const int r = r0 + (tid >> 3), part8 = tid & 7;
       float t = 0.f;
-      for (int c = lane; c < C; c += 32) t += p.w1[static_cast<size_t>(r) * C + c] * mean[c];
-      t = warp_sum(t);
-      if (lane == 0) hid[r] = fmaxf(t, 0.f);
+      if (r < p.R) {
+        const float4* wrow = reinterpret_cast<const float4*>(p.w1 + static_cast<size_t>(r) * C);
+        for (int c4 = part8; c4 < C / 4; c4 += 8) {
+          const float4 wv = __ldg(wrow + c4);
+          const float4 mv = *reinterpret_cast<const float4*>(mean + 4 * c4);
+          t += wv.x * mv.x + wv.y * mv.y + wv.z * mv.z + wv.w * mv.w;
+        }
+      }
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      if (r < p.R && part8 == 0) hid[r] = fmaxf(t, 0.f);
     }
     __syncthreads();
     for (int c = tid; c < C; c += kTailThreads) {       // w2 is stored transposed [R][C]: coalesced over c
       float t = 0.f;
-      for (int r = 0; r < p.R; ++r) t += p.w2[static_cast<size_t>(r) * C + c] * hid[r];
+#pragma unroll 8
+      for (int r = 0; r < p.R; ++r) t += __ldg(p.w2 + static_cast<size_t>(r) * C + c) * hid[r];
       const float sg = 1.f / (1.f + expf(-t));
       sc[c] = sg;
       if (p.scale_out && rank == 0) p.scale_out[static_cast<size_t>(n) * C + c] = sg;
@@ -380,8 +396,9 @@ stage_tail_kernel(const StageTailParams p) {
       t = warp_sum(t);
       if (lane == 0) { mx[q] = m; av[q] = t / static_cast<float>(C); }
     }
-    __syncthreads();
     const int ks = p.ks, pad = ks / 2, H = p.H;
+    for (int t = tid; t < 2 * ks * ks; t += kTailThreads) wc[t] = __ldg(p.wconv + t);
+    __syncthreads();
     for (int q = tid; q < NP; q += kTailThreads) {
       const int h = q / W, w = q - h * W;
       float t = 0.f;
@@ -391,7 +408,7 @@ stage_tail_kernel(const StageTailParams p) {
         for (int kw = 0; kw < ks; ++kw) {
           const int ww = w + kw - pad;
           if (ww < 0 || ww >= W) continue;
-          t += p.wconv[kh * ks + kw] * mx[hh * W + ww] + p.wconv[ks * ks + kh * ks + kw] * av[hh * W + ww];
+          t += wc[kh * ks + kw] * mx[hh * W + ww] + wc[ks * ks + kh * ks + kw] * av[hh * W + ww];
         }
       }
       const float a = 1.f / (1.f + expf(-t));
@@ -584,111 +601,192 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
   o4[32 + lane] = make_float4(y[4], y[5], y[6], y[7]);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Attention core, one WARP per (pair, head), one LANE per query: softmax(Q K^T / sqrt(32) [+ key mask]) V
-// with head_dim 32, up to 64 queries (two passes of 32) and up to TMAX keys.  Self-attention
-// (models/text_encoder.py:229-259; keys with mask == 0 get -inf, a fully masked row yields NaN exactly
-// like the reference) and cross-attention over the 49 image tokens
-// (models/cross_attention.py:164-197, no mask) share it.
-//   K and V rows of the head are staged in shared memory (coalesced) and read back as warp-wide
-//   broadcasts; each lane keeps its query row, its TMAX scores and its 32 output dims in registers,
-//   so there is no cross-lane reduction at all (the previous lane-per-key version spent its time in
-//   shuffles: 39 us for 2048 heads of 20x20).
 constexpr int kHd = 32;
 constexpr int kAttnWarps = 4;
 
-__host__ __device__ constexpr int attn_warp_floats(int T) { return 2 * T * kHd + 64; }
+// ------------------------------------------------------------------------------------------------
+// Attention core, one WARP per (pair, head): softmax(Q K^T / sqrt(32) [+ key mask]) V with head_dim 32, up
+// to 64 queries (blocks of 32) and up to 64 keys.  Self-attention (models/text_encoder.py:229-259; keys
+// with mask == 0 get -inf, a fully masked row yields NaN exactly like the reference) and
+// cross-attention over the 49 image tokens (models/cross_attention.py:164-197, no mask) share it.
+// S = Q K^T and O = P V run on mma.sync m16n8k8 with the 3xTF32 split (x = hi + lo; lo*hi + hi*lo + hi*hi:
+// fp32-level accuracy, the parity budget has no room for a plain tf32 attention); softmax stays in fp32
+// registers on the accumulator fragments.  CUDA-core versions measured 2-4x slower (lane per key: shuffle
+// bound, 57 us for the cross attention of 256 pairs; lane per query: LDS.128 broadcast bound, 69 us; this
+// kernel 31 us).  NT = key tiles of 8.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                           uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(d, al, bh0, bh1);
+  mma_tf32(d, ah, bl0, bl1);
+  mma_tf32(d, ah, bh0, bh1);
+}
 
-template <int TMAX>
+constexpr int kKs = 36, kVs = 40;                       // padded row strides (floats): conflict-free fragment loads
+__host__ __device__ constexpr int attn_mma_kreg(int nt) {           // K rows, later the probability tile [32][nt*8+4]
+  return nt * 8 * kKs > 32 * (nt * 8 + 4) ? nt * 8 * kKs : 32 * (nt * 8 + 4);
+}
+__host__ __device__ constexpr int attn_mma_warp_floats(int nt) { return attn_mma_kreg(nt) + nt * 8 * kVs; }
+
+template <int NT>
 __global__ void __launch_bounds__(kAttnWarps * 32)
-attn_lane_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                 const int* __restrict__ mask, float* __restrict__ out, float* __restrict__ weights, int n_units,
-                 int H, int L, int T, int ld_q, int ld_kv) {
+attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                const int* __restrict__ mask, float* __restrict__ out, float* __restrict__ weights, int n_units,
+                int H, int L, int T, int ld_q, int ld_kv) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int unit = blockIdx.x * kAttnWarps + warp;     // (pair, head)
   if (unit >= n_units) return;
   const int b = unit / H, h = unit - b * H;
-  float* ks = sm + warp * attn_warp_floats(T);         // [T][32] key rows
-  float* vs = ks + T * kHd;                            // [T][32] value rows
-  float* mb = vs + T * kHd;                            // [T] additive key mask: 0 or -inf
+  constexpr int PS = NT * 8 + 4;                        // probability tile row stride
+  float* Ks = sm + warp * attn_mma_warp_floats(NT);
+  float* Ps = Ks;
+  float* Vs = Ks + attn_mma_kreg(NT);
   const float* qb = q + static_cast<size_t>(b) * L * ld_q + h * kHd;
   const float* kb = k + static_cast<size_t>(b) * T * ld_kv + h * kHd;
   const float* vb = v + static_cast<size_t>(b) * T * ld_kv + h * kHd;
-  for (int t = lane; t < T * 8; t += 32) {             // 8 lanes cover one 128-byte row: coalesced
-    const int r = t >> 3, c4 = t & 7;
-    reinterpret_cast<float4*>(ks)[r * 8 + c4] = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(r) * ld_kv + c4 * 4);
-    reinterpret_cast<float4*>(vs)[r * 8 + c4] = *reinterpret_cast<const float4*>(vb + static_cast<size_t>(r) * ld_kv + c4 * 4);
+  for (int i = lane; i < NT * 8 * 8; i += 32) {         // V rows (zero beyond T), coalesced
+    const int r = i >> 3, c4 = i & 7;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < T) x = *reinterpret_cast<const float4*>(vb + static_cast<size_t>(r) * ld_kv + c4 * 4);
+    *reinterpret_cast<float4*>(Vs + r * kVs + c4 * 4) = x;
   }
-  for (int j = lane; j < T; j += 32) mb[j] = (mask == nullptr || mask[b * T + j] != 0) ? 0.f : -INFINITY;
-  __syncwarp();
+  float mb[NT][2];                                      // additive key mask of this lane's score columns
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = n * 8 + 2 * t + e;
+      mb[n][e] = (j < T && (mask == nullptr || mask[b * T + j] != 0)) ? 0.f : -INFINITY;
+    }
   const float scale = rsqrtf(static_cast<float>(kHd));
   for (int l0 = 0; l0 < L; l0 += 32) {
-    const int l = l0 + lane;
-    const bool act = l < L;
-    float qr[kHd];
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (act) a = *reinterpret_cast<const float4*>(qb + static_cast<size_t>(l) * ld_q + c4 * 4);
-      qr[4 * c4] = a.x; qr[4 * c4 + 1] = a.y; qr[4 * c4 + 2] = a.z; qr[4 * c4 + 3] = a.w;
+    __syncwarp();
+    for (int i = lane; i < NT * 8 * 8; i += 32) {       // K rows (the region is reused for P below)
+      const int r = i >> 3, c4 = i & 7;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < T) x = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(r) * ld_kv + c4 * 4);
+      *reinterpret_cast<float4*>(Ks + r * kKs + c4 * 4) = x;
     }
-    float s[TMAX];
-    float mx = -INFINITY;
+    // Q fragments (rows g, g+8 of each 16-row tile; dims t, t+4 of each 8-wide k step), pre-split
+    uint32_t qh[2][4][4], ql[2][4][4];
 #pragma unroll
-    for (int j = 0; j < TMAX; ++j) {
-      s[j] = -INFINITY;
-      if (j < T) {                                     // warp-uniform
-        float d = 0.f;
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 kk = reinterpret_cast<const float4*>(ks)[j * 8 + c4];   // broadcast read
-          d += qr[4 * c4] * kk.x + qr[4 * c4 + 1] * kk.y + qr[4 * c4 + 2] * kk.z + qr[4 * c4 + 3] * kk.w;
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = l0 + mt * 16 + g + (e & 1) * 8, col = ks * 8 + t + (e >> 1) * 4;
+          const float x = row < L ? __ldg(qb + static_cast<size_t>(row) * ld_q + col) : 0.f;
+          split_tf32(x, qh[mt][ks][e], ql[mt][ks][e]);
         }
-        s[j] = d * scale + mb[j];
-        mx = fmaxf(mx, s[j]);
+    __syncwarp();
+    float sacc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sacc[mt][n][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(Ks[(n * 8 + g) * kKs + ks * 8 + t], bh0, bl0);
+        split_tf32(Ks[(n * 8 + g) * kKs + ks * 8 + t + 4], bh1, bl1);
+        mma_3xtf32(sacc[0][n], qh[0][ks], ql[0][ks], bh0, bh1, bl0, bl1);
+        mma_3xtf32(sacc[1][n], qh[1][ks], ql[1][ks], bh0, bh1, bl0, bl1);
+      }
+    __syncwarp();                                       // every lane is done with K: the region becomes P
+    // softmax on the fragments: accumulator e -> row (e >> 1) * 8 + g of the tile, column 2t + (e & 1)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float sv = sacc[mt][n][hf * 2 + e] * scale + mb[n][e];
+            sacc[mt][n][hf * 2 + e] = sv;
+            mx = fmaxf(mx, sv);
+          }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;                                // exp(-inf - -inf) = NaN reproduces a fully masked row
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = expf(sacc[mt][n][hf * 2 + e] - mx);
+            sacc[mt][n][hf * 2 + e] = pv;
+            sum += pv;
+          }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = 1.f / sum;
+        float* prow = Ps + (mt * 16 + hf * 8 + g) * PS + 2 * t;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+          *reinterpret_cast<float2*>(prow + n * 8) = make_float2(sacc[mt][n][hf * 2] * inv, sacc[mt][n][hf * 2 + 1] * inv);
+      }
+    __syncwarp();
+    if (weights) {
+      const int rows = min(32, L - l0);
+      float* wb = weights + ((static_cast<size_t>(b) * H + h) * L + l0) * T;
+      for (int i = lane; i < rows * T; i += 32) wb[i] = Ps[(i / T) * PS + (i % T)];
+    }
+    float oacc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oacc[mt][n][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT; ++kk) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          split_tf32(Ps[(mt * 16 + g + (e & 1) * 8) * PS + kk * 8 + t + (e >> 1) * 4], ah[mt][e], al[mt][e]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(Vs[(kk * 8 + t) * kVs + n * 8 + g], bh0, bl0);
+        split_tf32(Vs[(kk * 8 + t + 4) * kVs + n * 8 + g], bh1, bl1);
+        mma_3xtf32(oacc[0][n], ah[0], al[0], bh0, bh1, bl0, bl1);
+        mma_3xtf32(oacc[1][n], ah[1], al[1], bh0, bh1, bl0, bl1);
       }
     }
-    // exp(-inf - -inf) = NaN reproduces the reference for a fully masked row
-    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < TMAX; ++j) {
-      if (j < T) {
-        s[j] = expf(s[j] - mx);
-        sum += s[j];
-      }
-    }
-    const float inv = 1.f / sum;
-    float o[kHd];
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
+      for (int hf = 0; hf < 2; ++hf) {
+        const int row = l0 + mt * 16 + hf * 8 + g;
+        if (row < L) {
+          float* orow = out + (static_cast<size_t>(b) * L + row) * (H * kHd) + h * kHd + 2 * t;
 #pragma unroll
-    for (int j = 0; j < TMAX; ++j) {
-      if (j < T) {
-        const float pj = s[j] * inv;
-        s[j] = pj;
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 vv = reinterpret_cast<const float4*>(vs)[j * 8 + c4];   // broadcast read
-          o[4 * c4] += pj * vv.x; o[4 * c4 + 1] += pj * vv.y; o[4 * c4 + 2] += pj * vv.z; o[4 * c4 + 3] += pj * vv.w;
+          for (int n = 0; n < 4; ++n)                   // tf32 operand of W_o
+            *reinterpret_cast<float2*>(orow + n * 8) = make_float2(round_tf32_rna(oacc[mt][n][hf * 2]),
+                                                                   round_tf32_rna(oacc[mt][n][hf * 2 + 1]));
         }
       }
-    }
-    if (act) {
-      float* orow = out + (static_cast<size_t>(b) * L + l) * (H * kHd) + h * kHd;
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4)                   // tf32 operand of W_o
-        *reinterpret_cast<float4*>(orow + 4 * c4) = make_float4(round_tf32_rna(o[4 * c4]), round_tf32_rna(o[4 * c4 + 1]),
-                                                                round_tf32_rna(o[4 * c4 + 2]), round_tf32_rna(o[4 * c4 + 3]));
-      if (weights) {
-        float* wrow = weights + ((static_cast<size_t>(b) * H + h) * L + l) * T;
-#pragma unroll
-        for (int j = 0; j < TMAX; ++j)
-          if (j < T) wrow[j] = s[j];
-      }
-    }
   }
 }
 
@@ -696,119 +794,85 @@ typedef void (*AttnFn)(const float*, const float*, const float*, const int*, flo
 
 static int launch_attn(const float* q, const float* k, const float* v, const int* mask, float* out, float* weights, int B,
                        int H, int L, int T, int ld_q, int ld_kv, cudaStream_t st) {
-  AttnFn fn = T <= 32 ? static_cast<AttnFn>(&attn_lane_kernel<32>) : static_cast<AttnFn>(&attn_lane_kernel<64>);
-  static bool attr_set = false;
-  if (!attr_set) {
-    const int worst = kAttnWarps * attn_warp_floats(64) * static_cast<int>(sizeof(float));
-    VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_lane_kernel<32>),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, worst));
-    VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&attn_lane_kernel<64>),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, worst));
-    attr_set = true;
+  const int nt = (T + 7) / 8;
+  VQA_REQUIRE(nt >= 1 && nt <= 8, VQA_E_INVALID, "attention: 1..64 keys");
+  const int ntt = nt <= 3 ? 3 : nt <= 4 ? 4 : nt <= 7 ? 7 : 8;
+  AttnFn fn = ntt == 3 ? static_cast<AttnFn>(&attn_mma_kernel<3>) : ntt == 4 ? static_cast<AttnFn>(&attn_mma_kernel<4>)
+            : ntt == 7 ? static_cast<AttnFn>(&attn_mma_kernel<7>) : static_cast<AttnFn>(&attn_mma_kernel<8>);
+  const size_t smem = static_cast<size_t>(kAttnWarps) * attn_mma_warp_floats(ntt) * sizeof(float);
+  static bool attr_set[9] = {false};
+  if (!attr_set[ntt]) {
+    VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    attr_set[ntt] = true;
   }
-  const size_t smem = static_cast<size_t>(kAttnWarps) * attn_warp_floats(T) * sizeof(float);
   VQA_CUDA_OK(vqa_launch(fn, dim3((B * H + kAttnWarps - 1) / kAttnWarps), dim3(kAttnWarps * 32), smem, st, q, k, v, mask, out,
                          weights, B * H, H, L, T, ld_q, ld_kv));
-  VQA_LAUNCH_OK("attn_lane_kernel");
+  VQA_LAUNCH_OK("attn_mma_kernel");
   return VQA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fusion tail, kTailRows pairs per CTA: masked mean pools of the cross-attended and text features
-// (denominator clamp(min=1)), gate g = sigmoid(W[att;txt]+b), g*att+(1-g)*txt (or the plain sum when
-// gating is disabled), output LayerNorm (models/fusion.py:299-326, :159-166).  D = 256 = blockDim.
-// The 512 KB gate matrix is read once per CTA and applied to all of its pairs.
-constexpr int kTailRows = 1;   // 1 measured fastest at batch 256 (4 halves the L2 traffic but leaves SMs idle)
-
+// Fusion tail, one pair per CTA, D = 256 = blockDim (models/fusion.py:299-326, :159-166):
+//   phase 1: masked mean pools of the cross-attended and text features (denominator clamp(min=1)),
+//            written as att_pooled / txt_pooled and as the tf32 row [att;txt] of the gate GEMM
+//   phase 2: g = sigmoid(pre) with pre = W[att;txt]+b from that GEMM, g*att+(1-g)*txt, output LayerNorm
+//   phase 0: no gating: att+txt, output LayerNorm (pools computed in place)
 __global__ void __launch_bounds__(256)
 pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text, const int* __restrict__ mask,
-                    const float* __restrict__ wg, const float* __restrict__ bg, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, float* __restrict__ fused, float* __restrict__ att_pooled,
-                    float* __restrict__ txt_pooled, int B, int L, int use_gate, float eps) {
+                    const float* __restrict__ pre, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ fused, float* __restrict__ att_pooled, float* __restrict__ txt_pooled,
+                    float* __restrict__ cat, int L, int phase, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int D = 256;
-  __shared__ float cat[kTailRows][2 * D];
-  __shared__ float gate[kTailRows][D];
-  __shared__ float red[kTailRows][16];
-  const int b0 = blockIdx.x * kTailRows, d = threadIdx.x;
+  __shared__ float red[16];
+  const int b = blockIdx.x, d = threadIdx.x;
   const int warp = d >> 5, lane = d & 31;
-  float ap[kTailRows], tp[kTailRows];
-#pragma unroll
-  for (int i = 0; i < kTailRows; ++i) {
-    const int b = b0 + i;
+  float ap, tp;
+  if (phase != 2) {
     float cnt = 0.f, sa = 0.f, st = 0.f;
-    if (b < B) {
-      for (int l = 0; l < L; ++l) {
-        const float m = mask ? static_cast<float>(mask[b * L + l]) : 1.f;
-        cnt += m;
-        sa += xatt[(static_cast<size_t>(b) * L + l) * D + d] * m;
-        st += text[(static_cast<size_t>(b) * L + l) * D + d] * m;
-      }
+    for (int l = 0; l < L; ++l) {
+      const float m = mask ? static_cast<float>(mask[b * L + l]) : 1.f;
+      cnt += m;
+      sa += xatt[(static_cast<size_t>(b) * L + l) * D + d] * m;
+      st += text[(static_cast<size_t>(b) * L + l) * D + d] * m;
     }
     const float den = fmaxf(cnt, 1.f);
-    ap[i] = sa / den;
-    tp[i] = st / den;
-    cat[i][d] = ap[i];
-    cat[i][D + d] = tp[i];
-    if (b < B) {
-      if (att_pooled) att_pooled[static_cast<size_t>(b) * D + d] = ap[i];
-      if (txt_pooled) txt_pooled[static_cast<size_t>(b) * D + d] = tp[i];
-    }
-  }
-  __syncthreads();
-  float f[kTailRows];
-  if (use_gate) {
-    for (int r = warp * 32; r < warp * 32 + 32; ++r) {      // 8 warps x 32 gate rows
-      const float* wr = wg + static_cast<size_t>(r) * 2 * D;
-      float s[kTailRows];
-#pragma unroll
-      for (int i = 0; i < kTailRows; ++i) s[i] = 0.f;
-      for (int k = lane; k < 2 * D; k += 32) {
-        const float w = wr[k];
-#pragma unroll
-        for (int i = 0; i < kTailRows; ++i) s[i] += w * cat[i][k];
-      }
-#pragma unroll
-      for (int i = 0; i < kTailRows; ++i) {
-        const float t = warp_sum(s[i]);
-        if (lane == 0) gate[i][r] = 1.f / (1.f + expf(-(t + bg[r])));
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < kTailRows; ++i) {
-      const float g = gate[i][d];
-      f[i] = g * ap[i] + (1.f - g) * tp[i];
+    ap = sa / den;
+    tp = st / den;
+    att_pooled[static_cast<size_t>(b) * D + d] = ap;
+    txt_pooled[static_cast<size_t>(b) * D + d] = tp;
+    if (phase == 1) {
+      cat[static_cast<size_t>(b) * 2 * D + d] = round_tf32_rna(ap);
+      cat[static_cast<size_t>(b) * 2 * D + D + d] = round_tf32_rna(tp);
+      return;
     }
   } else {
-#pragma unroll
-    for (int i = 0; i < kTailRows; ++i) f[i] = ap[i] + tp[i];
+    ap = att_pooled[static_cast<size_t>(b) * D + d];
+    tp = txt_pooled[static_cast<size_t>(b) * D + d];
   }
-  // block LayerNorm over 256 values (8 warps), all rows at once
-#pragma unroll
-  for (int i = 0; i < kTailRows; ++i) {
-    const float s = warp_sum(f[i]);
-    if (lane == 0) red[i][warp] = s;
+  float f;
+  if (phase == 2) {
+    const float g = 1.f / (1.f + expf(-pre[static_cast<size_t>(b) * D + d]));
+    f = g * ap + (1.f - g) * tp;
+  } else {
+    f = ap + tp;
   }
+  // block LayerNorm over 256 values (8 warps)
+  const float s = warp_sum(f);
+  if (lane == 0) red[warp] = s;
   __syncthreads();
-  float c[kTailRows];
-#pragma unroll
-  for (int i = 0; i < kTailRows; ++i) {
-    float mean = 0.f;
-    for (int w = 0; w < 8; ++w) mean += red[i][w];
-    c[i] = f[i] - mean * (1.f / D);
-    const float q = warp_sum(c[i] * c[i]);
-    if (lane == 0) red[i][8 + warp] = q;
-  }
+  float mean = 0.f;
+  for (int w = 0; w < 8; ++w) mean += red[w];
+  const float c = f - mean * (1.f / D);
+  const float q = warp_sum(c * c);
+  if (lane == 0) red[8 + warp] = q;
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < kTailRows; ++i) {
-    float var = 0.f;
-    for (int w = 0; w < 8; ++w) var += red[i][8 + w];
-    var *= (1.f / D);
-    if (b0 + i < B) fused[static_cast<size_t>(b0 + i) * D + d] = c[i] * rsqrtf(var + eps) * gamma[d] + beta[d];
-  }
+  float var = 0.f;
+  for (int w = 0; w < 8; ++w) var += red[8 + w];
+  var *= (1.f / D);
+  fused[static_cast<size_t>(b) * D + d] = c * rsqrtf(var + eps) * gamma[d] + beta[d];
 }
 
 // softmax over N answers + top-k (k <= 16), ties broken towards the lower index like torch.topk on
@@ -974,7 +1038,8 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(q.Po > 0 && q.RPIo % q.Po == 0, VQA_E_INVALID, "stage_tail: bad destination grid");
       const int NP = q.H / q.CS * q.W, lanes = kTailThreads / q.C8;
       VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= lanes * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
-      const size_t smem = static_cast<size_t>(NP) * C * 2 + sizeof(float) * (static_cast<size_t>(lanes) * C + 2 * C + 64 + NP);
+      VQA_REQUIRE(q.ks >= 0 && 2 * q.ks * q.ks <= 128, VQA_E_INVALID, "stage_tail: spatial kernel too large");
+      const size_t smem = static_cast<size_t>(NP) * C * 2 + sizeof(float) * (static_cast<size_t>(lanes) * C + 2 * C + 64 + NP + 128);
       VQA_REQUIRE(smem <= 227 * 1024, VQA_E_INVALID, "stage_tail: rows per CTA exceed shared memory (raise CS)");
       static size_t attr_smem = 0;
       if (smem > attr_smem) {
@@ -1045,13 +1110,20 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
                          I[CROSS_ATTN_I_ld_kv], st);
     }
     case VQA_OP_POOL_GATE_LN: {
+      const int phase = I[POOL_GATE_LN_I_phase];
       VQA_REQUIRE(I[POOL_GATE_LN_I_D] == 256, VQA_E_INVALID, "pool_gate_ln: D must be 256");
-      VQA_CUDA_OK(vqa_launch(pool_gate_ln_kernel, dim3((I[POOL_GATE_LN_I_B] + kTailRows - 1) / kTailRows), dim3(256), 0, st, 
+      VQA_REQUIRE(phase >= 0 && phase <= 2 && (phase != 0 || I[POOL_GATE_LN_I_use_gate] == 0), VQA_E_INVALID,
+                  "pool_gate_ln: gating runs as pool -> gate GEMM -> mix (phases 1, 2)");
+      VQA_REQUIRE(PTR(float*, POOL_GATE_LN_P_att_pooled) && PTR(float*, POOL_GATE_LN_P_txt_pooled), VQA_E_INVALID,
+                  "pool_gate_ln: pooled buffers are required");
+      VQA_REQUIRE(phase != 1 || PTR(float*, POOL_GATE_LN_P_cat), VQA_E_INVALID, "pool_gate_ln: phase 1 needs cat");
+      VQA_REQUIRE(phase != 2 || PTR(const float*, POOL_GATE_LN_P_pre), VQA_E_INVALID, "pool_gate_ln: phase 2 needs pre");
+      VQA_CUDA_OK(vqa_launch(pool_gate_ln_kernel, dim3(I[POOL_GATE_LN_I_B]), dim3(256), 0, st,
           PTR(const float*, POOL_GATE_LN_P_xatt), PTR(const float*, POOL_GATE_LN_P_text),
-          PTR(const int*, POOL_GATE_LN_P_mask), PTR(const float*, POOL_GATE_LN_P_wg), PTR(const float*, POOL_GATE_LN_P_bg),
+          PTR(const int*, POOL_GATE_LN_P_mask), PTR(const float*, POOL_GATE_LN_P_pre),
           PTR(const float*, POOL_GATE_LN_P_gamma), PTR(const float*, POOL_GATE_LN_P_beta),
           PTR(float*, POOL_GATE_LN_P_fused), PTR(float*, POOL_GATE_LN_P_att_pooled),
-          PTR(float*, POOL_GATE_LN_P_txt_pooled), I[POOL_GATE_LN_I_B], I[POOL_GATE_LN_I_L], I[POOL_GATE_LN_I_use_gate],
+          PTR(float*, POOL_GATE_LN_P_txt_pooled), PTR(float*, POOL_GATE_LN_P_cat), I[POOL_GATE_LN_I_L], phase,
           op.f[POOL_GATE_LN_F_eps]));
       VQA_LAUNCH_OK("pool_gate_ln_kernel");
       return VQA_OK;
@@ -1085,8 +1157,8 @@ const char* misc_kernel_name(int kind) {
     case VQA_OP_STAGE_TAIL: return "stage_tail_kernel";
     case VQA_OP_EMBED: return "embed_kernel";
     case VQA_OP_LAYERNORM: return "layernorm256_kernel";
-    case VQA_OP_SELF_ATTN: return "attn_lane_kernel(self)";
-    case VQA_OP_CROSS_ATTN: return "attn_lane_kernel(cross)";
+    case VQA_OP_SELF_ATTN: return "attn_mma_kernel(self)";
+    case VQA_OP_CROSS_ATTN: return "attn_mma_kernel(cross)";
     case VQA_OP_POOL_GATE_LN: return "pool_gate_ln_kernel";
     case VQA_OP_SOFTMAX_TOPK: return "softmax_topk_kernel";
     default: return "?";

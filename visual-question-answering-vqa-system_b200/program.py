@@ -65,9 +65,9 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
     "self_attn": {"i": ["B", "L", "H", "hd", "ld_qkv"], "p": ["qkv", "mask", "out"], "f": []},
     "cross_attn": {"i": ["B", "L", "H", "hd", "T", "ld_q", "ld_kv", "k_off", "v_off"],
                    "p": ["q", "kv", "out", "weights"], "f": []},
-    "pool_gate_ln": {"i": ["B", "L", "D", "use_gate"],
+    "pool_gate_ln": {"i": ["B", "L", "D", "use_gate", "phase"],
                      "p": ["xatt", "text", "mask", "wg", "bg", "gamma", "beta", "fused",
-                           "att_pooled", "txt_pooled"], "f": ["eps"]},
+                           "att_pooled", "txt_pooled", "cat", "pre"], "f": ["eps"]},
     "softmax_topk": {"i": ["B", "N", "k", "ld"], "p": ["logits", "idx", "probs"], "f": []},
     "mask_prep": {"i": ["B", "L", "dtype"], "p": ["src", "dst"], "f": []},
     "grid_to_nchw": {"i": ["B", "C", "H", "W", "P", "RPI"], "p": ["src", "dst"], "f": []},
@@ -347,7 +347,7 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
         W.add(f"x.{layer}.fc2.b", sd[q + ".ffn.3.bias"], f32)
         layer += 1
     if fz + ".gate.gate.0.weight" in sd:
-        W.add("gate.w", sd[fz + ".gate.gate.0.weight"], f32)
+        W.add("gate.w", round_tf32(sd[fz + ".gate.gate.0.weight"].float()), f32)
         W.add("gate.b", sd[fz + ".gate.gate.0.bias"], f32)
     W.add("out.ln.g", sd[fz + ".output_norm.weight"], f32)
     W.add("out.ln.b", sd[fz + ".output_norm.bias"], f32)
@@ -744,10 +744,18 @@ class Program(OpList):
         attp = self._buf("attended_pooled", f32, B, D)
         txtp = self._buf("text_pooled", f32, B, D)
         use_gate = "gate.w" in W
-        self._op("pool_gate_ln", "fusion.tail", dict(B=B, L=L, D=D, use_gate=int(use_gate)),
-                 dict(xatt=src_q, text=text, mask=mask, wg=W.buf("gate.w") if use_gate else None,
-                      bg=W.buf("gate.b") if use_gate else None, gamma=W.buf("out.ln.g"), beta=W.buf("out.ln.b"),
-                      fused=fused, att_pooled=attp, txt_pooled=txtp), dict(eps=1e-5))
+        tail_p = dict(xatt=src_q, text=text, mask=mask, wg=None, bg=None, gamma=W.buf("out.ln.g"), beta=W.buf("out.ln.b"),
+                      fused=fused, att_pooled=attp, txt_pooled=txtp, cat=None, pre=None)
+        if use_gate:
+            # masked pools -> [att;txt] (tf32) -> gate pre-activation on the tensor cores (the 512 KB gate matrix is
+            # read once instead of once per pair) -> sigmoid gate, mix, LayerNorm
+            cat = self._buf("fusion.cat", f32, B, 2 * D)
+            pre = self._buf("fusion.gate_pre", f32, B, D)
+            self._op("pool_gate_ln", "fusion.pool", dict(B=B, L=L, D=D, use_gate=1, phase=1), dict(tail_p, cat=cat), dict(eps=1e-5))
+            self.linear("fusion.gate", cat, B, 2 * D, "gate.w", "gate.b", pre, D)
+            self._op("pool_gate_ln", "fusion.mix", dict(B=B, L=L, D=D, use_gate=1, phase=2), dict(tail_p, pre=pre), dict(eps=1e-5))
+        else:
+            self._op("pool_gate_ln", "fusion.tail", dict(B=B, L=L, D=D, use_gate=0, phase=0), tail_p, dict(eps=1e-5))
 
         # ================= answer head =================
         NA = cfg["num_answers"]
