@@ -47,7 +47,8 @@ struct GemmParams {
   int acc_stages;    // TMEM accumulator double buffering (1 or 2)
   int win_per_tile;  // A windows one tile consumes (sum of chunks over groups)
   int steps_per_tile;// weight tiles one tile consumes (sum of chunks*taps over groups)
-  int m_tiles, n_tiles;
+  int m_tiles, n_tiles;   // tiles a CTA (or, in pair mode, a CTA pair) walks: m_tiles counts pairs of m tiles then
+  int m_tiles_cta;        // real number of per-CTA m tiles (pair mode: the last pair may hold a phantom tile)
   int ngroups;
   int chunk_elems;   // 64 (bf16) / 32 (tf32)
   int is_tf32;
@@ -110,7 +111,9 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
 }
 
 // ROW32: K chunks are 32-byte rows (the stem) instead of 128-byte rows.
-template <int BN, int MT, bool TF32, int EPI, bool ROW32>
+// PAIR: two CTAs of a cluster share one 256-row UMMA (cta_group::2): each loads its own A windows and HALF of every
+// weight tile, the even CTA issues the MMAs for both, each CTA drains its own 128 accumulator rows.
+template <int BN, int MT, bool TF32, int EPI, bool ROW32, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
@@ -125,6 +128,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;                  // 0 = leader (issues the MMAs)
+  const int walker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // tile-sequence id
+  const int n_walkers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // per-CTA m-tile index of a walked tile (pair mode: 2 * pair index + rank; may be a phantom tile >= m_tiles_cta)
+  auto cta_mtile = [&](int tile) { return PAIR ? 2 * (tile % p.m_tiles) + static_cast<int>(rank) : tile % p.m_tiles; };
   const int b_region_slots = p.b_resident ? p.k_chunks : p.b_slots;
 
   uint8_t* smem_a = smem;
@@ -159,7 +167,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps * (PAIR ? 2 : 1)); }
     for (int s = 0; s < kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
     mbar_fence_init();
     for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kRowBytes / 16);
@@ -168,11 +176,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(BN * MT * p.acc_stages)) tmem_cols <<= 1;   // power of two >= 32
   if (warp == 2) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
+    else      { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();       // pair: the peer's barriers must exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) VQA_DBG(1);
@@ -187,41 +195,47 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     bool b_loaded = false;
     const bool timed = p.dbg != nullptr && blockIdx.x == 0;
     long long w_aempty = 0, w_bempty = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = tile_m0(p, tile % p.m_tiles, MT);
-      const int n0 = (tile / p.m_tiles) * BN;
+    // pair mode: every load of either CTA completes on the LEADER's full barrier, which expects both CTAs' bytes
+    constexpr uint32_t kTxMul = PAIR ? 2u : 1u;
+    const bool expects = !PAIR || rank == 0;
+    auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+      if (PAIR) tma_load_2d_pair(dst, map, bar, x, y); else tma_load_2d(dst, map, bar, x, y);
+    };
+    for (int tile = walker; tile < total_tiles; tile += n_walkers) {
+      const int m0 = tile_m0(p, cta_mtile(tile), MT);
+      const int n0 = (tile / p.m_tiles) * BN + (PAIR ? static_cast<int>(rank) * (BN / 2) : 0);   // pair: this CTA's half of the N tile
       if (p.b_resident && !b_loaded) {   // n_tiles == 1 in this mode: load every weight chunk once
         if (elect_one()) {
-          mbar_expect_tx(&b_full[0], static_cast<uint32_t>(p.k_chunks * p.b_slot_bytes));
+          if (expects) mbar_expect_tx(&b_full[0], static_cast<uint32_t>(p.k_chunks * p.b_slot_bytes) * kTxMul);
           for (int q = 0; q < p.k_chunks; ++q)
-            tma_load_2d(smem_b + q * p.b_slot_bytes, &mapB, &b_full[0], q * p.chunk_elems, n0);
+            load(smem_b + q * p.b_slot_bytes, &mapB, &b_full[0], q * p.chunk_elems, n0);
         }
         __syncwarp();
         b_loaded = true;
       }
-      if (tile == static_cast<int>(blockIdx.x)) pdl_wait();   // weights are constants; the activations are not
+      if (tile == walker) pdl_wait();   // weights are constants; the activations are not
       for (int g = 0; g < p.ngroups; ++g) {
         const CUtensorMap* mapA = p.g_map[g] ? &mapA1 : &mapA0;
         const int row0 = m0 + p.g_delta[g] - p.halo;
         for (int c = 0; c < p.g_chunks[g]; ++c) {
           mbar_wait_t(&a_empty[as], aph ^ 1u, timed, w_aempty);
           if (elect_one()) {
-            mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_tx_bytes));
+            if (expects) mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.a_tx_bytes) * kTxMul);
             uint8_t* dst = smem_a + as * p.a_slot_bytes;
             const int x = p.g_acol[g] + c * p.chunk_elems;
             for (int b = 0; b < p.nboxes; ++b)
-              tma_load_2d(dst + b * p.box_rows * kRowBytes, mapA, &a_full[as], x, row0 + b * p.box_rows);
+              load(dst + b * p.box_rows * kRowBytes, mapA, &a_full[as], x, row0 + b * p.box_rows);
           }
           __syncwarp();
-          if (tile == blockIdx.x && g == 0 && c == 0) VQA_DBG(2);
+          if (tile == walker && g == 0 && c == 0) VQA_DBG(2);
           if (++as == p.a_slots) { as = 0; aph ^= 1u; }
           if (!p.b_resident) {
             for (int t = 0; t < p.g_ntaps[g]; ++t) {
               mbar_wait_t(&b_empty[bs], bph ^ 1u, timed, w_bempty);
               if (elect_one()) {
-                mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(p.b_slot_bytes));
+                if (expects) mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(p.b_slot_bytes) * kTxMul);
                 const int kcol = p.g_kbase[g] + (t * p.g_chunks[g] + c) * p.chunk_elems;
-                tma_load_2d(smem_b + bs * p.b_slot_bytes, &mapB, &b_full[bs], kcol, n0);
+                load(smem_b + bs * p.b_slot_bytes, &mapB, &b_full[bs], kcol, n0);
               }
               __syncwarp();
               if (++bs == p.b_slots) { bs = 0; bph ^= 1u; }
@@ -239,7 +253,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // the MMA issue itself (splitting the K slices over two issuer threads changed nothing and made
     // the accumulation order non-deterministic), so the common 9-tap window group is fully unrolled
     // with its tap offsets held in registers and loop-invariant parameters hoisted by hand.
-    if (elect_one()) {
+    if ((!PAIR || rank == 0) && elect_one()) {
       const int a_slots = p.a_slots, b_slots = p.b_slots, ngroups = p.ngroups, acc_stages = p.acc_stages;
       const bool resident = p.b_resident != 0;
       const uint32_t a_slot_lo = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
@@ -260,6 +274,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       uint32_t d_tile = 0, fresh = 1;
 
       // one (window, tap) step: kMmaPerChunk*MT MMAs over the K chunk
+      auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };   // pair: both CTAs' barriers
       auto issue_step = [&](uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
         for (int sub = 0; sub < MT; ++sub) {
@@ -268,8 +283,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             const uint64_t ad = kDescHi | (a_lo + sub * (128 * kRowBytes / 16) + 2 * k);
             const uint64_t bd = kDescHi | (b_lo + 2 * k);
             const uint32_t accum = (k == 0) ? (fresh ^ 1u) : 1u;
-            if (TF32) umma_tf32(d_tile + sub * BN, ad, bd, idesc, accum);
-            else      umma_f16(d_tile + sub * BN, ad, bd, idesc, accum);
+            if (PAIR)      umma_f16_pair(d_tile + sub * BN, ad, bd, idesc, accum);
+            else if (TF32) umma_tf32(d_tile + sub * BN, ad, bd, idesc, accum);
+            else           umma_f16(d_tile + sub * BN, ad, bd, idesc, accum);
           }
         }
         fresh = 0;
@@ -283,13 +299,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       };
       auto b_release = [&]() {
         if (!resident) {
-          umma_commit(&b_empty[bs]);       // weight slot is free once these MMAs retire
+          commit(&b_empty[bs]);            // weight slot is free once these MMAs retire
           if (++bs == b_slots) { bs = 0; bph ^= 1u; }
         }
       };
 
       if (resident) mbar_wait(&b_full[0], 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = walker; tile < total_tiles; tile += n_walkers) {
         mbar_wait_t(&acc_empty[acc], accph ^ 1u, timed, w_accempty);   // epilogue has drained this accumulator stage
         tc_fence_after();
         d_tile = tmem_base + acc * (BN * MT);
@@ -319,14 +335,14 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 b_release();
               }
             }
-            umma_commit(&a_empty[as]);       // window slot is free once all its taps retire
+            commit(&a_empty[as]);            // window slot is free once all its taps retire
             if (++as == a_slots) { as = 0; aph ^= 1u; }
           }
         }
-        umma_commit(&acc_full[acc]);
+        commit(&acc_full[acc]);
         if (timed) {
           if (tile == 0) p.dbg[4] = clock64();
-          if (tile + static_cast<int>(gridDim.x) >= total_tiles) p.dbg[9] = clock64();
+          if (tile + n_walkers >= total_tiles) p.dbg[9] = clock64();
         }
         if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
       }
@@ -354,11 +370,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     uint32_t accph = 0;
     const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
     long long w_accfull = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int img = tile / tpi, ip = tile - img * tpi;       // image, pooled row
+    for (int tile = walker; tile < total_tiles; tile += n_walkers) {
+      const int mt_idx = cta_mtile(tile);                      // this CTA's (image, pooled row) tile
+      const bool real = mt_idx < p.m_tiles_cta;                // pair mode: the last pair may carry a phantom tile
+      const int img = mt_idx / tpi, ip = mt_idx - img * tpi;   // image, pooled row
       mbar_wait_t(&acc_full[acc], accph, timed, w_accfull);
       tc_fence_after();
-      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(5);
+      if (warp == 2 && tile == walker) VQA_DBG(5);
       // No pad masking here: the pooling pass below only reads in-image conv positions.
       uint32_t v[MT][32];
       __syncwarp();
@@ -394,11 +412,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);         // TMEM stage drained: the next tile's MMAs may start
+      if (lane == 0) {                                     // TMEM stage drained: the next tile's MMAs may start
+        if (PAIR) mbar_arrive_leader(&acc_empty[acc]); else mbar_arrive(&acc_empty[acc]);
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");       // conv tile complete (epilogue warps only)
       // ---- pooling pass: item = (pooled column j', channel octet cg)
       const size_t orow = static_cast<size_t>(img) * rpio + static_cast<size_t>(ip) * Po;
-      for (int item = tid; item < Po * 8; item += 256) {
+      for (int item = tid; item < (real ? Po * 8 : 0); item += 256) {
         const int jp = item >> 3, cg = item & 7;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (jp < Wo) {
@@ -425,8 +445,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (ip == Ho - 1) out[(orow + Po + jp) * 8 + cg] = make_uint4(0u, 0u, 0u, 0u);   // the image's zero pad row
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");       // pooling done: the conv tile may be overwritten
-      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(6);
-      if (warp == 2 && tile + static_cast<int>(gridDim.x) >= total_tiles) VQA_DBG(7);
+      if (warp == 2 && tile == walker) VQA_DBG(6);
+      if (warp == 2 && tile + n_walkers >= total_tiles) VQA_DBG(7);
       if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
     }
     if (timed && lane == 0) p.dbg[21] = w_accfull;
@@ -466,19 +486,18 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     uint32_t accph = 0, resph = 0;
     const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
     long long w_accfull = 0;
-    const int tstep = static_cast<int>(gridDim.x);
+    const int tstep = n_walkers;
 
     auto issue_res = [&](int row0, int col0) {          // lane 0 only
       mbar_expect_tx(my_res_bar, kSlotBytes);
       tma_load_2d(res_slot, &mapRes, my_res_bar, col0, row0);
     };
-    if (kRes && lane == 0 && static_cast<int>(blockIdx.x) < total_tiles) {
-      const int t0 = blockIdx.x;
-      issue_res(tile_m0(p, t0 % m_tiles, MT) + quad * 32, (t0 / m_tiles) * BN + half * kCols);
+    if (kRes && lane == 0 && walker < total_tiles) {
+      issue_res(tile_m0(p, cta_mtile(walker), MT) + quad * 32, (walker / m_tiles) * BN + half * kCols);
     }
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += tstep) {
-      const int m0 = tile_m0(p, tile % m_tiles, MT);
+    for (int tile = walker; tile < total_tiles; tile += tstep) {
+      const int m0 = tile_m0(p, cta_mtile(tile), MT);
       const int n0 = (tile / m_tiles) * BN;
       const int colw = n0 + half * kCols;               // first column this warp owns
       // ---- work that does not need the accumulator: done while the MMAs are still running
@@ -493,12 +512,12 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       }
       const int ntile = tile + tstep;                   // the residual of its first chunk is prefetched at the end
       const bool has_ntile = ntile < total_tiles;
-      const int n_row0 = tile_m0(p, ntile % m_tiles, MT) + quad * 32;
+      const int n_row0 = tile_m0(p, cta_mtile(ntile), MT) + quad * 32;
       const int n_col0 = (ntile / m_tiles) * BN + half * kCols;
 
       mbar_wait_t(&acc_full[acc], accph, timed, w_accfull);
       tc_fence_after();
-      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(5);
+      if (warp == 2 && tile == walker) VQA_DBG(5);
 #pragma unroll
       for (int sub = 0; sub < MT; ++sub) {
         const int row0 = m0 + sub * 128 + quad * 32;
@@ -592,12 +611,14 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           }
         }
       }
-      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(13);
+      if (warp == 2 && tile == walker) VQA_DBG(13);
       // all TMEM reads of this warp are complete (wait::ld above): release the accumulator stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (warp == 2 && tile == static_cast<int>(blockIdx.x)) VQA_DBG(6);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&acc_empty[acc]); else mbar_arrive(&acc_empty[acc]);
+      }
+      if (warp == 2 && tile == walker) VQA_DBG(6);
       if (warp == 2 && tile + tstep >= total_tiles) VQA_DBG(7);
       if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
     }
@@ -606,8 +627,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  if (PAIR) cluster_sync(); else __syncthreads();       // pair: the leader's last commits land on the peer's barriers
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
+  }
   if (warp == 0) VQA_DBG(8);
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long ns;
@@ -691,9 +714,9 @@ int encode_box32(CUtensorMap* map, bool f32, uint64_t base, int rows, int cols, 
 
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format f32 [4,6)=1,
 // a/b format [7,10)/[10,13) (1 = bf16, 2 = tf32), K-major A and B, N>>3 at [17,23), M>>4 at [24,29).
-uint32_t make_idesc(bool tf32, int n) {
+uint32_t make_idesc(bool tf32, int n, int m) {
   const uint32_t fmt = tf32 ? 2u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 int num_sms(int device) {
@@ -712,24 +735,32 @@ typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 
 // Instantiated (BN, MT, operand type, epilogue) combinations: bf16 kernels with epilogues 0/1/2
 // (convolutions, image projector), tf32 kernels with MT = 1 and epilogues 2/3 (all nn.Linear layers).
-static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_bytes) {
+static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_bytes, bool pair) {
+#define VQA_K(BN_, MT_, TF_, EPI_, R32_, PAIR_) static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, TF_, EPI_, R32_, PAIR_>)
   if (row_bytes == 32) {   // the stem: 32-byte rows, bf16, N = 64, ReLU epilogue without residual
-    if (bn == 64 && mt == 1 && !tf32 && epi == 0) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 1, false, 0, true>);
-    if (bn == 64 && mt == 2 && !tf32 && epi == 0) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 2, false, 0, true>);
-    if (bn == 64 && mt == 2 && !tf32 && epi == 2) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 2, false, 2, true>);
-    if (bn == 64 && mt == 3 && !tf32 && epi == 4) return static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 3, false, 4, true>);
+    if (pair) {
+      if (bn == 64 && mt == 3 && !tf32 && epi == 4) return VQA_K(64, 3, false, 4, true, true);
+      if (bn == 64 && mt == 2 && !tf32 && epi == 0) return VQA_K(64, 2, false, 0, true, true);
+      return nullptr;
+    }
+    if (bn == 64 && mt == 1 && !tf32 && epi == 0) return VQA_K(64, 1, false, 0, true, false);
+    if (bn == 64 && mt == 2 && !tf32 && epi == 0) return VQA_K(64, 2, false, 0, true, false);
+    if (bn == 64 && mt == 2 && !tf32 && epi == 2) return VQA_K(64, 2, false, 2, true, false);
+    if (bn == 64 && mt == 3 && !tf32 && epi == 4) return VQA_K(64, 3, false, 4, true, false);
     return nullptr;
   }
-#define VQA_PICK(BN_, MT_, TF_, EPI_) \
-  if (bn == BN_ && mt == MT_ && tf32 == TF_ && epi == EPI_) return static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, TF_, EPI_, false>);
-#define VQA_PICK_BF16(BN_, MT_) VQA_PICK(BN_, MT_, false, 0) VQA_PICK(BN_, MT_, false, 1) VQA_PICK(BN_, MT_, false, 2)
-#define VQA_PICK_TF32(BN_) VQA_PICK(BN_, 1, true, 2) VQA_PICK(BN_, 1, true, 3)
+#define VQA_PICK(BN_, MT_, TF_, EPI_, PAIR_) \
+  if (bn == BN_ && mt == MT_ && tf32 == TF_ && epi == EPI_ && pair == PAIR_) return VQA_K(BN_, MT_, TF_, EPI_, false, PAIR_);
+#define VQA_PICK_BF16(BN_, MT_) VQA_PICK(BN_, MT_, false, 0, false) VQA_PICK(BN_, MT_, false, 1, false) \
+  VQA_PICK(BN_, MT_, false, 2, false) VQA_PICK(BN_, MT_, false, 0, true) VQA_PICK(BN_, MT_, false, 1, true)
+#define VQA_PICK_TF32(BN_) VQA_PICK(BN_, 1, true, 2, false) VQA_PICK(BN_, 1, true, 3, false)
   VQA_PICK_BF16(64, 1) VQA_PICK_BF16(64, 2) VQA_PICK_BF16(128, 1) VQA_PICK_BF16(128, 2)
   VQA_PICK_BF16(256, 1) VQA_PICK_BF16(256, 2)
   VQA_PICK_TF32(64) VQA_PICK_TF32(128) VQA_PICK_TF32(256)
 #undef VQA_PICK_TF32
 #undef VQA_PICK_BF16
 #undef VQA_PICK
+#undef VQA_K
   return nullptr;
 }
 
@@ -738,6 +769,7 @@ struct GemmLaunch {
   int epi;
   CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes;
   bool out_external;    // the output is a caller tensor (logits): its map is encoded per run
+  bool pair;            // CTA-pair (cta_group::2) launch: clusters of 2
   GemmParams prm;
   dim3 grid;
   int bn;
@@ -774,7 +806,10 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   // UMMA shared-memory descriptor high word: SBO (8 rows) >> 4 at [32,46), version 1 at [46,48),
   // swizzle mode at [61,64): 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
   p.desc_hi = static_cast<uint32_t>((8 * p.row_bytes) >> 4) | (1u << 14) | ((p.row_bytes == 128 ? 2u : 6u) << 29);
-  p.idesc = make_idesc(tf32, bn);
+  const bool pair = I[GEMM_I_pair] != 0;
+  L->pair = pair;
+  VQA_REQUIRE(!pair || (!tf32 && bn % 16 == 0), VQA_E_INVALID, "gemm: CTA pairs are implemented for bf16 operands");
+  p.idesc = make_idesc(tf32, bn, pair ? 256 : 128);
   VQA_REQUIRE(I[GEMM_I_Ktot] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: Ktot must be a multiple of the K chunk");
   p.k_chunks = I[GEMM_I_Ktot] / p.chunk_elems;
   bool lockstep = p.halo == 0 && halo_hi == 0;
@@ -814,7 +849,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.box_rows = ((win + p.nboxes - 1) / p.nboxes + 7) / 8 * 8;    // 8-row groups keep every box swizzle-aligned
   p.a_tx_bytes = p.nboxes * p.box_rows * p.row_bytes;
   p.a_slot_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
-  p.b_slot_bytes = bn * p.row_bytes;
+  p.b_slot_bytes = (pair ? bn / 2 : bn) * p.row_bytes;    // pair: each CTA holds half of the weight tile's rows
   VQA_REQUIRE(p.b_slot_bytes % 1024 == 0, VQA_E_INVALID, "gemm: weight tile must be a multiple of 1024 bytes");
   p.m_tiles = (p.M + 128 * p.MT - 1) / (128 * p.MT);
   p.tiles_per_img = I[GEMM_I_tiles_per_img];
@@ -826,6 +861,8 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
     VQA_REQUIRE(p.img_rows > 0 && p.tile_stride > 0 && I[GEMM_I_n_imgs] > 0, VQA_E_INVALID, "gemm: bad strided tiling");
     p.m_tiles = p.tiles_per_img * I[GEMM_I_n_imgs];
   }
+  p.m_tiles_cta = p.m_tiles;
+  if (pair) p.m_tiles = (p.m_tiles + 1) / 2;               // the kernel walks pairs of m tiles
   p.pool_P = I[GEMM_I_pool_P]; p.pool_W = I[GEMM_I_pool_W]; p.pool_Wo = I[GEMM_I_pool_Wo]; p.pool_Ho = I[GEMM_I_pool_Ho];
   p.pool_Po = I[GEMM_I_pool_Po]; p.pool_rpio = I[GEMM_I_pool_rpio];
   if (pool) {
@@ -884,7 +921,8 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   } else {
     L->mapA1 = L->mapA0;
   }
-  rc = encode_2d(&L->mapB, tf32, op.p[GEMM_P_b], I[GEMM_I_Npad], I[GEMM_I_Ktot], I[GEMM_I_Ktot], bn, p.row_bytes, "gemm B");
+  rc = encode_2d(&L->mapB, tf32, op.p[GEMM_P_b], I[GEMM_I_Npad], I[GEMM_I_Ktot], I[GEMM_I_Ktot], pair ? bn / 2 : bn, p.row_bytes,
+                 "gemm B");
   if (rc) return rc;
 
   p.ldo = I[GEMM_I_ldo];
@@ -907,7 +945,12 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   const int tiles = p.m_tiles * p.n_tiles;
   int sms = num_sms(device);
   if (I[GEMM_I_max_ctas] > 0 && I[GEMM_I_max_ctas] < sms) sms = I[GEMM_I_max_ctas];   // tests: force many tiles per CTA
-  L->grid = dim3(tiles < sms ? tiles : sms, 1, 1);
+  if (pair) {
+    const int pairs = sms / 2 > 0 ? sms / 2 : 1;
+    L->grid = dim3(2 * (tiles < pairs ? tiles : pairs), 1, 1);
+  } else {
+    L->grid = dim3(tiles < sms ? tiles : sms, 1, 1);
+  }
 
   L->out_external = (L->out_raw & VQA_EXT_TAG) != 0;
   L->mapOut = L->mapA0;
@@ -926,7 +969,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
       if (rc) return rc;
     }
   }
-  L->fn = pick_kernel(bn, p.MT, tf32, L->epi, p.row_bytes);
+  L->fn = pick_kernel(bn, p.MT, tf32, L->epi, p.row_bytes, pair);
   VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT/dtype/epilogue");
   VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
@@ -943,10 +986,11 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
     CUtensorMap mo;
     int rc = encode_box32(&mo, p.out_dtype != 0, reinterpret_cast<uint64_t>(p.out), p.M, p.N, p.ldo, "gemm output");
     if (rc) return rc;
-    VQA_CUDA_OK(vqa_launch(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->mapA0, L->mapA1, L->mapB, mo, L->mapRes, p));
+    VQA_CUDA_OK(vqa_launch_cluster(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->pair ? 2 : 1, L->mapA0, L->mapA1, L->mapB,
+                                   mo, L->mapRes, p));
   } else {
-    VQA_CUDA_OK(vqa_launch(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->mapA0, L->mapA1, L->mapB, L->mapOut,
-                           L->mapRes, p));
+    VQA_CUDA_OK(vqa_launch_cluster(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->pair ? 2 : 1, L->mapA0, L->mapA1, L->mapB,
+                                   L->mapOut, L->mapRes, p));
   }
   VQA_LAUNCH_OK("gemm_tap_kernel");
   return VQA_OK;
@@ -955,7 +999,7 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
 const char* gemm_kernel_name(const void* storage) {
   const GemmLaunch* L = reinterpret_cast<const GemmLaunch*>(storage);
   static thread_local char name[64];
-  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d%s>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16", L->epi,
-           L->prm.row_bytes == 32 ? ",row32" : "");
+  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d%s%s>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16", L->epi,
+           L->prm.row_bytes == 32 ? ",row32" : "", L->pair ? ",pair" : "");
   return name;
 }

@@ -21,6 +21,7 @@ overlapping-row tensor map so that 4 horizontal taps form one 64-wide K chunk.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -48,7 +49,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "a1_rows", "a1_cols", "a1_ld", "ngroups", "ntaps", "out_dtype", "ldo", "res_dtype", "ldr",
                    "relu", "round_tf32", "mask_en", "mP", "mRPI", "mH", "mW", "smem_budget", "max_ctas", "row_bytes",
                    "halo_hi", "tiles_per_img", "tile_stride", "tile_row0", "img_rows", "n_imgs", "pool", "pool_P",
-                   "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio"]
+                   "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio", "pair"]
                   + _GROUPS + _TAPS,
              "p": ["a0", "a1", "b", "out", "bias", "res", "dbg"], "f": []},
     "maxpool": {"i": ["B", "C", "Hin", "Win", "Pin", "RPIin", "Hout", "Wout", "Pout", "RPIout"],
@@ -379,6 +380,7 @@ class OpList:
         self.stem_window = window
         self.fuse_pool = window
         self.fused_tail = window
+        self.pair = window
         self.ws = Arena(device if device is not None else weights.arena.device)
         self.ops: List[Op] = []
         self.named: Dict[str, Tuple[Buf, torch.dtype, Tuple[int, ...]]] = {}
@@ -410,7 +412,7 @@ class OpList:
     def gemm(self, name, *, dtype, M, N, a0, a0_shape, groups, w, bias, out, ldo, out_dtype,
              a1=None, a1_shape=None, res=None, res_dtype=-1, ldr=0, relu=False, rnd=False,
              grid: Optional[Grid] = None, halo: int = 0, MT: int = 1, row_bytes: int = 128,
-             halo_hi: Optional[int] = None, pool_to: Optional[Grid] = None):
+             halo_hi: Optional[int] = None, pool_to: Optional[Grid] = None, pair: Optional[bool] = None):
         """Tap-shifted GEMM.  ``groups``: list of (map, row_delta, a_col, n_chunks, [tap_rel...]).
 
         For K-chunk c of group g the kernel loads ONE window of A rows
@@ -430,6 +432,11 @@ class OpList:
         # so more SMs work and each CTA's epilogue is shorter
         if bn == 256 and ((M + 127) // 128) * ((N + 255) // 256) < 100 and npad % 128 == 0 and MT == 1:
             bn = 128
+        # 256-row window convolutions with >= 256 output channels: 128-column tiles on a CTA pair (512 rows x 128
+        # columns per pair) keep two accumulator stages in TMEM, so the epilogue overlaps the next tile's MMAs
+        # (measured: stage 3 conv 66 -> 57 us; the 256-column tile fills TMEM with one stage)
+        if bn == 256 and dtype == DT_BF16 and out_dtype == OUT_BF16 and MT == 2 and self.pair:
+            bn = 128
         assert npad % bn == 0 and npad >= N, (name, npad, bn)
         assert len(groups) <= MAX_GROUPS and MT * bn <= 512
         i = dict(dtype=dtype, M=M, N=N, Npad=npad, Ktot=ktot, BN=bn, MT=MT, halo=halo,
@@ -440,6 +447,12 @@ class OpList:
                  mask_en=int(grid is not None), mP=grid.P if grid else 1, mRPI=grid.rpi if grid else 1,
                  mH=grid.H if grid else 1, mW=grid.W if grid else 1, smem_budget=0, max_ctas=0,
                  row_bytes=row_bytes, halo_hi=halo_hi)
+        # CTA pairs (cta_group::2): bf16 convolutions with a bf16 output; each CTA loads half of every weight tile
+        if pair is None:
+            pair_bns = [int(v) for v in os.environ.get("VQA_PAIR_BN", "128").split(",") if v]
+            pair = (self.pair and dtype == DT_BF16 and out_dtype == OUT_BF16 and bn in pair_bns
+                    and not (row_bytes == 32 and MT == 1))
+        i["pair"] = int(bool(pair))
         if pool_to is not None:
             # fused 3x3/2 max-pool epilogue: tile t = (image, pooled row i') covers conv rows 2i'-1 .. 2i'+1
             assert grid is not None and MT == 3 and 3 * grid.P <= 384 and pool_to.H * 2 == grid.H
