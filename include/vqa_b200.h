@@ -68,7 +68,8 @@ enum VqaOpKind {
   VQA_OP_GRID_TO_NCHW  = 15, /* padded-flat bf16 grid -> NCHW fp32 (aux['image_features'], models/vqa_model.py:301-309) */
   VQA_OP_COPY_ROWS     = 16, /* fp32 [rows, cols] copy between leading dimensions (logits whose num_answers is not a multiple of 4) */
   VQA_OP_STAGE_TAIL    = 17, /* fused stage tail: SE squeeze+excite, spatial attention, scale, relayout (attention_modules.py:91-136,198-243) */
-  VQA_OP_KIND_MAX      = 18
+  VQA_OP_SPLIT_TF32    = 18, /* fp32 -> [tf32 hi | tf32 lo] A operand of the 3xTF32 Linears of the tf32 precision mode */
+  VQA_OP_KIND_MAX      = 19
 };
 
 typedef struct VqaOp {

@@ -58,7 +58,8 @@ class Emulator:
         else:
             x = src.view(B, 224, 224, 3).float().div(255.0)
             x = ((x - MEAN) / STD).permute(0, 3, 1, 2)
-        dst = _t(op.p["dst"], torch.bfloat16, ext)[: rows * 16].view(rows, 16)
+        adt = torch.float32 if i.get("f32") else torch.bfloat16
+        dst = _t(op.p["dst"], adt, ext)[: rows * 16].view(rows, 16)
         dst.zero_()
         # [B,3,112,2,112,2] -> [B,112,112,ph,pw,c]
         xp = x.reshape(B, 3, 112, 2, 112, 2).permute(0, 2, 4, 3, 5, 1)
@@ -67,7 +68,7 @@ class Emulator:
         if i.get("ones"):
             packed[..., 0, :, 3] = 1.0   # bias columns of the fused stem (phases (0,0) and (0,1))
         idx = _grid_index(B, 112, 112, Pp, Pp * Pp)
-        dst[idx] = packed.reshape(-1, 16).to(torch.bfloat16)
+        dst[idx] = P.round_tf32(packed.reshape(-1, 16)) if i.get("f32") else packed.reshape(-1, 16).to(torch.bfloat16)
 
     def op_gemm(self, op, ext):
         i = op.i
@@ -136,16 +137,17 @@ class Emulator:
     def op_maxpool(self, op, ext):
         i = op.i
         B, C = i["B"], i["C"]
-        src = _t(op.p["src"], torch.bfloat16, ext)[: B * i["RPIin"] * C].view(B * i["RPIin"], C)
+        adt = torch.float32 if i.get("f32") else torch.bfloat16
+        src = _t(op.p["src"], adt, ext)[: B * i["RPIin"] * C].view(B * i["RPIin"], C)
         idx = _grid_index(B, i["Hin"], i["Win"], i["Pin"], i["RPIin"])
         x = src[idx].float().view(B, i["Hin"], i["Win"], C).permute(0, 3, 1, 2)
         y = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1).reshape(-1, C)
-        dst = _t(op.p["dst"], torch.bfloat16, ext)[: B * i["RPIout"] * C].view(B * i["RPIout"], C)
+        dst = _t(op.p["dst"], adt, ext)[: B * i["RPIout"] * C].view(B * i["RPIout"], C)
         dst.zero_()
-        dst[_grid_index(B, i["Hout"], i["Wout"], i["Pout"], i["RPIout"])] = y.to(torch.bfloat16)
+        dst[_grid_index(B, i["Hout"], i["Wout"], i["Pout"], i["RPIout"])] = y.to(adt)
 
-    def _grid_nhwc(self, ref, ext, B, C, H, W, Pp, rpi):
-        src = _t(ref, torch.bfloat16, ext)[: B * rpi * C].view(B * rpi, C)
+    def _grid_nhwc(self, ref, ext, B, C, H, W, Pp, rpi, dtype=torch.bfloat16):
+        src = _t(ref, dtype, ext)[: B * rpi * C].view(B * rpi, C)
         return src[_grid_index(B, H, W, Pp, rpi)].float().view(B, H, W, C)
 
     def op_se_squeeze(self, op, ext):
@@ -202,14 +204,16 @@ class Emulator:
 
     def op_grid_to_nchw(self, op, ext):
         i = op.i
-        x = self._grid_nhwc(op.p["src"], ext, i["B"], i["C"], i["H"], i["W"], i["P"], i["RPI"])
+        x = self._grid_nhwc(op.p["src"], ext, i["B"], i["C"], i["H"], i["W"], i["P"], i["RPI"],
+                            torch.float32 if i.get("f32") else torch.bfloat16)
         n = i["B"] * i["C"] * i["H"] * i["W"]
         _t(op.p["dst"], torch.float32, ext)[:n].view(i["B"], i["C"], i["H"], i["W"]).copy_(x.permute(0, 3, 1, 2))
 
     def op_stage_tail(self, op, ext):
         i = op.i
         B, C, H, W = i["B"], i["C"], i["H"], i["W"]
-        x = self._grid_nhwc(op.p["src"], ext, B, C, H, W, i["P"], i["RPI"])          # [B,H,W,C] fp32 (bf16 values)
+        adt = torch.float32 if i.get("f32") else torch.bfloat16
+        x = self._grid_nhwc(op.p["src"], ext, B, C, H, W, i["P"], i["RPI"], adt)     # [B,H,W,C] fp32 values
         sc = torch.ones(B, C)
         if op.p.get("w1") is not None:
             R = i["R"]
@@ -228,20 +232,30 @@ class Emulator:
             att = torch.sigmoid(F.conv2d(pooled, w, None, padding=ks // 2)).view(B, H, W)
             if op.p.get("att") is not None:
                 _t(op.p["att"], torch.float32, ext)[: B * H * W].view(B, H * W).copy_(att.view(B, H * W))
-        y = (x * sc.view(B, 1, 1, C) * att.view(B, H, W, 1)).to(torch.bfloat16)
+        y = x * sc.view(B, 1, 1, C) * att.view(B, H, W, 1)
+        y = P.round_tf32(y) if i.get("f32") else y.to(torch.bfloat16)
         Po, RPIo = i["Po"], i["RPIo"]
         if i["mode"]:
             pr = i["phase_rows"]
-            dst = _t(op.p["dst"], torch.bfloat16, ext)[: 4 * pr * C].view(4, pr, C)
+            dst = _t(op.p["dst"], adt, ext)[: 4 * pr * C].view(4, pr, C)
             dst.zero_()
             idx = _grid_index(B, H // 2, W // 2, Po, RPIo)
             for ph in range(2):
                 for pw in range(2):
                     dst[ph * 2 + pw][idx] = y[:, ph::2, pw::2, :].reshape(-1, C)
         else:
-            dst = _t(op.p["dst"], torch.bfloat16, ext)[: B * RPIo * C].view(B * RPIo, C)
+            dst = _t(op.p["dst"], adt, ext)[: B * RPIo * C].view(B * RPIo, C)
             dst.zero_()
             dst[_grid_index(B, H, W, Po, RPIo)] = y.reshape(-1, C)
+
+    def op_split_tf32(self, op, ext):
+        i = op.i
+        M, K = i["M"], i["K"]
+        src = torch.as_strided(_t(op.p["src"], torch.float32, ext), (M, K), (i["ld_src"], 1))
+        hi = P.round_tf32(src)
+        dst = _t(op.p["dst"], torch.float32, ext)[: M * 2 * K].view(M, 2 * K)
+        dst[:, :K] = hi
+        dst[:, K:] = P.round_tf32(src - hi)
 
     def op_copy_rows(self, op, ext):
         i = op.i
@@ -335,7 +349,8 @@ class Emulator:
             buf("att_pooled", B * D).view(B, D).copy_(ap)
             buf("txt_pooled", B * D).view(B, D).copy_(tp)
             if phase == 1:      # pools only; [att;txt] as the tf32 A operand of the gate GEMM
-                buf("cat", B * 2 * D).view(B, 2 * D).copy_(P.round_tf32(torch.cat([ap, tp], dim=-1)))
+                cat = torch.cat([ap, tp], dim=-1)
+                buf("cat", B * 2 * D).view(B, 2 * D).copy_(cat if i.get("no_round") else P.round_tf32(cat))
                 return
             assert not i["use_gate"]
             fz = ap + tp

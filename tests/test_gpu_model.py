@@ -23,9 +23,9 @@ def rel_err(got, want):
     return float((got - want).abs().max() / want.abs().max())
 
 
-def make(meta):
+def make(meta, precision="bf16"):
     torch.manual_seed(meta["seed_weights"])
-    model = VQAModel(**meta["ctor"]).eval()
+    model = VQAModel(**meta["ctor"], precision=precision).eval()
     sd = model.state_dict()
     if meta["randomise"]:
         sd = randomise_state(sd, 1)
@@ -56,6 +56,27 @@ def test_forward_matches_reference_golden(golden_meta, case):
     assert top_idx.dtype == torch.int64 and tuple(top_idx.shape) == (meta["batch"], 5)
     assert np.array_equal(top_idx[:, 0].cpu().numpy(), g["top_indices"][:, 0])
     np.testing.assert_allclose(top_p.cpu().numpy(), g["top_probs"], rtol=2e-2, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["default_b4", "plain_b2", "ablate_b3", "nospatial_b2"])
+def test_tf32_tolerance_mode_within_1e_3(golden_meta, case):
+    """BASELINE.json: "in fp32-accumulate TF32 mode, logits must be within 1e-3" (max-abs relative) of the fp32
+    reference.  precision="tf32": fp32 activations and tf32 operands in the backbone, 3xTF32 Linears in the tail."""
+    meta = golden_meta[case]
+    model, sd, u8, img, ids, mask = make(meta, precision="tf32")
+    g = np.load(os.path.join(GOLDEN, f"{case}.npz"))
+    with torch.no_grad():
+        logits, aux = model(img.cuda(), ids.cuda(), mask.cuda(), return_aux=True)
+        logits_u8, _ = model(u8.cuda(), ids.cuda(), mask.cuda())
+    errs = {"logits": rel_err(logits.cpu(), torch.from_numpy(g["logits"])),
+            "image_features": rel_err(aux["image_features"].cpu(), torch.from_numpy(g["image_features"])),
+            "text_features": rel_err(aux["text_features"].cpu(), torch.from_numpy(g["text_features"])),
+            "fused": rel_err(aux["fused"].cpu(), torch.from_numpy(g["fused"]))}
+    print("tf32", case, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["logits"] <= 1e-3, errs
+    assert errs["image_features"] <= 2e-3 and errs["text_features"] <= 1e-4 and errs["fused"] <= 1e-3, errs
+    assert torch.equal(logits_u8, logits)
+    assert np.array_equal(logits.argmax(1).cpu().numpy(), g["top_indices"][:, 0])
 
 
 def test_uint8_input_equals_normalised_input(golden_meta):

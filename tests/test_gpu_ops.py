@@ -24,7 +24,7 @@ OUTPUTS = {
     "pool_gate_ln": [("fused", torch.float32), ("att_pooled", torch.float32), ("txt_pooled", torch.float32),
                      ("cat", torch.float32)],
     "softmax_topk": [("idx", torch.int64), ("probs", torch.float32)], "mask_prep": [("dst", torch.int32)],
-    "grid_to_nchw": [("dst", torch.float32)], "copy_rows": [("dst", torch.float32)],
+    "grid_to_nchw": [("dst", torch.float32)], "copy_rows": [("dst", torch.float32)], "split_tf32": [("dst", torch.float32)],
     "stage_tail": [("dst", torch.bfloat16), ("scale", torch.float32), ("att", torch.float32)],
 }
 
@@ -35,7 +35,7 @@ def _view(ref, dtype, ext):
     return ref.arena.tensor[ref.offset: ref.offset + ref.nbytes].view(dtype)
 
 
-def _case(ctor, B, L, in_fmt, mask_kind, window=True, seed=0):
+def _case(ctor, B, L, in_fmt, mask_kind, window=True, seed=0, precision="bf16"):
     torch.manual_seed(seed)
     model = VQAModel(**ctor).eval()
     sd = randomise_state(model.state_dict(), 1)
@@ -45,23 +45,26 @@ def _case(ctor, B, L, in_fmt, mask_kind, window=True, seed=0):
     m = {"i64": mask, "f32": mask.float(), "none": None}[mask_kind]
     progs = {}
     for dev in ("cpu", "cuda"):
-        W = P.build_weights(sd, model.config, dev)
+        W = P.build_weights(sd, model.config, dev, precision=precision)
         progs[dev] = P.Program(W, model.config, B, L, in_fmt, code, want_aux=True, top_k=5, device=dev, window=window)
     NA = model.config["num_answers"]
     ext = [images, ids, m, torch.zeros(B, NA), torch.zeros(B, 5, dtype=torch.int64), torch.zeros(B, 5)]
     return progs["cpu"], progs["cuda"], ext
 
 
-@pytest.mark.parametrize("ctor,B,L,in_fmt,mask_kind,window", [
-    ({}, 2, 20, "nchw_f32", "i64", True),
-    ({}, 3, 20, "hwc_u8", "f32", False),
+@pytest.mark.parametrize("ctor,B,L,in_fmt,mask_kind,window,precision", [
+    ({}, 2, 20, "nchw_f32", "i64", True, "bf16"),
+    ({}, 2, 20, "hwc_u8", "i64", True, "tf32"),
+    ({}, 3, 20, "hwc_u8", "f32", False, "bf16"),
     (dict(use_se_attention=False, use_spatial_attention=False, use_gating=False, num_transformer_layers=1,
-          num_cross_layers=1, max_question_length=12, vocab_size=500, num_answers=37), 2, 12, "nchw_f32", "none", True),
+          num_cross_layers=1, max_question_length=12, vocab_size=500, num_answers=37), 2, 12, "nchw_f32", "none", True, "bf16"),
+    (dict(use_se_attention=False, use_spatial_attention=False, use_gating=False, num_transformer_layers=1,
+          num_cross_layers=1, max_question_length=12, vocab_size=500, num_answers=37), 2, 12, "nchw_f32", "none", True, "tf32"),
     (dict(use_spatial_attention=False, max_question_length=64, num_cross_layers=1, num_transformer_layers=1),
-     1, 64, "nchw_f32", "i64", True),
+     1, 64, "nchw_f32", "i64", True, "bf16"),
 ])
-def test_each_op_against_emulator(ctor, B, L, in_fmt, mask_kind, window):
-    cpu, gpu, ext = _case(ctor, B, L, in_fmt, mask_kind, window)
+def test_each_op_against_emulator(ctor, B, L, in_fmt, mask_kind, window, precision):
+    cpu, gpu, ext = _case(ctor, B, L, in_fmt, mask_kind, window, precision=precision)
     ext_gpu = [None if t is None else t.cuda() for t in ext]
     plan = Plan(gpu.ops, 0)
     emu = E.Emulator(cpu)
@@ -82,8 +85,14 @@ def test_each_op_against_emulator(ctor, B, L, in_fmt, mask_kind, window):
                 continue
             if dtype is None:
                 dtype = torch.bfloat16 if op.i["out_dtype"] == P.OUT_BF16 else torch.float32
+            if dtype == torch.bfloat16 and op.i.get("f32"):
+                dtype = torch.float32          # tf32 precision mode: fp32 activation grids
             want = _view(ref_c, dtype, ext)
             got = _view(ref_g, dtype, ext_gpu).cpu()
+            if op.kind == "split_tf32":        # hi may differ by one tf32 ulp on rounding ties; hi + lo may not
+                M, K = op.i["M"], op.i["K"]
+                want = want[: M * 2 * K].view(M, 2, K).sum(dim=1)
+                got = got[: M * 2 * K].view(M, 2, K).sum(dim=1)
             if dtype in (torch.int32, torch.int64):
                 ok = torch.equal(got, want)
                 msg = f"op {k} {op.name} ({plan.kernel_name(k)}) {field}: integer mismatch"

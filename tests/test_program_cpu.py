@@ -40,6 +40,26 @@ def test_program_matches_oracle(ctor, B, L, fmt, mk, window):
     assert all(op.lane in (0, 1) for op in prog.ops) and any(op.lane == 1 for op in prog.ops)
 
 
+@pytest.mark.parametrize("ctor,B,L", [({}, 2, 20), (ABL, 1, 12)])
+def test_tf32_precision_mode_within_1e_3(ctor, B, L):
+    """precision="tf32" (BASELINE.json's tolerance mode): fp32 activations, tf32 operands, fp32 accumulation in the
+    backbone too; logits within 1e-3 (max-abs relative) of the fp32 oracle."""
+    torch.manual_seed(0)
+    model = VQAModel(**ctor).eval()
+    sd = randomise_state(model.state_dict(), 1)
+    u8, img, ids, mask = synth_batch(B, 1234, max_len=L, vocab=model.config["vocab_size"])
+    W = P.build_weights(sd, model.config, "cpu", precision="tf32")
+    prog = P.Program(W, model.config, B, L, "nchw_f32", P.MASK_I64, want_aux=True, top_k=0, device="cpu")
+    assert prog.tf32 and not prog.pair and all(op.i["dtype"] == P.DT_TF32 for op in prog.ops if op.kind == "gemm")
+    logits, _ = E.run_program(prog, img, ids, mask)
+    want, aux = O.vqa_forward(sd, img, ids, mask, return_aux=True)
+    err = float((logits - want).abs().max() / want.abs().max())
+    print("tf32 mode max-abs relative logit error", err)
+    assert err < 1e-3
+    feat = prog.tensor("aux.image_features")
+    assert float((feat - aux["image_features"]).abs().max() / aux["image_features"].abs().max()) < 2e-3
+
+
 def test_weight_folding_is_exact_in_fp32():
     """BN fold + shortcut-as-extra-K reproduce conv->BN (+downsample->BN) exactly up to fp32 rounding."""
     torch.manual_seed(3)

@@ -283,9 +283,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             const uint64_t ad = kDescHi | (a_lo + sub * (128 * kRowBytes / 16) + 2 * k);
             const uint64_t bd = kDescHi | (b_lo + 2 * k);
             const uint32_t accum = (k == 0) ? (fresh ^ 1u) : 1u;
-            if (PAIR)      umma_f16_pair(d_tile + sub * BN, ad, bd, idesc, accum);
-            else if (TF32) umma_tf32(d_tile + sub * BN, ad, bd, idesc, accum);
-            else           umma_f16(d_tile + sub * BN, ad, bd, idesc, accum);
+            if (PAIR && TF32) umma_tf32_pair(d_tile + sub * BN, ad, bd, idesc, accum);
+            else if (PAIR)    umma_f16_pair(d_tile + sub * BN, ad, bd, idesc, accum);
+            else if (TF32)    umma_tf32(d_tile + sub * BN, ad, bd, idesc, accum);
+            else              umma_f16(d_tile + sub * BN, ad, bd, idesc, accum);
           }
         }
         fresh = 0;
@@ -808,7 +809,8 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.desc_hi = static_cast<uint32_t>((8 * p.row_bytes) >> 4) | (1u << 14) | ((p.row_bytes == 128 ? 2u : 6u) << 29);
   const bool pair = I[GEMM_I_pair] != 0;
   L->pair = pair;
-  VQA_REQUIRE(!pair || (!tf32 && bn % 16 == 0), VQA_E_INVALID, "gemm: CTA pairs are implemented for bf16 operands");
+  // (tf32 pairs were measured too: no gain for the latency-bound M = 5120 Linears, so they are not instantiated)
+  VQA_REQUIRE(!pair || (!tf32 && bn % 16 == 0), VQA_E_INVALID, "gemm: CTA pairs are instantiated for bf16 operands");
   p.idesc = make_idesc(tf32, bn, pair ? 256 : 128);
   VQA_REQUIRE(I[GEMM_I_Ktot] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: Ktot must be a multiple of the K chunk");
   p.k_chunks = I[GEMM_I_Ktot] / p.chunk_elems;

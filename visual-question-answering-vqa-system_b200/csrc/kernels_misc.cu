@@ -27,8 +27,9 @@ __device__ __forceinline__ float warp_max(float v) {
 // ToTensor + Normalize (data/preprocess.py:117-121): (u8/255 - mean)/std in fp32.
 // ones = 1: the two spare slots (phase (0,0) and (0,1), channel 3) of every in-image block hold 1.0 so that
 // the stem GEMM adds its bias through two K columns (bias_hi + bias_lo) instead of in the epilogue.
+// f32 = 1 (tf32 precision mode): the block is written as 16 tf32-rounded fp32 (64 bytes) instead of 16 bf16.
 __global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ dst, int B, int mode, int P,
-                              int rows, int ones) {
+                              int rows, int ones, int f32) {
   pdl_launch_dependents();
   pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,8 +38,14 @@ __global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ 
   const int n = r / rpi, rem = r - n * rpi;
   const int a = rem / P, b = rem - a * P;
   uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float v[2][2][4];
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+    for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[ph][pw][c] = 0.f;
   if (a < 112 && b < 112) {
-    float v[2][2][4];
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph)
 #pragma unroll
@@ -78,8 +85,46 @@ __global__ void ingest_kernel(const void* __restrict__ src, uint4* __restrict__ 
         w[(ph * 2 + pw) * 2 + 1] = pack_bf16x2(v[ph][pw][2], v[ph][pw][3]);
       }
   }
+  if (f32) {
+    float4* d4 = reinterpret_cast<float4*>(dst) + 4 * static_cast<size_t>(r);
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw)
+        d4[ph * 2 + pw] = make_float4(round_tf32_rna(v[ph][pw][0]), round_tf32_rna(v[ph][pw][1]),
+                                      round_tf32_rna(v[ph][pw][2]), round_tf32_rna(v[ph][pw][3]));
+    return;
+  }
   dst[2 * static_cast<size_t>(r)] = make_uint4(w[0], w[1], w[2], w[3]);
   dst[2 * static_cast<size_t>(r) + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// MAXPOOL, fp32 grids (tf32 precision mode): one thread = one output row x 4 channels.
+__global__ void maxpool_f32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int B, int C4, int Hin, int Win,
+                                   int Pin, int RPIin, int Hout, int Wout, int Pout, int RPIout) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(B) * RPIout * C4) return;
+  const int cg = static_cast<int>(t % C4);
+  const int r = static_cast<int>(t / C4);
+  const int n = r / RPIout, rem = r - n * RPIout;
+  const int i = rem / Pout, j = rem - i * Pout;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < Hout && j < Wout) {
+    o = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int h = 2 * i + dh;
+      if (h < 0 || h >= Hin) continue;
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int w = 2 * j + dw;
+        if (w < 0 || w >= Win) continue;
+        const float4 q = src[(static_cast<size_t>(n) * RPIin + h * Pin + w) * C4 + cg];
+        o.x = fmaxf(o.x, q.x); o.y = fmaxf(o.y, q.y); o.z = fmaxf(o.z, q.z); o.w = fmaxf(o.w, q.w);
+      }
+    }
+  }
+  dst[static_cast<size_t>(r) * C4 + cg] = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,8 +320,44 @@ struct StageTailParams {
   int C8, H, W, P, RPI, R, ks, mode, Po, RPIo, phase_rows, CS;
 };
 
+// One group of 8 channels of one pixel: one uint4 of bf16, or (F32, the tf32 precision mode) two uint4 of fp32.
+template <bool F32>
+struct TailVec {
+  static constexpr int N = F32 ? 2 : 1;
+  uint4 q[N];
+  __device__ __forceinline__ void to_float(float (&x)[8]) const {
+    if constexpr (F32) {
+      x[0] = __uint_as_float(q[0].x); x[1] = __uint_as_float(q[0].y); x[2] = __uint_as_float(q[0].z); x[3] = __uint_as_float(q[0].w);
+      x[4] = __uint_as_float(q[1].x); x[5] = __uint_as_float(q[1].y); x[6] = __uint_as_float(q[1].z); x[7] = __uint_as_float(q[1].w);
+    } else {
+      x[0] = bf16lo(q[0].x); x[1] = bf16hi(q[0].x); x[2] = bf16lo(q[0].y); x[3] = bf16hi(q[0].y);
+      x[4] = bf16lo(q[0].z); x[5] = bf16hi(q[0].z); x[6] = bf16lo(q[0].w); x[7] = bf16hi(q[0].w);
+    }
+  }
+  __device__ __forceinline__ void from_float(const float (&x)[8]) {
+    if constexpr (F32) {   // the next GEMM reads these as tf32 operands
+      q[0] = make_uint4(__float_as_uint(round_tf32_rna(x[0])), __float_as_uint(round_tf32_rna(x[1])),
+                        __float_as_uint(round_tf32_rna(x[2])), __float_as_uint(round_tf32_rna(x[3])));
+      q[1] = make_uint4(__float_as_uint(round_tf32_rna(x[4])), __float_as_uint(round_tf32_rna(x[5])),
+                        __float_as_uint(round_tf32_rna(x[6])), __float_as_uint(round_tf32_rna(x[7])));
+    } else {
+      q[0] = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+    }
+  }
+  __device__ __forceinline__ void load(const uint4* base, size_t group) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = base[group * N + i];
+  }
+  __device__ __forceinline__ void store(uint4* base, size_t group) const {
+#pragma unroll
+    for (int i = 0; i < N; ++i) base[group * N + i] = q[i];
+  }
+};
+
+template <bool F32>
 __global__ void __launch_bounds__(kTailThreads)
 stage_tail_kernel(const StageTailParams p) {
+  using Vec = TailVec<F32>;
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) uint8_t tail_smem[];
@@ -289,8 +370,8 @@ stage_tail_kernel(const StageTailParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lanes = kTailThreads / C8;                  // pixel lanes (C8 divides 256)
   const int cg = tid % C8, pl = tid / C8;
-  uint4* tile = reinterpret_cast<uint4*>(tail_smem);                       // [NP][C8]
-  float* red = reinterpret_cast<float*>(tile + static_cast<size_t>(NP) * C8);   // [lanes][C]; later mx/av maps
+  uint4* tile = reinterpret_cast<uint4*>(tail_smem);                       // [NP][C8] groups of 8 channels
+  float* red = reinterpret_cast<float*>(tile + static_cast<size_t>(NP) * C8 * Vec::N);   // [lanes][C]; later mx/av maps
   float* part = red + lanes * C;                        // [C] this CTA's channel sums (read by the cluster)
   float* sc = part + C;                                 // [C] SE scale
   float* hid = sc + C;                                  // [R]
@@ -300,25 +381,27 @@ stage_tail_kernel(const StageTailParams p) {
 
   // ---- 1. stage the rows, accumulate channel sums on the way
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8;
+  const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8 * Vec::N;
   constexpr int kLd = 8;                                // independent 16-byte loads in flight per thread
   for (int q0 = pl; q0 < NP; q0 += kLd * lanes) {
-    uint4 v[kLd];
+    Vec v[kLd];
 #pragma unroll
     for (int u = 0; u < kLd; ++u) {
       const int q = q0 + u * lanes;
       if (q < NP) {
         const int hl = q / W, w = q - hl * W;
-        v[u] = img[(static_cast<size_t>(h0 + hl) * p.P + w) * C8 + cg];
+        v[u].load(img, (static_cast<size_t>(h0 + hl) * p.P + w) * C8 + cg);
       }
     }
 #pragma unroll
     for (int u = 0; u < kLd; ++u) {
       const int q = q0 + u * lanes;
       if (q < NP) {
-        tile[static_cast<size_t>(q) * C8 + cg] = v[u];
-        acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x); acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
-        acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z); acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
+        v[u].store(tile, static_cast<size_t>(q) * C8 + cg);
+        float x[8];
+        v[u].to_float(x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += x[k];
       }
     }
   }
@@ -385,12 +468,13 @@ stage_tail_kernel(const StageTailParams p) {
     for (int q = warp; q < NP; q += kTailThreads / 32) {
       float m = -INFINITY, t = 0.f;
       for (int o = lane; o < C8; o += 32) {
-        const uint4 v = tile[static_cast<size_t>(q) * C8 + o];
+        Vec v;
+        v.load(tile, static_cast<size_t>(q) * C8 + o);
         const float* k = sc + o * 8;
-        const float x[8] = {bf16lo(v.x) * k[0], bf16hi(v.x) * k[1], bf16lo(v.y) * k[2], bf16hi(v.y) * k[3],
-                            bf16lo(v.z) * k[4], bf16hi(v.z) * k[5], bf16lo(v.w) * k[6], bf16hi(v.w) * k[7]};
+        float x[8];
+        v.to_float(x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { m = fmaxf(m, x[j]); t += x[j]; }
+        for (int j = 0; j < 8; ++j) { const float y = x[j] * k[j]; m = fmaxf(m, y); t += y; }
       }
       m = warp_max(m);
       t = warp_sum(t);
@@ -426,33 +510,54 @@ stage_tail_kernel(const StageTailParams p) {
   const int rows_o = p.RPIo / Po;                       // destination rows per image incl. padding
   for (int q = pl; q < NP; q += lanes) {
     const int hl = q / W, w = q - hl * W, h = h0 + hl;
-    const uint4 v = tile[static_cast<size_t>(q) * C8 + cg];
+    Vec v, o;
+    v.load(tile, static_cast<size_t>(q) * C8 + cg);
     const float a = use_sp ? att[q] : 1.f;
-    uint4 o;
-    o.x = pack_bf16x2(bf16lo(v.x) * k[0] * a, bf16hi(v.x) * k[1] * a);
-    o.y = pack_bf16x2(bf16lo(v.y) * k[2] * a, bf16hi(v.y) * k[3] * a);
-    o.z = pack_bf16x2(bf16lo(v.z) * k[4] * a, bf16hi(v.z) * k[5] * a);
-    o.w = pack_bf16x2(bf16lo(v.w) * k[6] * a, bf16hi(v.w) * k[7] * a);
+    float x[8];
+    v.to_float(x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = x[j] * k[j] * a;
+    o.from_float(x);
     size_t row;
     if (p.mode) row = static_cast<size_t>((h & 1) * 2 + (w & 1)) * p.phase_rows + static_cast<size_t>(n) * p.RPIo + (h >> 1) * Po + (w >> 1);
     else row = static_cast<size_t>(n) * p.RPIo + h * Po + w;
-    p.dst[row * C8 + cg] = o;
+    o.store(p.dst, row * C8 + cg);
   }
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   const int Ho = p.mode ? p.H / 2 : p.H, Wo = p.mode ? W / 2 : W, nph = p.mode ? 4 : 1;
   const int i0 = p.mode ? h0 / 2 : h0, i1 = p.mode ? (h0 + rows_l) / 2 : h0 + rows_l;
   const int padw = Po - Wo;                             // pad columns per destination row
   for (int ph = 0; ph < nph; ++ph) {
-    uint4* base = p.dst + (static_cast<size_t>(ph) * p.phase_rows + static_cast<size_t>(n) * p.RPIo) * C8;
-    for (int t = tid; t < (i1 - i0) * padw * C8; t += kTailThreads) {      // pad columns of this CTA's rows
-      const int c = t % C8, e = t / C8, i = i0 + e / padw, j = Wo + e % padw;
-      base[(static_cast<size_t>(i) * Po + j) * C8 + c] = z;
+    constexpr int VN = Vec::N;
+    const int CV = C8 * VN;                                                  // 16-byte vectors per pixel
+    uint4* base = p.dst + (static_cast<size_t>(ph) * p.phase_rows + static_cast<size_t>(n) * p.RPIo) * CV;
+    for (int t = tid; t < (i1 - i0) * padw * CV; t += kTailThreads) {      // pad columns of this CTA's rows
+      const int c = t % CV, e = t / CV, i = i0 + e / padw, j = Wo + e % padw;
+      base[(static_cast<size_t>(i) * Po + j) * CV + c] = z;
     }
     if (rank == CS - 1) {                                                   // pad rows below the image
-      for (int t = tid; t < (rows_o - Ho) * Po * C8; t += kTailThreads) base[static_cast<size_t>(Ho) * Po * C8 + t] = z;
+      for (int t = tid; t < (rows_o - Ho) * Po * CV; t += kTailThreads) base[static_cast<size_t>(Ho) * Po * CV + t] = z;
     }
   }
   if (CS > 1) cluster_sync_all();                       // peers may still be reading this CTA's partial sums
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPLIT_TF32 (tf32 precision mode): dst[m, 0:K] = tf32(src[m, :]), dst[m, K:2K] = tf32(src - hi): the A operand
+// of a 3xTF32 GEMM (program.py::linear).  One thread = 4 columns.
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int K4, int ld_src) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(M) * K4) return;
+  const int m = static_cast<int>(t / K4), c4 = static_cast<int>(t - static_cast<long long>(m) * K4);
+  const float4 x = *reinterpret_cast<const float4*>(src + static_cast<size_t>(m) * ld_src + 4 * c4);
+  const float4 hi = make_float4(round_tf32_rna(x.x), round_tf32_rna(x.y), round_tf32_rna(x.z), round_tf32_rna(x.w));
+  const float4 lo = make_float4(round_tf32_rna(x.x - hi.x), round_tf32_rna(x.y - hi.y), round_tf32_rna(x.z - hi.z),
+                                round_tf32_rna(x.w - hi.w));
+  float* drow = dst + static_cast<size_t>(m) * 8 * K4;
+  *reinterpret_cast<float4*>(drow + 4 * c4) = hi;
+  *reinterpret_cast<float4*>(drow + 4 * K4 + 4 * c4) = lo;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -507,8 +612,8 @@ __global__ void scale_relayout_kernel(const uint4* __restrict__ src, const float
   dst[static_cast<size_t>(r) * C8 + cg] = o;
 }
 
-__global__ void grid_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int B, int C,
-                                    int H, int W, int P, int RPI) {
+__global__ void grid_to_nchw_kernel(const void* __restrict__ src_, float* __restrict__ dst, int B, int C,
+                                    int H, int W, int P, int RPI, int f32) {
   pdl_launch_dependents();
   pdl_wait();
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -517,7 +622,8 @@ __global__ void grid_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
   const int h = static_cast<int>((t / W) % H);
   const int c = static_cast<int>((t / (static_cast<long long>(W) * H)) % C);
   const int n = static_cast<int>(t / (static_cast<long long>(W) * H * C));
-  dst[t] = __bfloat162float(src[(static_cast<size_t>(n) * RPI + h * P + w) * C + c]);
+  const size_t at = (static_cast<size_t>(n) * RPI + h * P + w) * C + c;
+  dst[t] = f32 ? reinterpret_cast<const float*>(src_)[at] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src_)[at]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -641,7 +747,7 @@ template <int NT>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 const int* __restrict__ mask, float* __restrict__ out, float* __restrict__ weights, int n_units,
-                int H, int L, int T, int ld_q, int ld_kv) {
+                int H, int L, int T, int ld_q, int ld_kv, int no_round) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) float sm[];
@@ -782,18 +888,20 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
         if (row < L) {
           float* orow = out + (static_cast<size_t>(b) * L + row) * (H * kHd) + h * kHd + 2 * t;
 #pragma unroll
-          for (int n = 0; n < 4; ++n)                   // tf32 operand of W_o
-            *reinterpret_cast<float2*>(orow + n * 8) = make_float2(round_tf32_rna(oacc[mt][n][hf * 2]),
-                                                                   round_tf32_rna(oacc[mt][n][hf * 2 + 1]));
+          for (int n = 0; n < 4; ++n) {                 // tf32 operand of W_o (left unrounded for the 3xTF32 split)
+            const float o0 = oacc[mt][n][hf * 2], o1 = oacc[mt][n][hf * 2 + 1];
+            *reinterpret_cast<float2*>(orow + n * 8) = no_round ? make_float2(o0, o1)
+                                                                : make_float2(round_tf32_rna(o0), round_tf32_rna(o1));
+          }
         }
       }
   }
 }
 
-typedef void (*AttnFn)(const float*, const float*, const float*, const int*, float*, float*, int, int, int, int, int, int);
+typedef void (*AttnFn)(const float*, const float*, const float*, const int*, float*, float*, int, int, int, int, int, int, int);
 
 static int launch_attn(const float* q, const float* k, const float* v, const int* mask, float* out, float* weights, int B,
-                       int H, int L, int T, int ld_q, int ld_kv, cudaStream_t st) {
+                       int H, int L, int T, int ld_q, int ld_kv, int no_round, cudaStream_t st) {
   const int nt = (T + 7) / 8;
   VQA_REQUIRE(nt >= 1 && nt <= 8, VQA_E_INVALID, "attention: 1..64 keys");
   const int ntt = nt <= 3 ? 3 : nt <= 4 ? 4 : nt <= 7 ? 7 : 8;
@@ -807,7 +915,7 @@ static int launch_attn(const float* q, const float* k, const float* v, const int
     attr_set[ntt] = true;
   }
   VQA_CUDA_OK(vqa_launch(fn, dim3((B * H + kAttnWarps - 1) / kAttnWarps), dim3(kAttnWarps * 32), smem, st, q, k, v, mask, out,
-                         weights, B * H, H, L, T, ld_q, ld_kv));
+                         weights, B * H, H, L, T, ld_q, ld_kv, no_round));
   VQA_LAUNCH_OK("attn_mma_kernel");
   return VQA_OK;
 }
@@ -822,7 +930,7 @@ __global__ void __launch_bounds__(256)
 pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text, const int* __restrict__ mask,
                     const float* __restrict__ pre, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ fused, float* __restrict__ att_pooled, float* __restrict__ txt_pooled,
-                    float* __restrict__ cat, int L, int phase, float eps) {
+                    float* __restrict__ cat, int L, int phase, int no_round, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int D = 256;
@@ -844,8 +952,8 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
     att_pooled[static_cast<size_t>(b) * D + d] = ap;
     txt_pooled[static_cast<size_t>(b) * D + d] = tp;
     if (phase == 1) {
-      cat[static_cast<size_t>(b) * 2 * D + d] = round_tf32_rna(ap);
-      cat[static_cast<size_t>(b) * 2 * D + D + d] = round_tf32_rna(tp);
+      cat[static_cast<size_t>(b) * 2 * D + d] = no_round ? ap : round_tf32_rna(ap);
+      cat[static_cast<size_t>(b) * 2 * D + D + d] = no_round ? tp : round_tf32_rna(tp);
       return;
     }
   } else {
@@ -948,11 +1056,21 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 || I[INGEST_I_mode] == 1, VQA_E_ALIGN,
                   "ingest: fp32 images must be 8-byte aligned");
       VQA_CUDA_OK(vqa_launch(ingest_kernel, dim3(blocks_for(rows, 256)), dim3(256), 0, st, src, PTR(uint4*, INGEST_P_dst), I[INGEST_I_B],
-                                                            I[INGEST_I_mode], I[INGEST_I_P], rows, I[INGEST_I_ones]));
+                                                            I[INGEST_I_mode], I[INGEST_I_P], rows, I[INGEST_I_ones], I[INGEST_I_f32]));
       VQA_LAUNCH_OK("ingest_kernel");
       return VQA_OK;
     }
     case VQA_OP_MAXPOOL: {
+      if (I[MAXPOOL_I_f32]) {
+        const int C4 = I[MAXPOOL_I_C] / 4;
+        const long long tot = static_cast<long long>(I[MAXPOOL_I_B]) * I[MAXPOOL_I_RPIout] * C4;
+        VQA_CUDA_OK(vqa_launch(maxpool_f32_kernel, dim3(blocks_for(tot, 256)), dim3(256), 0, st,
+            PTR(const float4*, MAXPOOL_P_src), PTR(float4*, MAXPOOL_P_dst), I[MAXPOOL_I_B], C4, I[MAXPOOL_I_Hin],
+            I[MAXPOOL_I_Win], I[MAXPOOL_I_Pin], I[MAXPOOL_I_RPIin], I[MAXPOOL_I_Hout], I[MAXPOOL_I_Wout],
+            I[MAXPOOL_I_Pout], I[MAXPOOL_I_RPIout]));
+        VQA_LAUNCH_OK("maxpool_f32_kernel");
+        return VQA_OK;
+      }
       const int C8 = I[MAXPOOL_I_C] / 8;
       const long long total = static_cast<long long>(I[MAXPOOL_I_B]) * I[MAXPOOL_I_RPIout] * C8;
       VQA_CUDA_OK(vqa_launch(maxpool_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, 
@@ -1011,8 +1129,9 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const long long total = static_cast<long long>(I[GRID_TO_NCHW_I_B]) * I[GRID_TO_NCHW_I_C] * I[GRID_TO_NCHW_I_H] *
                               I[GRID_TO_NCHW_I_W];
       VQA_CUDA_OK(vqa_launch(grid_to_nchw_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, 
-          PTR(const __nv_bfloat16*, GRID_TO_NCHW_P_src), PTR(float*, GRID_TO_NCHW_P_dst), I[GRID_TO_NCHW_I_B],
-          I[GRID_TO_NCHW_I_C], I[GRID_TO_NCHW_I_H], I[GRID_TO_NCHW_I_W], I[GRID_TO_NCHW_I_P], I[GRID_TO_NCHW_I_RPI]));
+          PTR(const void*, GRID_TO_NCHW_P_src), PTR(float*, GRID_TO_NCHW_P_dst), I[GRID_TO_NCHW_I_B],
+          I[GRID_TO_NCHW_I_C], I[GRID_TO_NCHW_I_H], I[GRID_TO_NCHW_I_W], I[GRID_TO_NCHW_I_P], I[GRID_TO_NCHW_I_RPI],
+          I[GRID_TO_NCHW_I_f32]));
       VQA_LAUNCH_OK("grid_to_nchw_kernel");
       return VQA_OK;
     }
@@ -1039,16 +1158,33 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int NP = q.H / q.CS * q.W, lanes = kTailThreads / q.C8;
       VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= lanes * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
       VQA_REQUIRE(q.ks >= 0 && 2 * q.ks * q.ks <= 128, VQA_E_INVALID, "stage_tail: spatial kernel too large");
-      const size_t smem = static_cast<size_t>(NP) * C * 2 + sizeof(float) * (static_cast<size_t>(lanes) * C + 2 * C + 64 + NP + 128);
+      const bool f32 = I[STAGE_TAIL_I_f32] != 0;
+      const size_t smem = static_cast<size_t>(NP) * C * (f32 ? 4 : 2) + sizeof(float) * (static_cast<size_t>(lanes) * C + 2 * C + 64 + NP + 128);
       VQA_REQUIRE(smem <= 227 * 1024, VQA_E_INVALID, "stage_tail: rows per CTA exceed shared memory (raise CS)");
-      static size_t attr_smem = 0;
-      if (smem > attr_smem) {
-        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&stage_tail_kernel),
+      static bool attr_set = false;
+      if (!attr_set) {
+        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&stage_tail_kernel<false>),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_smem = 227 * 1024;
+        VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&stage_tail_kernel<true>),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
       }
-      VQA_CUDA_OK(vqa_launch_cluster(stage_tail_kernel, dim3(I[STAGE_TAIL_I_B] * q.CS), dim3(kTailThreads), smem, st, q.CS, q));
+      if (f32) {
+        VQA_CUDA_OK(vqa_launch_cluster(stage_tail_kernel<true>, dim3(I[STAGE_TAIL_I_B] * q.CS), dim3(kTailThreads), smem, st, q.CS, q));
+      } else {
+        VQA_CUDA_OK(vqa_launch_cluster(stage_tail_kernel<false>, dim3(I[STAGE_TAIL_I_B] * q.CS), dim3(kTailThreads), smem, st, q.CS, q));
+      }
       VQA_LAUNCH_OK("stage_tail_kernel");
+      return VQA_OK;
+    }
+    case VQA_OP_SPLIT_TF32: {
+      const int M = I[SPLIT_TF32_I_M], K = I[SPLIT_TF32_I_K], ld = I[SPLIT_TF32_I_ld_src];
+      const float* src = PTR(const float*, SPLIT_TF32_P_src);
+      VQA_REQUIRE(K % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0, VQA_E_ALIGN,
+                  "split_tf32: K and the leading dimension must be multiples of 4");
+      VQA_CUDA_OK(vqa_launch(split_tf32_kernel, dim3(blocks_for(static_cast<long long>(M) * (K / 4), 256)), dim3(256), 0, st,
+                             src, PTR(float*, SPLIT_TF32_P_dst), M, K / 4, ld));
+      VQA_LAUNCH_OK("split_tf32_kernel");
       return VQA_OK;
     }
     case VQA_OP_COPY_ROWS: {
@@ -1096,7 +1232,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(ld % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, VQA_E_ALIGN, "self_attn: qkv alignment");
       VQA_REQUIRE((reinterpret_cast<uintptr_t>(PTR(float*, SELF_ATTN_P_out)) & 15) == 0, VQA_E_ALIGN, "self_attn: out alignment");
       return launch_attn(qkv, qkv + D, qkv + 2 * D, PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), nullptr, B,
-                         H, L, L, ld, ld, st);
+                         H, L, L, ld, ld, I[SELF_ATTN_I_no_round], st);
     }
     case VQA_OP_CROSS_ATTN: {
       const int L = I[CROSS_ATTN_I_L], T = I[CROSS_ATTN_I_T], H = I[CROSS_ATTN_I_H], B = I[CROSS_ATTN_I_B];
@@ -1107,7 +1243,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
                       I[CROSS_ATTN_I_v_off] % 4 == 0, VQA_E_ALIGN, "cross_attn: leading dimensions must be multiples of 4");
       return launch_attn(PTR(const float*, CROSS_ATTN_P_q), kv + I[CROSS_ATTN_I_k_off], kv + I[CROSS_ATTN_I_v_off], nullptr,
                          PTR(float*, CROSS_ATTN_P_out), PTR(float*, CROSS_ATTN_P_weights), B, H, L, T, I[CROSS_ATTN_I_ld_q],
-                         I[CROSS_ATTN_I_ld_kv], st);
+                         I[CROSS_ATTN_I_ld_kv], I[CROSS_ATTN_I_no_round], st);
     }
     case VQA_OP_POOL_GATE_LN: {
       const int phase = I[POOL_GATE_LN_I_phase];
@@ -1124,7 +1260,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
           PTR(const float*, POOL_GATE_LN_P_gamma), PTR(const float*, POOL_GATE_LN_P_beta),
           PTR(float*, POOL_GATE_LN_P_fused), PTR(float*, POOL_GATE_LN_P_att_pooled),
           PTR(float*, POOL_GATE_LN_P_txt_pooled), PTR(float*, POOL_GATE_LN_P_cat), I[POOL_GATE_LN_I_L], phase,
-          op.f[POOL_GATE_LN_F_eps]));
+          I[POOL_GATE_LN_I_no_round], op.f[POOL_GATE_LN_F_eps]));
       VQA_LAUNCH_OK("pool_gate_ln_kernel");
       return VQA_OK;
     }
@@ -1154,6 +1290,7 @@ const char* misc_kernel_name(int kind) {
     case VQA_OP_GRID_TO_NCHW: return "grid_to_nchw_kernel";
     case VQA_OP_MASK_PREP: return "mask_prep_kernel";
     case VQA_OP_COPY_ROWS: return "copy_rows_kernel";
+    case VQA_OP_SPLIT_TF32: return "split_tf32_kernel";
     case VQA_OP_STAGE_TAIL: return "stage_tail_kernel";
     case VQA_OP_EMBED: return "embed_kernel";
     case VQA_OP_LAYERNORM: return "layernorm256_kernel";

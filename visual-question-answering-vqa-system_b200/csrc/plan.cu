@@ -40,6 +40,7 @@ const FieldCount kFields[VQA_OP_KIND_MAX] = {
     {GRID_TO_NCHW_NI, GRID_TO_NCHW_NP, GRID_TO_NCHW_NF},
     {COPY_ROWS_NI, COPY_ROWS_NP, COPY_ROWS_NF},
     {STAGE_TAIL_NI, STAGE_TAIL_NP, STAGE_TAIL_NF},
+    {SPLIT_TF32_NI, SPLIT_TF32_NP, SPLIT_TF32_NF},
 };
 static_assert(GEMM_NI <= VQA_OP_NI, "VqaOp.i too small for the gemm op");
 static_assert(POOL_GATE_LN_NP <= VQA_OP_NP, "VqaOp.p too small");

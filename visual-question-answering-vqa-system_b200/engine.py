@@ -24,7 +24,8 @@ class Engine:
         self.device = p.device
         self.cfg = dict(model.config)
         with torch.no_grad():
-            self.weights = weights if weights is not None else P.build_weights(model.state_dict(), self.cfg, self.device)
+            self.weights = weights if weights is not None else P.build_weights(
+                model.state_dict(), self.cfg, self.device, precision=getattr(model, "precision", "bf16"))
         self._plans: Dict[tuple, Tuple[P.Program, Plan]] = {}
         self.window = True
 

@@ -36,7 +36,7 @@ KINDS = {
     "ingest": 1, "gemm": 2, "maxpool": 3, "se_squeeze": 4, "se_excite": 5, "spatial_map": 6,
     "scale_relayout": 7, "embed": 8, "layernorm": 9, "self_attn": 10, "cross_attn": 11,
     "pool_gate_ln": 12, "softmax_topk": 13, "mask_prep": 14, "grid_to_nchw": 15,
-    "copy_rows": 16, "stage_tail": 17,
+    "copy_rows": 16, "stage_tail": 17, "split_tf32": 18,
 }
 
 _GROUPS = [f"g_{k}{g}" for k in ("map", "delta", "acol", "chunks", "ntaps", "kbase", "tap0")
@@ -44,7 +44,7 @@ _GROUPS = [f"g_{k}{g}" for k in ("map", "delta", "acol", "chunks", "ntaps", "kba
 _TAPS = [f"tap_rel{t}" for t in range(MAX_TAPS)]
 
 FIELDS: Dict[str, Dict[str, List[str]]] = {
-    "ingest": {"i": ["B", "mode", "HW", "P", "rows", "ones"], "p": ["src", "dst"], "f": []},
+    "ingest": {"i": ["B", "mode", "HW", "P", "rows", "ones", "f32"], "p": ["src", "dst"], "f": []},
     "gemm": {"i": ["dtype", "M", "N", "Npad", "Ktot", "BN", "MT", "halo", "a0_rows", "a0_cols", "a0_ld",
                    "a1_rows", "a1_cols", "a1_ld", "ngroups", "ntaps", "out_dtype", "ldo", "res_dtype", "ldr",
                    "relu", "round_tf32", "mask_en", "mP", "mRPI", "mH", "mW", "smem_budget", "max_ctas", "row_bytes",
@@ -52,7 +52,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio", "pair"]
                   + _GROUPS + _TAPS,
              "p": ["a0", "a1", "b", "out", "bias", "res", "dbg"], "f": []},
-    "maxpool": {"i": ["B", "C", "Hin", "Win", "Pin", "RPIin", "Hout", "Wout", "Pout", "RPIout"],
+    "maxpool": {"i": ["B", "C", "Hin", "Win", "Pin", "RPIin", "Hout", "Wout", "Pout", "RPIout", "f32"],
                 "p": ["src", "dst"], "f": []},
     "se_squeeze": {"i": ["B", "C", "H", "W", "P", "RPI", "S"], "p": ["src", "sums"], "f": []},
     "se_excite": {"i": ["B", "C", "R", "HW", "S"], "p": ["sums", "w1", "w2", "scale"], "f": []},
@@ -63,17 +63,18 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
     "embed": {"i": ["B", "L", "D", "V"], "p": ["ids", "table", "pe", "dst"], "f": []},
     "layernorm": {"i": ["rows", "D", "ld_src", "mode", "round_tf32", "S", "Pg", "RPIg"],
                   "p": ["src", "gamma", "beta", "dst", "pos"], "f": ["eps"]},
-    "self_attn": {"i": ["B", "L", "H", "hd", "ld_qkv"], "p": ["qkv", "mask", "out"], "f": []},
-    "cross_attn": {"i": ["B", "L", "H", "hd", "T", "ld_q", "ld_kv", "k_off", "v_off"],
+    "self_attn": {"i": ["B", "L", "H", "hd", "ld_qkv", "no_round"], "p": ["qkv", "mask", "out"], "f": []},
+    "cross_attn": {"i": ["B", "L", "H", "hd", "T", "ld_q", "ld_kv", "k_off", "v_off", "no_round"],
                    "p": ["q", "kv", "out", "weights"], "f": []},
-    "pool_gate_ln": {"i": ["B", "L", "D", "use_gate", "phase"],
+    "pool_gate_ln": {"i": ["B", "L", "D", "use_gate", "phase", "no_round"],
                      "p": ["xatt", "text", "mask", "wg", "bg", "gamma", "beta", "fused",
                            "att_pooled", "txt_pooled", "cat", "pre"], "f": ["eps"]},
     "softmax_topk": {"i": ["B", "N", "k", "ld"], "p": ["logits", "idx", "probs"], "f": []},
     "mask_prep": {"i": ["B", "L", "dtype"], "p": ["src", "dst"], "f": []},
-    "grid_to_nchw": {"i": ["B", "C", "H", "W", "P", "RPI"], "p": ["src", "dst"], "f": []},
+    "grid_to_nchw": {"i": ["B", "C", "H", "W", "P", "RPI", "f32"], "p": ["src", "dst"], "f": []},
     "copy_rows": {"i": ["rows", "cols", "ld_src", "ld_dst"], "p": ["src", "dst"], "f": []},
-    "stage_tail": {"i": ["B", "C", "H", "W", "P", "RPI", "R", "ks", "mode", "Po", "RPIo", "phase_rows", "CS"],
+    "split_tf32": {"i": ["M", "K", "ld_src"], "p": ["src", "dst"], "f": []},
+    "stage_tail": {"i": ["B", "C", "H", "W", "P", "RPI", "R", "ks", "mode", "Po", "RPIo", "phase_rows", "CS", "f32"],
                    "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att"], "f": []},
 }
 
@@ -215,6 +216,7 @@ class Weights:
     """Packed device-resident parameters (one arena; this is what gets NCCL-broadcast)."""
 
     def __init__(self, device):
+        self.precision = "bf16"     # "bf16": bf16 backbone operands | "tf32": fp32 activations, tf32 operands everywhere
         self.arena = Arena(device)
         self.items: Dict[str, Tuple[Buf, torch.dtype, Tuple[int, ...]]] = {}
         self._pending: List[Tuple[str, torch.Tensor]] = []
@@ -262,15 +264,32 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
     return r.view(torch.float32)
 
 
-def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
-    """All load-time algebra; every product is formed in fp32 before the bf16 / tf32 cast."""
+def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device, precision: str = "bf16") -> Weights:
+    """All load-time algebra; every product is formed in fp32 before the bf16 / tf32 cast.
+
+    precision="tf32" (the tolerance mode of BASELINE.json: logits within 1e-3 of the fp32 reference) stores the
+    backbone weights as tf32-rounded fp32 instead of bf16; everything else is identical."""
+    assert precision in ("bf16", "tf32")
     W = Weights(device)
+    W.precision = precision
     sd = {k: v.detach().to("cpu") for k, v in sd.items()}
     bf, f32 = torch.bfloat16, torch.float32
+    tf = precision == "tf32"
+    cw = f32 if tf else bf                                    # storage type of the backbone GEMM operands
+    cast = (lambda m: round_tf32(m.float())) if tf else (lambda m: m)
+
+    def lin(name, w):
+        """A tf32 Linear weight; in tf32 precision mode also its 3xTF32 form [hi | hi | lo] along K, consumed with
+        A = [a_hi | a_lo]: a_hi*hi + a_lo*hi + a_hi*lo recovers fp32-level products on the tf32 tensor pipe."""
+        w = w.float()
+        hi = round_tf32(w)
+        W.add(name, hi, f32)
+        if tf:
+            W.add(name + ".x3", torch.cat([hi, hi, round_tf32(w - hi)], dim=1), f32)
 
     # ---- backbone (BN folded, OHWI, bf16 operands, fp32 bias)
     w, b = _fold_bn(sd, "image_encoder.stem.0.weight", "image_encoder.stem.1")
-    W.add("stem.w", _stem_matrix(w), bf)
+    W.add("stem.w", cast(_stem_matrix(w)), cw)
     W.add("stem.b", b, f32)
     # bias folded into K: ingest(ones=1) stores 1.0 in the spare channel of phases (0,0) and (0,1) of every
     # in-image block; the centre tap's weights there carry the bias as a bf16 hi + lo pair (error ~2^-17)
@@ -278,7 +297,8 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
     hi = b.to(bf).float()
     mb[:, 2, 2, 0, 0, 3] = hi
     mb[:, 2, 2, 0, 1, 3] = (b - hi).to(bf).float()
-    W.add("stem.wb", mb.reshape(-1, 256), bf)
+    if not tf:
+        W.add("stem.wb", mb.reshape(-1, 256), bf)
     for s in (1, 2, 3, 4):
         p = f"image_encoder.stage{s}"
         blk = 0
@@ -291,9 +311,9 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
                 wd, bd = _fold_bn(sd, q + ".downsample.0.weight", q + ".downsample.1")
                 m2 = torch.cat([m2, _ohwi(wd)], dim=1)
                 b2 = b2 + bd
-            W.add(f"s{s}.b{blk}.conv1.w", _ohwi(w1), bf)
+            W.add(f"s{s}.b{blk}.conv1.w", cast(_ohwi(w1)), cw)
             W.add(f"s{s}.b{blk}.conv1.b", b1, f32)
-            W.add(f"s{s}.b{blk}.conv2.w", m2, bf)
+            W.add(f"s{s}.b{blk}.conv2.w", cast(m2), cw)
             W.add(f"s{s}.b{blk}.conv2.b", b2, f32)
             blk += 1
         if f"{p}.attention.se.fc1.weight" in sd:
@@ -313,13 +333,13 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
         W.add(f"text.{layer}.ln1.g", sd[q + ".norm1.weight"], f32)
         W.add(f"text.{layer}.ln1.b", sd[q + ".norm1.bias"], f32)
         qkv = torch.cat([sd[q + f".self_attention.W_{n}.weight"] for n in "qkv"], dim=0)
-        W.add(f"text.{layer}.qkv.w", round_tf32(qkv.float()), f32)
-        W.add(f"text.{layer}.o.w", round_tf32(sd[q + ".self_attention.W_o.weight"].float()), f32)
+        lin(f"text.{layer}.qkv.w", qkv)
+        lin(f"text.{layer}.o.w", sd[q + ".self_attention.W_o.weight"])
         W.add(f"text.{layer}.ln2.g", sd[q + ".norm2.weight"], f32)
         W.add(f"text.{layer}.ln2.b", sd[q + ".norm2.bias"], f32)
-        W.add(f"text.{layer}.fc1.w", round_tf32(sd[q + ".ffn.fc1.weight"].float()), f32)
+        lin(f"text.{layer}.fc1.w", sd[q + ".ffn.fc1.weight"])
         W.add(f"text.{layer}.fc1.b", sd[q + ".ffn.fc1.bias"], f32)
-        W.add(f"text.{layer}.fc2.w", round_tf32(sd[q + ".ffn.fc2.weight"].float()), f32)
+        lin(f"text.{layer}.fc2.w", sd[q + ".ffn.fc2.weight"])
         W.add(f"text.{layer}.fc2.b", sd[q + ".ffn.fc2.bias"], f32)
         layer += 1
     W.add("text.lnf.g", sd[t + ".final_norm.weight"], f32)
@@ -327,7 +347,7 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
 
     # ---- fusion
     fz = "fusion"
-    W.add("proj.w", sd[fz + ".image_projector.projection.0.weight"], bf)      # A operand is the bf16 backbone output
+    W.add("proj.w", cast(sd[fz + ".image_projector.projection.0.weight"]), cw)   # A operand is the backbone output
     W.add("proj.b", sd[fz + ".image_projector.projection.0.bias"], f32)
     W.add("proj.ln.g", sd[fz + ".image_projector.projection.1.weight"], f32)
     W.add("proj.ln.b", sd[fz + ".image_projector.projection.1.bias"], f32)
@@ -338,17 +358,17 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
         for nm, key in (("lnq", "norm_query"), ("lnkv", "norm_kv"), ("lnf", "norm_ffn")):
             W.add(f"x.{layer}.{nm}.g", sd[f"{q}.{key}.weight"], f32)
             W.add(f"x.{layer}.{nm}.b", sd[f"{q}.{key}.bias"], f32)
-        W.add(f"x.{layer}.q.w", round_tf32(sd[q + ".cross_attention.W_q.weight"].float()), f32)
+        lin(f"x.{layer}.q.w", sd[q + ".cross_attention.W_q.weight"])
         kv = torch.cat([sd[q + ".cross_attention.W_k.weight"], sd[q + ".cross_attention.W_v.weight"]], dim=0)
-        W.add(f"x.{layer}.kv.w", round_tf32(kv.float()), f32)
-        W.add(f"x.{layer}.o.w", round_tf32(sd[q + ".cross_attention.W_o.weight"].float()), f32)
-        W.add(f"x.{layer}.fc1.w", round_tf32(sd[q + ".ffn.0.weight"].float()), f32)
+        lin(f"x.{layer}.kv.w", kv)
+        lin(f"x.{layer}.o.w", sd[q + ".cross_attention.W_o.weight"])
+        lin(f"x.{layer}.fc1.w", sd[q + ".ffn.0.weight"])
         W.add(f"x.{layer}.fc1.b", sd[q + ".ffn.0.bias"], f32)
-        W.add(f"x.{layer}.fc2.w", round_tf32(sd[q + ".ffn.3.weight"].float()), f32)
+        lin(f"x.{layer}.fc2.w", sd[q + ".ffn.3.weight"])
         W.add(f"x.{layer}.fc2.b", sd[q + ".ffn.3.bias"], f32)
         layer += 1
     if fz + ".gate.gate.0.weight" in sd:
-        W.add("gate.w", round_tf32(sd[fz + ".gate.gate.0.weight"].float()), f32)
+        lin("gate.w", sd[fz + ".gate.gate.0.weight"])
         W.add("gate.b", sd[fz + ".gate.gate.0.bias"], f32)
     W.add("out.ln.g", sd[fz + ".output_norm.weight"], f32)
     W.add("out.ln.b", sd[fz + ".output_norm.bias"], f32)
@@ -356,9 +376,8 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Weights:
     # ---- answer head (N padded to the GEMM tile so TMA boxes never leave the tensor)
     h = "answer_head.classifier"
     for idx, nm in ((0, "head0"), (3, "head1"), (6, "head2")):
-        w = round_tf32(sd[f"{h}.{idx}.weight"].float())
         b = sd[f"{h}.{idx}.bias"].float()
-        W.add(nm + ".w", _pad_rows(w, 256), f32)
+        lin(nm + ".w", _pad_rows(sd[f"{h}.{idx}.weight"].float(), 256))
         W.add(nm + ".b", _pad_rows(b, 256), f32)
     return W.finalize()
 
@@ -376,11 +395,12 @@ class OpList:
 
     def __init__(self, weights: Weights, device=None, window: bool = True):
         self.W = weights
+        self.tf32 = getattr(weights, "precision", "bf16") == "tf32"
         self.window = window
         self.stem_window = window
-        self.fuse_pool = window
-        self.fused_tail = window
-        self.pair = window
+        self.fuse_pool = window and not self.tf32
+        self.fused_tail = window or self.tf32
+        self.pair = window and not self.tf32
         self.ws = Arena(device if device is not None else weights.arena.device)
         self.ops: List[Op] = []
         self.named: Dict[str, Tuple[Buf, torch.dtype, Tuple[int, ...]]] = {}
@@ -475,7 +495,20 @@ class OpList:
                                         bias=self.W.buf(bias) if bias else None, res=res))
 
     def linear(self, name, a, M, K, w, bias, out, N, ldo=None, res=None, relu=False, rnd=False, lda=None):
-        """fp32/TF32 dense layer: out[M,N] = a[M,K] @ W^T (+bias)(+res)(relu)."""
+        """fp32/TF32 dense layer: out[M,N] = a[M,K] @ W^T (+bias)(+res)(relu).
+
+        tf32 precision mode: 3xTF32.  ``a`` (unrounded fp32) is split into [a_hi | a_lo] by a small kernel and the
+        GEMM runs three K groups against [W_hi | W_hi | W_lo]; the tf32 rounding of the plain path (5e-4 per
+        operand, the dominant term of the tail's error) drops to ~1e-6."""
+        if self.tf32 and (w + ".x3") in self.W:
+            sp = self._buf(name + ".split", torch.float32, M, 2 * K)
+            self._op("split_tf32", name + ".split", dict(M=M, K=K, ld_src=lda or K), dict(src=a, dst=sp))
+            kc = K // 32
+            self.gemm(name, dtype=DT_TF32, M=M, N=N, a0=sp, a0_shape=(M, 2 * K, 2 * K),
+                      groups=[(0, 0, 0, kc, [0]), (0, 0, K, kc, [0]), (0, 0, 0, kc, [0])],
+                      w=w + ".x3", bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F32, res=res,
+                      res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=False)
+            return
         self.gemm(name, dtype=DT_TF32, M=M, N=N, a0=a, a0_shape=(M, K, lda or K), groups=[(0, 0, 0, K // 32, [0])],
                   w=w, bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F32, res=res,
                   res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=rnd)
@@ -490,11 +523,12 @@ class OpList:
         if self.window:
             halo = g.P + 1
             rels = [halo + (kh - 1) * g.P + (kw - 1) for kh in range(3) for kw in range(3)]
-            mt = 2 if cout >= 128 else 1
+            mt = 2 if cout >= 128 and not self.tf32 else 1     # the tf32 kernels are instantiated for MT = 1
             return [(0, 0, 0, nchunks, rels)], halo, mt
         return [(0, (kh - 1) * g.P + (kw - 1), 0, nchunks, [0]) for kh in range(3) for kw in range(3)], 0, 1
 
     def layernorm(self, name, src, g, b, dst, rows, rnd=False, ld=256):
+        rnd = rnd and not self.tf32     # tf32 precision mode: consumers split the unrounded value into hi + lo
         self._op("layernorm", name, dict(rows=rows, D=256, ld_src=ld, mode=0, round_tf32=int(rnd), S=0, Pg=0, RPIg=0),
                  dict(src=src, gamma=self.W.buf(g), beta=self.W.buf(b), dst=dst, pos=None), dict(eps=1e-5))
 
@@ -521,17 +555,32 @@ class Program(OpList):
         bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
 
         # ================= image side =================
+        tf = self.tf32
+        act = f32 if tf else bf                      # backbone activation storage
+        esz = 4 if tf else 2
+        self.act, self.cdt, self.codt = act, (DT_TF32 if tf else DT_BF16), (OUT_F32 if tf else OUT_BF16)
+        self.cchunk = 32 if tf else 64               # channels per 128-byte K chunk
         g0 = Grid(B, 112, 112, pad=2)
-        GUARD = 32   # zero phase-pixels in front of the data (only the overlapping-row variant needs them)
-        s0g = self._buf("stem_in", bf, g0.rows + GUARD, 16)
-        s0 = Buf(s0g.arena, s0g.offset + GUARD * 32, g0.rows * 32, "stem_in.data")
+        GUARD = 32   # zero phase-pixels in front of the data (only the overlapping-row variants need them)
+        s0g = self._buf("stem_in", act, g0.rows + GUARD + 1, 16)
+        s0 = Buf(s0g.arena, s0g.offset + GUARD * 16 * esz, g0.rows * 16 * esz, "stem_in.data")
         fused = self.stem_window and self.fuse_pool
         self._op("ingest", "ingest", dict(B=B, mode=0 if self.in_fmt == "nchw_f32" else 1, HW=224, P=g0.P, rows=g0.rows,
-                                          ones=int(fused)),
+                                          ones=int(fused), f32=int(tf)),
                  dict(src=ExtRef(EXT["images"]), dst=s0))
         g = Grid(B, 56, 56)
-        x = self._buf("s1.in", bf, g.rows, 64)
-        if fused:
+        x = self._buf("s1.in", act, g.rows, 64)
+        if tf:
+            # tf32 mode: a phase-pixel is 16 fp32 = 64 bytes; every A row is TWO horizontally adjacent phase-pixels
+            # (32 fp32 = one 128-byte chunk) through an overlapping-row tensor map (rows start every 16 elements),
+            # 4 vertical x 2 horizontal taps; tap (ia, jb) covers weight columns (ia*4 + 2*jb)*16 .. +32
+            s1 = self._buf("stem_out", act, g0.rows, 64)
+            taps = [(0, (ia - 2) * g0.P + (2 * jb - 2) + GUARD, 0, 1, [0]) for ia in range(4) for jb in range(2)]
+            self.gemm("stem.conv", dtype=DT_TF32, M=g0.rows, N=64, a0=s0g, a0_shape=(g0.rows + GUARD, 32, 16), groups=taps,
+                      w="stem.w", bias="stem.b", out=s1, ldo=64, out_dtype=OUT_F32, relu=True, rnd=True, grid=g0)
+            self._op("maxpool", "stem.pool", dict(B=B, C=64, Hin=112, Win=112, Pin=g0.P, RPIin=g0.rpi,
+                                                  Hout=56, Wout=56, Pout=g.P, RPIout=g.rpi, f32=1), dict(src=s1, dst=x))
+        elif fused:
             lo, hi = 2 * g0.P + 2, g0.P + 1
             rels = [lo + (ia - 2) * g0.P + (ib - 2) for ia in range(4) for ib in range(4)]
             self.gemm("stem.conv+pool", dtype=DT_BF16, M=g0.rows, N=64, a0=s0, a0_shape=(g0.rows, 16, 16),
@@ -575,19 +624,21 @@ class Program(OpList):
         r = W.items[f"s{s}.se.w1"][2][0] if has_se else 0
         if s < 4:
             gn = Grid(B, g.H // 2, g.W // 2)
-            nxt = self._buf(f"s{s + 1}.in", bf, 4 * gn.rows, cout)
+            nxt = self._buf(f"s{s + 1}.in", self.act, 4 * gn.rows, cout)
             mode, Po, RPIo, prow, out = 1, gn.P, gn.rpi, gn.rows, (nxt, True, gn.rows)
         else:
-            nxt = self._buf("features", bf, g.rows, cout)
+            nxt = self._buf("features", self.act, g.rows, cout)
             mode, Po, RPIo, prow, out = 0, g.P, g.rpi, g.rows, (nxt, False, 0)
         # cluster size: rows per CTA small enough for two CTAs per SM (<= ~100 KB of pixels), whole image with spatial
         cs = 1
         if not has_sp:
-            while (g.H // cs) * g.W * cout * 2 > 104 * 1024 and cs < 8 and (g.H // (2 * cs)) % 2 == 0 and g.H % (2 * cs) == 0:
+            lim = (200 if self.tf32 else 104) * 1024     # fp32 rows: one CTA per SM
+            esz = 4 if self.tf32 else 2
+            while (g.H // cs) * g.W * cout * esz > lim and cs < 8 and (g.H // (2 * cs)) % 2 == 0 and g.H % (2 * cs) == 0:
                 cs *= 2
         self._op("stage_tail", f"s{s}.tail",
                  dict(B=B, C=cout, H=g.H, W=g.W, P=g.P, RPI=g.rpi, R=r, ks=ks, mode=mode, Po=Po, RPIo=RPIo,
-                      phase_rows=prow, CS=cs),
+                      phase_rows=prow, CS=cs, f32=int(self.tf32)),
                  dict(src=x, w1=W.buf(f"s{s}.se.w1") if has_se else None, w2=W.buf(f"s{s}.se.w2") if has_se else None,
                       wconv=W.buf(f"s{s}.spatial.w") if has_sp else None, dst=nxt, scale=scale, att=att))
         return out
@@ -605,9 +656,10 @@ class Program(OpList):
             while f"s{s}.b{nblk}.conv1.w" in W:
                 nblk += 1
             for blk in range(nblk):
-                y = self._buf(f"s{s}.b{blk}.mid", bf, g.rows, cout)
-                o = self._buf(f"s{s}.b{blk}.out", bf, g.rows, cout)
-                nch_in = cin // 64
+                y = self._buf(f"s{s}.b{blk}.mid", self.act, g.rows, cout)
+                o = self._buf(f"s{s}.b{blk}.out", self.act, g.rows, cout)
+                nch_in = cin // self.cchunk
+                cdt, codt, rnd = self.cdt, self.codt, self.tf32   # tf32 mode: outputs are the next GEMM's tf32 operands
                 if blk == 0 and x_is_phase:   # stride-2 3x3 over the 4-phase split
                     taps = []
                     for kh in range(3):
@@ -619,26 +671,26 @@ class Program(OpList):
                 else:
                     taps, halo1, mt1 = self._conv3x3_groups(g, nch_in, cout)
                     a_rows = g.rows
-                self.gemm(f"s{s}.b{blk}.conv1", dtype=DT_BF16, M=g.rows, N=cout, a0=x, a0_shape=(a_rows, cin, cin),
+                self.gemm(f"s{s}.b{blk}.conv1", dtype=cdt, M=g.rows, N=cout, a0=x, a0_shape=(a_rows, cin, cin),
                           groups=taps, w=f"s{s}.b{blk}.conv1.w", bias=f"s{s}.b{blk}.conv1.b", out=y, ldo=cout,
-                          out_dtype=OUT_BF16, relu=True, grid=g, halo=halo1, MT=mt1)
-                taps2, halo2, mt2 = self._conv3x3_groups(g, cout // 64, cout)
+                          out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo1, MT=mt1)
+                taps2, halo2, mt2 = self._conv3x3_groups(g, cout // self.cchunk, cout)
                 has_ds = W.items[f"s{s}.b{blk}.conv2.w"][2][1] > 9 * cout
                 if has_ds:
                     # shortcut conv1x1/stride: phase (0,0) of the block input, same flat row index
                     assert x_is_phase or cin != cout
                     taps2.append((1, 0, 0, nch_in, [halo2]))
-                    self.gemm(f"s{s}.b{blk}.conv2", dtype=DT_BF16, M=g.rows, N=cout, a0=y,
+                    self.gemm(f"s{s}.b{blk}.conv2", dtype=cdt, M=g.rows, N=cout, a0=y,
                               a0_shape=(g.rows, cout, cout), a1=x,
                               a1_shape=(phase_rows if x_is_phase else g.rows, cin, cin), groups=taps2,
                               w=f"s{s}.b{blk}.conv2.w", bias=f"s{s}.b{blk}.conv2.b", out=o, ldo=cout,
-                              out_dtype=OUT_BF16, relu=True, grid=g, halo=halo2, MT=mt2)
+                              out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo2, MT=mt2)
                 else:
                     assert not x_is_phase
-                    self.gemm(f"s{s}.b{blk}.conv2", dtype=DT_BF16, M=g.rows, N=cout, a0=y,
+                    self.gemm(f"s{s}.b{blk}.conv2", dtype=cdt, M=g.rows, N=cout, a0=y,
                               a0_shape=(g.rows, cout, cout), groups=taps2, w=f"s{s}.b{blk}.conv2.w",
-                              bias=f"s{s}.b{blk}.conv2.b", out=o, ldo=cout, out_dtype=OUT_BF16, relu=True,
-                              res=x, res_dtype=OUT_BF16, ldr=cin, grid=g, halo=halo2, MT=mt2)
+                              bias=f"s{s}.b{blk}.conv2.b", out=o, ldo=cout, out_dtype=codt, relu=True, rnd=rnd,
+                              res=x, res_dtype=codt, ldr=cin, grid=g, halo=halo2, MT=mt2)
                 x, cin, x_is_phase = o, cout, False
             # ---- stage attention + relayout for the next stage
             has_se, has_sp = f"s{s}.se.w1" in W, f"s{s}.spatial.w" in W
@@ -678,7 +730,7 @@ class Program(OpList):
         self.feat_name = next(k for k, v in self.named.items() if v[0] is feat)
         if self.want_aux:
             nchw = self._buf("aux.image_features", f32, B, 512, 7, 7)
-            self._op("grid_to_nchw", "aux.image_features", dict(B=B, C=512, H=7, W=7, P=gf.P, RPI=gf.rpi),
+            self._op("grid_to_nchw", "aux.image_features", dict(B=B, C=512, H=7, W=7, P=gf.P, RPI=gf.rpi, f32=int(self.tf32)),
                      dict(src=feat, dst=nchw))
 
         # ================= text side (independent of the image side: runs on the side stream) =================
@@ -703,7 +755,7 @@ class Program(OpList):
             p = f"text.{layer}"
             self.layernorm(p + ".ln1", xt, p + ".ln1.g", p + ".ln1.b", xn, T, rnd=True)
             self.linear(p + ".qkv", xn, T, D, p + ".qkv.w", None, qkv, 3 * D)
-            self._op("self_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, ld_qkv=3 * D),
+            self._op("self_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, ld_qkv=3 * D, no_round=int(self.tf32)),
                      dict(qkv=qkv, mask=mask, out=ctx))
             self.linear(p + ".o", ctx, T, D, p + ".o.w", None, xt, D, res=xt)
             self.layernorm(p + ".ln2", xt, p + ".ln2.g", p + ".ln2.b", xn, T, rnd=True)
@@ -716,8 +768,8 @@ class Program(OpList):
         # ================= fusion (joins both lanes) =================
         self.lane = 0
         praw = self._buf("proj.raw", f32, gf.rows, D)
-        self.gemm("proj", dtype=DT_BF16, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
-                  groups=[(0, 0, 0, 512 // 64, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
+        self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
+                  groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
         S = 7
         img = self._buf("image_projected", f32, B * S * S, D)
         self._op("layernorm", "proj.ln", dict(rows=B * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
@@ -743,11 +795,11 @@ class Program(OpList):
             if self.want_aux:
                 wts = self._buf(f"aux.xattn.{layer}", f32, B, H, L, S * S)
                 self.xattn_weights.append(f"aux.xattn.{layer}")
-            self._op("cross_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, T=S * S, ld_q=D, ld_kv=2 * D, k_off=0, v_off=D),
+            self._op("cross_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, T=S * S, ld_q=D, ld_kv=2 * D, k_off=0, v_off=D,
+                                                     no_round=int(self.tf32)),
                      dict(q=qp, kv=kv, out=cx, weights=wts))
             # q = src_q + W_o ctx   (first layer reads the text features as residual, writes the stream buffer)
-            self.gemm(p + ".o", dtype=DT_TF32, M=T, N=D, a0=cx, a0_shape=(T, D, D), groups=[(0, 0, 0, D // 32, [0])],
-                      w=p + ".o.w", bias=None, out=q, ldo=D, out_dtype=OUT_F32, res=src_q, res_dtype=OUT_F32, ldr=D)
+            self.linear(p + ".o", cx, T, D, p + ".o.w", None, q, D, res=src_q)
             self.layernorm(p + ".lnf", q, p + ".lnf.g", p + ".lnf.b", qn, T, rnd=True)
             self.linear(p + ".fc1", qn, T, D, p + ".fc1.w", p + ".fc1.b", hid, F, relu=True, rnd=True)
             self.linear(p + ".fc2", hid, T, F, p + ".fc2.w", p + ".fc2.b", q, D, res=q)
@@ -764,7 +816,8 @@ class Program(OpList):
             # read once instead of once per pair) -> sigmoid gate, mix, LayerNorm
             cat = self._buf("fusion.cat", f32, B, 2 * D)
             pre = self._buf("fusion.gate_pre", f32, B, D)
-            self._op("pool_gate_ln", "fusion.pool", dict(B=B, L=L, D=D, use_gate=1, phase=1), dict(tail_p, cat=cat), dict(eps=1e-5))
+            self._op("pool_gate_ln", "fusion.pool", dict(B=B, L=L, D=D, use_gate=1, phase=1, no_round=int(self.tf32)),
+                     dict(tail_p, cat=cat), dict(eps=1e-5))
             self.linear("fusion.gate", cat, B, 2 * D, "gate.w", "gate.b", pre, D)
             self._op("pool_gate_ln", "fusion.mix", dict(B=B, L=L, D=D, use_gate=1, phase=2), dict(tail_p, pre=pre), dict(eps=1e-5))
         else:
