@@ -136,13 +136,15 @@ def cpu_reference_run(steps: int, warmup: int, batch: int = 32):
     for _ in range(warmup):
         O.vqa_forward(sd, img, ids, mask)
     times = []
+    out = None
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.vqa_forward(sd, img, ids, mask)
+        out = O.vqa_forward(sd, img, ids, mask)
         times.append(time.perf_counter() - t0)
     total = sum(times)
+    logits = out[0] if isinstance(out, tuple) else out
     return {"value": batch * steps / total, "ms_per_step": 1e3 * total / steps, "cores": torch.get_num_threads(),
-            "best": batch / min(times), "batch": batch}
+            "best": batch / min(times), "batch": batch, "inputs": (img, ids, mask), "logits": logits}
 
 
 def run_reference(args):
@@ -370,10 +372,45 @@ def run_b200(args):
 
     # ---- host CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=4, warmup=1)
         cpu = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
                "sample": "4 timed fp32 oracle forwards of batch 32 (BASELINE configs[0]) on the host CPU"}
+        # parity on this box, same 32 pairs: both precision modes of the CUDA path against the oracle's fp32 logits
+        # (the model of the timed legs has the same seed-0 weights as the oracle run)
+        from vqa_b200.model import VQAModel as _VM
+        i32, d32, m32 = (t.to(dev) for t in r["inputs"])
+        want = r["logits"]
+        with torch.no_grad():
+            got_bf16 = model(i32, d32, m32)[0].float().cpu()
+            torch.manual_seed(0)
+            m_tf32 = _VM(precision="tf32").eval().to(dev)
+            got_tf32 = m_tf32(i32, d32, m32)[0].float().cpu()
+            # throughput of the tolerance mode, same batch-256 workload, CUDA-graph replay
+            for _ in range(2):
+                m_tf32(d_img, d_ids, d_mask)
+            torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                m_tf32(d_img, d_ids, d_mask)
+            for _ in range(3):
+                g2.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                g2.replay()
+            b.record()
+            torch.cuda.synchronize()
+        rel = lambda x: float((x - want).abs().max() / want.abs().max())
+        parity = {"pairs": int(want.shape[0]), "oracle": "fp32 CPU restatement of the reference (oracle/vqa_oracle.py)",
+                  "bf16_mode_max_abs_rel_err": rel(got_bf16), "bf16_gate": 2e-2,
+                  "bf16_top1_agree": float((got_bf16.argmax(1) == want.argmax(1)).float().mean()),
+                  "tf32_mode_max_abs_rel_err": rel(got_tf32), "tf32_gate": 1e-3,
+                  "tf32_top1_agree": float((got_tf32.argmax(1) == want.argmax(1)).float().mean()),
+                  "tf32_mode_pairs_per_sec": B * 5 / (a.elapsed_time(b) * 1e-3)}
+        del m_tf32, g2
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
@@ -384,7 +421,7 @@ def run_b200(args):
                            "parallelism": f"batch-sharded x{world}, weights broadcast once",
                            "l2": "inputs 154 MB/GPU (fp32 NCHW) exceed the 126 MB L2; no flush needed",
                            "launch": "one forward captured in a CUDA graph (87 kernels, programmatic dependent launch), replayed per step"},
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "parity": parity,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K, "h2d_pinned_copy_gbps": h2d_gbps,
                         "path": "VQAInference.predict_tensors_pipelined: pinned uint8 HWC + ids + mask -> H2D (copy "
