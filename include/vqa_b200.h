@@ -97,6 +97,17 @@ int  vqa_plan_num_launches(const VqaPlan* plan);      /* kernels one vqa_plan_ru
 int  vqa_plan_op_kernel_name(const VqaPlan* plan, int32_t op, char* buf, int32_t buflen);
 void vqa_plan_destroy(VqaPlan* plan);
 
+/* PIL-exact antialiased bilinear resize of one uint8 HWC image on the device.
+ * Replaces the CPU resize inside the reference transform: transforms.Resize((224,224)) -> Pillow
+ * Image.resize(BILINEAR) (data/preprocess.py:117-121, api/inference.py:153-167).  All pointers are device
+ * pointers.  bounds_* are int32 [out, 2] = (first input index, count), kk_* int32 [out, ksize_*] the 22-bit
+ * fixed-point weights of Pillow's Resample.c (the host computes them: vqa_b200/resize.py::coeffs).  tmp holds
+ * the horizontally resized intermediate (in_h * out_w * channels bytes; may be NULL when only one pass is
+ * needed).  Horizontal pass first, intermediate rounded to uint8: bit-exact with PIL. */
+int vqa_resize_bilinear_u8(const uint8_t* src, int32_t in_h, int32_t in_w, int32_t channels, uint8_t* tmp, uint8_t* dst,
+                           int32_t out_h, int32_t out_w, const int32_t* bounds_h, const int32_t* kk_h, int32_t ksize_h,
+                           const int32_t* bounds_v, const int32_t* kk_v, int32_t ksize_v, void* stream);
+
 /* counters (process-wide): kernels launched by this library since load */
 uint64_t vqa_launch_count(void);
 

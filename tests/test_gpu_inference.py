@@ -55,7 +55,7 @@ def test_predict_batch_and_resize(engine):
     res = engine.predict_batch(imgs, qs, top_k=3)
     assert [r["question"] for r in res] == qs and all(len(r["answers"]) == 3 for r in res)
     for im, q, r in zip(imgs, qs, res):
-        u8 = engine.preprocess_image_u8(im)
+        u8 = engine.preprocess_image_u8(im).cpu()          # non-224 inputs come back from the device-side resize
         idx, _ = _oracle_topk(engine, u8, q, 3)
         assert r["answers"][0]["index"] == int(idx[0, 0])
     single = engine.predict(imgs[0], qs[0], top_k=3)
@@ -78,3 +78,33 @@ def test_pipelined_throughput_path_matches_single_calls(engine):
     for (u8, ids, mask), (idx, probs) in zip(batches, outs):
         ridx, rprobs = engine._run(u8, ids, mask, 4)
         assert torch.equal(idx, ridx) and torch.equal(probs, rprobs)
+
+
+@pytest.mark.parametrize("hw", [(300, 400), (100, 160), (333, 211), (224, 500), (640, 224), (17, 23), (1080, 1920), (225, 223)])
+def test_device_resize_is_bit_exact_with_pil(engine, hw):
+    """vqa_resize_bilinear_u8 (csrc/resize.cu) against PIL.Image.resize(BILINEAR) itself: every byte equal."""
+    from vqa_b200.runtime import resize_bilinear_u8
+    rng = np.random.default_rng(hw[0] * 7919 + hw[1])
+    img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img, "RGB").resize((224, 224), Image.BILINEAR))
+    got = resize_bilinear_u8(torch.from_numpy(img).cuda(), 224, 224).cpu().numpy()
+    assert got.shape == (224, 224, 3) and np.array_equal(got, want)
+
+
+def test_device_resize_matches_golden_and_host_path(engine):
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    for name in ("down", "up", "odd"):
+        im = Image.fromarray(g[f"{name}.u8"], "RGB")
+        dev = engine.preprocess_image_u8(im)                        # CUDA kernels
+        host = engine.preprocess_image_u8(im, device_resize=False)  # PIL on the host
+        assert dev.is_cuda and not host.is_cuda
+        assert np.array_equal(dev.cpu().numpy(), g[f"{name}.resized_u8"]) and torch.equal(dev.cpu(), host)
+    im = Image.fromarray(g["down.u8"], "RGB")
+    engine.gpu_resize = True
+    a = engine.predict(im, "what is this", top_k=5)
+    engine.gpu_resize = False
+    b = engine.predict(im, "what is this", top_k=5)
+    engine.gpu_resize = True
+    assert a == b

@@ -54,3 +54,23 @@ def test_accepts_bytes_paths_and_non_rgb(g, tmp_path):
 def test_no_cpu_path():
     with pytest.raises(RuntimeError):
         VQAInference(device="cpu").load()
+
+
+@pytest.mark.parametrize("hw", [(300, 400), (100, 160), (333, 211), (224, 500), (640, 224), (17, 23), (225, 223), (1, 1)])
+def test_resize_restatement_is_bit_exact_with_pil(hw):
+    """vqa_b200/resize.py (windows + 22-bit weights handed to the CUDA kernels, and the numpy two-pass
+    restatement) against PIL.Image.resize(BILINEAR) itself."""
+    from vqa_b200.resize import coeffs, numpy_resize
+    rng = np.random.default_rng(hw[0] * 7919 + hw[1])
+    img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img, "RGB").resize((224, 224), Image.BILINEAR))
+    assert np.array_equal(numpy_resize(img, 224, 224), want)
+    b, kk = coeffs(hw[1], 224)
+    assert b.shape == (224, 2) and kk.shape[0] == 224 and (b[:, 0] + b[:, 1] <= hw[1]).all()
+    assert (kk.sum(axis=1) - (1 << 22)).__abs__().max() <= kk.shape[1]      # weights sum to 1.0 in fixed point
+
+
+def test_resize_restatement_matches_golden(g):
+    from vqa_b200.resize import numpy_resize
+    for name in ("down", "up", "odd"):
+        assert np.array_equal(numpy_resize(g[f"{name}.u8"], 224, 224), g[f"{name}.resized_u8"])

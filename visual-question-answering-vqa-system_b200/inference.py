@@ -59,6 +59,7 @@ class VQAInference:
         self.answer_vocab: Optional[AnswerVocabulary] = None
         self.transform = None
         self.use_cuda_graph = use_cuda_graph
+        self.gpu_resize = True      # PIL-exact resize of non-224x224 inputs on the device
         self._graphs: Dict[Tuple[int, int], dict] = {}
         self._is_loaded = False
 
@@ -104,19 +105,30 @@ class VQAInference:
             pil = pil.convert("RGB")
         return pil
 
-    def preprocess_image_u8(self, image: ImageLike) -> torch.Tensor:
+    def preprocess_image_u8(self, image: ImageLike, device_resize: Optional[bool] = None) -> torch.Tensor:
         """Decode + resize to 224x224 exactly like the reference's transform does for PIL inputs
         (torchvision Resize -> PIL antialiased bilinear, data/preprocess.py:117-121), but stop at
-        uint8 HWC [224,224,3]: /255 and mean/std normalisation happen in the GPU ingest kernel."""
+        uint8 HWC [224,224,3]: /255 and mean/std normalisation happen in the GPU ingest kernel.
+
+        ``device_resize`` (default: on when the engine device is CUDA): images that are not 224x224 are uploaded
+        at their native size and resized by the PIL-exact CUDA kernels (``vqa_resize_bilinear_u8``); the result
+        is then a uint8 CUDA tensor, bit-identical to ``PIL.Image.resize`` (tested).  Off: PIL on the host."""
         pil = self._open(image)
         size = DEFAULT_IMAGE_SIZE
+        if device_resize is None:
+            device_resize = self.gpu_resize and str(self.device).startswith("cuda") and torch.cuda.is_available()
         if pil.size != (size, size):
+            if device_resize:
+                from .runtime import resize_bilinear_u8
+                w, h = pil.size
+                raw = torch.frombuffer(bytearray(pil.tobytes()), dtype=torch.uint8).view(h, w, 3)
+                return resize_bilinear_u8(raw.to(self.device, non_blocking=True), size, size)
             pil = pil.resize((size, size), Image.BILINEAR)
         return torch.frombuffer(bytearray(pil.tobytes()), dtype=torch.uint8).view(size, size, 3)
 
     def preprocess_image(self, image: ImageLike) -> torch.Tensor:
         """Reference-compatible output: normalised float32 [1,3,224,224] on the CPU."""
-        u8 = self.preprocess_image_u8(image)
+        u8 = self.preprocess_image_u8(image, device_resize=False)
         x = u8.to(torch.float32).div(255.0).permute(2, 0, 1)
         mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
         std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
@@ -142,7 +154,11 @@ class VQAInference:
         if g is None:
             g = self._capture(B, L, k)
             self._graphs[key] = g
-        g["h_u8"].copy_(u8)
+        if u8.is_cuda:                      # resized on the device already
+            g["d_u8"].copy_(u8, non_blocking=True)
+        else:
+            g["h_u8"].copy_(u8)
+            g["d_u8"].copy_(g["h_u8"], non_blocking=True)
         g["h_ids"].copy_(ids)
         g["h_mask"].copy_(mask)
         g["graph"].replay()
@@ -168,8 +184,7 @@ class VQAInference:
                 engine.predict(g["d_u8"], g["d_ids"], g["d_mask"], k)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                g["d_u8"].copy_(g["h_u8"], non_blocking=True)
+            with torch.cuda.graph(graph):       # the image copy stays outside: it may come from the device-side resize
                 g["d_ids"].copy_(g["h_ids"], non_blocking=True)
                 g["d_mask"].copy_(g["h_mask"], non_blocking=True)
                 idx, probs = engine.predict(g["d_u8"], g["d_ids"], g["d_mask"], k)
@@ -256,7 +271,10 @@ class VQAInference:
             raise ValueError("Number of images must match number of questions")
         if not self._is_loaded:
             self.load()
-        u8 = torch.stack([self.preprocess_image_u8(im) for im in images], dim=0)
+        tensors = [self.preprocess_image_u8(im) for im in images]
+        if any(t.is_cuda for t in tensors):
+            tensors = [t.to(self.device, non_blocking=True) for t in tensors]
+        u8 = torch.stack(tensors, dim=0)
         pairs = [self.preprocess_question(q) for q in questions]
         ids = torch.cat([p[0] for p in pairs], dim=0)
         mask = torch.cat([p[1] for p in pairs], dim=0)

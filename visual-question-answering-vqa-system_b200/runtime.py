@@ -50,6 +50,9 @@ def lib():
     L.vqa_plan_destroy.argtypes = [C.c_void_p]
     L.vqa_plan_destroy.restype = None
     L.vqa_launch_count.restype = C.c_uint64
+    L.vqa_resize_bilinear_u8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p]
     if L.vqa_abi_version() != ABI_VERSION:
         raise VqaError(f"libvqa_b200.so ABI {L.vqa_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     for kind, code in P.KINDS.items():  # both sides of the op field tables must agree
@@ -121,6 +124,37 @@ class Plan:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._L.vqa_plan_destroy(h)
+
+
+def resize_bilinear_u8(src, out_h: int = 224, out_w: int = 224, stream=None):
+    """PIL-exact antialiased bilinear resize of one uint8 HWC CUDA tensor (``vqa_resize_bilinear_u8``)."""
+    import torch
+    from .resize import coeffs
+    if src.device.type != "cuda" or src.dtype != torch.uint8 or src.dim() != 3:
+        raise VqaError("resize_bilinear_u8 expects a uint8 [H, W, C] CUDA tensor (there is no CPU path)")
+    src = src.contiguous()
+    in_h, in_w, ch = src.shape
+    dev = src.device
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    dst = torch.empty(out_h, out_w, ch, dtype=torch.uint8, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    bh = kh = bv = kv = tmp = None
+    ksh = ksv = 0
+    with torch.cuda.stream(st):
+        if in_w != out_w:
+            b, k = coeffs(in_w, out_w)
+            bh, kh, ksh = torch.from_numpy(b).to(dev), torch.from_numpy(k).to(dev), k.shape[1]
+        if in_h != out_h:
+            b, k = coeffs(in_h, out_h)
+            bv, kv, ksv = torch.from_numpy(b).to(dev), torch.from_numpy(k).to(dev), k.shape[1]
+        if in_w != out_w and in_h != out_h:
+            tmp = torch.empty(in_h, out_w, ch, dtype=torch.uint8, device=dev)
+        check(lib().vqa_resize_bilinear_u8(ptr(src), in_h, in_w, ch, ptr(tmp), ptr(dst), out_h, out_w, ptr(bh), ptr(kh), ksh,
+                                           ptr(bv), ptr(kv), ksv, C.c_void_p(st.cuda_stream)))
+        for t in (src, tmp, bh, kh, bv, kv):
+            if t is not None:
+                t.record_stream(st)
+    return dst
 
 
 def launch_count() -> int:
