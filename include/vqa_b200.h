@@ -41,6 +41,7 @@ extern "C" {
 #define VQA_EXT_TAG   0x8000000000000000ull
 #define VQA_MAX_TAPS   16
 #define VQA_MAX_GROUPS 12
+#define VQA_LANE_JOIN  4
 #define VQA_OP_NI      144
 #define VQA_OP_NP     12
 #define VQA_OP_NF     4
@@ -74,7 +75,8 @@ enum VqaOpKind {
 
 typedef struct VqaOp {
   int32_t  kind;
-  int32_t  lane;            /* 0 = caller's stream; 1 = the plan's side stream (forked/joined per run) */
+  int32_t  lane;            /* bit 0: 0 = caller's stream, 1 = the plan's side stream (forked at its first op, joined at
+                               the end of the run); VQA_LANE_JOIN: wait for the other lane's work issued so far */
   int32_t  i[VQA_OP_NI];
   float    f[VQA_OP_NF];
   uint64_t p[VQA_OP_NP];

@@ -37,7 +37,8 @@ def test_program_matches_oracle(ctor, B, L, fmt, mk, window):
     assert torch.equal(ext[P.EXT["top_idx"]][:, 0], want.argmax(1))
     kinds = [op.kind for op in prog.ops]
     assert kinds.count("gemm") >= 30 and kinds[0] == "ingest"
-    assert all(op.lane in (0, 1) for op in prog.ops) and any(op.lane == 1 for op in prog.ops)
+    assert all((op.lane & ~P.LANE_JOIN) in (0, 1) for op in prog.ops) and any(op.lane & 1 for op in prog.ops)
+    assert any(op.lane & P.LANE_JOIN for op in prog.ops)
 
 
 @pytest.mark.parametrize("ctor,B,L", [({}, 2, 20), (ABL, 1, 12)])

@@ -371,47 +371,55 @@ stage_tail_kernel(const StageTailParams p) {
   const int lanes = kTailThreads / C8;                  // pixel lanes (C8 divides 256)
   const int cg = tid % C8, pl = tid / C8;
   uint4* tile = reinterpret_cast<uint4*>(tail_smem);                       // [NP][C8] groups of 8 channels
-  float* red = reinterpret_cast<float*>(tile + static_cast<size_t>(NP) * C8 * Vec::N);   // [lanes][C]; later mx/av maps
-  float* part = red + lanes * C;                        // [C] this CTA's channel sums (read by the cluster)
+  const int lpw = C8 < 32 ? 32 / C8 : 1;                // pixel lanes that share one warp (reduced by shuffles)
+  const int red_rows = lanes / lpw;                     // partial-sum rows that go through shared memory
+  float* red = reinterpret_cast<float*>(tile + static_cast<size_t>(NP) * C8 * Vec::N);   // [red_rows][C]; later mx/av maps
+  float* part = red + red_rows * C;                     // [C] this CTA's channel sums (read by the cluster)
   float* sc = part + C;                                 // [C] SE scale
   float* hid = sc + C;                                  // [R]
   float* att = hid + 64;                                // [NP] spatial attention (CS == 1)
   float* wc = att + NP;                                 // [2*ks*ks] spatial conv weights
   const bool use_se = p.w1 != nullptr;
 
-  // ---- 1. stage the rows, accumulate channel sums on the way
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // ---- 1. stage the rows with cp.async (every 16-byte piece of the CTA's rows in flight at once: one DRAM round
+  // trip instead of a register-limited sequence of them), then accumulate the channel sums from shared memory
   const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8 * Vec::N;
-  constexpr int kLd = 8;                                // independent 16-byte loads in flight per thread
-  for (int q0 = pl; q0 < NP; q0 += kLd * lanes) {
-    Vec v[kLd];
+  for (int q = pl; q < NP; q += lanes) {
+    const int hl = q / W, w = q - hl * W;
+    const uint4* g = img + ((static_cast<size_t>(h0 + hl) * p.P + w) * C8 + cg) * Vec::N;
+    uint4* d = tile + (static_cast<size_t>(q) * C8 + cg) * Vec::N;
 #pragma unroll
-    for (int u = 0; u < kLd; ++u) {
-      const int q = q0 + u * lanes;
-      if (q < NP) {
-        const int hl = q / W, w = q - hl * W;
-        v[u].load(img, (static_cast<size_t>(h0 + hl) * p.P + w) * C8 + cg);
-      }
-    }
+    for (int i = 0; i < Vec::N; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(d + i))),
+                   "l"(g + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (use_se) {
+    for (int q = pl; q < NP; q += lanes) {
+      Vec v;
+      v.load(tile, static_cast<size_t>(q) * C8 + cg);
+      float x[8];
+      v.to_float(x);
 #pragma unroll
-    for (int u = 0; u < kLd; ++u) {
-      const int q = q0 + u * lanes;
-      if (q < NP) {
-        v[u].store(tile, static_cast<size_t>(q) * C8 + cg);
-        float x[8];
-        v[u].to_float(x);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += x[k];
-      }
+      for (int k = 0; k < 8; ++k) acc[k] += x[k];
     }
   }
   if (use_se) {
+    for (int off = C8; off < 32; off <<= 1) {           // C8 < 32: the warp's pixel lanes first (fixed order)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) red[pl * C + cg * 8 + k] = acc[k];
+      for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+    }
+    if (pl % lpw == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[(pl / lpw) * C + cg * 8 + k] = acc[k];
+    }
     __syncthreads();
     for (int c = tid; c < C; c += kTailThreads) {
       float t = 0.f;
-      for (int l = 0; l < lanes; ++l) t += red[l * C + c];
+      for (int l = 0; l < red_rows; ++l) t += red[l * C + c];
       part[c] = t;
     }
     // ---- 2. cluster-wide channel sums (rank order) -> mean
@@ -465,20 +473,37 @@ stage_tail_kernel(const StageTailParams p) {
   if (use_sp) {
     float* mx = red;                                    // [NP]
     float* av = red + NP;                               // [NP]  (2*NP <= lanes*C floats, checked on the host)
-    for (int q = warp; q < NP; q += kTailThreads / 32) {
-      float m = -INFINITY, t = 0.f;
+    // one warp reduces 4 pixels at a time: the 4 x (max, sum) shuffle trees are independent and pipeline
+    for (int q0 = warp * 4; q0 < NP; q0 += (kTailThreads / 32) * 4) {
+      float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, t[4] = {0.f, 0.f, 0.f, 0.f};
       for (int o = lane; o < C8; o += 32) {
-        Vec v;
-        v.load(tile, static_cast<size_t>(q) * C8 + o);
         const float* k = sc + o * 8;
-        float x[8];
-        v.to_float(x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float y = x[j] * k[j]; m = fmaxf(m, y); t += y; }
+        for (int u = 0; u < 4; ++u) {
+          if (q0 + u < NP) {
+            Vec v;
+            v.load(tile, static_cast<size_t>(q0 + u) * C8 + o);
+            float x[8];
+            v.to_float(x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float y = x[j] * k[j]; m[u] = fmaxf(m[u], y); t[u] += y; }
+          }
+        }
       }
-      m = warp_max(m);
-      t = warp_sum(t);
-      if (lane == 0) { mx[q] = m; av[q] = t / static_cast<float>(C); }
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], sh));
+          t[u] += __shfl_xor_sync(0xffffffffu, t[u], sh);
+        }
+      }
+      if (lane < 4 && q0 + lane < NP) {
+        const float mm = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : m[3];
+        const float tt = lane == 0 ? t[0] : lane == 1 ? t[1] : lane == 2 ? t[2] : t[3];
+        mx[q0 + lane] = mm;
+        av[q0 + lane] = tt / static_cast<float>(C);
+      }
     }
     const int ks = p.ks, pad = ks / 2, H = p.H;
     for (int t = tid; t < 2 * ks * ks; t += kTailThreads) wc[t] = __ldg(p.wconv + t);
@@ -1156,10 +1181,12 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(q.R <= 64 && (q.w1 == nullptr) == (q.w2 == nullptr), VQA_E_INVALID, "stage_tail: bad SE weights");
       VQA_REQUIRE(q.Po > 0 && q.RPIo % q.Po == 0, VQA_E_INVALID, "stage_tail: bad destination grid");
       const int NP = q.H / q.CS * q.W, lanes = kTailThreads / q.C8;
-      VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= lanes * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
+      const int red_rows = lanes / (q.C8 < 32 ? 32 / q.C8 : 1);
+      VQA_REQUIRE(q.C8 >= 32 || 32 % q.C8 == 0, VQA_E_INVALID, "stage_tail: C/8 must divide 32 or be a multiple of it");
+      VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= red_rows * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
       VQA_REQUIRE(q.ks >= 0 && 2 * q.ks * q.ks <= 128, VQA_E_INVALID, "stage_tail: spatial kernel too large");
       const bool f32 = I[STAGE_TAIL_I_f32] != 0;
-      const size_t smem = static_cast<size_t>(NP) * C * (f32 ? 4 : 2) + sizeof(float) * (static_cast<size_t>(lanes) * C + 2 * C + 64 + NP + 128);
+      const size_t smem = static_cast<size_t>(NP) * C * (f32 ? 4 : 2) + sizeof(float) * (static_cast<size_t>(red_rows) * C + 2 * C + 64 + NP + 128);
       VQA_REQUIRE(smem <= 227 * 1024, VQA_E_INVALID, "stage_tail: rows per CTA exceed shared memory (raise CS)");
       static bool attr_set = false;
       if (!attr_set) {

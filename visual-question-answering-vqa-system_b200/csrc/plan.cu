@@ -60,12 +60,13 @@ struct VqaPlan {
   std::vector<void*> gemm;   // per op: prepared GemmLaunch (64-byte aligned) or nullptr
   bool has_side = false;     // some op runs on lane 1
   cudaStream_t side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  static constexpr int kEvents = 16;   // fork / join edges of one run (cycled)
+  cudaEvent_t events[kEvents] = {};
   ~VqaPlan() {
     for (void* g : gemm)
       if (g) std::free(g);
-    if (fork) cudaEventDestroy(fork);
-    if (join) cudaEventDestroy(join);
+    for (cudaEvent_t e : events)
+      if (e) cudaEventDestroy(e);
     if (side) cudaStreamDestroy(side);
   }
 };
@@ -133,11 +134,21 @@ int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** o
       }
     }
   }
-  for (const VqaOp& op : plan->ops) plan->has_side |= op.lane == 1;
+  int edges = 0;
+  for (const VqaOp& op : plan->ops) {
+    plan->has_side |= (op.lane & 1) != 0;
+    edges += (op.lane & VQA_LANE_JOIN) != 0;
+  }
+  if (edges + 2 > VqaPlan::kEvents) {
+    vqa_set_error("too many lane joins in one plan");
+    delete plan;
+    return VQA_E_INVALID;
+  }
   if (plan->has_side) {
-    if (cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&plan->fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&plan->join, cudaEventDisableTiming) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int e = 0; ok && e < VqaPlan::kEvents; ++e)
+      ok = cudaEventCreateWithFlags(&plan->events[e], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
       vqa_set_error("could not create the side stream / events");
       delete plan;
       return VQA_E_CUDA;
@@ -153,25 +164,32 @@ int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const u
   const int n = static_cast<int>(plan->ops.size());
   VQA_REQUIRE(first >= 0 && last <= n && first <= last, VQA_E_INVALID, "vqa_plan_run: bad op range");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Whole-plan runs fork lane-1 ops (the text encoder, independent of the backbone) onto the side
-  // stream and join before the first lane-0 op that follows them; partial ranges run serially.
+  // Whole-plan runs put lane-1 ops (bit 0 of VqaOp.lane) on the plan's side stream.  The first lane-1 op of a
+  // run forks (the side stream waits for everything the caller's stream holds so far); an op with
+  // VQA_LANE_JOIN set waits for all work issued so far on the OTHER lane before it starts; the end of the plan
+  // joins the side stream back.  Partial ranges run serially on the caller's stream.
   const bool two_lanes = plan->has_side && first == 0 && last == n;
-  bool forked = false, pending_join = false;
+  bool side_used = false;
+  int ev = 0;
+  auto edge = [&](cudaStream_t from, cudaStream_t to) -> int {
+    cudaEvent_t e = plan->events[ev];
+    ev = (ev + 1) % VqaPlan::kEvents;
+    VQA_CUDA_OK(cudaEventRecord(e, from));
+    VQA_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
+    return VQA_OK;
+  };
   for (int k = first; k < last; ++k) {
     const VqaOp& op = plan->ops[k];
     cudaStream_t s = st;
-    if (two_lanes && op.lane == 1) {
-      if (!forked) {
-        VQA_CUDA_OK(cudaEventRecord(plan->fork, st));
-        VQA_CUDA_OK(cudaStreamWaitEvent(plan->side, plan->fork, 0));
-        forked = true;
+    if (two_lanes) {
+      const bool side = (op.lane & 1) != 0, join = (op.lane & VQA_LANE_JOIN) != 0;
+      if (side && !side_used) {
+        if (int rc = edge(st, plan->side)) return rc;
+        side_used = true;
+      } else if (join && side_used) {
+        if (int rc = side ? edge(st, plan->side) : edge(plan->side, st)) return rc;
       }
-      s = plan->side;
-      pending_join = true;
-    } else if (two_lanes && pending_join && forked && k > 0 && plan->ops[k - 1].lane == 1) {
-      VQA_CUDA_OK(cudaEventRecord(plan->join, plan->side));
-      VQA_CUDA_OK(cudaStreamWaitEvent(st, plan->join, 0));
-      pending_join = false;
+      if (side) s = plan->side;
     }
     int rc = (op.kind == VQA_OP_GEMM) ? gemm_run(plan->gemm[k], ext, n_ext, s) : run_misc_op(op, ext, n_ext, s);
     if (rc) {
@@ -179,9 +197,8 @@ int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const u
       return rc;
     }
   }
-  if (pending_join) {   // plan ended on the side lane: the caller's stream must still observe it
-    VQA_CUDA_OK(cudaEventRecord(plan->join, plan->side));
-    VQA_CUDA_OK(cudaStreamWaitEvent(st, plan->join, 0));
+  if (side_used) {   // the caller's stream must observe everything the side lane did
+    if (int rc = edge(plan->side, st)) return rc;
   }
   return VQA_OK;
 }

@@ -153,7 +153,10 @@ class Op:
     i: Dict[str, int] = field(default_factory=dict)
     p: Dict[str, object] = field(default_factory=dict)   # Buf | ExtRef | None
     f: Dict[str, float] = field(default_factory=dict)
-    lane: int = 0   # 0 = caller's stream, 1 = side stream (independent of lane-0 work until the join)
+    lane: int = 0   # bit 0: 0 = caller's stream, 1 = side stream; LANE_JOIN: wait for the other lane's work so far
+
+
+LANE_JOIN = 4      # VQA_LANE_JOIN: this op needs everything issued so far on the other lane
 
 
 @dataclass
@@ -765,46 +768,70 @@ class Program(OpList):
         text = self._buf("text_features", f32, T, D)
         self.layernorm("text.lnf", xt, "text.lnf.g", "text.lnf.b", text, T)
 
-        # ================= fusion (joins both lanes) =================
+        # ================= fusion =================
+        # Two lanes stay busy: the side lane (which just finished the text encoder) goes on with the first layer's
+        # query projection (needs only the text) and later with the K/V projections of layers >= 1 (need only the
+        # projected image); the main lane runs projector -> K/V of layer 0 -> attention / FFN chain and joins the
+        # side lane right before each attention.  Ops are issued in list order, so a JOIN waits only for what
+        # precedes it in the list.
+        S = 7
+        TI = B * S * S
+        n_layers = 0
+        while f"x.{n_layers}.q.w" in W:
+            n_layers += 1
+        q = self._buf("x.q", f32, T, D)          # running query (residual stream)
+        qn = self._buf("x.qn", f32, T, D)
+        qp = self._buf("x.qp", f32, T, D)
+        cx = self._buf("x.ctx", f32, T, D)
+        imns = [self._buf(f"x.{l}.imgn", f32, TI, D) for l in range(n_layers)]
+        kvs = [self._buf(f"x.{l}.kv", f32, TI, 2 * D) for l in range(n_layers)]
+        if n_layers:                              # side lane: LN_q + W_q of layer 0
+            qn0 = self._buf("x.0.qn", f32, T, D)
+            self.layernorm("x.0.lnq", text, "x.0.lnq.g", "x.0.lnq.b", qn0, T, rnd=True)
+            self.linear("x.0.q", qn0, T, D, "x.0.q.w", None, qp, D)
         self.lane = 0
         praw = self._buf("proj.raw", f32, gf.rows, D)
         self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
                   groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
-        S = 7
         img = self._buf("image_projected", f32, B * S * S, D)
         self._op("layernorm", "proj.ln", dict(rows=B * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
                  dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos")),
                  dict(eps=1e-5))
-        TI = B * S * S
-        q = self._buf("x.q", f32, T, D)          # running query (residual stream)
-        qn = self._buf("x.qn", f32, T, D)
-        qp = self._buf("x.qp", f32, T, D)
-        imn = self._buf("x.imgn", f32, TI, D)
-        kv = self._buf("x.kv", f32, TI, 2 * D)
-        cx = self._buf("x.ctx", f32, T, D)
-        layer = 0
+
+        def kv_proj(l):
+            self.layernorm(f"x.{l}.lnkv", img, f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imns[l], TI, rnd=True)
+            self.linear(f"x.{l}.kv", imns[l], TI, D, f"x.{l}.kv.w", None, kvs[l], 2 * D)
+
+        if n_layers:
+            kv_proj(0)
         src_q = text
         self.xattn_weights = []
-        while f"x.{layer}.q.w" in W:
+        for layer in range(n_layers):
             p = f"x.{layer}"
-            self.layernorm(p + ".lnq", src_q, p + ".lnq.g", p + ".lnq.b", qn, T, rnd=True)
-            self.layernorm(p + ".lnkv", img, p + ".lnkv.g", p + ".lnkv.b", imn, TI, rnd=True)
-            self.linear(p + ".q", qn, T, D, p + ".q.w", None, qp, D)
-            self.linear(p + ".kv", imn, TI, D, p + ".kv.w", None, kv, 2 * D)
+            if layer > 0:
+                self.layernorm(p + ".lnq", src_q, p + ".lnq.g", p + ".lnq.b", qn, T, rnd=True)
+                self.linear(p + ".q", qn, T, D, p + ".q.w", None, qp, D)
             wts = None
             if self.want_aux:
                 wts = self._buf(f"aux.xattn.{layer}", f32, B, H, L, S * S)
                 self.xattn_weights.append(f"aux.xattn.{layer}")
             self._op("cross_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, T=S * S, ld_q=D, ld_kv=2 * D, k_off=0, v_off=D,
                                                      no_round=int(self.tf32)),
-                     dict(q=qp, kv=kv, out=cx, weights=wts))
+                     dict(q=qp, kv=kvs[layer], out=cx, weights=wts))
+            self.ops[-1].lane |= LANE_JOIN        # needs the side lane's q (layer 0) / K,V (layers >= 1)
+            if layer == 0 and n_layers > 1:       # side lane: K/V of every later layer, concurrent with this layer's chain
+                self.lane = 1
+                first = len(self.ops)
+                for l in range(1, n_layers):
+                    kv_proj(l)
+                self.ops[first].lane |= LANE_JOIN  # needs image_projected from the main lane
+                self.lane = 0
             # q = src_q + W_o ctx   (first layer reads the text features as residual, writes the stream buffer)
             self.linear(p + ".o", cx, T, D, p + ".o.w", None, q, D, res=src_q)
             self.layernorm(p + ".lnf", q, p + ".lnf.g", p + ".lnf.b", qn, T, rnd=True)
             self.linear(p + ".fc1", qn, T, D, p + ".fc1.w", p + ".fc1.b", hid, F, relu=True, rnd=True)
             self.linear(p + ".fc2", hid, T, F, p + ".fc2.w", p + ".fc2.b", q, D, res=q)
             src_q = q
-            layer += 1
         fused = self._buf("fused", f32, B, D)
         attp = self._buf("attended_pooled", f32, B, D)
         txtp = self._buf("text_pooled", f32, B, D)
