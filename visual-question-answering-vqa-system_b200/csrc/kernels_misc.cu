@@ -310,7 +310,7 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank)
   return v;
 }
 
-constexpr int kTailThreads = 256;
+constexpr int kTailThreads = 512;   // 256 measured 23 % warp occupancy and latency-bound phases (ncu, profiles/r01_g_*)
 
 struct StageTailParams {
   const uint4* src;
@@ -372,7 +372,8 @@ stage_tail_kernel(const StageTailParams p) {
   const int cg = tid % C8, pl = tid / C8;
   uint4* tile = reinterpret_cast<uint4*>(tail_smem);                       // [NP][C8] groups of 8 channels
   const int lpw = C8 < 32 ? 32 / C8 : 1;                // pixel lanes that share one warp (reduced by shuffles)
-  const int red_rows = lanes / lpw;                     // partial-sum rows that go through shared memory
+  const int part_rows = lanes / lpw;                    // partial sums left after the in-warp reduction
+  const int red_rows = part_rows > 8 ? part_rows / 2 : part_rows;   // rows of the shared-memory scratch (folded once if > 8)
   float* red = reinterpret_cast<float*>(tile + static_cast<size_t>(NP) * C8 * Vec::N);   // [red_rows][C]; later mx/av maps
   float* part = red + red_rows * C;                     // [C] this CTA's channel sums (read by the cluster)
   float* sc = part + C;                                 // [C] SE scale
@@ -412,9 +413,22 @@ stage_tail_kernel(const StageTailParams p) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
     }
-    if (pl % lpw == 0) {
+    const int prow = pl / lpw;
+    if (part_rows > 8) {                                // fold the upper half of the partial rows onto the lower half
+      if (pl % lpw == 0 && prow >= red_rows) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) red[(pl / lpw) * C + cg * 8 + k] = acc[k];
+        for (int k = 0; k < 8; ++k) red[(prow - red_rows) * C + cg * 8 + k] = acc[k];
+      }
+      __syncthreads();
+      if (pl % lpw == 0 && prow < red_rows) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += red[prow * C + cg * 8 + k];
+      }
+      __syncthreads();
+    }
+    if (pl % lpw == 0 && prow < red_rows) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[prow * C + cg * 8 + k] = acc[k];
     }
     __syncthreads();
     for (int c = tid; c < C; c += kTailThreads) {
@@ -1173,7 +1187,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       q.C8 = C / 8; q.H = I[STAGE_TAIL_I_H]; q.W = I[STAGE_TAIL_I_W]; q.P = I[STAGE_TAIL_I_P]; q.RPI = I[STAGE_TAIL_I_RPI];
       q.R = I[STAGE_TAIL_I_R]; q.ks = I[STAGE_TAIL_I_ks]; q.mode = I[STAGE_TAIL_I_mode]; q.Po = I[STAGE_TAIL_I_Po];
       q.RPIo = I[STAGE_TAIL_I_RPIo]; q.phase_rows = I[STAGE_TAIL_I_phase_rows]; q.CS = I[STAGE_TAIL_I_CS];
-      VQA_REQUIRE(C % 8 == 0 && q.C8 >= 1 && kTailThreads % q.C8 == 0, VQA_E_INVALID, "stage_tail: C/8 must divide 256");
+      VQA_REQUIRE(C % 8 == 0 && q.C8 >= 1 && kTailThreads % q.C8 == 0, VQA_E_INVALID, "stage_tail: C/8 must divide 512");
       VQA_REQUIRE(q.CS == 1 || q.CS == 2 || q.CS == 4 || q.CS == 8, VQA_E_INVALID, "stage_tail: cluster size must be 1, 2, 4 or 8");
       VQA_REQUIRE(q.H % q.CS == 0 && (!q.mode || (q.H / q.CS) % 2 == 0) && (!q.mode || q.W % 2 == 0), VQA_E_INVALID,
                   "stage_tail: rows per CTA must be whole (and even for the phase split)");
@@ -1181,7 +1195,8 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(q.R <= 64 && (q.w1 == nullptr) == (q.w2 == nullptr), VQA_E_INVALID, "stage_tail: bad SE weights");
       VQA_REQUIRE(q.Po > 0 && q.RPIo % q.Po == 0, VQA_E_INVALID, "stage_tail: bad destination grid");
       const int NP = q.H / q.CS * q.W, lanes = kTailThreads / q.C8;
-      const int red_rows = lanes / (q.C8 < 32 ? 32 / q.C8 : 1);
+      const int part_rows = lanes / (q.C8 < 32 ? 32 / q.C8 : 1);
+      const int red_rows = part_rows > 8 ? part_rows / 2 : part_rows;
       VQA_REQUIRE(q.C8 >= 32 || 32 % q.C8 == 0, VQA_E_INVALID, "stage_tail: C/8 must divide 32 or be a multiple of it");
       VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= red_rows * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
       VQA_REQUIRE(q.ks >= 0 && 2 * q.ks * q.ks <= 128, VQA_E_INVALID, "stage_tail: spatial kernel too large");
