@@ -15,10 +15,13 @@
 // CTA = 10 warps, one CTA per SM, looping over output tiles (static round-robin):
 //   warp 0      TMA producer: A-window ring + weight ring (or all weights resident when they fit)
 //   warp 1      MMA issuer: one thread issues tcgen05.mma; tcgen05.commit frees ring slots
-//   warps 2..9  epilogue: TMEM -> registers -> bias / residual / ReLU / pad-mask -> global; two
-//               warps per TMEM lane quadrant, each taking half of the tile's columns
+//   warps 2..9  epilogue: TMEM -> registers -> bias / TMA-loaded residual / ReLU / pad-mask -> swizzled staging ->
+//               TMA store; two warps per TMEM lane quadrant, each taking half of the tile's columns
+//               (EPI 4, the stem: ReLU -> shared-memory conv tile -> 3x3/2 max-pool -> global)
 // Accumulators are double-buffered in TMEM (when 2*MT*BN <= 512 columns) so the epilogue of tile
-// i overlaps the MMAs of tile i+1.
+// i overlaps the MMAs of tile i+1.  PAIR = true runs two CTAs of a cluster as one cta_group::2 unit
+// (256-row UMMA, half of every weight tile per CTA).  Every launch carries the programmatic-dependent-
+// launch attribute: prologue and weight prefetch run before griddepcontrol.wait.
 #include <cstdio>
 #include <type_traits>
 

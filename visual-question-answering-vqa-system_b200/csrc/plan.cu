@@ -168,7 +168,8 @@ int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const u
   // run forks (the side stream waits for everything the caller's stream holds so far); an op with
   // VQA_LANE_JOIN set waits for all work issued so far on the OTHER lane before it starts; the end of the plan
   // joins the side stream back.  Partial ranges run serially on the caller's stream.
-  const bool two_lanes = plan->has_side && first == 0 && last == n;
+  static const bool lanes_off = std::getenv("VQA_NO_LANES") != nullptr;   // A/B switch: everything on the caller's stream
+  const bool two_lanes = plan->has_side && first == 0 && last == n && !lanes_off;
   bool side_used = false;
   int ev = 0;
   auto edge = [&](cudaStream_t from, cudaStream_t to) -> int {
