@@ -167,14 +167,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     if (EPI != 4) tma_prefetch_desc(&mapOut);
     if (EPI & 1) tma_prefetch_desc(&mapRes);
   }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.a_slots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps * (PAIR ? 2 : 1)); }
-    for (int s = 0; s < kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
-    mbar_fence_init();
-    for (int t = 0; t < VQA_MAX_TAPS; ++t) s_rel[t] = static_cast<uint32_t>(p.tap_rel[t]) * (kRowBytes / 16);
-    for (int g = 0; g < VQA_MAX_GROUPS; ++g) s_grp[g] = make_int4(p.g_chunks[g], p.g_ntaps[g], p.g_tap0[g], p.g_q0[g]);
+  if (warp == 1) {   // barrier / table initialisation spread over the warp's lanes (one thread took ~1k cycles)
+    if (lane < kMaxASlots) { mbar_init(&a_full[lane], 1); mbar_init(&a_empty[lane], 1); }
+    if (lane < kMaxBSlots) { mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
+    if (lane >= 16 && lane < 18) { mbar_init(&acc_full[lane - 16], 1); mbar_init(&acc_empty[lane - 16], kEpiWarps * (PAIR ? 2 : 1)); }
+    if (lane >= 24 && lane < 24 + kEpiWarps) mbar_init(&res_bar[lane - 24], 1);
+    if (lane < VQA_MAX_TAPS) s_rel[lane] = static_cast<uint32_t>(p.tap_rel[lane]) * (kRowBytes / 16);
+    if (lane < VQA_MAX_GROUPS) s_grp[lane] = make_int4(p.g_chunks[lane], p.g_ntaps[lane], p.g_tap0[lane], p.g_q0[lane]);
+    __syncwarp();
+    if (lane == 0) mbar_fence_init();
   }
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(BN * MT * p.acc_stages)) tmem_cols <<= 1;   // power of two >= 32
