@@ -72,8 +72,8 @@ class Emulator:
 
     def op_gemm(self, op, ext):
         i = op.i
-        dt = torch.bfloat16 if i["dtype"] == P.DT_BF16 else torch.float32
-        chunk = i.get("row_bytes", 128) // (2 if i["dtype"] == P.DT_BF16 else 4)
+        dt = {P.DT_BF16: torch.bfloat16, P.DT_TF32: torch.float32, P.DT_F16: torch.float16}[i["dtype"]]
+        chunk = i.get("row_bytes", 128) // (4 if i["dtype"] == P.DT_TF32 else 2)
         M, N, Npad, Ktot = i["M"], i["N"], i["Npad"], i["Ktot"]
         amaps = []
         for k in ("a0", "a1"):
@@ -120,7 +120,7 @@ class Emulator:
             acc = torch.where(valid.view(-1, 1), acc, torch.zeros(()))
         if i["round_tf32"]:
             acc = P.round_tf32(acc)
-        odt = torch.bfloat16 if i["out_dtype"] == P.OUT_BF16 else torch.float32
+        odt = {P.OUT_BF16: torch.bfloat16, P.OUT_F32: torch.float32, P.OUT_F16: torch.float16}[i["out_dtype"]]
         if i.get("pool"):
             # fused 3x3/2 max-pool of the (bf16-rounded) conv map, written to the pooled padded grid
             B, H, W_ = i["n_imgs"], i["mH"], i["mW"]
@@ -294,6 +294,9 @@ class Emulator:
             S = i["S"]
             pos = _t(op.p["pos"], torch.float32, ext)[: S * S * D].view(1, S * S, D)
             y = (y.view(-1, S * S, D) + pos).view(rows, D)
+        if i["round_tf32"] == 2:          # fp16 operand of the next Linear
+            _t(op.p["dst"], torch.float16, ext)[: rows * D].view(rows, D).copy_(y.half())
+            return
         if i["round_tf32"]:
             y = P.round_tf32(y)
         _t(op.p["dst"], torch.float32, ext)[: rows * D].view(rows, D).copy_(y)
@@ -316,7 +319,8 @@ class Emulator:
         if op.p.get("mask") is not None:
             mask = _t(op.p["mask"], torch.int32, ext)[: B * L].view(B, L)
         ctx, _ = self._attend(q, k, v, hd, mask)
-        _t(op.p["out"], torch.float32, ext)[: B * L * D].view(B, L, D).copy_(ctx.transpose(1, 2).reshape(B, L, D))
+        odt = torch.float16 if i.get("no_round") == 2 else torch.float32
+        _t(op.p["out"], odt, ext)[: B * L * D].view(B, L, D).copy_(ctx.transpose(1, 2).reshape(B, L, D).to(odt))
 
     def op_cross_attn(self, op, ext):
         i = op.i
@@ -327,7 +331,8 @@ class Emulator:
         k = torch.as_strided(kvf[i["k_off"]:], (B * T, D), (i["ld_kv"], 1)).view(B, T, H, hd).transpose(1, 2)
         v = torch.as_strided(kvf[i["v_off"]:], (B * T, D), (i["ld_kv"], 1)).view(B, T, H, hd).transpose(1, 2)
         ctx, w = self._attend(q, k, v, hd)
-        _t(op.p["out"], torch.float32, ext)[: B * L * D].view(B, L, D).copy_(ctx.transpose(1, 2).reshape(B, L, D))
+        odt = torch.float16 if i.get("no_round") == 2 else torch.float32
+        _t(op.p["out"], odt, ext)[: B * L * D].view(B, L, D).copy_(ctx.transpose(1, 2).reshape(B, L, D).to(odt))
         if op.p.get("weights") is not None:
             _t(op.p["weights"], torch.float32, ext)[: B * H * L * T].view(B, H, L, T).copy_(w)
 
@@ -350,7 +355,10 @@ class Emulator:
             buf("txt_pooled", B * D).view(B, D).copy_(tp)
             if phase == 1:      # pools only; [att;txt] as the tf32 A operand of the gate GEMM
                 cat = torch.cat([ap, tp], dim=-1)
-                buf("cat", B * 2 * D).view(B, 2 * D).copy_(cat if i.get("no_round") else P.round_tf32(cat))
+                if i.get("no_round") == 2:
+                    _t(op.p["cat"], torch.float16, ext)[: B * 2 * D].view(B, 2 * D).copy_(cat.half())
+                else:
+                    buf("cat", B * 2 * D).view(B, 2 * D).copy_(cat if i.get("no_round") else P.round_tf32(cat))
                 return
             assert not i["use_gate"]
             fz = ap + tp
@@ -360,6 +368,8 @@ class Emulator:
             fz = g * ap + (1 - g) * tp
         fz = F.layer_norm(fz, (D,), buf("gamma", D), buf("beta", D), op.f["eps"])
         buf("fused", B * D).view(B, D).copy_(fz)
+        if i.get("no_round") == 2 and op.p.get("cat") is not None:
+            _t(op.p["cat"], torch.float16, ext)[: B * D].view(B, D).copy_(fz.half())
 
     def op_softmax_topk(self, op, ext):
         i = op.i

@@ -340,6 +340,19 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   return d;
 }
 
+// fp16 pairs (the tail GEMMs of the bf16 precision mode take fp16 operands: the 11-bit significand of tf32 in
+// half the bytes and at twice the MMA rate)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 #endif  // __CUDACC__
 
 // ----------------------------------------------------------------------------- host-side op access

@@ -66,6 +66,7 @@ struct GemmParams {
   const void* res;
   int ldo, ldr, out_dtype, res_dtype;
   int relu, round_tf32, mask_en, mP, mRPI, mH, mW;
+  int out_f16;       // 16-bit outputs are fp16 instead of bf16 (operands of the fp16 tail GEMMs)
   // strided M tiling (fused stem + max-pool): tile t starts at (t / tiles_per_img) * img_rows +
   // (t % tiles_per_img) * tile_stride + tile_row0 instead of t * 128 * MT  (tiles_per_img = 0: linear)
   int tiles_per_img, tile_stride, tile_row0, img_rows;
@@ -476,7 +477,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const uint8_t* const res_row = res_slot + lane * kRowB;
     // loop-invariant parameters in registers (the asm volatile barriers would otherwise force reloads)
     const int N = p.N;
-    const bool relu = p.relu != 0, rnd = p.round_tf32 != 0, mask_en = p.mask_en != 0;
+    const bool relu = p.relu != 0, rnd = p.round_tf32 != 0, mask_en = p.mask_en != 0, out_f16 = p.out_f16 != 0;
     const int mRPI = p.mRPI, mP = p.mP, mH = p.mH, mW = p.mW;
     const int m_tiles = p.m_tiles, acc_stages = p.acc_stages;
     const bool has_bias = p.bias != nullptr;
@@ -577,7 +578,15 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           __syncwarp();
           if constexpr (kOutBf16) {
             uint32_t w[16];
-            if (relu) {
+            if (out_f16) {
+              if (relu) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) w[k] = pack_relu_f16x2(x[2 * k], x[2 * k + 1]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) w[k] = pack_f16x2(x[2 * k], x[2 * k + 1]);
+              }
+            } else if (relu) {
 #pragma unroll
               for (int k = 0; k < 16; ++k) w[k] = pack_relu_bf16x2(x[2 * k], x[2 * k + 1]);
             } else {
@@ -719,8 +728,8 @@ int encode_box32(CUtensorMap* map, bool f32, uint64_t base, int rows, int cols, 
 
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format f32 [4,6)=1,
 // a/b format [7,10)/[10,13) (1 = bf16, 2 = tf32), K-major A and B, N>>3 at [17,23), M>>4 at [24,29).
-uint32_t make_idesc(bool tf32, int n, int m) {
-  const uint32_t fmt = tf32 ? 2u : 1u;
+uint32_t make_idesc(bool tf32, bool f16, int n, int m) {
+  const uint32_t fmt = tf32 ? 2u : (f16 ? 0u : 1u);     // kind::f16: 0 = fp16, 1 = bf16; kind::tf32: 2
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
@@ -758,10 +767,13 @@ static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_byte
   if (bn == BN_ && mt == MT_ && tf32 == TF_ && epi == EPI_ && pair == PAIR_) return VQA_K(BN_, MT_, TF_, EPI_, false, PAIR_);
 #define VQA_PICK_BF16(BN_, MT_) VQA_PICK(BN_, MT_, false, 0, false) VQA_PICK(BN_, MT_, false, 1, false) \
   VQA_PICK(BN_, MT_, false, 2, false) VQA_PICK(BN_, MT_, false, 0, true) VQA_PICK(BN_, MT_, false, 1, true)
+#define VQA_PICK_F16RES(BN_) VQA_PICK(BN_, 1, false, 3, false)   /* 16-bit operands, fp32 out + fp32 residual (fp16 tail) */
 #define VQA_PICK_TF32(BN_) VQA_PICK(BN_, 1, true, 2, false) VQA_PICK(BN_, 1, true, 3, false)
   VQA_PICK_BF16(64, 1) VQA_PICK_BF16(64, 2) VQA_PICK_BF16(128, 1) VQA_PICK_BF16(128, 2)
   VQA_PICK_BF16(256, 1) VQA_PICK_BF16(256, 2)
   VQA_PICK_TF32(64) VQA_PICK_TF32(128) VQA_PICK_TF32(256)
+  VQA_PICK_F16RES(64) VQA_PICK_F16RES(128) VQA_PICK_F16RES(256)
+#undef VQA_PICK_F16RES
 #undef VQA_PICK_TF32
 #undef VQA_PICK_BF16
 #undef VQA_PICK
@@ -789,6 +801,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   GemmParams& p = L->prm;
   const int32_t* I = op.i;
   const bool tf32 = I[GEMM_I_dtype] == 1;
+  const bool f16 = I[GEMM_I_dtype] == 2;                 // fp16 operands: same kernels as bf16, other format code
   const int bn = I[GEMM_I_BN];
   VQA_REQUIRE(bn == 64 || bn == 128 || bn == 256, VQA_E_INVALID, "gemm: BN must be 64, 128 or 256");
   p.M = I[GEMM_I_M];
@@ -815,7 +828,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   L->pair = pair;
   // (tf32 pairs were measured too: no gain for the latency-bound M = 5120 Linears, so they are not instantiated)
   VQA_REQUIRE(!pair || (!tf32 && bn % 16 == 0), VQA_E_INVALID, "gemm: CTA pairs are instantiated for bf16 operands");
-  p.idesc = make_idesc(tf32, bn, pair ? 256 : 128);
+  p.idesc = make_idesc(tf32, f16, bn, pair ? 256 : 128);
   VQA_REQUIRE(I[GEMM_I_Ktot] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: Ktot must be a multiple of the K chunk");
   p.k_chunks = I[GEMM_I_Ktot] / p.chunk_elems;
   bool lockstep = p.halo == 0 && halo_hi == 0;
@@ -884,7 +897,9 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.out_dtype = I[GEMM_I_out_dtype];
   p.res_dtype = I[GEMM_I_res_dtype];
   VQA_REQUIRE(!has_res || p.res_dtype == p.out_dtype, VQA_E_INVALID, "gemm: the residual must have the output's dtype");
-  L->epi = pool ? 4 : (p.out_dtype == 0 ? 0 : 2) + (has_res ? 1 : 0);
+  VQA_REQUIRE(p.out_dtype >= 0 && p.out_dtype <= 2, VQA_E_INVALID, "gemm: out_dtype must be 0 (bf16), 1 (fp32) or 2 (fp16)");
+  p.out_f16 = p.out_dtype == 2 ? 1 : 0;
+  L->epi = pool ? 4 : (p.out_dtype != 1 ? 0 : 2) + (has_res ? 1 : 0);
   VQA_REQUIRE(p.n_tiles * bn <= kBiasTable, VQA_E_INVALID, "gemm: N exceeds the epilogue's bias table");
 
   // shared-memory plan: one CTA per SM (persistent): rings + epilogue staging + bias table + barriers <= 227 KB
@@ -966,12 +981,12 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
                 "gemm: the pooled output is a bf16 arena buffer without residual");
   } else {
     if (!L->out_external) {
-      rc = encode_box32(&L->mapOut, p.out_dtype != 0, L->out_raw, p.M, p.N, p.ldo, "gemm output");
+      rc = encode_box32(&L->mapOut, p.out_dtype == 1, L->out_raw, p.M, p.N, p.ldo, "gemm output");
       if (rc) return rc;
     }
     if (has_res) {
       VQA_REQUIRE(!(L->res_raw & VQA_EXT_TAG), VQA_E_INVALID, "gemm: the residual must be an arena buffer");
-      rc = encode_box32(&L->mapRes, p.res_dtype != 0, L->res_raw, p.M, p.N, p.ldr, "gemm residual");
+      rc = encode_box32(&L->mapRes, p.res_dtype == 1, L->res_raw, p.M, p.N, p.ldr, "gemm residual");
       if (rc) return rc;
     }
   }
@@ -990,7 +1005,7 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
   VQA_REQUIRE(p.out != nullptr, VQA_E_INVALID, "gemm: unresolved external output");
   if (L->out_external) {   // caller-owned output: encode its store map for this call (host-only work, graph-capturable)
     CUtensorMap mo;
-    int rc = encode_box32(&mo, p.out_dtype != 0, reinterpret_cast<uint64_t>(p.out), p.M, p.N, p.ldo, "gemm output");
+    int rc = encode_box32(&mo, p.out_dtype == 1, reinterpret_cast<uint64_t>(p.out), p.M, p.N, p.ldo, "gemm output");
     if (rc) return rc;
     VQA_CUDA_OK(vqa_launch_cluster(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->pair ? 2 : 1, L->mapA0, L->mapA1, L->mapB,
                                    mo, L->mapRes, p));
@@ -1005,7 +1020,8 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
 const char* gemm_kernel_name(const void* storage) {
   const GemmLaunch* L = reinterpret_cast<const GemmLaunch*>(storage);
   static thread_local char name[64];
-  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d%s%s>", L->bn, L->prm.MT, L->prm.is_tf32 ? "tf32" : "bf16", L->epi,
+  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d%s%s>", L->bn, L->prm.MT,
+           L->prm.is_tf32 ? "tf32" : (((L->prm.idesc >> 7) & 7u) == 0u ? "f16" : "bf16"), L->epi,
            L->prm.row_bytes == 32 ? ",row32" : "", L->pair ? ",pair" : "");
   return name;
 }

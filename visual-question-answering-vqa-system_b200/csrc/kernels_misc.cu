@@ -2,6 +2,8 @@
 // Each launcher takes the generic VqaOp (fields in op_fields.h) with external pointers resolved.
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -737,6 +739,12 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
     y[0] += p0.x; y[1] += p0.y; y[2] += p0.z; y[3] += p0.w;
     y[4] += p1.x; y[5] += p1.y; y[6] += p1.z; y[7] += p1.w;
   }
+  if (rnd == 2) {   // fp16 operand of the next GEMM: 8 bytes per float4
+    uint2* o2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dst) + static_cast<size_t>(row) * 256);
+    o2[lane] = make_uint2(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]));
+    o2[32 + lane] = make_uint2(pack_f16x2(y[4], y[5]), pack_f16x2(y[6], y[7]));
+    return;
+  }
   if (rnd) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) y[k] = round_tf32_rna(y[k]);
@@ -927,10 +935,15 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
         if (row < L) {
           float* orow = out + (static_cast<size_t>(b) * L + row) * (H * kHd) + h * kHd + 2 * t;
 #pragma unroll
-          for (int n = 0; n < 4; ++n) {                 // tf32 operand of W_o (left unrounded for the 3xTF32 split)
+          for (int n = 0; n < 4; ++n) {                 // operand of W_o: fp16 (2), unrounded for the 3xTF32 split (1), tf32 (0)
             const float o0 = oacc[mt][n][hf * 2], o1 = oacc[mt][n][hf * 2 + 1];
-            *reinterpret_cast<float2*>(orow + n * 8) = no_round ? make_float2(o0, o1)
-                                                                : make_float2(round_tf32_rna(o0), round_tf32_rna(o1));
+            if (no_round == 2) {
+              __half* hrow = reinterpret_cast<__half*>(out) + (static_cast<size_t>(b) * L + row) * (H * kHd) + h * kHd + 2 * t;
+              *reinterpret_cast<uint32_t*>(hrow + n * 8) = pack_f16x2(o0, o1);
+            } else {
+              *reinterpret_cast<float2*>(orow + n * 8) = no_round ? make_float2(o0, o1)
+                                                                  : make_float2(round_tf32_rna(o0), round_tf32_rna(o1));
+            }
           }
         }
       }
@@ -991,8 +1004,14 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
     att_pooled[static_cast<size_t>(b) * D + d] = ap;
     txt_pooled[static_cast<size_t>(b) * D + d] = tp;
     if (phase == 1) {
-      cat[static_cast<size_t>(b) * 2 * D + d] = no_round ? ap : round_tf32_rna(ap);
-      cat[static_cast<size_t>(b) * 2 * D + D + d] = no_round ? tp : round_tf32_rna(tp);
+      if (no_round == 2) {   // fp16 operand of the gate GEMM
+        __half* hc = reinterpret_cast<__half*>(cat) + static_cast<size_t>(b) * 2 * D;
+        hc[d] = __float2half_rn(ap);
+        hc[D + d] = __float2half_rn(tp);
+      } else {
+        cat[static_cast<size_t>(b) * 2 * D + d] = no_round ? ap : round_tf32_rna(ap);
+        cat[static_cast<size_t>(b) * 2 * D + D + d] = no_round ? tp : round_tf32_rna(tp);
+      }
       return;
     }
   } else {
@@ -1019,7 +1038,10 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
   float var = 0.f;
   for (int w = 0; w < 8; ++w) var += red[8 + w];
   var *= (1.f / D);
-  fused[static_cast<size_t>(b) * D + d] = c * rsqrtf(var + eps) * gamma[d] + beta[d];
+  const float y = c * rsqrtf(var + eps) * gamma[d] + beta[d];
+  fused[static_cast<size_t>(b) * D + d] = y;
+  if (no_round == 2 && cat != nullptr)   // phases 0 / 2: fp16 copy of the fused feature = operand of the first head Linear
+    reinterpret_cast<__half*>(cat)[static_cast<size_t>(b) * D + d] = __float2half_rn(y);
 }
 
 // softmax over N answers + top-k (k <= 16), ties broken towards the lower index like torch.topk on

@@ -78,8 +78,8 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att"], "f": []},
 }
 
-DT_BF16, DT_TF32 = 0, 1          # gemm operand dtype
-OUT_BF16, OUT_F32 = 0, 1         # gemm output / residual dtype
+DT_BF16, DT_TF32, DT_F16 = 0, 1, 2      # gemm operand dtype
+OUT_BF16, OUT_F32, OUT_F16 = 0, 1, 2    # gemm output / residual dtype
 MASK_NONE, MASK_I64, MASK_F32, MASK_I32, MASK_U8 = 0, 1, 2, 3, 4
 
 # external slots (order of the ext[] array given to vqa_plan_run)
@@ -289,6 +289,10 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device, precision: str
         W.add(name, hi, f32)
         if tf:
             W.add(name + ".x3", torch.cat([hi, hi, round_tf32(w - hi)], dim=1), f32)
+        else:
+            # throughput mode: fp16 operands -- the 11-bit significand of tf32 in half the bytes and at twice
+            # the MMA rate (the Linears of this path are bound by their operand fill, 40-48 B/clk per SM)
+            W.add(name + ".h", w, torch.float16)
 
     # ---- backbone (BN folded, OHWI, bf16 operands, fp32 bias)
     w, b = _fold_bn(sd, "image_encoder.stem.0.weight", "image_encoder.stem.1")
@@ -401,6 +405,9 @@ class OpList:
         self.tf32 = getattr(weights, "precision", "bf16") == "tf32"
         self.window = window
         self.stem_window = window
+        self.half_tail = not self.tf32              # fp16 operands for the text / fusion / head Linears
+        self.out_mode = 1 if self.tf32 else 2       # producers of Linear operands: 1 = unrounded fp32 (3xTF32), 2 = fp16
+        self.tdt = torch.float16 if self.half_tail else torch.float32   # storage of their A operands
         self.fuse_pool = window and not self.tf32
         self.fused_tail = window or self.tf32
         self.pair = window and not self.tf32
@@ -448,7 +455,7 @@ class OpList:
         """
         wbuf, _, wshape = self.W.items[w]
         npad, ktot = wshape
-        chunk = row_bytes // (2 if dtype == DT_BF16 else 4)
+        chunk = row_bytes // (4 if dtype == DT_TF32 else 2)
         halo_hi = halo if halo_hi is None else halo_hi
         bn = _bn_tile(N)
         # small-M layers (text / fusion / head): halve the N tile when that still leaves fewer tiles than SMs,
@@ -512,6 +519,13 @@ class OpList:
                       w=w + ".x3", bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F32, res=res,
                       res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=False)
             return
+        if self.half_tail and (w + ".h") in self.W:
+            # fp16 operands; an output that feeds another Linear (rnd=True) is stored as fp16 too
+            assert not (rnd and res is not None)
+            self.gemm(name, dtype=DT_F16, M=M, N=N, a0=a, a0_shape=(M, K, lda or K), groups=[(0, 0, 0, K // 64, [0])],
+                      w=w + ".h", bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F16 if rnd else OUT_F32, res=res,
+                      res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=False)
+            return
         self.gemm(name, dtype=DT_TF32, M=M, N=N, a0=a, a0_shape=(M, K, lda or K), groups=[(0, 0, 0, K // 32, [0])],
                   w=w, bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F32, res=res,
                   res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=rnd)
@@ -531,8 +545,10 @@ class OpList:
         return [(0, (kh - 1) * g.P + (kw - 1), 0, nchunks, [0]) for kh in range(3) for kw in range(3)], 0, 1
 
     def layernorm(self, name, src, g, b, dst, rows, rnd=False, ld=256):
-        rnd = rnd and not self.tf32     # tf32 precision mode: consumers split the unrounded value into hi + lo
-        self._op("layernorm", name, dict(rows=rows, D=256, ld_src=ld, mode=0, round_tf32=int(rnd), S=0, Pg=0, RPIg=0),
+        # output mode: 0 = fp32, 1 = tf32-rounded fp32, 2 = fp16 (operand of an fp16 Linear); tf32 precision mode:
+        # consumers split the unrounded value into hi + lo
+        mode = 0 if (not rnd or self.tf32) else (2 if self.half_tail else 1)
+        self._op("layernorm", name, dict(rows=rows, D=256, ld_src=ld, mode=0, round_tf32=mode, S=0, Pg=0, RPIg=0),
                  dict(src=src, gamma=self.W.buf(g), beta=self.W.buf(b), dst=dst, pos=None), dict(eps=1e-5))
 
 
@@ -746,10 +762,10 @@ class Program(OpList):
             self._op("mask_prep", "mask", dict(B=B, L=L, dtype=self.mask_dtype),
                      dict(src=ExtRef(EXT["mask"]), dst=mask))
         xt = self._buf("text.x", f32, T, D)
-        xn = self._buf("text.xn", f32, T, D)
+        xn = self._buf("text.xn", self.tdt, T, D)
         qkv = self._buf("text.qkv", f32, T, 3 * D)
-        ctx = self._buf("text.ctx", f32, T, D)
-        hid = self._buf("text.hid", f32, T, F)
+        ctx = self._buf("text.ctx", self.tdt, T, D)
+        hid = self._buf("text.hid", self.tdt, T, F)
         V = W.items["text.emb"][2][0]
         self._op("embed", "text.embed", dict(B=B, L=L, D=D, V=V),
                  dict(ids=ExtRef(EXT["ids"]), table=W.buf("text.emb"), pe=W.buf("text.pe"), dst=xt))
@@ -758,7 +774,7 @@ class Program(OpList):
             p = f"text.{layer}"
             self.layernorm(p + ".ln1", xt, p + ".ln1.g", p + ".ln1.b", xn, T, rnd=True)
             self.linear(p + ".qkv", xn, T, D, p + ".qkv.w", None, qkv, 3 * D)
-            self._op("self_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, ld_qkv=3 * D, no_round=int(self.tf32)),
+            self._op("self_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, ld_qkv=3 * D, no_round=self.out_mode),
                      dict(qkv=qkv, mask=mask, out=ctx))
             self.linear(p + ".o", ctx, T, D, p + ".o.w", None, xt, D, res=xt)
             self.layernorm(p + ".ln2", xt, p + ".ln2.g", p + ".ln2.b", xn, T, rnd=True)
@@ -780,13 +796,13 @@ class Program(OpList):
         while f"x.{n_layers}.q.w" in W:
             n_layers += 1
         q = self._buf("x.q", f32, T, D)          # running query (residual stream)
-        qn = self._buf("x.qn", f32, T, D)
+        qn = self._buf("x.qn", self.tdt, T, D)
         qp = self._buf("x.qp", f32, T, D)
-        cx = self._buf("x.ctx", f32, T, D)
-        imns = [self._buf(f"x.{l}.imgn", f32, TI, D) for l in range(n_layers)]
+        cx = self._buf("x.ctx", self.tdt, T, D)
+        imns = [self._buf(f"x.{l}.imgn", self.tdt, TI, D) for l in range(n_layers)]
         kvs = [self._buf(f"x.{l}.kv", f32, TI, 2 * D) for l in range(n_layers)]
         if n_layers:                              # side lane: LN_q + W_q of layer 0
-            qn0 = self._buf("x.0.qn", f32, T, D)
+            qn0 = self._buf("x.0.qn", self.tdt, T, D)
             self.layernorm("x.0.lnq", text, "x.0.lnq.g", "x.0.lnq.b", qn0, T, rnd=True)
             self.linear("x.0.q", qn0, T, D, "x.0.q.w", None, qp, D)
         self.lane = 0
@@ -816,7 +832,7 @@ class Program(OpList):
                 wts = self._buf(f"aux.xattn.{layer}", f32, B, H, L, S * S)
                 self.xattn_weights.append(f"aux.xattn.{layer}")
             self._op("cross_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, T=S * S, ld_q=D, ld_kv=2 * D, k_off=0, v_off=D,
-                                                     no_round=int(self.tf32)),
+                                                     no_round=self.out_mode),
                      dict(q=qp, kv=kvs[layer], out=cx, weights=wts))
             self.ops[-1].lane |= LANE_JOIN        # needs the side lane's q (layer 0) / K,V (layers >= 1)
             if layer == 0 and n_layers > 1:       # side lane: K/V of every later layer, concurrent with this layer's chain
@@ -836,25 +852,28 @@ class Program(OpList):
         attp = self._buf("attended_pooled", f32, B, D)
         txtp = self._buf("text_pooled", f32, B, D)
         use_gate = "gate.w" in W
+        fused_h = self._buf("fused.h", torch.float16, B, D) if self.half_tail else None   # fp16 operand of head0
         tail_p = dict(xatt=src_q, text=text, mask=mask, wg=None, bg=None, gamma=W.buf("out.ln.g"), beta=W.buf("out.ln.b"),
                       fused=fused, att_pooled=attp, txt_pooled=txtp, cat=None, pre=None)
         if use_gate:
             # masked pools -> [att;txt] (tf32) -> gate pre-activation on the tensor cores (the 512 KB gate matrix is
             # read once instead of once per pair) -> sigmoid gate, mix, LayerNorm
-            cat = self._buf("fusion.cat", f32, B, 2 * D)
+            cat = self._buf("fusion.cat", self.tdt, B, 2 * D)
             pre = self._buf("fusion.gate_pre", f32, B, D)
-            self._op("pool_gate_ln", "fusion.pool", dict(B=B, L=L, D=D, use_gate=1, phase=1, no_round=int(self.tf32)),
+            self._op("pool_gate_ln", "fusion.pool", dict(B=B, L=L, D=D, use_gate=1, phase=1, no_round=self.out_mode),
                      dict(tail_p, cat=cat), dict(eps=1e-5))
             self.linear("fusion.gate", cat, B, 2 * D, "gate.w", "gate.b", pre, D)
-            self._op("pool_gate_ln", "fusion.mix", dict(B=B, L=L, D=D, use_gate=1, phase=2), dict(tail_p, pre=pre), dict(eps=1e-5))
+            self._op("pool_gate_ln", "fusion.mix", dict(B=B, L=L, D=D, use_gate=1, phase=2, no_round=self.out_mode),
+                     dict(tail_p, pre=pre, cat=fused_h), dict(eps=1e-5))
         else:
-            self._op("pool_gate_ln", "fusion.tail", dict(B=B, L=L, D=D, use_gate=0, phase=0), tail_p, dict(eps=1e-5))
+            self._op("pool_gate_ln", "fusion.tail", dict(B=B, L=L, D=D, use_gate=0, phase=0, no_round=self.out_mode),
+                     dict(tail_p, cat=fused_h), dict(eps=1e-5))
 
         # ================= answer head =================
         NA = cfg["num_answers"]
-        h0 = self._buf("head.h0", f32, B, 2 * D)
-        h1 = self._buf("head.h1", f32, B, D)
-        self.linear("head0", fused, B, D, "head0.w", "head0.b", h0, 2 * D, relu=True, rnd=True)
+        h0 = self._buf("head.h0", self.tdt, B, 2 * D)
+        h1 = self._buf("head.h1", self.tdt, B, D)
+        self.linear("head0", fused_h if self.half_tail else fused, B, D, "head0.w", "head0.b", h0, 2 * D, relu=True, rnd=True)
         self.linear("head1", h0, B, 2 * D, "head1.w", "head1.b", h1, D, relu=True, rnd=True)
         if NA % 4 == 0:
             self.linear("head2", h1, B, D, "head2.w", "head2.b", ExtRef(EXT["logits"]), NA, ldo=NA)
