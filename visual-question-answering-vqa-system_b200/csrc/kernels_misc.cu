@@ -810,12 +810,18 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
   const float* qb = q + static_cast<size_t>(b) * L * ld_q + h * kHd;
   const float* kb = k + static_cast<size_t>(b) * T * ld_kv + h * kHd;
   const float* vb = v + static_cast<size_t>(b) * T * ld_kv + h * kHd;
-  for (int i = lane; i < NT * 8 * 8; i += 32) {         // V rows (zero beyond T), coalesced
-    const int r = i >> 3, c4 = i & 7;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < T) x = *reinterpret_cast<const float4*>(vb + static_cast<size_t>(r) * ld_kv + c4 * 4);
-    *reinterpret_cast<float4*>(Vs + r * kVs + c4 * 4) = x;
-  }
+  // K / V rows go global -> shared with cp.async (all 16-byte pieces of the head in flight at once; rows beyond T
+  // are zero-filled through the src-size operand).  A register-staged loop serialised 14 + 14 DRAM/L2 round trips
+  // per warp and was 1/3 of the kernel's stall samples (ncu source view, profiles/r01_h_*).
+  auto stage_rows = [&](float* dst, int stride, const float* src) {
+    for (int i = lane; i < NT * 8 * 8; i += 32) {
+      const int r = i >> 3, c4 = i & 7;
+      const float* g = src + static_cast<size_t>(r < T ? r : 0) * ld_kv + c4 * 4;
+      const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * stride + c4 * 4));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(r < T ? 16 : 0) : "memory");
+    }
+  };
+  stage_rows(Vs, kVs, vb);
   float mb[NT][2];                                      // additive key mask of this lane's score columns
 #pragma unroll
   for (int n = 0; n < NT; ++n)
@@ -827,12 +833,8 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
   const float scale = rsqrtf(static_cast<float>(kHd));
   for (int l0 = 0; l0 < L; l0 += 32) {
     __syncwarp();
-    for (int i = lane; i < NT * 8 * 8; i += 32) {       // K rows (the region is reused for P below)
-      const int r = i >> 3, c4 = i & 7;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < T) x = *reinterpret_cast<const float4*>(kb + static_cast<size_t>(r) * ld_kv + c4 * 4);
-      *reinterpret_cast<float4*>(Ks + r * kKs + c4 * 4) = x;
-    }
+    stage_rows(Ks, kKs, kb);                            // K rows (the region is reused for P below)
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // Q fragments (rows g, g+8 of each 16-row tile; dims t, t+4 of each 8-wide k step), pre-split
     uint32_t qh[2][4][4], ql[2][4][4];
 #pragma unroll
@@ -845,6 +847,7 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
           const float x = row < L ? __ldg(qb + static_cast<size_t>(row) * ld_q + col) : 0.f;
           split_tf32(x, qh[mt][ks][e], ql[mt][ks][e]);
         }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // this lane's K (and, first pass, V) pieces have landed
     __syncwarp();
     float sacc[2][NT][4];
 #pragma unroll
