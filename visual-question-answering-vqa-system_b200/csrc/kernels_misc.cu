@@ -995,6 +995,7 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
   float ap, tp;
   if (phase != 2) {
     float cnt = 0.f, sa = 0.f, st = 0.f;
+#pragma unroll 4
     for (int l = 0; l < L; ++l) {
       const float m = mask ? static_cast<float>(mask[b * L + l]) : 1.f;
       cnt += m;
