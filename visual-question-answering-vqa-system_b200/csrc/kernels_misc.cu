@@ -459,6 +459,7 @@ stage_tail_kernel(const StageTailParams p) {
       float t = 0.f;
       if (r < p.R) {
         const float4* wrow = reinterpret_cast<const float4*>(p.w1 + static_cast<size_t>(r) * C);
+#pragma unroll 4
         for (int c4 = part8; c4 < C / 4; c4 += 8) {
           const float4 wv = __ldg(wrow + c4);
           const float4 mv = *reinterpret_cast<const float4*>(mean + 4 * c4);

@@ -465,7 +465,7 @@ class OpList:
         # 256-row window convolutions with >= 256 output channels: 128-column tiles on a CTA pair (512 rows x 128
         # columns per pair) keep two accumulator stages in TMEM, so the epilogue overlaps the next tile's MMAs
         # (measured: stage 3 conv 66 -> 57 us; the 256-column tile fills TMEM with one stage)
-        if bn == 256 and dtype == DT_BF16 and out_dtype == OUT_BF16 and MT == 2 and self.pair:
+        if bn == 256 and dtype == DT_BF16 and out_dtype == OUT_BF16 and MT == 2 and self.pair and halo > 0:
             bn = 128
         assert npad % bn == 0 and npad >= N, (name, npad, bn)
         assert len(groups) <= MAX_GROUPS and MT * bn <= 512
@@ -686,7 +686,7 @@ class Program(OpList):
                         for kw in range(3):
                             pw, dj = (1, -1) if kw == 0 else ((0, 0) if kw == 1 else (1, 0))
                             taps.append((0, (ph * 2 + pw) * phase_rows + di * g.P + dj, 0, nch_in, [0]))
-                    a_rows, halo1, mt1 = 4 * phase_rows, 0, 1
+                    a_rows, halo1, mt1 = 4 * phase_rows, 0, (2 if cout >= 256 and not self.tf32 else 1)   # 256-row tiles: one wave instead of 1.7
                 else:
                     taps, halo1, mt1 = self._conv3x3_groups(g, nch_in, cout)
                     a_rows = g.rows
