@@ -328,8 +328,11 @@ class Emulator:
         D = H * hd
         q = torch.as_strided(_t(op.p["q"], torch.float32, ext), (B * L, D), (i["ld_q"], 1)).view(B, L, H, hd).transpose(1, 2)
         kvf = _t(op.p["kv"], torch.float32, ext)
-        k = torch.as_strided(kvf[i["k_off"]:], (B * T, D), (i["ld_kv"], 1)).view(B, T, H, hd).transpose(1, 2)
-        v = torch.as_strided(kvf[i["v_off"]:], (B * T, D), (i["ld_kv"], 1)).view(B, T, H, hd).transpose(1, 2)
+        qk = max(i.get("q_per_kv", 1), 1)           # consecutive queries that share one image's K / V
+        Bi = B // qk
+        k = torch.as_strided(kvf[i["k_off"]:], (Bi * T, D), (i["ld_kv"], 1)).view(Bi, T, H, hd).transpose(1, 2)
+        v = torch.as_strided(kvf[i["v_off"]:], (Bi * T, D), (i["ld_kv"], 1)).view(Bi, T, H, hd).transpose(1, 2)
+        k, v = k.repeat_interleave(qk, dim=0), v.repeat_interleave(qk, dim=0)
         ctx, w = self._attend(q, k, v, hd)
         odt = torch.float16 if i.get("no_round") == 2 else torch.float32
         _t(op.p["out"], odt, ext)[: B * L * D].view(B, L, D).copy_(ctx.transpose(1, 2).reshape(B, L, D).to(odt))

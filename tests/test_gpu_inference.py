@@ -108,3 +108,18 @@ def test_device_resize_matches_golden_and_host_path(engine):
     b = engine.predict(im, "what is this", top_k=5)
     engine.gpu_resize = True
     assert a == b
+
+
+def test_predict_questions_shares_the_image(engine):
+    """One image, many questions: same dicts as predict() per question."""
+    engine.use_cuda_graph = True
+    im = Image.fromarray(synth_images_u8(1, 21)[0].numpy(), "RGB")
+    qs = ["what is this", "what color is this", "how many are there", "where is this", "is there what type"]
+    res = engine.predict_questions(im, qs, top_k=4)
+    assert [r["question"] for r in res] == qs
+    for q, r in zip(qs, res):
+        single = engine.predict(im, q, top_k=4)
+        assert [a["index"] for a in r["answers"]] == [a["index"] for a in single["answers"]]
+        np.testing.assert_allclose([a["probability"] for a in r["answers"]],
+                                   [a["probability"] for a in single["answers"]], rtol=1e-5, atol=1e-7)
+    assert engine.predict_questions(im, []) == []

@@ -79,6 +79,32 @@ def test_tf32_tolerance_mode_within_1e_3(golden_meta, case):
     assert np.array_equal(logits.argmax(1).cpu().numpy(), g["top_indices"][:, 0])
 
 
+def test_one_image_many_questions():
+    """BASELINE configs[4]: one image, 16 questions of 64 tokens on VQAModel(max_question_length=64); the backbone,
+    projector and K/V projections run once per image.  Must equal the plain forward on the repeated image bit for
+    bit, and match the fp32 oracle within the bf16 gate."""
+    torch.manual_seed(0)
+    model = VQAModel(max_question_length=64).eval()
+    sd = randomise_state(model.state_dict(), 1)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    u8, img, ids, mask = synth_batch(16, 77, max_len=64)
+    one = img[:1]
+    with torch.no_grad():
+        shared, aux = model(one.cuda(), ids.cuda(), mask.cuda(), return_aux=True)
+        plain, _ = model(one.repeat(16, 1, 1, 1).cuda(), ids.cuda(), mask.cuda())
+        two, _ = model(img[:2].cuda(), ids.cuda(), mask.cuda())          # 2 images x 8 questions
+        plain2, _ = model(img[:2].repeat_interleave(8, dim=0).cuda(), ids.cuda(), mask.cuda())
+    assert tuple(shared.shape) == (16, 1000) and tuple(aux["image_features"].shape) == (1, 512, 7, 7)
+    assert torch.equal(shared, plain) and torch.equal(two, plain2)
+    want, _ = O.vqa_forward(sd, one.repeat(16, 1, 1, 1), ids, mask)
+    assert rel_err(shared.cpu(), want) <= LOGIT_REL_TOL
+    idx, probs = model.predict(one.cuda(), ids.cuda(), mask.cuda(), top_k=3)
+    assert tuple(idx.shape) == (16, 3)
+    with pytest.raises(ValueError):
+        model(img[:3].cuda(), ids.cuda(), mask.cuda())                    # 16 questions over 3 images
+
+
 def test_uint8_input_equals_normalised_input(golden_meta):
     model, sd, u8, img, ids, mask = make(golden_meta["plain_b2"])
     with torch.no_grad():

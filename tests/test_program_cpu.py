@@ -61,6 +61,25 @@ def test_tf32_precision_mode_within_1e_3(ctor, B, L):
     assert float((feat - aux["image_features"]).abs().max() / aux["image_features"].abs().max()) < 2e-3
 
 
+def test_one_image_many_questions_program():
+    """n_images < B (BASELINE config "one image, many questions"): the image side of the program runs once per image
+    and its K/V are shared by B / n_images questions; same logits as the oracle on the repeated image."""
+    torch.manual_seed(0)
+    ctor = dict(max_question_length=24, num_transformer_layers=1, vocab_size=300, num_answers=40)
+    model = VQAModel(**ctor).eval()
+    sd = randomise_state(model.state_dict(), 1)
+    u8, img, ids, mask = synth_batch(6, 99, max_len=24, vocab=300)
+    img2 = img[:2]                                            # 2 images x 3 questions each
+    W = P.build_weights(sd, model.config, "cpu")
+    prog = P.Program(W, model.config, 6, 24, "nchw_f32", P.MASK_I64, want_aux=False, top_k=0, device="cpu", n_images=2)
+    assert prog.Bi == 2 and [op.i["q_per_kv"] for op in prog.ops if op.kind == "cross_attn"] == [3, 3]
+    assert next(op for op in prog.ops if op.kind == "ingest").i["B"] == 2
+    logits, _ = E.run_program(prog, img2, ids, mask)
+    want, _ = O.vqa_forward(sd, img2.repeat_interleave(3, dim=0), ids, mask, return_aux=True)
+    assert float((logits - want).abs().max() / want.abs().max()) < 1e-2
+    assert torch.equal(logits.argmax(1), want.argmax(1))
+
+
 def test_weight_folding_is_exact_in_fp32():
     """BN fold + shortcut-as-extra-K reproduce conv->BN (+downsample->BN) exactly up to fp32 rounding."""
     torch.manual_seed(3)

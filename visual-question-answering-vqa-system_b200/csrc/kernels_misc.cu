@@ -795,7 +795,7 @@ template <int NT>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 const int* __restrict__ mask, float* __restrict__ out, float* __restrict__ weights, int n_units,
-                int H, int L, int T, int ld_q, int ld_kv, int no_round) {
+                int H, int L, int T, int ld_q, int ld_kv, int no_round, int q_per_kv) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) float sm[];
@@ -809,8 +809,9 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
   float* Ps = Ks;
   float* Vs = Ks + attn_mma_kreg(NT);
   const float* qb = q + static_cast<size_t>(b) * L * ld_q + h * kHd;
-  const float* kb = k + static_cast<size_t>(b) * T * ld_kv + h * kHd;
-  const float* vb = v + static_cast<size_t>(b) * T * ld_kv + h * kHd;
+  const int bkv = b / q_per_kv;                         // q_per_kv consecutive queries share one image's K / V
+  const float* kb = k + static_cast<size_t>(bkv) * T * ld_kv + h * kHd;
+  const float* vb = v + static_cast<size_t>(bkv) * T * ld_kv + h * kHd;
   // K / V rows go global -> shared with cp.async (all 16-byte pieces of the head in flight at once; rows beyond T
   // are zero-filled through the src-size operand).  A register-staged loop serialised 14 + 14 DRAM/L2 round trips
   // per warp and was 1/3 of the kernel's stall samples (ncu source view, profiles/r01_h_*).
@@ -829,7 +830,7 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int j = n * 8 + 2 * t + e;
-      mb[n][e] = (j < T && (mask == nullptr || mask[b * T + j] != 0)) ? 0.f : -INFINITY;
+      mb[n][e] = (j < T && (mask == nullptr || mask[b * T + j] != 0)) ? 0.f : -INFINITY;   // self-attention only (q_per_kv = 1)
     }
   const float scale = rsqrtf(static_cast<float>(kHd));
   for (int l0 = 0; l0 < L; l0 += 32) {
@@ -954,10 +955,12 @@ attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
   }
 }
 
-typedef void (*AttnFn)(const float*, const float*, const float*, const int*, float*, float*, int, int, int, int, int, int, int);
+typedef void (*AttnFn)(const float*, const float*, const float*, const int*, float*, float*, int, int, int, int, int, int, int,
+                       int);
 
 static int launch_attn(const float* q, const float* k, const float* v, const int* mask, float* out, float* weights, int B,
-                       int H, int L, int T, int ld_q, int ld_kv, int no_round, cudaStream_t st) {
+                       int H, int L, int T, int ld_q, int ld_kv, int no_round, int q_per_kv, cudaStream_t st) {
+  VQA_REQUIRE(q_per_kv >= 1 && B % q_per_kv == 0, VQA_E_INVALID, "attention: the batch must be a multiple of q_per_kv");
   const int nt = (T + 7) / 8;
   VQA_REQUIRE(nt >= 1 && nt <= 8, VQA_E_INVALID, "attention: 1..64 keys");
   const int ntt = nt <= 3 ? 3 : nt <= 4 ? 4 : nt <= 7 ? 7 : 8;
@@ -971,7 +974,7 @@ static int launch_attn(const float* q, const float* k, const float* v, const int
     attr_set[ntt] = true;
   }
   VQA_CUDA_OK(vqa_launch(fn, dim3((B * H + kAttnWarps - 1) / kAttnWarps), dim3(kAttnWarps * 32), smem, st, q, k, v, mask, out,
-                         weights, B * H, H, L, T, ld_q, ld_kv, no_round));
+                         weights, B * H, H, L, T, ld_q, ld_kv, no_round, q_per_kv));
   VQA_LAUNCH_OK("attn_mma_kernel");
   return VQA_OK;
 }
@@ -1301,7 +1304,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(ld % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, VQA_E_ALIGN, "self_attn: qkv alignment");
       VQA_REQUIRE((reinterpret_cast<uintptr_t>(PTR(float*, SELF_ATTN_P_out)) & 15) == 0, VQA_E_ALIGN, "self_attn: out alignment");
       return launch_attn(qkv, qkv + D, qkv + 2 * D, PTR(const int*, SELF_ATTN_P_mask), PTR(float*, SELF_ATTN_P_out), nullptr, B,
-                         H, L, L, ld, ld, I[SELF_ATTN_I_no_round], st);
+                         H, L, L, ld, ld, I[SELF_ATTN_I_no_round], 1, st);
     }
     case VQA_OP_CROSS_ATTN: {
       const int L = I[CROSS_ATTN_I_L], T = I[CROSS_ATTN_I_T], H = I[CROSS_ATTN_I_H], B = I[CROSS_ATTN_I_B];
@@ -1312,7 +1315,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
                       I[CROSS_ATTN_I_v_off] % 4 == 0, VQA_E_ALIGN, "cross_attn: leading dimensions must be multiples of 4");
       return launch_attn(PTR(const float*, CROSS_ATTN_P_q), kv + I[CROSS_ATTN_I_k_off], kv + I[CROSS_ATTN_I_v_off], nullptr,
                          PTR(float*, CROSS_ATTN_P_out), PTR(float*, CROSS_ATTN_P_weights), B, H, L, T, I[CROSS_ATTN_I_ld_q],
-                         I[CROSS_ATTN_I_ld_kv], I[CROSS_ATTN_I_no_round], st);
+                         I[CROSS_ATTN_I_ld_kv], I[CROSS_ATTN_I_no_round], I[CROSS_ATTN_I_q_per_kv] > 0 ? I[CROSS_ATTN_I_q_per_kv] : 1, st);
     }
     case VQA_OP_POOL_GATE_LN: {
       const int phase = I[POOL_GATE_LN_I_phase];

@@ -30,15 +30,16 @@ class Engine:
         self.window = True
 
     # ------------------------------------------------------------------ plans
-    def plan_for(self, B: int, L: int, in_fmt: str, mask_dtype: int, want_aux: bool, top_k: int):
-        key = (B, L, in_fmt, mask_dtype, want_aux, top_k, self.window)
+    def plan_for(self, B: int, L: int, in_fmt: str, mask_dtype: int, want_aux: bool, top_k: int, n_images: int = 0):
+        n_images = n_images or B
+        key = (B, L, in_fmt, mask_dtype, want_aux, top_k, self.window, n_images)
         hit = self._plans.get(key)
         if hit is None:
             if L > self.cfg["max_question_length"]:
                 raise RuntimeError(f"sequence length {L} exceeds max_question_length "
                                    f"{self.cfg['max_question_length']} (size of the positional-encoding buffer)")
             prog = P.Program(self.weights, self.cfg, B, L, in_fmt, mask_dtype, want_aux, top_k, self.device,
-                             window=self.window)
+                             window=self.window, n_images=n_images)
             idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
             hit = (prog, Plan(prog.ops, idx))
             self._plans[key] = hit
@@ -71,8 +72,11 @@ class Engine:
             if images.dtype != torch.float32:
                 images = images.float()
         B, L = token_ids.shape
-        if images.shape[0] != B:
-            raise ValueError("images and token_ids disagree on the batch size")
+        Bi = int(images.shape[0])
+        if Bi < 1 or B % Bi != 0:
+            # Bi == B is the reference contract; Bi < B (one image, many questions) is this engine's extension:
+            # image i answers the B / Bi consecutive questions i * B/Bi .. (i + 1) * B/Bi - 1
+            raise ValueError("the number of questions must be a multiple of the number of images")
         images = images.contiguous()
         ids = token_ids.contiguous()
         if ids.dtype != torch.int64:
@@ -87,7 +91,7 @@ class Engine:
             if tuple(mask.shape) != (B, L):
                 raise ValueError("attention_mask must be [B, L]")
             mask = mask.contiguous()
-        prog, plan = self.plan_for(B, L, in_fmt, code, want_aux, top_k)
+        prog, plan = self.plan_for(B, L, in_fmt, code, want_aux, top_k, Bi)
         NA = self.cfg["num_answers"]
         logits = torch.empty(B, NA, dtype=torch.float32, device=self.device)
         top_idx = torch.empty(B, max(top_k, 1), dtype=torch.int64, device=self.device)
@@ -119,7 +123,7 @@ class Engine:
             "text_pooled": prog.tensor("text_pooled").clone(),
             "fused": prog.tensor("fused").clone(),
             "cross_attention_weights": [prog.tensor(n).clone() for n in prog.xattn_weights],
-            "image_projected": prog.tensor("image_projected").view(B, 49, D).clone(),
+            "image_projected": prog.tensor("image_projected").view(-1, 49, D).clone(),
             "attended_pooled": prog.tensor("attended_pooled").clone(),
         }
         return logits, aux

@@ -266,6 +266,24 @@ class VQAInference:
         return self._format(question, idx[0].tolist(), probs[0].tolist())
 
     @torch.no_grad()
+    def predict_questions(self, image: ImageLike, questions: List[str], top_k: int = DEFAULT_TOP_K) -> List[Dict]:
+        """One image, many questions (not in the reference API): the backbone, the projector and
+        the K/V projections of the cross-attention layers run once, every question cross-attends the same 49-token
+        feature map.  Same result dicts as ``predict`` called per question."""
+        if not self._is_loaded:
+            self.load()
+        if not questions:
+            return []
+        u8 = self.preprocess_image_u8(image).unsqueeze(0).to(self.device, non_blocking=True)
+        pairs = [self.preprocess_question(q) for q in questions]
+        ids = torch.cat([p[0] for p in pairs], dim=0).to(self.device, non_blocking=True)
+        mask = torch.cat([p[1] for p in pairs], dim=0).to(self.device, non_blocking=True)
+        k = min(top_k, self.model.num_answers)
+        idx, probs = self.model.predict(u8, ids, mask, top_k=k)
+        idx, probs = idx.cpu(), probs.cpu()
+        return [self._format(q, idx[i].tolist(), probs[i].tolist()) for i, q in enumerate(questions)]
+
+    @torch.no_grad()
     def predict_batch(self, images: List[ImageLike], questions: List[str], top_k: int = DEFAULT_TOP_K) -> List[Dict]:
         if len(images) != len(questions):
             raise ValueError("Number of images must match number of questions")

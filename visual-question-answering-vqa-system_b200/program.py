@@ -64,7 +64,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
     "layernorm": {"i": ["rows", "D", "ld_src", "mode", "round_tf32", "S", "Pg", "RPIg"],
                   "p": ["src", "gamma", "beta", "dst", "pos"], "f": ["eps"]},
     "self_attn": {"i": ["B", "L", "H", "hd", "ld_qkv", "no_round"], "p": ["qkv", "mask", "out"], "f": []},
-    "cross_attn": {"i": ["B", "L", "H", "hd", "T", "ld_q", "ld_kv", "k_off", "v_off", "no_round"],
+    "cross_attn": {"i": ["B", "L", "H", "hd", "T", "ld_q", "ld_kv", "k_off", "v_off", "no_round", "q_per_kv"],
                    "p": ["q", "kv", "out", "weights"], "f": []},
     "pool_gate_ln": {"i": ["B", "L", "D", "use_gate", "phase", "no_round"],
                      "p": ["xatt", "text", "mask", "wg", "bg", "gamma", "beta", "fused",
@@ -557,10 +557,15 @@ class Program(OpList):
 
     def __init__(self, weights: Weights, cfg: dict, B: int, L: int, in_fmt: str = "nchw_f32",
                  mask_dtype: int = MASK_I64, want_aux: bool = False, top_k: int = 0, device=None,
-                 window: bool = True):
+                 window: bool = True, n_images: Optional[int] = None):
+        """``n_images`` (default B): the image side runs on n_images images and every image answers B / n_images
+        consecutive questions (BASELINE config "one image, many questions": backbone, projector and the K/V
+        projections of both cross-attention layers run once per image)."""
         super().__init__(weights, device, window)
         self.cfg = cfg
         self.B, self.L = B, L
+        self.Bi = B if n_images is None else int(n_images)
+        assert self.Bi >= 1 and B % self.Bi == 0, "the number of questions must be a multiple of the number of images"
         self.in_fmt = in_fmt
         self.mask_dtype = mask_dtype
         self.want_aux = want_aux
@@ -570,7 +575,7 @@ class Program(OpList):
 
     # -- network definition
     def _build(self):
-        B, L, W, cfg = self.B, self.L, self.W, self.cfg
+        B, L, W, cfg = self.Bi, self.L, self.W, self.cfg   # B = images on this side of the program
         bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
 
         # ================= image side =================
@@ -610,7 +615,7 @@ class Program(OpList):
         self._build_rest(g, x)
 
     def _stem_unfused(self, g0, s0, s0g, GUARD, g, x):
-        B = self.B
+        B = self.Bi
         bf = torch.bfloat16
         s1 = self._buf("stem_out", bf, g0.rows, 64)
         if self.stem_window:
@@ -635,7 +640,7 @@ class Program(OpList):
 
     def _stage_tail(self, s, x, g, cout, has_se, has_sp):
         """One fused kernel per stage: SE squeeze/excite, spatial attention, scaling and the relayout."""
-        B, W = self.B, self.W
+        B, W = self.Bi, self.W
         bf, f32 = torch.bfloat16, torch.float32
         scale = self._buf(f"s{s}.se.scale", f32, B, cout) if has_se else None
         att = self._buf(f"s{s}.spatial.att", f32, B, g.H * g.W) if has_sp else None
@@ -663,7 +668,7 @@ class Program(OpList):
         return out
 
     def _build_rest(self, g, x):
-        B, L, W, cfg = self.B, self.L, self.W, self.cfg
+        B, L, W, cfg = self.Bi, self.L, self.W, self.cfg   # B = images on this side of the program
         bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
         cin = 64
         x_is_phase = False
@@ -753,6 +758,7 @@ class Program(OpList):
                      dict(src=feat, dst=nchw))
 
         # ================= text side (independent of the image side: runs on the side stream) =================
+        Bi, B = self.Bi, self.B                    # from here on B = (image, question) pairs
         self.lane = 1
         D, H, F = cfg["embed_dim"], cfg["num_attention_heads"], cfg["ffn_hidden_dim"]
         T = B * L
@@ -791,7 +797,7 @@ class Program(OpList):
         # side lane right before each attention.  Ops are issued in list order, so a JOIN waits only for what
         # precedes it in the list.
         S = 7
-        TI = B * S * S
+        TI = Bi * S * S
         n_layers = 0
         while f"x.{n_layers}.q.w" in W:
             n_layers += 1
@@ -809,8 +815,8 @@ class Program(OpList):
         praw = self._buf("proj.raw", f32, gf.rows, D)
         self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
                   groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
-        img = self._buf("image_projected", f32, B * S * S, D)
-        self._op("layernorm", "proj.ln", dict(rows=B * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
+        img = self._buf("image_projected", f32, Bi * S * S, D)
+        self._op("layernorm", "proj.ln", dict(rows=Bi * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
                  dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos")),
                  dict(eps=1e-5))
 
@@ -832,7 +838,7 @@ class Program(OpList):
                 wts = self._buf(f"aux.xattn.{layer}", f32, B, H, L, S * S)
                 self.xattn_weights.append(f"aux.xattn.{layer}")
             self._op("cross_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, T=S * S, ld_q=D, ld_kv=2 * D, k_off=0, v_off=D,
-                                                     no_round=self.out_mode),
+                                                     no_round=self.out_mode, q_per_kv=B // Bi),
                      dict(q=qp, kv=kvs[layer], out=cx, weights=wts))
             self.ops[-1].lane |= LANE_JOIN        # needs the side lane's q (layer 0) / K,V (layers >= 1)
             if layer == 0 and n_layers > 1:       # side lane: K/V of every later layer, concurrent with this layer's chain
