@@ -367,14 +367,15 @@ def run_b200(args):
         conv_ops = [k for k in gemm_ops if prog.ops[k].i["dtype"] == P.DT_BF16 and prog.ops[k].i["out_dtype"] == P.OUT_BF16]
         gemm_ms = b2b(gemm_ops)
         conv_ms = b2b(conv_ops)
-        traffic = None
+        traffic = traffic_note = None
         try:
             with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_e_ncu_gemm_summary.json")) as f:
                 nc = json.load(f)
-            traffic = {"bytes_per_step": (nc["dram_read_mb"] + nc["dram_write_mb"]) * 1e6,
-                       "launches": "the 17 convolution launches of one 256-pair forward",
-                       "algorithmic_bytes_per_step": 9.07e6 * B,
-                       "source": "profiles/r01_e_ncu_gemm_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+            traffic = (nc["dram_read_mb"] + nc["dram_write_mb"]) * 1e6     # bytes per 256-pair forward
+            traffic_note = {"launches": "sum over the 17 convolution launches of one 256-pair forward",
+                            "algorithmic_bytes": 9.07e6 * B,
+                            "source": "profiles/r01_e_ncu_gemm_summary.md (ncu --set full, dram__bytes_read.sum + "
+                                      "dram__bytes_write.sum)"}
         except Exception:
             pass
         for k, t in enumerate(op_ms):
@@ -384,7 +385,7 @@ def run_b200(args):
         achieved = FLOP_PER_PAIR * B / (gemm_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "gemm_tap_kernel (all conv + linear launches of one forward)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "gemm_ms_per_step": gemm_ms,
                 "gemm_launches_per_step": len(gemm_ops),
                 "timing": "CUDA events around the 48 gemm_tap_kernel launches of one forward issued back to back",

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 4
+#define VQA_ABI_VERSION 5
 
 #define VQA_OK            0
 #define VQA_E_INVALID    -1   /* bad argument / unsupported shape */

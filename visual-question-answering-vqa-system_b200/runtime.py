@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqa_b200.so")
 
 OP_NI, OP_NP, OP_NF = 144, 12, 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class VqaOp(C.Structure):
