@@ -366,7 +366,8 @@ stage_tail_kernel(const StageTailParams p) {
   const int C8 = p.C8, C = C8 * 8, W = p.W, CS = p.CS;
   const int rows_l = p.H / CS;                          // pixel rows of this CTA
   const int NP = rows_l * W;                            // pixels of this CTA
-  const int n = blockIdx.x / CS;
+  // images in DESCENDING order: the producer (conv2) wrote them ascending, so the last images are still in L2
+  const int n = static_cast<int>(gridDim.x / CS) - 1 - static_cast<int>(blockIdx.x) / CS;
   const int rank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int h0 = rank * rows_l;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
