@@ -54,7 +54,8 @@ def test_plain_bf16_gemm(M, K, N, out_dtype):
 
 
 @pytest.mark.parametrize("M,K,N,ldo", [(256, 256, 256, 256), (100, 256, 768, 768), (77, 1024, 256, 256),
-                                      (256, 256, 1000, 1000), (5, 512, 36, 40), (1500, 256, 256, 256)])
+                                      (256, 256, 1000, 1000), (5, 512, 36, 40), (1500, 256, 256, 256),
+                                      (64, 256, 3000, 3000)])   # N beyond the 2048-entry bias table
 @pytest.mark.parametrize("max_ctas", [0, 2])
 def test_tf32_linear_with_residual(M, K, N, ldo, max_ctas):
     def build(device):

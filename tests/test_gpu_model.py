@@ -79,6 +79,21 @@ def test_tf32_tolerance_mode_within_1e_3(golden_meta, case):
     assert np.array_equal(logits.argmax(1).cpu().numpy(), g["top_indices"][:, 0])
 
 
+def test_large_answer_and_word_vocabularies():
+    """VQA-v2-sized head (3129 answers: wider than the epilogue's 2048-entry bias table) and a 20k-word embedding."""
+    torch.manual_seed(0)
+    model = VQAModel(vocab_size=20000, num_answers=3129, num_transformer_layers=1, num_cross_layers=1).eval()
+    sd = randomise_state(model.state_dict(), 1)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    u8, img, ids, mask = synth_batch(3, 5, vocab=20000)
+    with torch.no_grad():
+        logits, _ = model(img.cuda(), ids.cuda(), mask.cuda())
+    want, _ = O.vqa_forward(sd, img, ids, mask)
+    assert tuple(logits.shape) == (3, 3129) and rel_err(logits.cpu(), want) <= LOGIT_REL_TOL
+    assert torch.equal(logits.argmax(1).cpu(), want.argmax(1))
+
+
 def test_one_image_many_questions():
     """BASELINE configs[4]: one image, 16 questions of 64 tokens on VQAModel(max_question_length=64); the backbone,
     projector and K/V projections run once per image.  Must equal the plain forward on the repeated image bit for

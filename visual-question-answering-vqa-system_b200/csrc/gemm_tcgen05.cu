@@ -95,7 +95,7 @@ __device__ __forceinline__ int tile_m0(const GemmParams& p, int tile_m, int mt) 
 // swizzled box into its private staging slot and one lane issues a TMA store, which also clips
 // the M and N edges.  The residual box of the NEXT chunk is in flight while the current one is
 // processed.  Slots are 32 rows x 64 B (bf16, SWIZZLE_64B) or 32 rows x 128 B (fp32, SWIZZLE_128B).
-constexpr int kBiasTable = 1024;        // floats: bias of every N tile of the launch
+constexpr int kBiasTable = 2048;        // floats: bias of every N tile of the launch (wider layers read it from global)
 constexpr int kPoolTileBytes = 384 * 128;
 
 __host__ __device__ constexpr int epi_stage_bytes(int epi) {
@@ -536,13 +536,17 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           uint32_t v[32];
           __syncwarp();                                 // tcgen05.ld is .sync.aligned
           tmem_ld32(taddr + 32 * c, v);
-          const float* bsrc = s_bias + col0;            // table covers every N tile of the launch
+          const bool tabled = p.n_tiles * BN <= kBiasTable;   // else (N > 2048): broadcast loads from global
+          const float* bsrc = s_bias + (tabled ? col0 : 0);
           if (kRes) mbar_wait(my_res_bar, resph);       // this chunk's residual box has landed
           tmem_ld_wait();
           float x[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
-          if (has_bias) {
+          if (has_bias && !tabled) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[k] += (col0 + k < N) ? __ldg(p.bias + col0 + k) : 0.f;
+          } else if (has_bias) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const float4 bq = *reinterpret_cast<const float4*>(bsrc + 4 * k);   // same address in every lane: broadcast
@@ -900,7 +904,6 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   VQA_REQUIRE(p.out_dtype >= 0 && p.out_dtype <= 2, VQA_E_INVALID, "gemm: out_dtype must be 0 (bf16), 1 (fp32) or 2 (fp16)");
   p.out_f16 = p.out_dtype == 2 ? 1 : 0;
   L->epi = pool ? 4 : (p.out_dtype != 1 ? 0 : 2) + (has_res ? 1 : 0);
-  VQA_REQUIRE(p.n_tiles * bn <= kBiasTable, VQA_E_INVALID, "gemm: N exceeds the epilogue's bias table");
 
   // shared-memory plan: one CTA per SM (persistent): rings + epilogue staging + bias table + barriers <= 227 KB
   const int stage_bytes = epi_stage_bytes(L->epi);
