@@ -82,7 +82,7 @@ def test_tf32_tolerance_mode_within_1e_3(golden_meta, case):
 def test_large_answer_and_word_vocabularies():
     """VQA-v2-sized head (3129 answers: wider than the epilogue's 2048-entry bias table) and a 20k-word embedding."""
     torch.manual_seed(0)
-    model = VQAModel(vocab_size=20000, num_answers=3129, num_transformer_layers=1, num_cross_layers=1).eval()
+    model = VQAModel(vocab_size=20000, num_answers=3129, num_transformer_layers=1, num_cross_layers=3, se_reduction=4).eval()
     sd = randomise_state(model.state_dict(), 1)
     model.load_state_dict(sd, strict=True)
     model = model.cuda()

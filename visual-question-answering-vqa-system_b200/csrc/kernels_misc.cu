@@ -381,7 +381,7 @@ stage_tail_kernel(const StageTailParams p) {
   float* part = red + red_rows * C;                     // [C] this CTA's channel sums (read by the cluster)
   float* sc = part + C;                                 // [C] SE scale
   float* hid = sc + C;                                  // [R]
-  float* att = hid + 64;                                // [NP] spatial attention (CS == 1)
+  float* att = hid + 256;                               // [NP] spatial attention (CS == 1)
   float* wc = att + NP;                                 // [2*ks*ks] spatial conv weights
   const bool use_se = p.w1 != nullptr;
 
@@ -1223,7 +1223,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(q.H % q.CS == 0 && (!q.mode || (q.H / q.CS) % 2 == 0) && (!q.mode || q.W % 2 == 0), VQA_E_INVALID,
                   "stage_tail: rows per CTA must be whole (and even for the phase split)");
       VQA_REQUIRE(q.wconv == nullptr || q.CS == 1, VQA_E_INVALID, "stage_tail: spatial attention needs the whole image (CS = 1)");
-      VQA_REQUIRE(q.R <= 64 && (q.w1 == nullptr) == (q.w2 == nullptr), VQA_E_INVALID, "stage_tail: bad SE weights");
+      VQA_REQUIRE(q.R <= 256 && (q.w1 == nullptr) == (q.w2 == nullptr), VQA_E_INVALID, "stage_tail: SE hidden width > 256");
       VQA_REQUIRE(q.Po > 0 && q.RPIo % q.Po == 0, VQA_E_INVALID, "stage_tail: bad destination grid");
       const int NP = q.H / q.CS * q.W, lanes = kTailThreads / q.C8;
       const int part_rows = lanes / (q.C8 < 32 ? 32 / q.C8 : 1);
@@ -1232,7 +1232,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= red_rows * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
       VQA_REQUIRE(q.ks >= 0 && 2 * q.ks * q.ks <= 128, VQA_E_INVALID, "stage_tail: spatial kernel too large");
       const bool f32 = I[STAGE_TAIL_I_f32] != 0;
-      const size_t smem = static_cast<size_t>(NP) * C * (f32 ? 4 : 2) + sizeof(float) * (static_cast<size_t>(red_rows) * C + 2 * C + 64 + NP + 128);
+      const size_t smem = static_cast<size_t>(NP) * C * (f32 ? 4 : 2) + sizeof(float) * (static_cast<size_t>(red_rows) * C + 2 * C + 256 + NP + 128);
       VQA_REQUIRE(smem <= 227 * 1024, VQA_E_INVALID, "stage_tail: rows per CTA exceed shared memory (raise CS)");
       static bool attr_set = false;
       if (!attr_set) {
