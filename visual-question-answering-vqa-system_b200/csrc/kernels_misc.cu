@@ -769,10 +769,12 @@ constexpr int kAttnWarps = 4;
 // registers on the accumulator fragments.  CUDA-core versions measured 2-4x slower (lane per key: shuffle
 // bound, 57 us for the cross attention of 256 pairs; lane per query: LDS.128 broadcast bound, 69 us; this
 // kernel 31 us).  NT = key tiles of 8.
+// x = hi + lo with both parts exact tf32 values: hi keeps the top 19 bits (truncation), x - hi is exact in fp32 and
+// is truncated again (loses < 2^-21 |x|).  Three ALU instructions; cvt.rna.tf32.f32 is emulated on sm_100a (~5
+// instructions each) and made the splits half of this kernel's instruction count (ncu source view).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xFFFFE000u;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
