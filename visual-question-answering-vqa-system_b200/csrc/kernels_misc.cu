@@ -706,9 +706,12 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
                                     const float* __restrict__ pos, int rows, int ld, int mode, int rnd, int S, int Pg,
                                     int RPIg, float eps) {
   pdl_launch_dependents();
-  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // gamma / beta are weights: fetch them before waiting for the kernel that produces the rows
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 32 + lane);
+  pdl_wait();
   if (row >= rows) return;
   size_t srow = row;
   int pix = 0;
@@ -728,8 +731,6 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
 #pragma unroll
   for (int k = 0; k < 8; ++k) { v[k] -= mean; q += v[k] * v[k]; }
   const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
-  const float4 g0 = reinterpret_cast<const float4*>(gamma)[lane], g1 = reinterpret_cast<const float4*>(gamma)[32 + lane];
-  const float4 b0 = reinterpret_cast<const float4*>(beta)[lane], b1 = reinterpret_cast<const float4*>(beta)[32 + lane];
   const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
   const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float y[8];
@@ -994,6 +995,7 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
                     float* __restrict__ fused, float* __restrict__ att_pooled, float* __restrict__ txt_pooled,
                     float* __restrict__ cat, int L, int phase, int no_round, float eps) {
   pdl_launch_dependents();
+  const float gam = __ldg(gamma + threadIdx.x), bet = __ldg(beta + threadIdx.x);   // weights: before the dependency wait
   pdl_wait();
   constexpr int D = 256;
   __shared__ float red[16];
@@ -1049,7 +1051,7 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
   float var = 0.f;
   for (int w = 0; w < 8; ++w) var += red[8 + w];
   var *= (1.f / D);
-  const float y = c * rsqrtf(var + eps) * gamma[d] + beta[d];
+  const float y = c * rsqrtf(var + eps) * gam + bet;
   fused[static_cast<size_t>(b) * D + d] = y;
   if (no_round == 2 && cat != nullptr)   // phases 0 / 2: fp16 copy of the fused feature = operand of the first head Linear
     reinterpret_cast<__half*>(cat)[static_cast<size_t>(b) * D + d] = __float2half_rn(y);
