@@ -700,10 +700,11 @@ class Program(OpList):
                 self.gemm(f"s{s}.b{blk}.conv1", dtype=cdt, M=g.rows, N=cout, a0=x, a0_shape=(a_rows, cin, cin),
                           groups=taps, w=f"s{s}.b{blk}.conv1.w", bias=f"s{s}.b{blk}.conv1.b", out=y, ldo=cout,
                           out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo1, MT=mt1)
-                taps2, halo2, mt2 = self._conv3x3_groups(g, cout // self.cchunk, cout, residual=True)
                 has_ds = W.items[f"s{s}.b{blk}.conv2.w"][2][1] > 9 * cout
+                taps2, halo2, mt2 = self._conv3x3_groups(g, cout // self.cchunk, cout, residual=not has_ds)
                 if has_ds:
-                    # shortcut conv1x1/stride: phase (0,0) of the block input, same flat row index
+                    # shortcut conv1x1/stride as extra K columns: phase (0,0) of the block input, same flat row index
+                    # (the identity residual as K columns too was measured: 77 -> 85 us at 64 channels, not used)
                     assert x_is_phase or cin != cout
                     taps2.append((1, 0, 0, nch_in, [halo2]))
                     self.gemm(f"s{s}.b{blk}.conv2", dtype=cdt, M=g.rows, N=cout, a0=y,
