@@ -693,7 +693,7 @@ class Program(OpList):
                         for kw in range(3):
                             pw, dj = (1, -1) if kw == 0 else ((0, 0) if kw == 1 else (1, 0))
                             taps.append((0, (ph * 2 + pw) * phase_rows + di * g.P + dj, 0, nch_in, [0]))
-                    a_rows, halo1, mt1 = 4 * phase_rows, 0, (2 if cout >= 256 and not self.tf32 else 1)   # 256-row tiles: one wave instead of 1.7
+                    a_rows, halo1, mt1 = 4 * phase_rows, 0, (2 if cout >= 128 and not self.tf32 else 1)   # 256-row tiles (s2: 55 -> 43 us, s3/s4: one wave instead of 1.7)
                 else:
                     taps, halo1, mt1 = self._conv3x3_groups(g, nch_in, cout)
                     a_rows = g.rows
