@@ -269,6 +269,37 @@ def run_b200(args):
     del g3, u8_3, ids_3, mask_3
     torch.cuda.empty_cache()
 
+    # ---- the image side cached (encode_images once), only the question side per step
+    cached_leg = None
+    if world == 1:
+        with torch.no_grad():
+            eng = model.engine()
+            cache = eng.encode_images(d_img)
+            for _ in range(2):
+                eng.answer(cache, d_ids, d_mask, top_k=5)
+            torch.cuda.synchronize()
+            gq = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gq):
+                q_out = eng.answer(cache, d_ids, d_mask, top_k=5)
+            for _ in range(3):
+                gq.replay()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(q_out[0], model(d_img, d_ids, d_mask)[0]))
+            kq = max(5, K)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(kq):
+                gq.replay()
+            c1.record()
+            torch.cuda.synchronize()
+            msq = c0.elapsed_time(c1) / kq
+        cached_leg = {"workload": "question side only against cached images (VQAModel.encode_images once, then answer): "
+                                  "text encoder + cross-attention + gate + head + top-5, 256 questions per step",
+                      "ms_per_step": msq, "questions_per_sec": B / (msq * 1e-3), "cache_bytes_per_image": cache.nbytes // B,
+                      "logits_bit_identical_to_forward": same}
+        del gq, cache, q_out
+        torch.cuda.empty_cache()
+
     # ---- end to end from host buffers through the predict API's batch path (uint8 HWC -> top-5):
     # pinned host buffers -> H2D -> GPU normalise + forward + softmax/top-k -> D2H, all inside the timed region
     from vqa_b200.inference import VQAInference
@@ -448,11 +479,12 @@ def run_b200(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "seq_len": L,
-                           "precision": "bf16 backbone operands / tf32 text+fusion+head, fp32 accumulate",
+                           "precision": "bf16 backbone operands / fp16 text+fusion+head operands, fp32 accumulate",
                            "parallelism": f"batch-sharded x{world}, weights broadcast once",
                            "l2": "inputs 154 MB/GPU (fp32 NCHW) exceed the 126 MB L2; no flush needed",
                            "launch": "one forward captured in a CUDA graph (87 kernels, programmatic dependent launch), replayed per step"},
                 "roofline": roof, "cpu_baseline": cpu, "parity": parity, "config3_batch1024_u8": config3,
+                "cached_image_side": cached_leg,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K, "h2d_pinned_copy_gbps": h2d_gbps,
                         "path": "VQAInference.predict_tensors_pipelined: pinned uint8 HWC + ids + mask -> H2D (copy "

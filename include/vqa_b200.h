@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 5
+#define VQA_ABI_VERSION 6
 
 #define VQA_OK            0
 #define VQA_E_INVALID    -1   /* bad argument / unsupported shape */
@@ -109,6 +109,18 @@ void vqa_plan_destroy(VqaPlan* plan);
 int vqa_resize_bilinear_u8(const uint8_t* src, int32_t in_h, int32_t in_w, int32_t channels, uint8_t* tmp, uint8_t* dst,
                            int32_t out_h, int32_t out_w, const int32_t* bounds_h, const int32_t* kk_h, int32_t ksize_h,
                            const int32_t* bounds_v, const int32_t* kk_v, int32_t ksize_v, void* stream);
+
+/* Fused top-1 / top-k accuracy accumulation.  Replaces VQAAccuracy.update's argmax + topk(5) +
+ * .cpu() + .item() per batch (utils/metrics.py:56-105, called from training/evaluate.py:77-106 and
+ * training/train.py:229-264).  Give either logits (fp32 [batch, num_classes], row pitch ld) or pred_in (int64
+ * [batch], the 1-D form of update(): top-1 only); targets int64 [batch] (a target outside [0, num_classes) is never
+ * correct but counts in the total).  counters = uint64[3] in device memory {top-1 correct, top-k correct, total},
+ * ADDED to (zero them to reset).  pred_out (int64 [batch], argmax with ties to the lower index) and rank_out (int32
+ * [batch], rank of the target's logit in its row, num_classes for an invalid target) may be NULL.  All pointers are
+ * device pointers; one launch, no synchronisation. */
+int vqa_accuracy_update(const float* logits, int32_t ld, int32_t num_classes, const int64_t* pred_in,
+                        const int64_t* targets, int32_t batch, int32_t k, uint64_t* counters, int64_t* pred_out,
+                        int32_t* rank_out, void* stream);
 
 /* counters (process-wide): kernels launched by this library since load */
 uint64_t vqa_launch_count(void);

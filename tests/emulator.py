@@ -383,11 +383,14 @@ class Emulator:
         ext[op.p["probs"].slot].view(B, k).copy_(probs)
 
 
-def run_program(prog: P.Program, images, ids, mask, top_k=0, tf32_truncate=True):
-    """Run a CPU-resident program; returns (logits, ext list)."""
+def run_program(prog: P.Program, images, ids, mask, top_k=0, tf32_truncate=True, extra=None):
+    """Run a CPU-resident program; returns (logits, ext list).  ``extra``: {slot name: flat tensor} for further
+    external slots (the cached K/V of a question-side program)."""
     B = prog.B
     NA = prog.cfg["num_answers"]
-    ext = [None] * 6
+    ext = [None] * len(P.EXT)
+    for name, t in (extra or {}).items():
+        ext[P.EXT[name]] = t
     ext[P.EXT["images"]] = images
     ext[P.EXT["ids"]] = ids
     ext[P.EXT["mask"]] = mask

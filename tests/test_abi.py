@@ -23,7 +23,8 @@ def test_exports_every_declared_symbol(lib):
     names = set(re.findall(r"\b(vqa_[a-z_0-9]+)\s*\(", header))
     assert {"vqa_plan_create", "vqa_plan_run", "vqa_plan_run_range", "vqa_plan_destroy", "vqa_last_error",
             "vqa_abi_version", "vqa_device_check", "vqa_op_num_fields", "vqa_launch_count",
-            "vqa_plan_num_launches", "vqa_plan_op_kernel_name", "vqa_resize_bilinear_u8"} <= names
+            "vqa_plan_num_launches", "vqa_plan_op_kernel_name", "vqa_resize_bilinear_u8",
+            "vqa_accuracy_update"} <= names
     for n in names:
         assert hasattr(lib, n), n
     assert lib.vqa_abi_version() == R.ABI_VERSION

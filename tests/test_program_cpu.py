@@ -93,3 +93,45 @@ def test_weight_folding_is_exact_in_fp32():
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
     m = P._stem_matrix(torch.arange(64 * 3 * 49, dtype=torch.float32).view(64, 3, 7, 7))
     assert m.shape == (64, 256) and int((m != 0).sum()) == 64 * 147 - 1   # every tap placed once (one weight is 0)
+
+
+def test_image_side_and_question_side_programs_compose():
+    """side="image" + side="question" (the cache that outlives a call): the image-side program's K/V
+    buffers, handed to the question-side program as external slots, give exactly the logits of the whole forward; a
+    cached image reused for several questions and a per-question gather of cache rows do too."""
+    torch.manual_seed(0)
+    ctor = dict(max_question_length=16, num_transformer_layers=1, vocab_size=300, num_answers=40)
+    model = VQAModel(**ctor).eval()
+    sd = randomise_state(model.state_dict(), 1)
+    u8, img, ids, mask = synth_batch(4, 77, max_len=16, vocab=300)
+    W = P.build_weights(sd, model.config, "cpu")
+    whole = P.Program(W, model.config, 4, 16, "nchw_f32", P.MASK_I64, top_k=0, device="cpu", n_images=2)
+    want, _ = E.run_program(whole, img[:2], ids, mask)
+
+    image_side = P.Program(W, model.config, 2, 16, "nchw_f32", P.MASK_NONE, top_k=0, device="cpu", n_images=2, side="image")
+    kinds = [op.kind for op in image_side.ops]
+    assert kinds[0] == "ingest" and "embed" not in kinds and "cross_attn" not in kinds and "self_attn" not in kinds
+    assert all(op.lane == 0 for op in image_side.ops)
+    E.Emulator(image_side).run([img[:2]] + [None] * (len(P.EXT) - 1))
+    n_layers = image_side.n_cross_layers
+    assert n_layers == 2
+    kv = [image_side.tensor(f"x.{l}.kv").clone() for l in range(n_layers)]          # [2 * 49, 512] fp32 per layer
+    assert kv[0].shape == (2 * 49, 512)
+
+    question_side = P.Program(W, model.config, 4, 16, "nchw_f32", P.MASK_I64, top_k=0, device="cpu", n_images=2,
+                              side="question")
+    kinds = [op.kind for op in question_side.ops]
+    assert "ingest" not in kinds and "stage_tail" not in kinds and kinds.count("cross_attn") == 2
+    assert all(op.lane == 0 for op in question_side.ops)
+    assert all(isinstance(op.p["kv"], P.ExtRef) for op in question_side.ops if op.kind == "cross_attn")
+    got, _ = E.run_program(question_side, None, ids, mask, extra={f"kv{l}": kv[l].view(-1) for l in range(n_layers)})
+    assert torch.equal(got, want)
+
+    # per-question gather: questions 0..3 ask about images 1, 0, 0, 1
+    pick = torch.tensor([1, 0, 0, 1])
+    gathered = {f"kv{l}": kv[l].view(2, 49 * 512)[pick].reshape(-1) for l in range(n_layers)}
+    q4 = P.Program(W, model.config, 4, 16, "nchw_f32", P.MASK_I64, top_k=0, device="cpu", n_images=4, side="question")
+    got4, _ = E.run_program(q4, None, ids, mask, extra=gathered)
+    ref4 = P.Program(W, model.config, 4, 16, "nchw_f32", P.MASK_I64, top_k=0, device="cpu")
+    want4, _ = E.run_program(ref4, img[:2][pick], ids, mask)
+    assert torch.equal(got4, want4)

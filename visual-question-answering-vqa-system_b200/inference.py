@@ -15,7 +15,9 @@ whole launch sequence is captured once in a CUDA graph and replayed (batch-1 lat
 """
 from __future__ import annotations
 
+import hashlib
 import os
+from collections import OrderedDict
 from io import BytesIO
 from typing import Dict, List, Optional, Tuple, Union
 
@@ -49,7 +51,7 @@ def get_device() -> str:
 class VQAInference:
     def __init__(self, checkpoint_path: Optional[str] = None, device: Optional[str] = None,
                  question_vocab_path: Optional[str] = None, answer_vocab_path: Optional[str] = None,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, image_cache_size: int = 0):
         self.device = device or get_device()
         self.checkpoint_path = checkpoint_path or DEFAULT_CHECKPOINT
         self.question_vocab_path = question_vocab_path or DEFAULT_QUESTION_VOCAB
@@ -62,6 +64,11 @@ class VQAInference:
         self.gpu_resize = True      # PIL-exact resize of non-224x224 inputs on the device
         self._graphs: Dict[Tuple[int, int], dict] = {}
         self._is_loaded = False
+        # LRU of per-image K/V entries (200 KB each) keyed by image content; 0 = off (reference behaviour:
+        # every call recomputes the image side)
+        self.image_cache_size = int(image_cache_size)
+        self._image_cache: "OrderedDict[tuple, object]" = OrderedDict()
+        self.cache_hits = self.cache_misses = 0
 
     # ------------------------------------------------------------------ loading
     def load(self):
@@ -269,10 +276,67 @@ class VQAInference:
         return {"question": question, "answers": answers, "top_answer": answers[0]["answer"],
                 "confidence": answers[0]["probability"]}
 
+    # ------------------------------------------------------------------ image cache
+    @staticmethod
+    def image_key(image: ImageLike) -> tuple:
+        """Content key of an input image: file identity for paths, SHA-1 of the bytes / pixels otherwise."""
+        if isinstance(image, str):
+            st = os.stat(image)
+            return ("path", os.path.abspath(image), st.st_mtime_ns, st.st_size)
+        if isinstance(image, (bytes, bytearray)):
+            return ("bytes", hashlib.sha1(image).hexdigest())
+        h = hashlib.sha1(f"{image.mode}|{image.size}".encode())
+        h.update(image.tobytes())
+        return ("pil", h.hexdigest())
+
+    @torch.no_grad()
+    def encode_image(self, image: ImageLike):
+        """Backbone + projector + cross-attention K/V of one image (an ``engine.ImageCache`` of one entry).  With
+        ``image_cache_size > 0`` entries are kept in an LRU keyed by ``image_key`` and reused across calls."""
+        if not self._is_loaded:
+            self.load()
+        key = self.image_key(image) if self.image_cache_size > 0 else None
+        if key is not None and key in self._image_cache:
+            self._image_cache.move_to_end(key)
+            self.cache_hits += 1
+            return self._image_cache[key]
+        u8 = self.preprocess_image_u8(image).unsqueeze(0).to(self.device, non_blocking=True)
+        entry = self.model.encode_images(u8)
+        if key is not None:
+            self.cache_misses += 1
+            self._image_cache[key] = entry
+            while len(self._image_cache) > self.image_cache_size:
+                self._image_cache.popitem(last=False)
+        return entry
+
+    @torch.no_grad()
+    def answer(self, cache, questions: List[str], top_k: int = DEFAULT_TOP_K) -> List[Dict]:
+        """Questions against encoded images: ``cache`` is what ``encode_image`` returned (or an ``ImageCache`` of n
+        entries with ``len(questions) % n == 0``: entry i answers the next len(questions) / n questions).  Only the text
+        encoder, the cross-attention, the gate and the head run; results equal ``predict`` on the same image."""
+        if not self._is_loaded:
+            self.load()
+        if not questions:
+            return []
+        pairs = [self.preprocess_question(q) for q in questions]
+        ids = torch.cat([p[0] for p in pairs], dim=0).to(self.device, non_blocking=True)
+        mask = torch.cat([p[1] for p in pairs], dim=0).to(self.device, non_blocking=True)
+        k = min(top_k, self.model.num_answers)
+        _, idx, probs = self.model.engine().answer(cache, ids, mask, top_k=k)
+        idx, probs = idx.cpu(), probs.cpu()
+        return [self._format(q, idx[i].tolist(), probs[i].tolist()) for i, q in enumerate(questions)]
+
+    def cache_info(self) -> Dict:
+        return {"size": len(self._image_cache), "capacity": self.image_cache_size, "hits": self.cache_hits,
+                "misses": self.cache_misses,
+                "bytes": sum(e.nbytes for e in self._image_cache.values())}
+
     @torch.no_grad()
     def predict(self, image: ImageLike, question: str, top_k: int = DEFAULT_TOP_K) -> Dict:
         if not self._is_loaded:
             self.load()
+        if self.image_cache_size > 0:       # image side from the LRU (computed on a miss), question side per call
+            return self.answer(self.encode_image(image), [question], top_k)[0]
         u8 = self.preprocess_image_u8(image).unsqueeze(0)
         ids, mask = self.preprocess_question(question)
         idx, probs = self._run(u8, ids, mask, top_k)

@@ -105,6 +105,22 @@ class VQAModel(nn.Module):
         with torch.no_grad():
             return self.engine().predict(images, token_ids, attention_mask, top_k)
 
+    # ------------------------------------------------------------------ extension: image cache
+    def encode_images(self, images: torch.Tensor):
+        """Question-independent half of ``forward`` (backbone, projector, cross-attention K/V) for ``images``: an
+        ``ImageCache`` that can be kept across calls.  ``answer(cache, ids, mask)`` then equals ``forward`` bit for bit."""
+        if self.training:
+            raise NotImplementedError("eval-mode inference path only; call .eval()")
+        with torch.no_grad():
+            return self.engine().encode_images(images)
+
+    def answer(self, cache, token_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Logits ``[B, num_answers]`` of ``token_ids`` asked about the cached images (``cache.n_images`` divides B)."""
+        if self.training:
+            raise NotImplementedError("eval-mode inference path only; call .eval()")
+        with torch.no_grad():
+            return self.engine().answer(cache, token_ids, attention_mask)[0]
+
     def get_attention_maps(self, images, token_ids, attention_mask=None) -> Dict[str, torch.Tensor]:
         _, aux = self.forward(images, token_ids, attention_mask, return_aux=True)
         vis = self.fusion.get_attention_visualization(

@@ -84,6 +84,9 @@ MASK_NONE, MASK_I64, MASK_F32, MASK_I32, MASK_U8 = 0, 1, 2, 3, 4
 
 # external slots (order of the ext[] array given to vqa_plan_run)
 EXT = {"images": 0, "ids": 1, "mask": 2, "logits": 3, "top_idx": 4, "top_probs": 5}
+MAX_CACHED_LAYERS = 8
+# K/V of a cached image side (question-side programs): one slot per cross-attention layer
+EXT.update({f"kv{l}": 6 + l for l in range(MAX_CACHED_LAYERS)})
 
 
 def generate_fields_header() -> str:
@@ -559,11 +562,20 @@ class Program(OpList):
 
     def __init__(self, weights: Weights, cfg: dict, B: int, L: int, in_fmt: str = "nchw_f32",
                  mask_dtype: int = MASK_I64, want_aux: bool = False, top_k: int = 0, device=None,
-                 window: bool = True, n_images: Optional[int] = None):
+                 window: bool = True, n_images: Optional[int] = None, side: str = "both"):
         """``n_images`` (default B): the image side runs on n_images images and every image answers B / n_images
         consecutive questions (BASELINE config "one image, many questions": backbone, projector and the K/V
-        projections of both cross-attention layers run once per image)."""
+        projections of both cross-attention layers run once per image).
+
+        ``side`` splits the forward at the only place the two modalities meet, the cross-attention K/V
+        (models/cross_attention.py:160-161,286-287 recompute them per pair although they do not depend on the question):
+        "image" = ingest .. backbone .. projector .. K/V projections of every layer (the per-image cache entry, buffers
+        ``x.{l}.kv``); "question" = text encoder, cross-attention against K/V given as external slots ``kv{l}``, gate,
+        head; "both" = the whole forward in one op list."""
         super().__init__(weights, device, window)
+        assert side in ("both", "image", "question"), side
+        self.side = side
+        assert not (want_aux and side != "both"), "aux outputs need the whole forward"
         self.cfg = cfg
         self.B, self.L = B, L
         self.Bi = B if n_images is None else int(n_images)
@@ -579,6 +591,9 @@ class Program(OpList):
     def _build(self):
         B, L, W, cfg = self.Bi, self.L, self.W, self.cfg   # B = images on this side of the program
         bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+        if self.side == "question":
+            self._build_text_fusion(None, None)
+            return
 
         # ================= image side =================
         tf = self.tf32
@@ -759,12 +774,41 @@ class Program(OpList):
             nchw = self._buf("aux.image_features", f32, B, 512, 7, 7)
             self._op("grid_to_nchw", "aux.image_features", dict(B=B, C=512, H=7, W=7, P=gf.P, RPI=gf.rpi, f32=int(self.tf32)),
                      dict(src=feat, dst=nchw))
+        self._build_text_fusion(feat, gf)
 
-        # ================= text side (independent of the image side: runs on the side stream) =================
+    def _build_text_fusion(self, feat, gf):
+        L, W, cfg = self.L, self.W, self.cfg
+        bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
         Bi, B = self.Bi, self.B                    # from here on B = (image, question) pairs
-        self.lane = 1
         D, H, F = cfg["embed_dim"], cfg["num_attention_heads"], cfg["ffn_hidden_dim"]
         T = B * L
+        S = 7
+        TI = Bi * S * S
+        n_layers = 0
+        while f"x.{n_layers}.q.w" in W:
+            n_layers += 1
+        self.n_cross_layers = n_layers
+        if self.side == "image":
+            # the cache entry of these images: projector + LayerNorm + position, then K/V of every cross-attention layer
+            praw = self._buf("proj.raw", f32, gf.rows, D)
+            self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
+                      groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
+            img = self._buf("image_projected", f32, TI, D)
+            self._op("layernorm", "proj.ln", dict(rows=TI, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
+                     dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos")),
+                     dict(eps=1e-5))
+            for l in range(n_layers):
+                imn = self._buf(f"x.{l}.imgn", self.tdt, TI, D)
+                kv = self._buf(f"x.{l}.kv", f32, TI, 2 * D)
+                self.layernorm(f"x.{l}.lnkv", img, f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imn, TI, rnd=True)
+                self.linear(f"x.{l}.kv", imn, TI, D, f"x.{l}.kv.w", None, kv, 2 * D)
+            return
+        cached = self.side == "question"
+        if cached and n_layers > MAX_CACHED_LAYERS:
+            raise NotImplementedError(f"cached image side supports up to {MAX_CACHED_LAYERS} cross-attention layers")
+
+        # ================= text side (independent of the image side: runs on the side stream) =================
+        self.lane = 0 if cached else 1             # question-side programs are a single chain: one lane
         mask = None
         if self.mask_dtype != MASK_NONE:
             mask = self._buf("mask_i32", i32, B, L)
@@ -799,35 +843,34 @@ class Program(OpList):
         # projected image); the main lane runs projector -> K/V of layer 0 -> attention / FFN chain and joins the
         # side lane right before each attention.  Ops are issued in list order, so a JOIN waits only for what
         # precedes it in the list.
-        S = 7
-        TI = Bi * S * S
-        n_layers = 0
-        while f"x.{n_layers}.q.w" in W:
-            n_layers += 1
         q = self._buf("x.q", f32, T, D)          # running query (residual stream)
         qn = self._buf("x.qn", self.tdt, T, D)
         qp = self._buf("x.qp", f32, T, D)
         cx = self._buf("x.ctx", self.tdt, T, D)
-        imns = [self._buf(f"x.{l}.imgn", self.tdt, TI, D) for l in range(n_layers)]
-        kvs = [self._buf(f"x.{l}.kv", f32, TI, 2 * D) for l in range(n_layers)]
+        if cached:
+            imns, kvs = [], [ExtRef(EXT[f"kv{l}"]) for l in range(n_layers)]
+        else:
+            imns = [self._buf(f"x.{l}.imgn", self.tdt, TI, D) for l in range(n_layers)]
+            kvs = [self._buf(f"x.{l}.kv", f32, TI, 2 * D) for l in range(n_layers)]
         if n_layers:                              # side lane: LN_q + W_q of layer 0
             qn0 = self._buf("x.0.qn", self.tdt, T, D)
             self.layernorm("x.0.lnq", text, "x.0.lnq.g", "x.0.lnq.b", qn0, T, rnd=True)
             self.linear("x.0.q", qn0, T, D, "x.0.q.w", None, qp, D)
         self.lane = 0
-        praw = self._buf("proj.raw", f32, gf.rows, D)
-        self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
-                  groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
-        img = self._buf("image_projected", f32, Bi * S * S, D)
-        self._op("layernorm", "proj.ln", dict(rows=Bi * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
-                 dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos")),
-                 dict(eps=1e-5))
+        if not cached:
+            praw = self._buf("proj.raw", f32, gf.rows, D)
+            self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
+                      groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
+            img = self._buf("image_projected", f32, Bi * S * S, D)
+            self._op("layernorm", "proj.ln", dict(rows=Bi * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
+                     dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos")),
+                     dict(eps=1e-5))
 
         def kv_proj(l):
             self.layernorm(f"x.{l}.lnkv", img, f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imns[l], TI, rnd=True)
             self.linear(f"x.{l}.kv", imns[l], TI, D, f"x.{l}.kv.w", None, kvs[l], 2 * D)
 
-        if n_layers:
+        if n_layers and not cached:
             kv_proj(0)
         src_q = text
         self.xattn_weights = []
@@ -843,8 +886,9 @@ class Program(OpList):
             self._op("cross_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, T=S * S, ld_q=D, ld_kv=2 * D, k_off=0, v_off=D,
                                                      no_round=self.out_mode, q_per_kv=B // Bi),
                      dict(q=qp, kv=kvs[layer], out=cx, weights=wts))
-            self.ops[-1].lane |= LANE_JOIN        # needs the side lane's q (layer 0) / K,V (layers >= 1)
-            if layer == 0 and n_layers > 1:       # side lane: K/V of every later layer, concurrent with this layer's chain
+            if not cached:
+                self.ops[-1].lane |= LANE_JOIN    # needs the side lane's q (layer 0) / K,V (layers >= 1)
+            if layer == 0 and n_layers > 1 and not cached:   # side lane: K/V of every later layer, concurrent with this layer's chain
                 self.lane = 1
                 first = len(self.ops)
                 for l in range(1, n_layers):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqa_b200.so")
 
 OP_NI, OP_NP, OP_NF = 144, 12, 4
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class VqaOp(C.Structure):
@@ -53,6 +53,8 @@ def lib():
     L.vqa_resize_bilinear_u8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_void_p]
+    L.vqa_accuracy_update.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.vqa_abi_version() != ABI_VERSION:
         raise VqaError(f"libvqa_b200.so ABI {L.vqa_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     for kind, code in P.KINDS.items():  # both sides of the op field tables must agree
@@ -155,6 +157,46 @@ def resize_bilinear_u8(src, out_h: int = 224, out_w: int = 224, stream=None):
             if t is not None:
                 t.record_stream(st)
     return dst
+
+
+def accuracy_update(predictions, targets, counters, k: int = 5, pred_out=None, rank_out=None, stream=None):
+    """``vqa_accuracy_update``: add this batch's top-1 / top-k hits and row count to ``counters`` (uint64-as-int64 [3]
+    CUDA tensor).  ``predictions``: fp32 logits [B, N] or int64 indices [B]."""
+    import torch
+    if predictions.device.type != "cuda" or targets.device != predictions.device or counters.device != predictions.device:
+        raise VqaError("accuracy_update expects CUDA tensors on one device (there is no CPU path)")
+    if counters.dtype != torch.int64 or counters.numel() != 3 or not counters.is_contiguous():
+        raise VqaError("counters must be a contiguous int64 [3] tensor")
+    if targets.dtype != torch.int64 or targets.dim() != 1:
+        raise VqaError("targets must be int64 [B]")
+    targets = targets.contiguous()
+    B = targets.shape[0]
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    st = stream if stream is not None else torch.cuda.current_stream(predictions.device)
+    if predictions.dim() == 2:
+        if predictions.dtype != torch.float32:
+            predictions = predictions.float()
+        if predictions.stride(1) != 1:
+            predictions = predictions.contiguous()
+        if predictions.shape[0] != B:
+            raise ValueError("predictions and targets disagree on the batch size")
+        lg, ld, N, pi = predictions, predictions.stride(0) if B > 1 else predictions.shape[1], predictions.shape[1], None
+    elif predictions.dim() == 1:
+        if predictions.shape[0] != B:
+            raise ValueError("predictions and targets disagree on the batch size")
+        lg, ld, N, pi = None, 0, 1, predictions.long().contiguous()
+    else:
+        raise ValueError("predictions must be logits [B, N] or indices [B]")
+    for t, dt in ((pred_out, torch.int64), (rank_out, torch.int32)):
+        if t is not None and (t.dtype != dt or t.numel() < B or not t.is_contiguous() or t.device != targets.device):
+            raise VqaError("pred_out must be int64 [B], rank_out int32 [B], contiguous, on the same device")
+    with torch.cuda.stream(st):
+        check(lib().vqa_accuracy_update(ptr(lg), int(ld), int(N), ptr(pi), ptr(targets), B, int(k), ptr(counters),
+                                        ptr(pred_out), ptr(rank_out), C.c_void_p(st.cuda_stream)))
+    if not torch.cuda.is_current_stream_capturing():
+        for t in (lg, pi, targets):
+            if t is not None:
+                t.record_stream(st)
 
 
 def launch_count() -> int:
