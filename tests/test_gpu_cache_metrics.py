@@ -130,7 +130,7 @@ def test_accuracy_kernel_matches_reference_update(B, N):
     accuracy_update(logits.cuda(), targets.cuda(), counters, k=5)          # counters accumulate
     assert counters.tolist() == [2 * want1, 2 * want5, 2 * B]
     assert torch.equal(pred.cpu(), logits.argmax(-1))
-    order = logits.argsort(-1, descending=True, stable=True)
+    order = logits.argsort(dim=-1, descending=True, stable=True)
     want_rank = torch.where(targets >= 0, (order == targets.unsqueeze(1)).float().argmax(-1), torch.full_like(targets, N))
     assert torch.equal(rank.cpu().long(), want_rank)
 

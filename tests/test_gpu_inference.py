@@ -66,14 +66,21 @@ def test_predict_batch_and_resize(engine):
     assert info["num_answers"] == 1000 and info["vocab_size"] == 13 and info["parameters"]["total"] == 19310316
 
 
-def test_pipelined_throughput_path_matches_single_calls(engine):
+@pytest.mark.parametrize("lanes,graph", [(2, True), (1, True), (2, False)])
+def test_pipelined_throughput_path_matches_single_calls(engine, lanes, graph):
+    """Two compute lanes (own stream + own plan workspace each) overlap consecutive batches; results must come back in
+    order and equal the one-call path bit for bit, also when slots and lanes are reused (11 batches over 4 slots)."""
     from vqa_b200.synth import synth_batch
+    engine.pipeline_lanes, engine.use_cuda_graph = lanes, graph
     batches = []
-    for i in range(5):
+    for i in range(11):
         u8, _, ids, mask = synth_batch(6, 50 + i)
         batches.append((u8.pin_memory(), ids.pin_memory(), mask.pin_memory()))
     outs = list(engine.predict_tensors_pipelined(batches, top_k=4))
-    assert len(outs) == 5
+    assert len(outs) == 11
+    outs2 = list(engine.predict_tensors_pipelined(batches[::-1], top_k=4))      # second call reuses the captured slots
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(outs, outs2[::-1]))
+    engine.pipeline_lanes = 2
     engine.use_cuda_graph = False
     for (u8, ids, mask), (idx, probs) in zip(batches, outs):
         ridx, rprobs = engine._run(u8, ids, mask, 4)

@@ -59,9 +59,11 @@ class Engine:
 
     # ------------------------------------------------------------------ plans
     def plan_for(self, B: int, L: int, in_fmt: str, mask_dtype: int, want_aux: bool, top_k: int, n_images: int = 0,
-                 side: str = "both"):
+                 side: str = "both", slot: int = 0):
+        """``slot``: plans with different slot numbers have their own workspace, so forwards issued on different
+        streams may overlap on the GPU (the pipelined predict path runs two)."""
         n_images = n_images or B
-        key = (B, L, in_fmt, mask_dtype, want_aux, top_k, self.window, n_images, side)
+        key = (B, L, in_fmt, mask_dtype, want_aux, top_k, self.window, n_images, side, slot)
         hit = self._plans.get(key)
         if hit is None:
             if L > self.cfg["max_question_length"]:
@@ -172,7 +174,7 @@ class Engine:
         return logits, top_idx, top_p
 
     def run(self, images: torch.Tensor, token_ids: torch.Tensor, attention_mask: Optional[torch.Tensor],
-            want_aux: bool = False, top_k: int = 0):
+            want_aux: bool = False, top_k: int = 0, slot: int = 0):
         """Launch the forward on the current stream.  Returns (logits, top_idx, top_probs, program)."""
         if images.device != self.device or token_ids.device != self.device:
             raise VqaError(f"inputs must live on {self.device} (got images on {images.device}, "
@@ -209,7 +211,7 @@ class Engine:
             if tuple(mask.shape) != (B, L):
                 raise ValueError("attention_mask must be [B, L]")
             mask = mask.contiguous()
-        prog, plan = self.plan_for(B, L, in_fmt, code, want_aux, top_k, Bi)
+        prog, plan = self.plan_for(B, L, in_fmt, code, want_aux, top_k, Bi, slot=slot)
         NA = self.cfg["num_answers"]
         logits = torch.empty(B, NA, dtype=torch.float32, device=self.device)
         top_idx = torch.empty(B, max(top_k, 1), dtype=torch.int64, device=self.device)
@@ -246,6 +248,6 @@ class Engine:
         }
         return logits, aux
 
-    def predict(self, images, token_ids, attention_mask=None, top_k=5):
-        _, idx, probs, _ = self.run(images, token_ids, attention_mask, top_k=top_k)
+    def predict(self, images, token_ids, attention_mask=None, top_k=5, slot: int = 0):
+        _, idx, probs, _ = self.run(images, token_ids, attention_mask, top_k=top_k, slot=slot)
         return idx, probs

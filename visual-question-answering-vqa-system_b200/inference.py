@@ -61,6 +61,7 @@ class VQAInference:
         self.answer_vocab: Optional[AnswerVocabulary] = None
         self.transform = None
         self.use_cuda_graph = use_cuda_graph
+        self.pipeline_lanes = 2     # concurrent forwards in predict_tensors_pipelined (each lane: own stream + plan workspace)
         self.gpu_resize = True      # PIL-exact resize of non-224x224 inputs on the device
         self._graphs: Dict[Tuple[int, int], dict] = {}
         self._is_loaded = False
@@ -204,18 +205,25 @@ class VQAInference:
     @torch.no_grad()
     def predict_tensors_pipelined(self, batches, top_k: int = DEFAULT_TOP_K):
         """Throughput path: iterate over host batches ``(u8 [B,224,224,3], ids [B,L], mask [B,L])`` (ideally
-        pinned) and yield ``(top_idx, top_probs)`` host tensors in order.  The host-to-device copy of batch
-        i+1 runs on a copy stream while batch i computes (inputs are double buffered; the engine's
-        workspace is shared because compute is serialised on one stream), and each result comes back in
-        one small device-to-host copy."""
+        pinned) and yield ``(top_idx, top_probs)`` host tensors in order.
+
+        ``pipeline_lanes`` compute lanes (default 2) run on their own streams with their own plan workspace, so the
+        forward of batch i+1 overlaps the forward of batch i on the GPU: the small launch-latency-bound kernels of one
+        batch's text / fusion / head path and the last, partially filled wave of each persistent convolution leave SMs
+        idle that the other batch's kernels fill.  Inputs go through ``2 * lanes`` device slots filled by a copy stream
+        (the host-to-device copy of a later batch runs while earlier ones compute); each slot's forward is captured in
+        its own CUDA graph; each result comes back in one small device-to-host copy."""
         if not self._is_loaded:
             self.load()
         dev = torch.device(self.device)
-        copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        lanes = max(1, int(getattr(self, "pipeline_lanes", 2)))
+        n_slots = 2 * lanes
+        if not hasattr(self, "_pipe_streams") or len(self._pipe_streams[1]) != lanes:
+            self._pipe_streams = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev) for _ in range(lanes)])
+            self._pipe_slots = {}       # (B, L, k) -> input/output slots with their captured graphs (kept across calls)
+        copy_s, comp = self._pipe_streams
         k = min(top_k, self.model.num_answers)
         engine = self.model.engine()
-        if not hasattr(self, "_pipe_slots"):
-            self._pipe_slots = {}       # (B, L, k) -> two input/output slots with their captured graphs (kept across calls)
         pending = []   # (done_event, h_idx, h_probs)
 
         def drain(n_keep):
@@ -226,8 +234,11 @@ class VQAInference:
 
         for i, (u8, ids, mask) in enumerate(batches):
             B, L = ids.shape
-            slots = self._pipe_slots.setdefault((B, L, k), [None, None])
-            sl = slots[i & 1]
+            slots = self._pipe_slots.setdefault((B, L, k), [None] * n_slots)
+            j = i % n_slots
+            lane = j % lanes
+            comp_s = comp[lane]
+            sl = slots[j]
             if sl is None:
                 sl = {"shape": (B, L),
                       "d_u8": torch.empty(B, 224, 224, 3, dtype=torch.uint8, device=dev),
@@ -236,7 +247,7 @@ class VQAInference:
                       "h_idx": torch.empty(B, k, dtype=torch.long).pin_memory(),
                       "h_probs": torch.empty(B, k, dtype=torch.float32).pin_memory(),
                       "copied": torch.cuda.Event(), "free": None}
-                slots[i & 1] = sl
+                slots[j] = sl
             with torch.cuda.stream(copy_s):
                 if sl["free"] is not None:
                     copy_s.wait_event(sl["free"])          # the forward that last read this slot has finished
@@ -248,16 +259,16 @@ class VQAInference:
                 comp_s.wait_event(sl["copied"])
                 if self.use_cuda_graph:
                     if sl.get("graph") is None:             # capture this slot's forward once (static buffers)
-                        engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k)   # builds the plan, loads kernels
-                        comp_s.synchronize()
+                        engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k, slot=lane)   # builds the plan, loads kernels
+                        torch.cuda.synchronize(dev)
                         gr = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(gr, stream=comp_s):
-                            sl["idx"], sl["probs"] = engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k)
+                            sl["idx"], sl["probs"] = engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k, slot=lane)
                         sl["graph"] = gr
                     sl["graph"].replay()
                     idx, probs = sl["idx"], sl["probs"]
                 else:
-                    idx, probs = engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k)
+                    idx, probs = engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k, slot=lane)
                 sl["free"] = torch.cuda.Event()
                 sl["free"].record(comp_s)
                 sl["h_idx"].copy_(idx, non_blocking=True)
@@ -265,7 +276,7 @@ class VQAInference:
                 done = torch.cuda.Event()
                 done.record(comp_s)
             pending.append((done, sl["h_idx"], sl["h_probs"]))
-            yield from drain(1)                             # keep one batch in flight behind the current one
+            yield from drain(n_slots - 1)                   # a slot's host buffers are read before the slot is refilled
         yield from drain(0)
 
     def _format(self, question: str, idx_row, prob_row) -> Dict:
