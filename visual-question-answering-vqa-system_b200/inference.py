@@ -217,9 +217,10 @@ class VQAInference:
             self.load()
         dev = torch.device(self.device)
         lanes = max(1, int(getattr(self, "pipeline_lanes", 2)))
-        n_slots = 2 * lanes
-        if not hasattr(self, "_pipe_streams") or len(self._pipe_streams[1]) != lanes:
+        n_slots = max(lanes, int(getattr(self, "pipeline_slots", 0) or 2 * lanes))
+        if not hasattr(self, "_pipe_streams") or len(self._pipe_streams[1]) != lanes or self._pipe_nslots != n_slots:
             self._pipe_streams = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev) for _ in range(lanes)])
+            self._pipe_nslots = n_slots
             self._pipe_slots = {}       # (B, L, k) -> input/output slots with their captured graphs (kept across calls)
         copy_s, comp = self._pipe_streams
         k = min(top_k, self.model.num_answers)
