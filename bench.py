@@ -325,11 +325,12 @@ def run_b200(args):
             c1.record(cur)
             barrier()
             ms3_by[nl] = reduce_max(c0.elapsed_time(c1))
-        ms3 = ms3_by[LANES]
+        best3 = min(ms3_by, key=ms3_by.get)     # at 1024 pairs per step the small kernels are no longer latency-bound:
+        ms3 = ms3_by[best3]                       # one stream is usually as fast as several lanes here
     config3 = {"workload": "BASELINE configs[2]: uint8 HWC images + questions, 1024 pairs per GPU per step, GPU preprocessing included",
-               "global_batch": world * B3, "steps": k3, "ms_per_step": ms3 / k3, "compute_lanes": LANES,
+               "global_batch": world * B3, "steps": k3, "ms_per_step": ms3 / k3, "compute_lanes": best3,
                "pairs_per_sec": world * B3 * k3 / (ms3 * 1e-3),
-               "single_stream_pairs_per_sec": world * B3 * k3 / (ms3_by[1] * 1e-3),
+               "pairs_per_sec_by_lanes": {str(nl): world * B3 * k3 / (t * 1e-3) for nl, t in ms3_by.items()},
                "frac_of_peak": FLOP_PER_PAIR * B3 * k3 / (ms3 * 1e-3) / 1e12 / measured_peaks()["bf16_tflops_sustained"]}
     g3 = g3s
     del g3, g3s, u8_3, ids_3, mask_3
@@ -403,7 +404,7 @@ def run_b200(args):
             return reduce_max(ms_local), top_idx.clone()
 
     ms_e2e_1, idx_1 = e2e_run(1)                      # A/B: one compute lane (forwards strictly one after another)
-    ms_e2e, idx_2 = e2e_run(max(LANES, 2))                       # the API's default: two lanes, forwards of consecutive batches overlap
+    ms_e2e, idx_2 = e2e_run(2)                       # the API's default: two lanes, forwards of consecutive batches overlap
     assert torch.equal(idx_1, idx_2)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
     h2d = h_u8.numel() + h_ids.numel() * 8 + h_mask.numel() * 8
@@ -569,7 +570,7 @@ def run_b200(args):
                 "cached_image_side": cached_leg,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K, "h2d_pinned_copy_gbps": h2d_gbps,
-                        "single_lane_value": world * B * K / (ms_e2e_1 * 1e-3), "compute_lanes": max(LANES, 2),
+                        "single_lane_value": world * B * K / (ms_e2e_1 * 1e-3), "compute_lanes": 2,
                         "path": "VQAInference.predict_tensors_pipelined: pinned uint8 HWC + ids + mask -> H2D (copy "
                                 "stream, 4 device slots) -> normalise+forward+top-5 (two compute lanes: the forwards of "
                                 "consecutive batches overlap on the GPU) -> D2H; every step copies its own "
