@@ -25,6 +25,8 @@
 #include <cstdio>
 #include <type_traits>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -910,6 +912,10 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   const int fixed_bytes = 1024 + stage_bytes + 4 * kBiasTable + 8 * (2 * kMaxASlots + 2 * kMaxBSlots + 4 + kEpiWarps) + 16 +
                           4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS;
   int budget = I[GEMM_I_smem_budget];
+  if (budget <= 0) {   // experiment switch: cap the CTA's total shared memory (KB) so CTAs of other kernels can co-reside
+    static const int cap_kb = std::getenv("VQA_GEMM_SMEM_KB") ? std::atoi(std::getenv("VQA_GEMM_SMEM_KB")) : 0;
+    if (cap_kb > 0 && cap_kb * 1024 > fixed_bytes + 32 * 1024) budget = cap_kb * 1024 - fixed_bytes;
+  }
   if (budget <= 0 || budget > 227 * 1024 - fixed_bytes) budget = 227 * 1024 - fixed_bytes;
   const long long b_all = static_cast<long long>(p.k_chunks) * p.b_slot_bytes;
   p.b_resident = (p.n_tiles == 1 && b_all <= 96 * 1024 && b_all + 2LL * p.a_slot_bytes <= budget) ? 1 : 0;
