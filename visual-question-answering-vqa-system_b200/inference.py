@@ -363,6 +363,8 @@ class VQAInference:
             self.load()
         if not questions:
             return []
+        if self.image_cache_size > 0:       # image side from the LRU, question side only
+            return self.answer(self.encode_image(image), questions, top_k)
         u8 = self.preprocess_image_u8(image).unsqueeze(0).to(self.device, non_blocking=True)
         pairs = [self.preprocess_question(q) for q in questions]
         ids = torch.cat([p[0] for p in pairs], dim=0).to(self.device, non_blocking=True)
