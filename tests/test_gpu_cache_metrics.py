@@ -148,6 +148,13 @@ def test_accuracy_ties_strided_logits_and_index_form():
     c.zero_()
     accuracy_update(wide.cuda()[:, :40], t.cuda(), c, k=5)
     assert c.tolist()[:2] == list(_reference_update(wide[:, :40], t))
+    for n in (38, 5, 3):                      # 16-byte row pitch, N not a multiple of 4: vector body + scalar tail
+        c.zero_()
+        tn = t % n
+        accuracy_update(wide.cuda()[:, :n], tn.cuda(), c, k=2)
+        want1 = int((wide[:, :n].argmax(-1) == tn).sum())
+        want2 = int((wide[:, :n].topk(2, -1).indices == tn.unsqueeze(1)).any(-1).sum())
+        assert c.tolist() == [want1, want2, 9]
     # the [B] form of update(): indices, top-1 only
     c.zero_()
     accuracy_update(torch.tensor([3, 1, 2], device="cuda"), torch.tensor([3, 0, 2], device="cuda"), c)

@@ -45,10 +45,27 @@ accuracy_kernel(const float* __restrict__ logits, int ld, int N, const long long
       int above = 0;
       float best = -INFINITY;
       int bi = 0x7fffffff;
-      for (int j = lane; j < N; j += 32) {
-        const float x = v[j];
+      auto visit = [&](float x, int j) {
         above += (x > tv || (x == tv && j < ti)) ? 1 : 0;
         if (x > best || (x == best && j < bi)) { best = x; bi = j; }
+      };
+      if (((reinterpret_cast<uintptr_t>(v) | (static_cast<uintptr_t>(ld) * 4)) & 15) == 0) {
+        // 16-byte loads (row pitch and base aligned): 512 bytes per warp instruction, two in flight per lane
+        const float4* v4 = reinterpret_cast<const float4*>(v);
+        const int n4 = N >> 2;
+        int q = lane;
+        for (; q + 32 < n4; q += 64) {
+          const float4 a = __ldg(v4 + q), b = __ldg(v4 + q + 32);
+          visit(a.x, 4 * q); visit(a.y, 4 * q + 1); visit(a.z, 4 * q + 2); visit(a.w, 4 * q + 3);
+          visit(b.x, 4 * q + 128); visit(b.y, 4 * q + 129); visit(b.z, 4 * q + 130); visit(b.w, 4 * q + 131);
+        }
+        for (; q < n4; q += 32) {
+          const float4 a = __ldg(v4 + q);
+          visit(a.x, 4 * q); visit(a.y, 4 * q + 1); visit(a.z, 4 * q + 2); visit(a.w, 4 * q + 3);
+        }
+        for (int j = (n4 << 2) + lane; j < N; j += 32) visit(v[j], j);
+      } else {
+        for (int j = lane; j < N; j += 32) visit(v[j], j);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
