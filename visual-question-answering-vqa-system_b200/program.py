@@ -195,6 +195,17 @@ def _fold_bn(sd, conv_key, bn_prefix):
     return w * s.view(-1, 1, 1, 1), b
 
 
+# Stride-2 3x3 convolution over the 4-phase split, taps grouped by the phase they read (one A window per phase):
+# phase (1,1) serves (kh,kw) = (0,0),(0,2),(2,0),(2,2); phase (1,0) serves (0,1),(2,1); phase (0,1) serves (1,0),(1,2);
+# phase (0,0) serves the centre tap.  The weight matrix of the windowed form is stored in this tap order.
+PHASE_TAP_ORDER = [(0, 0), (0, 2), (2, 0), (2, 2), (0, 1), (2, 1), (1, 0), (1, 2), (1, 1)]
+
+
+def _ohwi_phase_order(w):
+    """[Cout,Cin,3,3] -> [Cout, 9*Cin] with the taps in PHASE_TAP_ORDER (K index = tap*Cin + c)."""
+    return torch.cat([w[:, :, kh, kw] for kh, kw in PHASE_TAP_ORDER], dim=1).contiguous()
+
+
 def _ohwi(w):
     """[Cout,Cin,kh,kw] -> [Cout, kh*kw*Cin] with K index = (kh*KW+kw)*Cin + c."""
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
@@ -322,6 +333,8 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device, precision: str
                 m2 = torch.cat([m2, _ohwi(wd)], dim=1)
                 b2 = b2 + bd
             W.add(f"s{s}.b{blk}.conv1.w", cast(_ohwi(w1)), cw)
+            if not tf and q + ".downsample.0.weight" in sd and tuple(w1.shape[2:]) == (3, 3) and w1.shape[0] != w1.shape[1]:
+                W.add(f"s{s}.b{blk}.conv1.wp", _ohwi_phase_order(w1), cw)     # stride-2 block entry, windowed form
             W.add(f"s{s}.b{blk}.conv1.b", b1, f32)
             W.add(f"s{s}.b{blk}.conv2.w", cast(m2), cw)
             W.add(f"s{s}.b{blk}.conv2.b", b2, f32)
@@ -414,6 +427,7 @@ class OpList:
         self.fuse_pool = window and not self.tf32
         self.fused_tail = window or self.tf32
         self.pair = window and not self.tf32
+        self.phase_windows = os.environ.get("VQA_PHASE_WINDOWS", "1") != "0"   # A/B switch for the stride-2 block entries
         self.ws = Arena(device if device is not None else weights.arena.device)
         self.ops: List[Op] = []
         self.named: Dict[str, Tuple[Buf, torch.dtype, Tuple[int, ...]]] = {}
@@ -701,6 +715,7 @@ class Program(OpList):
                 o = self._buf(f"s{s}.b{blk}.out", self.act, g.rows, cout)
                 nch_in = cin // self.cchunk
                 cdt, codt, rnd = self.cdt, self.codt, self.tf32   # tf32 mode: outputs are the next GEMM's tf32 operands
+                w1name, halo1_hi = f"s{s}.b{blk}.conv1.w", None
                 if blk == 0 and x_is_phase:   # stride-2 3x3 over the 4-phase split
                     taps = []
                     for kh in range(3):
@@ -709,12 +724,22 @@ class Program(OpList):
                             pw, dj = (1, -1) if kw == 0 else ((0, 0) if kw == 1 else (1, 0))
                             taps.append((0, (ph * 2 + pw) * phase_rows + di * g.P + dj, 0, nch_in, [0]))
                     a_rows, halo1, mt1 = 4 * phase_rows, 0, (2 if cout >= 128 and not self.tf32 else 1)   # 256-row tiles (s2: 55 -> 43 us, s3/s4: one wave instead of 1.7)
+                    if self.window and self.phase_windows and not self.tf32 and f"s{s}.b{blk}.conv1.wp" in W:
+                        # one A window per PHASE instead of one A tile per tap: the 9 taps read 4 phases, and the taps of
+                        # one phase are row shifts (-P-1, -P, -1, 0) of each other, so 4 windows of tile + P+1 rows
+                        # replace 9 tiles in shared memory (these layers are bound by the L2 -> shared-memory fill)
+                        halo1, halo1_hi, w1name = g.P + 1, 0, f"s{s}.b{blk}.conv1.wp"
+                        rel = lambda di, dj: halo1 + di * g.P + dj
+                        taps = [(0, 3 * phase_rows, 0, nch_in, [rel(-1, -1), rel(-1, 0), rel(0, -1), rel(0, 0)]),
+                                (0, 2 * phase_rows, 0, nch_in, [rel(-1, 0), rel(0, 0)]),
+                                (0, 1 * phase_rows, 0, nch_in, [rel(0, -1), rel(0, 0)]),
+                                (0, 0, 0, nch_in, [rel(0, 0)])]
                 else:
                     taps, halo1, mt1 = self._conv3x3_groups(g, nch_in, cout)
                     a_rows = g.rows
                 self.gemm(f"s{s}.b{blk}.conv1", dtype=cdt, M=g.rows, N=cout, a0=x, a0_shape=(a_rows, cin, cin),
-                          groups=taps, w=f"s{s}.b{blk}.conv1.w", bias=f"s{s}.b{blk}.conv1.b", out=y, ldo=cout,
-                          out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo1, MT=mt1)
+                          groups=taps, w=w1name, bias=f"s{s}.b{blk}.conv1.b", out=y, ldo=cout,
+                          out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo1, halo_hi=halo1_hi, MT=mt1)
                 has_ds = W.items[f"s{s}.b{blk}.conv2.w"][2][1] > 9 * cout
                 taps2, halo2, mt2 = self._conv3x3_groups(g, cout // self.cchunk, cout, residual=not has_ds)
                 if has_ds:
