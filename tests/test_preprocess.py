@@ -58,9 +58,10 @@ def test_no_cpu_path():
 
 @pytest.mark.parametrize("hw", [(300, 400), (100, 160), (333, 211), (224, 500), (640, 224), (17, 23), (225, 223), (1, 1)])
 def test_resize_restatement_is_bit_exact_with_pil(hw):
-    """vqa_b200/resize.py (windows + 22-bit weights handed to the CUDA kernels, and the numpy two-pass
-    restatement) against PIL.Image.resize(BILINEAR) itself."""
-    from vqa_b200.resize import coeffs, numpy_resize
+    """vqa_b200/resize.py (windows + 22-bit weights handed to the CUDA kernels) and the numpy two-pass
+    restatement in oracle/resize_oracle.py against PIL.Image.resize(BILINEAR) itself."""
+    from oracle.resize_oracle import numpy_resize
+    from vqa_b200.resize import coeffs
     rng = np.random.default_rng(hw[0] * 7919 + hw[1])
     img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
     want = np.asarray(Image.fromarray(img, "RGB").resize((224, 224), Image.BILINEAR))
@@ -71,6 +72,6 @@ def test_resize_restatement_is_bit_exact_with_pil(hw):
 
 
 def test_resize_restatement_matches_golden(g):
-    from vqa_b200.resize import numpy_resize
+    from oracle.resize_oracle import numpy_resize
     for name in ("down", "up", "odd"):
         assert np.array_equal(numpy_resize(g[f"{name}.u8"], 224, 224), g[f"{name}.resized_u8"])

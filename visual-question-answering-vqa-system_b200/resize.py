@@ -13,7 +13,7 @@ image; C source ``src/libImaging/Resample.c`` is not vendored), so its published
 
 The windows / fixed-point weights are computed here in double precision exactly as the C code does and handed
 to the CUDA kernels (``csrc/resize.cu``), which do the two integer passes.  Bit-exactness against PIL itself is
-tested on the CPU (``numpy_resize`` below is the oracle-side restatement) and on the GPU.
+tested on the CPU (``oracle/resize_oracle.py`` restates the two integer passes in numpy) and on the GPU.
 """
 from __future__ import annotations
 
@@ -64,26 +64,3 @@ def coeffs(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]:
             kk[xx, x] = int(v - 0.5) if k[x] < 0 else int(v + 0.5)
         bounds[xx, 0], bounds[xx, 1] = xmin, xmax
     return bounds, kk
-
-
-def numpy_resize(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    """CPU restatement of the two integer passes (uint8 [H, W, C] -> [out_h, out_w, C]); test infrastructure."""
-    h, w, _ = img.shape
-    x = img.astype(np.int64)
-    if w != out_w:
-        b, kk = coeffs(w, out_w)
-        out = np.empty((h, out_w, x.shape[2]), dtype=np.int64)
-        for xx in range(out_w):
-            x0, n = int(b[xx, 0]), int(b[xx, 1])
-            acc = (x[:, x0:x0 + n, :] * kk[xx, :n].astype(np.int64)[None, :, None]).sum(axis=1) + (1 << (PRECISION_BITS - 1))
-            out[:, xx, :] = np.clip(acc >> PRECISION_BITS, 0, 255)
-        x = out
-    if h != out_h:
-        b, kk = coeffs(h, out_h)
-        out = np.empty((out_h, x.shape[1], x.shape[2]), dtype=np.int64)
-        for yy in range(out_h):
-            y0, n = int(b[yy, 0]), int(b[yy, 1])
-            acc = (x[y0:y0 + n, :, :] * kk[yy, :n].astype(np.int64)[:, None, None]).sum(axis=0) + (1 << (PRECISION_BITS - 1))
-            out[yy, :, :] = np.clip(acc >> PRECISION_BITS, 0, 255)
-        x = out
-    return x.astype(np.uint8)
