@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 6
+#define VQA_ABI_VERSION 7
 
 #define VQA_OK            0
 #define VQA_E_INVALID    -1   /* bad argument / unsupported shape */
@@ -42,12 +42,12 @@ extern "C" {
 #define VQA_MAX_TAPS   16
 #define VQA_MAX_GROUPS 12
 #define VQA_LANE_JOIN  4
-#define VQA_OP_NI      144
+#define VQA_OP_NI      160
 #define VQA_OP_NP     12
 #define VQA_OP_NF     4
 
 /* Op kinds.  Field layouts (indices into VqaOp.i / .p / .f) are listed in program.py
- * (FIELDS) and mirrored by the *_I / *_P enums in csrc/ops.h; vqa_op_num_fields() lets the
+ * (FIELDS) and mirrored by the *_I / *_P enums in csrc/op_fields.h (generated); vqa_op_num_fields() lets the
  * host verify both sides agree. */
 enum VqaOpKind {
   VQA_OP_INGEST        = 1,  /* NCHW fp32 (models/vqa_model.py:243-258) or uint8 HWC + normalise

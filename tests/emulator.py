@@ -85,8 +85,10 @@ class Emulator:
             flat = _t(ref, dt, ext)
             amaps.append(torch.as_strided(flat, (rows, cols), (ld, 1)))
         Wt = _t(op.p["b"], dt, ext)[: Npad * Ktot].view(Npad, Ktot).float()
-        acc = torch.zeros(M, Npad)
-        m = torch.arange(M)
+        sf, sf_step = i.get("sf", 1) or 1, i.get("sf_step", 1) or 1
+        Mx = M + (sf - 1) * sf_step          # shift-fused form: accumulator rows past M feed the last outputs
+        acc = torch.zeros(Mx, Npad)
+        m = torch.arange(Mx)
         halo = i["halo"]
         covered = 0
         for g in range(i["ngroups"]):
@@ -97,7 +99,7 @@ class Emulator:
             for t in range(ntaps):
                 idx = m + delta - halo + i[f"tap_rel{tap0 + t}"]
                 ok = (idx >= 0) & (idx < A.shape[0])
-                a = torch.zeros(M, kw)
+                a = torch.zeros(Mx, kw)
                 a[ok] = A[idx[ok], acol: acol + kw].float()
                 if i["dtype"] == P.DT_TF32 and self.tf32_truncate:
                     a = trunc_tf32(a)
@@ -105,7 +107,12 @@ class Emulator:
                 acc += a @ Wt[:, kcol: kcol + kw].t()
                 covered += kw
         assert covered == Ktot
-        acc = acc[:, :N]
+        if sf > 1:   # out[m] = sum_j acc[m + j*step, j*BN + n]
+            bn = i["BN"]
+            acc = sum(acc[j * sf_step: j * sf_step + M, j * bn: j * bn + N] for j in range(sf))
+        else:
+            acc = acc[:, :N]
+        m = torch.arange(M)
         if op.p.get("bias") is not None:
             acc = acc + _t(op.p["bias"], torch.float32, ext)[:N]
         if op.p.get("res") is not None:
@@ -266,6 +273,8 @@ class Emulator:
         i = op.i
         src = ext[op.p["src"].slot]
         _t(op.p["dst"], torch.int32, ext)[: i["B"] * i["L"]].view(i["B"], i["L"]).copy_((src != 0).to(torch.int32))
+        if op.p.get("dstf") is not None:   # pooling weights: attention_mask.float()
+            _t(op.p["dstf"], torch.float32, ext)[: i["B"] * i["L"]].view(i["B"], i["L"]).copy_(src.float())
 
     def op_embed(self, op, ext):
         i = op.i
@@ -348,7 +357,7 @@ class Emulator:
             xa = buf("xatt", B * L * D).view(B, L, D)
             tx = buf("text", B * L * D).view(B, L, D)
             if op.p.get("mask") is not None:
-                m = _t(op.p["mask"], torch.int32, ext)[: B * L].view(B, L, 1).float()
+                m = _t(op.p["mask"], torch.float32, ext)[: B * L].view(B, L, 1)
             else:
                 m = torch.ones(B, L, 1)
             den = m.sum(dim=1).clamp(min=1)

@@ -222,3 +222,53 @@ def test_stem_window_fused_maxpool(B, HW, max_ctas):
     cpu, gpu, _, _ = G.run_pair(build)
     G.report(f"stem + fused max-pool B{B} {HW}x{HW} max_ctas={max_ctas}", G.named(gpu, "o"), G.named(cpu, "o"),
              atol=2e-2, rtol=1e-2)
+
+
+def _conv_sf_case(device, B, H, Wd, residual, max_ctas, pair):
+    """Shift-fused 64 -> 64 3x3 convolution (N = 192 MMAs, horizontal taps added in the epilogue)."""
+    g = P.Grid(B, H, Wd)
+    gen = torch.Generator().manual_seed(17)
+    w4 = torch.randn(64, 64, 3, 3, generator=gen) * (1.0 / 576 ** 0.5)
+    W = P.Weights(device)
+    W.add("c.wsf", P._ohwi_shift_fused(w4), torch.bfloat16)
+    W.add("c.w4", w4.to(torch.bfloat16).float(), torch.float32)     # the same (bf16-rounded) weights for F.conv2d
+    W.add("c.b", torch.randn(64, generator=gen), torch.float32)
+    W.finalize()
+    ol = P.OpList(W, device)
+    x = ol._buf("x", torch.bfloat16, g.rows, 64)
+    o = ol._buf("o", torch.bfloat16, g.rows, 64)
+    groups, halo, halo_hi = ol._conv3x3_sf(g, 1)
+    ol.gemm("conv", dtype=P.DT_BF16, M=g.rows, N=64, a0=x, a0_shape=(g.rows, 64, 64), groups=groups, w="c.wsf", bias="c.b",
+            out=o, ldo=64, out_dtype=P.OUT_BF16, relu=True, res=x if residual else None,
+            res_dtype=P.OUT_BF16 if residual else -1, ldr=64, grid=g, halo=halo, halo_hi=halo_hi, MT=1, sf=3, pair=pair)
+    ol.ops[-1].i["max_ctas"] = max_ctas
+    ol.commit()
+    xv = torch.randn(g.rows, 64, generator=gen)
+    r = torch.arange(g.rows) % g.rpi
+    xv[~(((r // g.P) < g.H) & ((r % g.P) < g.W))] = 0
+    G.named(ol, "x").copy_(xv.to(torch.bfloat16))
+    G.named(ol, "o").fill_(3.0)            # every row, pads included, must be written
+    return ol
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("max_ctas", [0, 3])
+@pytest.mark.parametrize("B,H,W,residual", [(2, 8, 8, False), (1, 56, 56, True), (3, 20, 13, True), (5, 56, 56, False)])
+def test_conv3x3_shift_fused(B, H, W, residual, max_ctas, pair):
+    """sf = 3: one 192-column MMA per vertical tap; the epilogue adds the three horizontal taps with row shifts
+    0 / 1 / 2 (warp shuffles + the exchange between 32-row slabs), tiles advance by 126 rows and the last slab of
+    every tile is stored through a 30-row box.  Checked against the emulator and against F.conv2d itself."""
+    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_sf_case(d, B, H, W, residual, max_ctas, pair))
+    G.report(f"conv sf3 {B}x{H}x{W} res={residual} max_ctas={max_ctas} pair={pair}", G.named(gpu, "o"), G.named(cpu, "o"),
+             atol=3e-2, rtol=2e-2)
+    g = P.Grid(B, H, W)
+    import emulator as E
+    idx = E._grid_index(B, H, W, g.P, g.rpi)
+    x = G.named(cpu, "x")[idx].float().view(B, H, W, 64).permute(0, 3, 1, 2)
+    want = torch.nn.functional.conv2d(x, cpu.W.tensor("c.w4"), cpu.W.tensor("c.b"), padding=1)
+    want = torch.relu(want + x if residual else want)
+    got = G.named(gpu, "o").cpu()[idx].float().view(B, H, W, 64).permute(0, 3, 1, 2)
+    G.report("conv sf3 vs F.conv2d", got, want, atol=3e-2, rtol=2e-2)
+    pads = torch.ones(g.rows, dtype=torch.bool)
+    pads[idx] = False
+    assert G.named(gpu, "o").cpu()[pads].abs().max() == 0   # shared zero padding is rewritten as zeros

@@ -134,4 +134,7 @@ def test_image_side_and_question_side_programs_compose():
     got4, _ = E.run_program(q4, None, ids, mask, extra=gathered)
     ref4 = P.Program(W, model.config, 4, 16, "nchw_f32", P.MASK_I64, top_k=0, device="cpu")
     want4, _ = E.run_program(ref4, img[:2][pick], ids, mask)
-    assert torch.equal(got4, want4)
+    # the image side ran at batch 2 here and at batch 4 in ref4: the CPU BLAS behind the emulator blocks its fp32 sums by
+    # matrix shape, so a bf16 rounding may flip (the CUDA kernels are batch-invariant: tests/test_gpu_cache_metrics.py
+    # checks this composition bit for bit)
+    torch.testing.assert_close(got4, want4, atol=5e-3, rtol=0)

@@ -17,6 +17,7 @@ W = P.build_weights(model.state_dict(), model.config, "cuda")
 prog = P.Program.__new__(P.Program)
 P.OpList.__init__(prog, W, "cuda", True)
 prog.cfg, prog.B, prog.L, prog.in_fmt, prog.mask_dtype, prog.want_aux, prog.top_k = model.config, B, 20, "nchw_f32", P.MASK_I64, False, 0
+prog.Bi, prog.side = B, "both"
 prog._build()
 gemms = [k for k, op in enumerate(prog.ops) if op.kind == "gemm"]
 for k in gemms:
@@ -32,7 +33,10 @@ for _ in range(3):
     plan.run(ext, st)
 torch.cuda.synchronize()
 print("op name: setup | first_tma | first_a_full | tile0_mma_issued | tile0_acc_full_seen | tile0_epi_done | last_mma_issued | last_epi_done | exit   (cycles from kernel entry)")
+only = os.environ.get("VQA_TIMELINE_ONLY", "")
 for k in gemms:
+    if only and not prog.ops[k].name.startswith(only):
+        continue
     t = prog.tensor(f"dbg{k}").cpu().tolist()
     d = [x - t[0] for x in t]
     oi = prog.ops[k].i
@@ -40,4 +44,5 @@ for k in gemms:
     print(f"{k:3d} {prog.ops[k].name:14s} setup {d[1]:5d} tma0 {d[2]:5d} a_full0 {d[3]:6d} mma0_issued {d[4]:6d} acc_seen0 {d[5]:6d} "
           f"epi0_done {d[6]:6d} last_mma {d[9]:7d} last_epi {d[7]:7d} exit {d[8]:7d} | waits: prod a_empty {t[16]:7d} b_empty {t[17]:7d} "
           f"| mma acc_empty {t[18]:7d} a_full {t[19]:7d} b_full {t[20]:7d} | epi(w2) acc_full {t[21]:7d} | m_tiles {tiles} "
-          f"| wall {(t[23] - t[22]) / 1e3:7.1f} us sm_clk {d[8] / max(t[23] - t[22], 1) * 1e3:6.0f} MHz")
+          f"| wall {(t[23] - t[22]) / 1e3:7.1f} us sm_clk {d[8] / max(t[23] - t[22], 1) * 1e3:6.0f} MHz "
+          f"| epi(w2) phases: tmem_ld {t[10]} xchg {t[11]} combine {t[12]} finish {t[14]} store_wait {t[15]}")

@@ -33,6 +33,9 @@ namespace {
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);   // producer, MMA issuer, 8 epilogue warps
+constexpr int kSfEpiWarps = 16;                  // shift-fused kernels: 16 epilogue warps (their epilogue is issue-bound)
+constexpr int kSfThreads = 32 * (2 + kSfEpiWarps);
+constexpr int kMaxEpiWarps = 16;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBSlots = 12;
 
@@ -74,6 +77,10 @@ struct GemmParams {
   int tiles_per_img, tile_stride, tile_row0, img_rows;
   // fused 3x3/2 max-pool epilogue (EPI 4): conv grid pitch / width, pooled grid geometry
   int pool_P, pool_W, pool_Wo, pool_Ho, pool_Po, pool_rpio;
+  // shift-fused form (template SF > 1): the accumulator holds SF column blocks of BN; out[r] = sum_j acc[r + j*sf_step][j*BN + n]
+  int sf_step;
+  // pad mask without integer division: n / d = umulhi(n, magic) >> shift for every n < 2^31 (checked on the host)
+  uint32_t rpi_magic, rpi_shift, mp_magic, mp_shift;
   long long* dbg;    // optional: 16 clock64() timestamps of CTA 0 (profiling aid, nullptr in production)
 };
 
@@ -81,6 +88,14 @@ __device__ __forceinline__ int tile_m0(const GemmParams& p, int tile_m, int mt) 
   if (p.tiles_per_img == 0) return tile_m * 128 * mt;
   const int img = tile_m / p.tiles_per_img;
   return img * p.img_rows + (tile_m - img * p.tiles_per_img) * p.tile_stride + p.tile_row0;
+}
+
+// rem = row % rpi, then (rem / P, rem % P) against (H, W): true for an in-image position of the padded-flat grid
+__device__ __forceinline__ bool grid_pixel(const GemmParams& p, int row) {
+  const uint32_t n = static_cast<uint32_t>(row);
+  const uint32_t rem = n - (__umulhi(n, p.rpi_magic) >> p.rpi_shift) * static_cast<uint32_t>(p.mRPI);
+  const uint32_t h = __umulhi(rem, p.mp_magic) >> p.mp_shift;
+  return h < static_cast<uint32_t>(p.mH) && rem - h * static_cast<uint32_t>(p.mP) < static_cast<uint32_t>(p.mW);
 }
 
 #define VQA_DBG(slot)                                                         \
@@ -98,9 +113,12 @@ __device__ __forceinline__ int tile_m0(const GemmParams& p, int tile_m, int mt) 
 // the M and N edges.  The residual box of the NEXT chunk is in flight while the current one is
 // processed.  Slots are 32 rows x 64 B (bf16, SWIZZLE_64B) or 32 rows x 128 B (fp32, SWIZZLE_128B).
 constexpr int kBiasTable = 2048;        // floats: bias of every N tile of the launch (wider layers read it from global)
+constexpr int kXchgRows = 4;            // shift-fused epilogue: accumulator rows a warp publishes for the warp above it
+constexpr int kXchgBytes = 2 * kSfEpiWarps * kXchgRows * 16 * 4; // double-buffered, one slot of 16-column rows per warp
 constexpr int kPoolTileBytes = 384 * 128;
 
-__host__ __device__ constexpr int epi_stage_bytes(int epi) {
+__host__ __device__ constexpr int epi_stage_bytes(int epi, int sf = 1) {
+  if (sf > 1) return kSfEpiWarps * 2048 * ((epi & 1) ? 2 : 1);   // shift-fused: 32 rows x 32 bf16 channels per warp
   return epi == 4 ? kPoolTileBytes : kEpiWarps * ((epi < 2 ? 2048 : 4096) * ((epi & 1) ? 2 : 1));
 }
 
@@ -119,11 +137,20 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
 // ROW32: K chunks are 32-byte rows (the stem) instead of 128-byte rows.
 // PAIR: two CTAs of a cluster share one 256-row UMMA (cta_group::2): each loads its own A windows and HALF of every
 // weight tile, the even CTA issues the MMAs for both, each CTA drains its own 128 accumulator rows.
-template <int BN, int MT, bool TF32, int EPI, bool ROW32, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+// SF > 1 (shift-fused, MT = 1): every MMA is SF*BN columns wide -- block j of the weight tile holds horizontal tap j --
+// and the epilogue adds block j shifted up by j*sf_step accumulator rows (warp shuffles; the rows that come from the
+// next 32-row slab go through a small shared-memory exchange).  A 128x64x16 SS-mode MMA is bound by its shared-memory
+// operand reads (6 KB per 32 math cycles: 48.6 clk measured, tools/ubench.cu); at N = 192 the same A bytes feed three
+// times the math and the MMA runs at its 96-cycle floor.  The last (SF-1)*sf_step rows of a tile have no complete sum:
+// tiles advance by 128 - (SF-1)*sf_step rows and the last slab is stored through a shorter box (mapOutLast).
+template <int BN, int MT, bool TF32, int EPI, bool ROW32, bool PAIR, int SF = 1>
+__global__ void __launch_bounds__(SF > 1 ? kSfThreads : kThreads, 1)
 gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
-                const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ GemmParams p) {
+                const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ CUtensorMap mapOutLast,
+                const __grid_constant__ GemmParams p) {
+  static_assert(SF == 1 || (MT == 1 && EPI < 2 && !TF32 && !ROW32), "shift-fused tiles: MT = 1, bf16 output");
+  constexpr int kAcc = SF * BN;                 // accumulator columns of one 128-row sub-tile
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window.
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -144,7 +171,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.a_slots * p.a_slot_bytes;
   uint8_t* smem_stage = smem_b + b_region_slots * p.b_slot_bytes;     // 1024-byte aligned (slots are 1 KB multiples)
-  float* s_bias = reinterpret_cast<float*>(smem_stage + epi_stage_bytes(EPI));
+  float* s_bias = reinterpret_cast<float*>(smem_stage + epi_stage_bytes(EPI, SF));
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kBiasTable);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxASlots;
@@ -153,9 +180,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   uint64_t* acc_full = b_empty + kMaxBSlots;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* res_bar = acc_empty + 2;           // one per epilogue warp: "residual box landed"
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kMaxEpiWarps);
   uint32_t* s_rel = tmem_slot + 4;                                   // tap row offsets, pre-shifted for descriptors
   int4* s_grp = reinterpret_cast<int4*>(s_rel + VQA_MAX_TAPS);      // per group {chunks, taps, tap0, q0}
+  float* s_xchg = reinterpret_cast<float*>(s_grp + VQA_MAX_GROUPS); // SF > 1 only: boundary rows between epilogue warps
 
   if (warp == 0) VQA_DBG(0);
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -168,20 +196,24 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
     if (EPI != 4) tma_prefetch_desc(&mapOut);
+    if (SF > 1) tma_prefetch_desc(&mapOutLast);
     if (EPI & 1) tma_prefetch_desc(&mapRes);
   }
   if (warp == 1) {   // barrier / table initialisation spread over the warp's lanes (one thread took ~1k cycles)
     if (lane < kMaxASlots) { mbar_init(&a_full[lane], 1); mbar_init(&a_empty[lane], 1); }
     if (lane < kMaxBSlots) { mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
-    if (lane >= 16 && lane < 18) { mbar_init(&acc_full[lane - 16], 1); mbar_init(&acc_empty[lane - 16], kEpiWarps * (PAIR ? 2 : 1)); }
-    if (lane >= 24 && lane < 24 + kEpiWarps) mbar_init(&res_bar[lane - 24], 1);
+    if (lane >= 16 && lane < 18) {   // shift-fused kernels: each accumulator stage is drained by one group of four warps
+      mbar_init(&acc_full[lane - 16], 1);
+      mbar_init(&acc_empty[lane - 16], kEpiWarps * (PAIR ? 2 : 1));   // SF: 8 of the 16 warps drain each stage
+    }
+    if (lane < kMaxEpiWarps) mbar_init(&res_bar[lane], 1);
     if (lane < VQA_MAX_TAPS) s_rel[lane] = static_cast<uint32_t>(p.tap_rel[lane]) * (kRowBytes / 16);
     if (lane < VQA_MAX_GROUPS) s_grp[lane] = make_int4(p.g_chunks[lane], p.g_ntaps[lane], p.g_tap0[lane], p.g_q0[lane]);
     __syncwarp();
     if (lane == 0) mbar_fence_init();
   }
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(BN * MT * p.acc_stages)) tmem_cols <<= 1;   // power of two >= 32
+  while (tmem_cols < static_cast<uint32_t>(kAcc * MT * p.acc_stages)) tmem_cols <<= 1;   // power of two >= 32
   if (warp == 2) {
     if (PAIR) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
     else      { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
@@ -210,7 +242,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     };
     for (int tile = walker; tile < total_tiles; tile += n_walkers) {
       const int m0 = tile_m0(p, cta_mtile(tile), MT);
-      const int n0 = (tile / p.m_tiles) * BN + (PAIR ? static_cast<int>(rank) * (BN / 2) : 0);   // pair: this CTA's half of the N tile
+      const int n0 = (tile / p.m_tiles) * kAcc + (PAIR ? static_cast<int>(rank) * (kAcc / 2) : 0);   // pair: this CTA's half of the N tile
       if (p.b_resident && !b_loaded) {   // n_tiles == 1 in this mode: load every weight chunk once
         if (elect_one()) {
           if (expects) mbar_expect_tx(&b_full[0], static_cast<uint32_t>(p.k_chunks * p.b_slot_bytes) * kTxMul);
@@ -290,10 +322,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             const uint64_t ad = kDescHi | (a_lo + sub * (128 * kRowBytes / 16) + 2 * k);
             const uint64_t bd = kDescHi | (b_lo + 2 * k);
             const uint32_t accum = (k == 0) ? (fresh ^ 1u) : 1u;
-            if (PAIR && TF32) umma_tf32_pair(d_tile + sub * BN, ad, bd, idesc, accum);
-            else if (PAIR)    umma_f16_pair(d_tile + sub * BN, ad, bd, idesc, accum);
-            else if (TF32)    umma_tf32(d_tile + sub * BN, ad, bd, idesc, accum);
-            else              umma_f16(d_tile + sub * BN, ad, bd, idesc, accum);
+            if (PAIR && TF32) umma_tf32_pair(d_tile + sub * kAcc, ad, bd, idesc, accum);
+            else if (PAIR)    umma_f16_pair(d_tile + sub * kAcc, ad, bd, idesc, accum);
+            else if (TF32)    umma_tf32(d_tile + sub * kAcc, ad, bd, idesc, accum);
+            else              umma_f16(d_tile + sub * kAcc, ad, bd, idesc, accum);
           }
         }
         fresh = 0;
@@ -316,7 +348,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       for (int tile = walker; tile < total_tiles; tile += n_walkers) {
         mbar_wait_t(&acc_empty[acc], accph ^ 1u, timed, w_accempty);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        d_tile = tmem_base + acc * (BN * MT);
+        d_tile = tmem_base + acc * (kAcc * MT);
         fresh = 1;                           // first MMA of each accumulator overwrites, the rest accumulate
         for (int g = 0; g < ngroups; ++g) {
           const int4 grp = s_grp[g];
@@ -458,6 +490,184 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
     }
     if (timed && lane == 0) p.dbg[21] = w_accfull;
+  } else if constexpr (SF > 1) {
+    // ===================== epilogue warps, shift-fused tiles (MT = 1, BN = 64, bf16 output) =====================
+    // x[r] = sum_j acc_j[r + j*step] costs two warp shuffles and three adds per output on top of the usual bias /
+    // residual / pack work: ~850 warp instructions per 128x64 tile and quadrant, against ~1150-1430 cycles of MMAs.
+    // Measured with 8 epilogue warps (two per scheduler): 0.29 instructions per clock and scheduler, the epilogue and
+    // not the tensor pipe sets the pace.  Hence 16 epilogue warps for these kernels, four per scheduler:
+    //   warp = (group g, column half, TMEM lane quadrant); group g drains accumulator stage g, i.e. every other tile,
+    //   so the two groups run one tile apart and their phases (TMEM loads, shuffles, staging, TMA) interleave;
+    //   a warp owns 32 accumulator rows x 32 output channels, handled as two 16-channel passes to stay within the
+    //   112 registers that 576 threads leave per thread.
+    // Rows r + j*step >= 32 live in the next quadrant's slab: every warp publishes its first rows in shared memory,
+    // and lanes < j*step (whose own rows nobody in this warp needs) pick up the next slab's rows, so ONE rotate-
+    // shuffle per value serves all 32 lanes.  (tcgen05.shift was measured for this too: it shifts 8 columns by one
+    // row inside each 32-lane quadrant in ~48 cycles of the tensor pipe -- 24 of them per tile cost as much as the
+    // tile's MMAs; tools/ubench_shift.cu.)
+    static_assert(BN == 64, "shift-fused epilogue: 64 output channels");
+    constexpr bool kRes = (EPI & 1) != 0;
+    constexpr int kSlotBytes = 32 * 64;       // 32 rows x 32 bf16 channels, SWIZZLE_64B
+    const int ew = warp - 2;                  // 0..15
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may read
+    const int grp = ew >> 3;                  // tile parity / accumulator stage this warp serves
+    const int half = (ew >> 2) & 1;           // which 32 of the 64 output channels
+    uint8_t* const out_slot = smem_stage + ew * ((kRes ? 2 : 1) * kSlotBytes);
+    uint8_t* const res_slot = out_slot + kSlotBytes;
+    uint64_t* const my_res_bar = &res_bar[ew];
+    const uint32_t swz = (lane >> 1) & 3;     // SWIZZLE_64B: 16-byte unit u of row `lane` lives at ((u ^ swz) << 4)
+    uint8_t* const out_row = out_slot + lane * 64;
+    const uint8_t* const res_row = res_slot + lane * 64;
+    const bool relu = p.relu != 0, mask_en = p.mask_en != 0, out_f16 = p.out_f16 != 0;
+    const int step = p.sf_step;
+    const bool has_bias = p.bias != nullptr;
+    const int bar_id = 2 + (ew >> 2);         // named barrier of the four quadrant warps of this (group, half)
+    for (int i = threadIdx.x - 64; i < BN; i += 32 * kSfEpiWarps) s_bias[i] = (has_bias && i < p.N) ? __ldg(p.bias + i) : 0.f;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    pdl_wait();   // residual loads / output stores below touch buffers of the preceding kernels
+
+    uint32_t accph = 0, resph = 0;
+    int xpar = 0;
+    const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
+    long long w_accfull = 0;
+    long long ph_ld = 0, ph_xch = 0, ph_comb = 0, ph_fin = 0, ph_st = 0, ph_t = 0;   // epilogue phase cycles (dbg only)
+#define VQA_PHASE(accu) do { if (timed) { const long long now__ = clock64(); accu += now__ - ph_t; ph_t = now__; } } while (0)
+    const int tstep = 2 * n_walkers;          // this group's next tile
+    const int first = walker + grp * n_walkers;
+    auto issue_res = [&](int row0) {          // lane 0 only: 32 rows x 32 channels of the residual
+      mbar_expect_tx(my_res_bar, kSlotBytes);
+      tma_load_2d(res_slot, &mapRes, my_res_bar, 32 * half, row0);
+    };
+    if (kRes && lane == 0 && first < total_tiles) issue_res(tile_m0(p, cta_mtile(first), 1) + quad * 32);
+
+    for (int tile = first; tile < total_tiles; tile += tstep) {
+      const int row0 = tile_m0(p, cta_mtile(tile), 1) + quad * 32;
+      const bool pix = !mask_en || grid_pixel(p, row0 + lane);
+      const int ntile = tile + tstep;
+      const int n_row0 = tile_m0(p, cta_mtile(ntile), 1) + quad * 32;
+      mbar_wait_t(&acc_full[grp], accph, timed, w_accfull);
+      accph ^= 1u;
+      tc_fence_after();
+      if (warp == 2 && tile == walker) VQA_DBG(5);
+      if (timed) ph_t = clock64();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * kAcc + 32 * half;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {           // 16-channel passes
+        uint32_t v[SF][16];
+        __syncwarp();                         // tcgen05.ld is .sync.aligned
+#pragma unroll
+        for (int j = 0; j < SF; ++j) tmem_ld16(taddr + j * BN + 16 * c, v[j]);
+        if (kRes && c == 0) { mbar_wait(my_res_bar, resph); resph ^= 1u; }   // this tile's residual box has landed
+        tmem_ld_wait();
+        if (c == 1) {                         // every TMEM read of this warp is complete: release the accumulator stage
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_leader(&acc_empty[grp]); else mbar_arrive(&acc_empty[grp]);
+          }
+        }
+        VQA_PHASE(ph_ld);
+        // publish the first rows of blocks j >= 1 for the warp that owns the 32 rows before them
+        float* const xmine = s_xchg + (((xpar * 4 + (ew >> 2)) * 4 + quad) * kXchgRows) * 16;
+#pragma unroll
+        for (int j = 1; j < SF; ++j) {
+          if (lane < j * step) {
+            float4* dst = reinterpret_cast<float4*>(xmine + (step * (j * (j - 1) / 2) + lane) * 16);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              dst[u] = make_float4(__uint_as_float(v[j][4 * u]), __uint_as_float(v[j][4 * u + 1]),
+                                   __uint_as_float(v[j][4 * u + 2]), __uint_as_float(v[j][4 * u + 3]));
+          }
+        }
+        // split barrier: every thread arrives twice (here, after publishing, and in the bar.sync below), so the barrier
+        // expects 2 x 128 arrivals and the work on block 0 overlaps the other warps' publishing
+        asm volatile("bar.arrive %0, 256;" ::"r"(bar_id) : "memory");
+        float x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = __uint_as_float(v[0][k]);
+        if (has_bias) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 bq = *reinterpret_cast<const float4*>(s_bias + 32 * half + 16 * c + 4 * k);   // broadcast
+            x[4 * k] += bq.x; x[4 * k + 1] += bq.y; x[4 * k + 2] += bq.z; x[4 * k + 3] += bq.w;
+          }
+        }
+        if constexpr (kRes) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint4 q = *reinterpret_cast<const uint4*>(res_row + (((2 * c + u) ^ swz) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              x[8 * u + 2 * k] += __uint_as_float(w[k] << 16);
+              x[8 * u + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+            }
+          }
+          if (c == 1) {
+            __syncwarp();                     // every lane has consumed the residual slot: prefetch the next tile's box
+            if (lane == 0 && ntile < total_tiles) issue_res(n_row0);
+          }
+        }
+        VQA_PHASE(ph_fin);
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // every quadrant warp has published
+        VQA_PHASE(ph_xch);
+        const float* const xnext = xmine + kXchgRows * 16;           // quadrant + 1; nothing for quadrant 3
+#pragma unroll
+        for (int j = 1; j < SF; ++j) {
+          const int sh = j * step;
+          if (lane < sh && quad < 3) {
+            const float4* src = reinterpret_cast<const float4*>(xnext + (step * (j * (j - 1) / 2) + lane) * 16);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 q = src[u];
+              v[j][4 * u] = __float_as_uint(q.x); v[j][4 * u + 1] = __float_as_uint(q.y);
+              v[j][4 * u + 2] = __float_as_uint(q.z); v[j][4 * u + 3] = __float_as_uint(q.w);
+            }
+          }
+          const int from = (lane + sh) & 31;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) x[k] += __shfl_sync(0xffffffffu, __uint_as_float(v[j][k]), from);
+        }
+        xpar ^= 1;
+        VQA_PHASE(ph_comb);
+        uint32_t w[8];
+        if (out_f16) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = relu ? pack_relu_f16x2(x[2 * k], x[2 * k + 1]) : pack_f16x2(x[2 * k], x[2 * k + 1]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = relu ? pack_relu_bf16x2(x[2 * k], x[2 * k + 1]) : pack_bf16x2(x[2 * k], x[2 * k + 1]);
+        }
+        if (!pix) {                           // keep the grid's shared zero padding intact
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = 0u;
+        }
+        VQA_PHASE(ph_fin);
+        if (c == 0) {
+          if (lane == 0) bulk_wait_read0();   // the previous tile's TMA store has drained the out slot
+          __syncwarp();
+          VQA_PHASE(ph_st);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          *reinterpret_cast<uint4*>(out_row + (((2 * c + u) ^ swz) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+      }
+      fence_proxy_async();                    // staging writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(quad == 3 ? &mapOutLast : &mapOut, out_slot, 32 * half, row0);
+        bulk_commit();
+      }
+      VQA_PHASE(ph_fin);
+      if (warp == 2 && tile == walker) { VQA_DBG(13); VQA_DBG(6); }
+      if (warp == 2 && tile + tstep >= total_tiles) VQA_DBG(7);
+    }
+    if (lane == 0) bulk_wait_all();           // outstanding TMA stores complete before the CTA exits
+    if (timed && lane == 0) {
+      p.dbg[21] = w_accfull;
+      p.dbg[10] = ph_ld; p.dbg[11] = ph_xch; p.dbg[12] = ph_comb; p.dbg[14] = ph_fin; p.dbg[15] = ph_st;
+    }
+#undef VQA_PHASE
   } else {
     // ===================== epilogue warps =====================
     constexpr bool kOutBf16 = EPI < 2;
@@ -480,7 +690,6 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // loop-invariant parameters in registers (the asm volatile barriers would otherwise force reloads)
     const int N = p.N;
     const bool relu = p.relu != 0, rnd = p.round_tf32 != 0, mask_en = p.mask_en != 0, out_f16 = p.out_f16 != 0;
-    const int mRPI = p.mRPI, mP = p.mP, mH = p.mH, mW = p.mW;
     const int m_tiles = p.m_tiles, acc_stages = p.acc_stages;
     const bool has_bias = p.bias != nullptr;
     {   // bias of all N tiles -> shared memory (zero beyond N), read back as warp-wide broadcasts
@@ -494,6 +703,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     uint32_t accph = 0, resph = 0;
     const bool timed = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
     long long w_accfull = 0;
+    long long ph_ld = 0, ph_fin = 0, ph_st = 0, ph_t = 0;   // epilogue phase cycles (dbg only)
+#define VQA_PHASE(accu) do { if (timed) { const long long now__ = clock64(); accu += now__ - ph_t; ph_t = now__; } } while (0)
     const int tstep = n_walkers;
 
     auto issue_res = [&](int row0, int col0) {          // lane 0 only
@@ -513,10 +724,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
       for (int sub = 0; sub < MT; ++sub) {
         pix[sub] = true;
-        if (mask_en) {
-          const int rem = (m0 + sub * 128 + quad * 32 + lane) % mRPI;
-          pix[sub] = (rem / mP) < mH && (rem % mP) < mW;
-        }
+        if (mask_en) pix[sub] = grid_pixel(p, m0 + sub * 128 + quad * 32 + lane);
       }
       const int ntile = tile + tstep;                   // the residual of its first chunk is prefetched at the end
       const bool has_ntile = ntile < total_tiles;
@@ -526,23 +734,25 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       mbar_wait_t(&acc_full[acc], accph, timed, w_accfull);
       tc_fence_after();
       if (warp == 2 && tile == walker) VQA_DBG(5);
+      if (timed) ph_t = clock64();
 #pragma unroll
       for (int sub = 0; sub < MT; ++sub) {
         const int row0 = m0 + sub * 128 + quad * 32;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (BN * MT) + sub * BN +
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (kAcc * MT) + sub * kAcc +
                                half * kCols;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           const int col0 = colw + 32 * c;               // first column of this 32-wide chunk (warp-uniform)
           if (!kRes && col0 >= N) continue;             // chunk entirely beyond N (the residual chain never skips)
+          const bool tabled = p.n_tiles * BN <= kBiasTable;   // else (N > 2048): broadcast loads from global
+          const float* bsrc = s_bias + (tabled ? col0 : 0);
+          float x[32];
           uint32_t v[32];
           __syncwarp();                                 // tcgen05.ld is .sync.aligned
           tmem_ld32(taddr + 32 * c, v);
-          const bool tabled = p.n_tiles * BN <= kBiasTable;   // else (N > 2048): broadcast loads from global
-          const float* bsrc = s_bias + (tabled ? col0 : 0);
           if (kRes) mbar_wait(my_res_bar, resph);       // this chunk's residual box has landed
           tmem_ld_wait();
-          float x[32];
+          VQA_PHASE(ph_ld);
 #pragma unroll
           for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
           if (has_bias && !tabled) {
@@ -580,8 +790,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               else if (has_ntile) issue_res(n_row0, n_col0);
             }
           }
+          VQA_PHASE(ph_fin);
           if (lane == 0) bulk_wait_read0();             // the previous chunk's TMA store has drained the out slot
           __syncwarp();
+          VQA_PHASE(ph_st);
           if constexpr (kOutBf16) {
             uint32_t w[16];
             if (out_f16) {
@@ -629,6 +841,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             tma_store_2d(&mapOut, out_slot, col0, row0);
             bulk_commit();
           }
+          VQA_PHASE(ph_fin);
         }
       }
       if (warp == 2 && tile == walker) VQA_DBG(13);
@@ -643,7 +856,11 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
     }
     if (lane == 0) bulk_wait_all();                     // outstanding TMA stores complete before the CTA exits
-    if (timed && lane == 0) p.dbg[21] = w_accfull;
+    if (timed && lane == 0) {
+      p.dbg[21] = w_accfull;
+      p.dbg[10] = ph_ld; p.dbg[11] = 0; p.dbg[12] = 0; p.dbg[14] = ph_fin; p.dbg[15] = ph_st;
+    }
+#undef VQA_PHASE
   }
 
   tc_fence_before();
@@ -706,7 +923,8 @@ int encode_2d(CUtensorMap* map, bool tf32, uint64_t base, int rows, int cols, in
 
 // Epilogue tensor map over the output (or residual) matrix: 32 x 32 element boxes, SWIZZLE_64B for bf16
 // (64-byte box rows) / SWIZZLE_128B for fp32 (128-byte box rows), matching the staging slots of the kernel.
-int encode_box32(CUtensorMap* map, bool f32, uint64_t base, int rows, int cols, int ld, const char* what) {
+int encode_box32(CUtensorMap* map, bool f32, uint64_t base, int rows, int cols, int ld, const char* what, int box_rows = 32,
+                 int box_cols = 32) {
   EncodeTiledFn fn = get_encode_fn();
   VQA_REQUIRE(fn != nullptr, VQA_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const int esz = f32 ? 4 : 2;
@@ -719,11 +937,12 @@ int encode_box32(CUtensorMap* map, bool f32, uint64_t base, int rows, int cols, 
               std::string(what) + ": N must be a multiple of 16 bytes (4 fp32 / 8 bf16 columns)");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const bool sw128 = box_cols * esz == 128;     // 128-byte box rows: SWIZZLE_128B, 64-byte rows: SWIZZLE_64B
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                   reinterpret_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     vqa_set_error(std::string(what) + ": cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
@@ -751,12 +970,20 @@ int num_sms(int device) {
 }  // namespace
 
 typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                             const CUtensorMap, const GemmParams);
+                             const CUtensorMap, const CUtensorMap, const GemmParams);
 
 // Instantiated (BN, MT, operand type, epilogue) combinations: bf16 kernels with epilogues 0/1/2
 // (convolutions, image projector), tf32 kernels with MT = 1 and epilogues 2/3 (all nn.Linear layers).
-static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_bytes, bool pair) {
+static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_bytes, bool pair, int sf) {
 #define VQA_K(BN_, MT_, TF_, EPI_, R32_, PAIR_) static_cast<GemmKernelFn>(&gemm_tap_kernel<BN_, MT_, TF_, EPI_, R32_, PAIR_>)
+  if (sf > 1) {   // shift-fused 64-channel convolutions: N = sf * 64 MMAs, bf16 output with / without residual
+    if (bn != 64 || mt != 1 || tf32 || row_bytes != 128 || epi > 1) return nullptr;
+#define VQA_KSF(EPI_, PAIR_, SF_) static_cast<GemmKernelFn>(&gemm_tap_kernel<64, 1, false, EPI_, false, PAIR_, SF_>)
+    if (sf == 3) return pair ? (epi ? VQA_KSF(1, true, 3) : VQA_KSF(0, true, 3)) : (epi ? VQA_KSF(1, false, 3) : VQA_KSF(0, false, 3));
+    if (sf == 2) return pair ? (epi ? VQA_KSF(1, true, 2) : VQA_KSF(0, true, 2)) : (epi ? VQA_KSF(1, false, 2) : VQA_KSF(0, false, 2));
+#undef VQA_KSF
+    return nullptr;
+  }
   if (row_bytes == 32) {   // the stem: 32-byte rows, bf16, N = 64, ReLU epilogue without residual
     if (pair) {
       if (bn == 64 && mt == 3 && !tf32 && epi == 4) return VQA_K(64, 3, false, 4, true, true);
@@ -790,12 +1017,13 @@ static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_byte
 struct GemmLaunch {
   GemmKernelFn fn;
   int epi;
-  CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes;
+  CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes, mapOutLast;
   bool out_external;    // the output is a caller tensor (logits): its map is encoded per run
   bool pair;            // CTA-pair (cta_group::2) launch: clusters of 2
   GemmParams prm;
   dim3 grid;
   int bn;
+  int threads;          // CTA size: 10 warps, 18 for the shift-fused kernels
   size_t smem;
   uint64_t out_raw, res_raw;
 };
@@ -815,7 +1043,13 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.MT = I[GEMM_I_MT];
   p.halo = I[GEMM_I_halo];
   VQA_REQUIRE(p.MT >= 1 && p.MT <= 3, VQA_E_INVALID, "gemm: MT must be 1, 2 or 3");
-  VQA_REQUIRE(p.MT * bn <= 512, VQA_E_INVALID, "gemm: accumulators exceed 512 TMEM columns");
+  const int sf = I[GEMM_I_sf] > 1 ? I[GEMM_I_sf] : 1;   // shift-fused form: sf column blocks of bn per MMA
+  const int n_mma = sf * bn;
+  p.sf_step = I[GEMM_I_sf_step] > 0 ? I[GEMM_I_sf_step] : 1;
+  VQA_REQUIRE(p.MT * n_mma <= 512, VQA_E_INVALID, "gemm: accumulators exceed 512 TMEM columns");
+  VQA_REQUIRE(sf == 1 || (sf <= 3 && p.MT == 1 && bn == 64 && I[GEMM_I_out_dtype] != 1 && p.N <= bn && I[GEMM_I_Npad] == n_mma &&
+                          p.sf_step * (sf * (sf - 1) / 2) <= kXchgRows && (sf - 1) * p.sf_step < 32),
+              VQA_E_INVALID, "gemm: shift-fused form needs MT = 1, N <= BN, Npad = sf * BN <= 256 and at most 4 exchanged rows");
   VQA_REQUIRE(p.M > 0 && p.N > 0 && I[GEMM_I_Npad] % bn == 0 && I[GEMM_I_Npad] >= p.N, VQA_E_INVALID,
               "gemm: bad M/N/Npad");
   p.ngroups = I[GEMM_I_ngroups];
@@ -834,7 +1068,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   L->pair = pair;
   // (tf32 pairs were measured too: no gain for the latency-bound M = 5120 Linears, so they are not instantiated)
   VQA_REQUIRE(!pair || (!tf32 && bn % 16 == 0), VQA_E_INVALID, "gemm: CTA pairs are instantiated for bf16 operands");
-  p.idesc = make_idesc(tf32, f16, bn, pair ? 256 : 128);
+  p.idesc = make_idesc(tf32, f16, n_mma, pair ? 256 : 128);
   VQA_REQUIRE(I[GEMM_I_Ktot] % p.chunk_elems == 0, VQA_E_INVALID, "gemm: Ktot must be a multiple of the K chunk");
   p.k_chunks = I[GEMM_I_Ktot] / p.chunk_elems;
   bool lockstep = p.halo == 0 && halo_hi == 0;
@@ -874,7 +1108,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.box_rows = ((win + p.nboxes - 1) / p.nboxes + 7) / 8 * 8;    // 8-row groups keep every box swizzle-aligned
   p.a_tx_bytes = p.nboxes * p.box_rows * p.row_bytes;
   p.a_slot_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
-  p.b_slot_bytes = (pair ? bn / 2 : bn) * p.row_bytes;    // pair: each CTA holds half of the weight tile's rows
+  p.b_slot_bytes = (pair ? n_mma / 2 : n_mma) * p.row_bytes;    // pair: each CTA holds half of the weight tile's rows
   VQA_REQUIRE(p.b_slot_bytes % 1024 == 0, VQA_E_INVALID, "gemm: weight tile must be a multiple of 1024 bytes");
   p.m_tiles = (p.M + 128 * p.MT - 1) / (128 * p.MT);
   p.tiles_per_img = I[GEMM_I_tiles_per_img];
@@ -897,7 +1131,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
                 "gemm: the fused max-pool epilogue needs 3 conv rows per tile (MT=3, BN=64, 32-byte rows)");
   }
   p.n_tiles = (p.N + bn - 1) / bn;        // only N tiles that contain real columns run
-  p.acc_stages = (2 * p.MT * bn <= 512) ? 2 : 1;
+  p.acc_stages = (2 * p.MT * n_mma <= 512) ? 2 : 1;
 
   const bool has_res = op.p[GEMM_P_res] != 0;
   p.out_dtype = I[GEMM_I_out_dtype];
@@ -908,9 +1142,9 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   L->epi = pool ? 4 : (p.out_dtype != 1 ? 0 : 2) + (has_res ? 1 : 0);
 
   // shared-memory plan: one CTA per SM (persistent): rings + epilogue staging + bias table + barriers <= 227 KB
-  const int stage_bytes = epi_stage_bytes(L->epi);
-  const int fixed_bytes = 1024 + stage_bytes + 4 * kBiasTable + 8 * (2 * kMaxASlots + 2 * kMaxBSlots + 4 + kEpiWarps) + 16 +
-                          4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS;
+  const int stage_bytes = epi_stage_bytes(L->epi, sf);
+  const int fixed_bytes = 1024 + stage_bytes + 4 * kBiasTable + 8 * (2 * kMaxASlots + 2 * kMaxBSlots + 4 + kMaxEpiWarps) + 16 +
+                          4 * VQA_MAX_TAPS + 16 * VQA_MAX_GROUPS + (sf > 1 ? kXchgBytes : 0);
   int budget = I[GEMM_I_smem_budget];
   if (budget <= 0) {   // experiment switch: cap the CTA's total shared memory (KB) so CTAs of other kernels can co-reside
     static const int cap_kb = std::getenv("VQA_GEMM_SMEM_KB") ? std::atoi(std::getenv("VQA_GEMM_SMEM_KB")) : 0;
@@ -951,8 +1185,8 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   } else {
     L->mapA1 = L->mapA0;
   }
-  rc = encode_2d(&L->mapB, tf32, op.p[GEMM_P_b], I[GEMM_I_Npad], I[GEMM_I_Ktot], I[GEMM_I_Ktot], pair ? bn / 2 : bn, p.row_bytes,
-                 "gemm B");
+  rc = encode_2d(&L->mapB, tf32, op.p[GEMM_P_b], I[GEMM_I_Npad], I[GEMM_I_Ktot], I[GEMM_I_Ktot], pair ? n_mma / 2 : n_mma,
+                 p.row_bytes, "gemm B");
   if (rc) return rc;
 
   p.ldo = I[GEMM_I_ldo];
@@ -964,6 +1198,22 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   p.mRPI = I[GEMM_I_mRPI] > 0 ? I[GEMM_I_mRPI] : 1;
   p.mH = I[GEMM_I_mH];
   p.mW = I[GEMM_I_mW];
+  auto magic = [](int d, uint32_t* m, uint32_t* sh) {   // n / d == umulhi(n, m) >> sh for 0 <= n < 2^31, d >= 2
+    int k = 0;
+    while ((1LL << k) < d) ++k;
+    *m = static_cast<uint32_t>((1ULL << (31 + k)) / static_cast<unsigned long long>(d) + 1ULL);
+    *sh = static_cast<uint32_t>(k - 1);
+  };
+  p.rpi_magic = p.rpi_shift = p.mp_magic = p.mp_shift = 0;
+  if (p.mask_en) {
+    VQA_REQUIRE(p.mP >= 2 && p.mRPI >= 2 && p.M < (1 << 30), VQA_E_INVALID, "gemm: pad-mask grid out of range");
+    magic(p.mRPI, &p.rpi_magic, &p.rpi_shift);
+    magic(p.mP, &p.mp_magic, &p.mp_shift);
+    for (long long n = 0; n < (1LL << 31); n += 104729) {   // spot check of the division identity
+      const uint32_t q = static_cast<uint32_t>((static_cast<unsigned long long>(n) * p.rpi_magic) >> 32) >> p.rpi_shift;
+      VQA_REQUIRE(q == static_cast<uint32_t>(n / p.mRPI), VQA_E_INVALID, "gemm: division magic failed");
+    }
+  }
   p.bias = reinterpret_cast<const float*>(op.p[GEMM_P_bias]);
   VQA_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, VQA_E_ALIGN,
               "gemm: bias must be 16-byte aligned");
@@ -972,6 +1222,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   L->res_raw = op.p[GEMM_P_res];
   VQA_REQUIRE(L->out_raw != 0, VQA_E_INVALID, "gemm: null output");
   L->bn = bn;
+  L->threads = sf > 1 ? kSfThreads : kThreads;
   const int tiles = p.m_tiles * p.n_tiles;
   int sms = num_sms(device);
   if (I[GEMM_I_max_ctas] > 0 && I[GEMM_I_max_ctas] < sms) sms = I[GEMM_I_max_ctas];   // tests: force many tiles per CTA
@@ -985,13 +1236,21 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   L->out_external = (L->out_raw & VQA_EXT_TAG) != 0;
   L->mapOut = L->mapA0;
   L->mapRes = L->mapA0;
+  L->mapOutLast = L->mapA0;
   if (pool) {
     VQA_REQUIRE(!has_res && p.out_dtype == 0 && !L->out_external, VQA_E_INVALID,
                 "gemm: the pooled output is a bf16 arena buffer without residual");
   } else {
+    VQA_REQUIRE(sf == 1 || !L->out_external, VQA_E_INVALID, "gemm: shift-fused outputs are arena buffers");
     if (!L->out_external) {
+      // shift-fused kernels: the last 32-row slab of a tile stores only its complete rows
       rc = encode_box32(&L->mapOut, p.out_dtype == 1, L->out_raw, p.M, p.N, p.ldo, "gemm output");
       if (rc) return rc;
+      if (sf > 1) {
+        rc = encode_box32(&L->mapOutLast, p.out_dtype == 1, L->out_raw, p.M, p.N, p.ldo, "gemm output (last slab)",
+                          32 - (sf - 1) * p.sf_step);
+        if (rc) return rc;
+      }
     }
     if (has_res) {
       VQA_REQUIRE(!(L->res_raw & VQA_EXT_TAG), VQA_E_INVALID, "gemm: the residual must be an arena buffer");
@@ -999,7 +1258,7 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
       if (rc) return rc;
     }
   }
-  L->fn = pick_kernel(bn, p.MT, tf32, L->epi, p.row_bytes, pair);
+  L->fn = pick_kernel(bn, p.MT, tf32, L->epi, p.row_bytes, pair, sf);
   VQA_REQUIRE(L->fn != nullptr, VQA_E_INVALID, "gemm: no kernel instantiation for this BN/MT/dtype/epilogue");
   VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
@@ -1016,11 +1275,11 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
     CUtensorMap mo;
     int rc = encode_box32(&mo, p.out_dtype == 1, reinterpret_cast<uint64_t>(p.out), p.M, p.N, p.ldo, "gemm output");
     if (rc) return rc;
-    VQA_CUDA_OK(vqa_launch_cluster(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->pair ? 2 : 1, L->mapA0, L->mapA1, L->mapB,
-                                   mo, L->mapRes, p));
+    VQA_CUDA_OK(vqa_launch_cluster(L->fn, L->grid, dim3(L->threads), L->smem, stream, L->pair ? 2 : 1, L->mapA0, L->mapA1, L->mapB,
+                                   mo, L->mapRes, L->mapOutLast, p));
   } else {
-    VQA_CUDA_OK(vqa_launch_cluster(L->fn, L->grid, dim3(kThreads), L->smem, stream, L->pair ? 2 : 1, L->mapA0, L->mapA1, L->mapB,
-                                   L->mapOut, L->mapRes, p));
+    VQA_CUDA_OK(vqa_launch_cluster(L->fn, L->grid, dim3(L->threads), L->smem, stream, L->pair ? 2 : 1, L->mapA0, L->mapA1, L->mapB,
+                                   L->mapOut, L->mapRes, L->mapOutLast, p));
   }
   VQA_LAUNCH_OK("gemm_tap_kernel");
   return VQA_OK;
@@ -1029,8 +1288,9 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
 const char* gemm_kernel_name(const void* storage) {
   const GemmLaunch* L = reinterpret_cast<const GemmLaunch*>(storage);
   static thread_local char name[64];
-  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d%s%s>", L->bn, L->prm.MT,
+  const int sf = static_cast<int>((L->prm.idesc >> 17) & 63u) * 8 / L->bn;
+  snprintf(name, sizeof(name), "gemm_tap_kernel<%d,%d,%s,e%d%s%s%s>", L->bn, L->prm.MT,
            L->prm.is_tf32 ? "tf32" : (((L->prm.idesc >> 7) & 7u) == 0u ? "f16" : "bf16"), L->epi,
-           L->prm.row_bytes == 32 ? ",row32" : "", L->pair ? ",pair" : "");
+           L->prm.row_bytes == 32 ? ",row32" : "", L->pair ? ",pair" : "", sf == 3 ? ",sf3" : sf == 2 ? ",sf2" : "");
   return name;
 }

@@ -670,17 +670,21 @@ __global__ void grid_to_nchw_kernel(const void* __restrict__ src_, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void mask_prep_kernel(const void* __restrict__ src, int* __restrict__ dst, int n, int dtype) {
+// attention_mask (int64 | fp32 | int32 | uint8 / bool) -> binary int32 key mask of the self-attention (mask == 0 -> -inf,
+// models/text_encoder.py:244) and fp32 pooling weights attention_mask.float() (models/fusion.py:299-312)
+__global__ void mask_prep_kernel(const void* __restrict__ src, int* __restrict__ dst, float* __restrict__ dstf, int n,
+                                 int dtype) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  int v = 1;
-  if (dtype == 1) v = reinterpret_cast<const long long*>(src)[t] != 0;
-  else if (dtype == 2) v = reinterpret_cast<const float*>(src)[t] != 0.f;
-  else if (dtype == 3) v = reinterpret_cast<const int*>(src)[t] != 0;
-  else if (dtype == 4) v = reinterpret_cast<const unsigned char*>(src)[t] != 0;
-  dst[t] = v;
+  float v = 1.f;
+  if (dtype == 1) v = static_cast<float>(reinterpret_cast<const long long*>(src)[t]);
+  else if (dtype == 2) v = reinterpret_cast<const float*>(src)[t];
+  else if (dtype == 3) v = static_cast<float>(reinterpret_cast<const int*>(src)[t]);
+  else if (dtype == 4) v = static_cast<float>(reinterpret_cast<const unsigned char*>(src)[t]);
+  dst[t] = v != 0.f;
+  if (dstf) dstf[t] = v;
 }
 
 // x = table[ids]*sqrt(D) (pre-scaled at load) + pe[l]   (models/text_encoder.py:504-512)
@@ -990,7 +994,7 @@ static int launch_attn(const float* q, const float* k, const float* v, const int
 //   phase 2: g = sigmoid(pre) with pre = W[att;txt]+b from that GEMM, g*att+(1-g)*txt, output LayerNorm
 //   phase 0: no gating: att+txt, output LayerNorm (pools computed in place)
 __global__ void __launch_bounds__(256)
-pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text, const int* __restrict__ mask,
+pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ text, const float* __restrict__ mask,
                     const float* __restrict__ pre, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ fused, float* __restrict__ att_pooled, float* __restrict__ txt_pooled,
                     float* __restrict__ cat, int L, int phase, int no_round, float eps) {
@@ -1006,7 +1010,7 @@ pool_gate_ln_kernel(const float* __restrict__ xatt, const float* __restrict__ te
     float cnt = 0.f, sa = 0.f, st = 0.f;
 #pragma unroll 4
     for (int l = 0; l < L; ++l) {
-      const float m = mask ? static_cast<float>(mask[b * L + l]) : 1.f;
+      const float m = mask ? mask[b * L + l] : 1.f;   // attention_mask.float() as pooling weight
       cnt += m;
       sa += xatt[(static_cast<size_t>(b) * L + l) * D + d] * m;
       st += text[(static_cast<size_t>(b) * L + l) * D + d] * m;
@@ -1063,13 +1067,16 @@ __global__ void softmax_topk_kernel(const float* __restrict__ logits, long long*
                                     float* __restrict__ probs, int N, int k, int ld) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];  // vals[N], red[64]
+  extern __shared__ float sm[];  // vals[N], red[64], taken bits[(N + 31) / 32]
   float* vals = sm;
   float* red = sm + N;
   int* redi = reinterpret_cast<int*>(red + 32);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(red + 64);
+  auto taken = [&](int i) { return (flags[i >> 5] >> (i & 31)) & 1u; };
   const int b = blockIdx.x, tid = threadIdx.x, nw = blockDim.x >> 5;
   const float* row = logits + static_cast<size_t>(b) * ld;
   float m = -INFINITY;
+  for (int i = tid; i < (N + 31) / 32; i += blockDim.x) flags[i] = 0u;
   for (int i = tid; i < N; i += blockDim.x) { vals[i] = row[i]; m = fmaxf(m, vals[i]); }
   m = warp_max(m);
   if ((tid & 31) == 0) red[tid >> 5] = m;
@@ -1085,11 +1092,17 @@ __global__ void softmax_topk_kernel(const float* __restrict__ logits, long long*
   s = 0.f;
   for (int w = 0; w < nw; ++w) s += red[w];
   __syncthreads();
+  // Selection key: NaN ranks above everything (torch.topk's order), so a row of NaNs -- the reference's result for a fully
+  // masked question, models/text_encoder.py:244 -- yields indices 0..k-1 with NaN probabilities instead of no winner at
+  // all; a picked entry is retired through the `taken` flag (bit 0 of its key slot), never by its value.
   for (int t = 0; t < k; ++t) {
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = tid; i < N; i += blockDim.x)
-      if (vals[i] > best || (vals[i] == best && i < bi)) { best = vals[i]; bi = i; }
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float v = vals[i];
+      const float key = (v != v) ? INFINITY : v;
+      if (!taken(i) && (key > best || (key == best && i < bi))) { best = key; bi = i; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -1103,9 +1116,10 @@ __global__ void softmax_topk_kernel(const float* __restrict__ logits, long long*
       int ii = redi[0];
       for (int w = 1; w < nw; ++w)
         if (red[w] > bb || (red[w] == bb && redi[w] < ii)) { bb = red[w]; ii = redi[w]; }
+      if (ii < 0 || ii >= N) ii = t < N ? t : N - 1;      // cannot happen with k <= N; never index out of the row
       idx[static_cast<size_t>(b) * k + t] = ii;
-      probs[static_cast<size_t>(b) * k + t] = expf(bb - m) / s;
-      vals[ii] = -INFINITY;
+      probs[static_cast<size_t>(b) * k + t] = expf(vals[ii] - m) / s;
+      flags[ii >> 5] |= 1u << (ii & 31);
     }
     __syncthreads();
   }
@@ -1276,7 +1290,8 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int n = I[MASK_PREP_I_B] * I[MASK_PREP_I_L];
       const void* src = PTR(const void*, MASK_PREP_P_src);
       VQA_REQUIRE(src != nullptr || I[MASK_PREP_I_dtype] == 0, VQA_E_INVALID, "mask_prep: null mask");
-      VQA_CUDA_OK(vqa_launch(mask_prep_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, PTR(int*, MASK_PREP_P_dst), n, I[MASK_PREP_I_dtype]));
+      VQA_CUDA_OK(vqa_launch(mask_prep_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, PTR(int*, MASK_PREP_P_dst),
+                             PTR(float*, MASK_PREP_P_dstf), n, I[MASK_PREP_I_dtype]));
       VQA_LAUNCH_OK("mask_prep_kernel");
       return VQA_OK;
     }
@@ -1333,7 +1348,7 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(phase != 2 || PTR(const float*, POOL_GATE_LN_P_pre), VQA_E_INVALID, "pool_gate_ln: phase 2 needs pre");
       VQA_CUDA_OK(vqa_launch(pool_gate_ln_kernel, dim3(I[POOL_GATE_LN_I_B]), dim3(256), 0, st,
           PTR(const float*, POOL_GATE_LN_P_xatt), PTR(const float*, POOL_GATE_LN_P_text),
-          PTR(const int*, POOL_GATE_LN_P_mask), PTR(const float*, POOL_GATE_LN_P_pre),
+          PTR(const float*, POOL_GATE_LN_P_mask), PTR(const float*, POOL_GATE_LN_P_pre),
           PTR(const float*, POOL_GATE_LN_P_gamma), PTR(const float*, POOL_GATE_LN_P_beta),
           PTR(float*, POOL_GATE_LN_P_fused), PTR(float*, POOL_GATE_LN_P_att_pooled),
           PTR(float*, POOL_GATE_LN_P_txt_pooled), PTR(float*, POOL_GATE_LN_P_cat), I[POOL_GATE_LN_I_L], phase,
@@ -1343,8 +1358,8 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
     }
     case VQA_OP_SOFTMAX_TOPK: {
       const int N = I[SOFTMAX_TOPK_I_N], k = I[SOFTMAX_TOPK_I_k];
-      VQA_REQUIRE(k >= 1 && k <= 16 && k <= N && N <= 10000, VQA_E_INVALID, "softmax_topk: 1<=k<=16, N<=10000");
-      VQA_CUDA_OK(vqa_launch(softmax_topk_kernel, dim3(I[SOFTMAX_TOPK_I_B]), dim3(256), (N + 64) * sizeof(float), st, 
+      VQA_REQUIRE(k >= 1 && k <= 128 && k <= N && N <= 10000, VQA_E_INVALID, "softmax_topk: 1<=k<=min(128, N), N<=10000");
+      VQA_CUDA_OK(vqa_launch(softmax_topk_kernel, dim3(I[SOFTMAX_TOPK_I_B]), dim3(256), (N + 64 + (N + 31) / 32) * sizeof(float), st, 
           PTR(const float*, SOFTMAX_TOPK_P_logits), PTR(long long*, SOFTMAX_TOPK_P_idx),
           PTR(float*, SOFTMAX_TOPK_P_probs), N, k, I[SOFTMAX_TOPK_I_ld]));
       VQA_LAUNCH_OK("softmax_topk_kernel");

@@ -49,7 +49,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "a1_rows", "a1_cols", "a1_ld", "ngroups", "ntaps", "out_dtype", "ldo", "res_dtype", "ldr",
                    "relu", "round_tf32", "mask_en", "mP", "mRPI", "mH", "mW", "smem_budget", "max_ctas", "row_bytes",
                    "halo_hi", "tiles_per_img", "tile_stride", "tile_row0", "img_rows", "n_imgs", "pool", "pool_P",
-                   "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio", "pair"]
+                   "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio", "pair", "sf", "sf_step"]
                   + _GROUPS + _TAPS,
              "p": ["a0", "a1", "b", "out", "bias", "res", "dbg"], "f": []},
     "maxpool": {"i": ["B", "C", "Hin", "Win", "Pin", "RPIin", "Hout", "Wout", "Pout", "RPIout", "f32"],
@@ -70,7 +70,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                      "p": ["xatt", "text", "mask", "wg", "bg", "gamma", "beta", "fused",
                            "att_pooled", "txt_pooled", "cat", "pre"], "f": ["eps"]},
     "softmax_topk": {"i": ["B", "N", "k", "ld"], "p": ["logits", "idx", "probs"], "f": []},
-    "mask_prep": {"i": ["B", "L", "dtype"], "p": ["src", "dst"], "f": []},
+    "mask_prep": {"i": ["B", "L", "dtype"], "p": ["src", "dst", "dstf"], "f": []},
     "grid_to_nchw": {"i": ["B", "C", "H", "W", "P", "RPI", "f32"], "p": ["src", "dst"], "f": []},
     "copy_rows": {"i": ["rows", "cols", "ld_src", "ld_dst"], "p": ["src", "dst"], "f": []},
     "split_tf32": {"i": ["M", "K", "ld_src"], "p": ["src", "dst"], "f": []},
@@ -206,6 +206,14 @@ def _ohwi_phase_order(w):
     return torch.cat([w[:, :, kh, kw] for kh, kw in PHASE_TAP_ORDER], dim=1).contiguous()
 
 
+def _ohwi_shift_fused(w):
+    """[Cout,Cin,3,3] -> [3*Cout, 3*Cin] for the shift-fused form of a 3x3 convolution: row kw*Cout + co holds the
+    weights of horizontal tap kw, K index = kh*Cin + c.  One N = 3*Cout MMA per vertical tap then produces the three
+    horizontal taps' partial sums side by side; the epilogue adds them with row shifts 0 / 1 / 2."""
+    cout, cin = w.shape[:2]
+    return w.permute(3, 0, 2, 1).reshape(3 * cout, 3 * cin).contiguous()
+
+
 def _ohwi(w):
     """[Cout,Cin,kh,kw] -> [Cout, kh*kw*Cin] with K index = (kh*KW+kw)*Cin + c."""
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
@@ -336,6 +344,10 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device, precision: str
             if not tf and q + ".downsample.0.weight" in sd and tuple(w1.shape[2:]) == (3, 3) and w1.shape[0] != w1.shape[1]:
                 W.add(f"s{s}.b{blk}.conv1.wp", _ohwi_phase_order(w1), cw)     # stride-2 block entry, windowed form
             W.add(f"s{s}.b{blk}.conv1.b", b1, f32)
+            if not tf and w1.shape[0] == 64 and w1.shape[1] == 64 and q + ".downsample.0.weight" not in sd:
+                # 64-channel layers: shift-fused form (N = 192 MMAs; a 128x64 MMA is bound by its shared-memory reads)
+                W.add(f"s{s}.b{blk}.conv1.wsf", _ohwi_shift_fused(w1), cw)
+                W.add(f"s{s}.b{blk}.conv2.wsf", _ohwi_shift_fused(w2), cw)
             W.add(f"s{s}.b{blk}.conv2.w", cast(m2), cw)
             W.add(f"s{s}.b{blk}.conv2.b", b2, f32)
             blk += 1
@@ -428,6 +440,10 @@ class OpList:
         self.fused_tail = window or self.tf32
         self.pair = window and not self.tf32
         self.phase_windows = os.environ.get("VQA_PHASE_WINDOWS", "1") != "0"   # A/B switch for the stride-2 block entries
+        # shift-fused form of the 64-channel 3x3 convolutions (N = 192 MMAs + shuffle epilogue): correct and tested, but
+        # measured slower than the 9-tap form on B200 (70-82 us against 66-78 us per stage-1 convolution: the MMAs reach
+        # their 96-cycle floor, the epilogue's two shuffles per output do not keep up), so it is opt-in
+        self.shift_fused = window and not self.tf32 and os.environ.get("VQA_SHIFT_FUSED", "0") != "0"
         self.ws = Arena(device if device is not None else weights.arena.device)
         self.ops: List[Op] = []
         self.named: Dict[str, Tuple[Buf, torch.dtype, Tuple[int, ...]]] = {}
@@ -459,7 +475,8 @@ class OpList:
     def gemm(self, name, *, dtype, M, N, a0, a0_shape, groups, w, bias, out, ldo, out_dtype,
              a1=None, a1_shape=None, res=None, res_dtype=-1, ldr=0, relu=False, rnd=False,
              grid: Optional[Grid] = None, halo: int = 0, MT: int = 1, row_bytes: int = 128,
-             halo_hi: Optional[int] = None, pool_to: Optional[Grid] = None, pair: Optional[bool] = None):
+             halo_hi: Optional[int] = None, pool_to: Optional[Grid] = None, pair: Optional[bool] = None,
+             sf: int = 1, sf_step: int = 1):
         """Tap-shifted GEMM.  ``groups``: list of (map, row_delta, a_col, n_chunks, [tap_rel...]).
 
         For K-chunk c of group g the kernel loads ONE window of A rows
@@ -469,6 +486,10 @@ class OpList:
         ``row_bytes`` is the K-chunk width in bytes: 128 (SWIZZLE_128B, 4 MMAs per chunk) or 32
         (SWIZZLE_32B, one K=16 MMA per chunk: the stem, whose "channels" are 16 packed values).
         The window may be asymmetric: ``halo`` rows before the tile, ``halo_hi`` (default = halo) after.
+
+        ``sf`` > 1 (shift-fused form, N <= 64): the weight matrix has ``sf`` row blocks of BN rows and every MMA is
+        sf*BN columns wide; the epilogue forms out[m] = sum_j acc[m + j*sf_step, j*BN + n].  A 128-row tile then
+        yields 128 - (sf-1)*sf_step output rows (the M tiling is strided accordingly).
         """
         wbuf, _, wshape = self.W.items[w]
         npad, ktot = wshape
@@ -485,7 +506,8 @@ class OpList:
         if bn == 256 and dtype == DT_BF16 and out_dtype == OUT_BF16 and MT == 2 and self.pair and halo > 0:
             bn = 128
         assert npad % bn == 0 and npad >= N, (name, npad, bn)
-        assert len(groups) <= MAX_GROUPS and MT * bn <= 512
+        assert len(groups) <= MAX_GROUPS and MT * bn * sf <= 512
+        assert sf == 1 or (1 < sf <= 3 and npad == sf * bn and MT == 1 and pool_to is None and (sf - 1) * sf_step <= 4)
         i = dict(dtype=dtype, M=M, N=N, Npad=npad, Ktot=ktot, BN=bn, MT=MT, halo=halo,
                  a0_rows=a0_shape[0], a0_cols=a0_shape[1], a0_ld=a0_shape[2],
                  a1_rows=a1_shape[0] if a1_shape else 0, a1_cols=a1_shape[1] if a1_shape else 0,
@@ -493,12 +515,17 @@ class OpList:
                  res_dtype=res_dtype, ldr=ldr, relu=int(relu), round_tf32=int(rnd),
                  mask_en=int(grid is not None), mP=grid.P if grid else 1, mRPI=grid.rpi if grid else 1,
                  mH=grid.H if grid else 1, mW=grid.W if grid else 1, smem_budget=0, max_ctas=0,
-                 row_bytes=row_bytes, halo_hi=halo_hi)
+                 row_bytes=row_bytes, halo_hi=halo_hi, sf=sf, sf_step=sf_step)
+        if sf > 1:   # strided M tiling: tile t covers accumulator rows [t*stride, t*stride + 128), outputs the first `stride`
+            stride = 128 * MT - (sf - 1) * sf_step
+            i.update(tiles_per_img=(M + stride - 1) // stride, tile_stride=stride, tile_row0=0, img_rows=M, n_imgs=1)
         # CTA pairs (cta_group::2): bf16 convolutions with a bf16 output; each CTA loads half of every weight tile
         if pair is None:
             pair_bns = [int(v) for v in os.environ.get("VQA_PAIR_BN", "128").split(",") if v]
             pair = (self.pair and dtype == DT_BF16 and out_dtype == OUT_BF16 and bn in pair_bns
                     and not (row_bytes == 32 and MT == 1))
+            if sf > 1:
+                pair = self.pair and os.environ.get("VQA_SF_PAIR", "0") != "0"
         i["pair"] = int(bool(pair))
         if pool_to is not None:
             # fused 3x3/2 max-pool epilogue: tile t = (image, pooled row i') covers conv rows 2i'-1 .. 2i'+1
@@ -562,6 +589,14 @@ class OpList:
             mt = 2 if (cout >= 128 or not residual) and not self.tf32 else 1
             return [(0, 0, 0, nchunks, rels)], halo, mt
         return [(0, (kh - 1) * g.P + (kw - 1), 0, nchunks, [0]) for kh in range(3) for kw in range(3)], 0, 1
+
+    def _conv3x3_sf(self, g: Grid, nchunks: int):
+        """Shift-fused stride-1 3x3 conv (64 output channels): 3 vertical taps per K chunk, each one MMA that is
+        3 x 64 columns wide (horizontal taps kw = 0, 1, 2 side by side).  acc_kw[r] = sum_kh A[r + (kh-1)P - 1] W[kh,kw]
+        and out[m] = acc_0[m] + acc_1[m+1] + acc_2[m+2]  ->  (groups, halo, halo_hi)."""
+        halo = g.P + 1
+        rels = [halo + (kh - 1) * g.P - 1 for kh in range(3)]
+        return [(0, 0, 0, nchunks, rels)], halo, g.P - 1
 
     def layernorm(self, name, src, g, b, dst, rows, rnd=False, ld=256):
         # output mode: 0 = fp32, 1 = tf32-rounded fp32, 2 = fp16 (operand of an fp16 Linear); tf32 precision mode:
@@ -737,11 +772,17 @@ class Program(OpList):
                 else:
                     taps, halo1, mt1 = self._conv3x3_groups(g, nch_in, cout)
                     a_rows = g.rows
+                sf = 3 if (self.shift_fused and f"s{s}.b{blk}.conv1.wsf" in W) else 1
+                if sf > 1:
+                    (taps, halo1, halo1_hi), mt1, w1name = self._conv3x3_sf(g, nch_in), 1, f"s{s}.b{blk}.conv1.wsf"
                 self.gemm(f"s{s}.b{blk}.conv1", dtype=cdt, M=g.rows, N=cout, a0=x, a0_shape=(a_rows, cin, cin),
                           groups=taps, w=w1name, bias=f"s{s}.b{blk}.conv1.b", out=y, ldo=cout,
-                          out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo1, halo_hi=halo1_hi, MT=mt1)
+                          out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo1, halo_hi=halo1_hi, MT=mt1, sf=sf)
                 has_ds = W.items[f"s{s}.b{blk}.conv2.w"][2][1] > 9 * cout
                 taps2, halo2, mt2 = self._conv3x3_groups(g, cout // self.cchunk, cout, residual=not has_ds)
+                halo2_hi, w2name = None, f"s{s}.b{blk}.conv2.w"
+                if sf > 1:
+                    (taps2, halo2, halo2_hi), mt2, w2name = self._conv3x3_sf(g, cout // self.cchunk), 1, f"s{s}.b{blk}.conv2.wsf"
                 if has_ds:
                     # shortcut conv1x1/stride as extra K columns: phase (0,0) of the block input, same flat row index
                     # (the identity residual as K columns too was measured: 77 -> 85 us at 64 channels, not used)
@@ -755,9 +796,9 @@ class Program(OpList):
                 else:
                     assert not x_is_phase
                     self.gemm(f"s{s}.b{blk}.conv2", dtype=cdt, M=g.rows, N=cout, a0=y,
-                              a0_shape=(g.rows, cout, cout), groups=taps2, w=f"s{s}.b{blk}.conv2.w",
+                              a0_shape=(g.rows, cout, cout), groups=taps2, w=w2name,
                               bias=f"s{s}.b{blk}.conv2.b", out=o, ldo=cout, out_dtype=codt, relu=True, rnd=rnd,
-                              res=x, res_dtype=codt, ldr=cin, grid=g, halo=halo2, MT=mt2)
+                              res=x, res_dtype=codt, ldr=cin, grid=g, halo=halo2, halo_hi=halo2_hi, MT=mt2, sf=sf)
                 x, cin, x_is_phase = o, cout, False
             # ---- stage attention + relayout for the next stage
             has_se, has_sp = f"s{s}.se.w1" in W, f"s{s}.spatial.w" in W
@@ -834,11 +875,14 @@ class Program(OpList):
 
         # ================= text side (independent of the image side: runs on the side stream) =================
         self.lane = 0 if cached else 1             # question-side programs are a single chain: one lane
-        mask = None
+        # the key mask of the self-attention is binary (mask == 0 -> -inf, models/text_encoder.py:244); the masked mean
+        # pools weigh every token with attention_mask.float() (models/fusion.py:299-312): both forms are kept
+        mask = maskw = None
         if self.mask_dtype != MASK_NONE:
             mask = self._buf("mask_i32", i32, B, L)
+            maskw = self._buf("mask_f32", f32, B, L)
             self._op("mask_prep", "mask", dict(B=B, L=L, dtype=self.mask_dtype),
-                     dict(src=ExtRef(EXT["mask"]), dst=mask))
+                     dict(src=ExtRef(EXT["mask"]), dst=mask, dstf=maskw))
         xt = self._buf("text.x", f32, T, D)
         xn = self._buf("text.xn", self.tdt, T, D)
         qkv = self._buf("text.qkv", f32, T, 3 * D)
@@ -931,7 +975,7 @@ class Program(OpList):
         txtp = self._buf("text_pooled", f32, B, D)
         use_gate = "gate.w" in W
         fused_h = self._buf("fused.h", torch.float16, B, D) if self.half_tail else None   # fp16 operand of head0
-        tail_p = dict(xatt=src_q, text=text, mask=mask, wg=None, bg=None, gamma=W.buf("out.ln.g"), beta=W.buf("out.ln.b"),
+        tail_p = dict(xatt=src_q, text=text, mask=maskw, wg=None, bg=None, gamma=W.buf("out.ln.g"), beta=W.buf("out.ln.b"),
                       fused=fused, att_pooled=attp, txt_pooled=txtp, cat=None, pre=None)
         if use_gate:
             # masked pools -> [att;txt] (tf32) -> gate pre-activation on the tensor cores (the 512 KB gate matrix is

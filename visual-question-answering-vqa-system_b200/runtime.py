@@ -13,8 +13,8 @@ from . import program as P
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqa_b200.so")
 
-OP_NI, OP_NP, OP_NF = 144, 12, 4
-ABI_VERSION = 6
+OP_NI, OP_NP, OP_NF = 160, 12, 4
+ABI_VERSION = 7
 
 
 class VqaOp(C.Structure):
