@@ -11,8 +11,15 @@
  * Conventions
  *   - plain C types only: device pointers as uint64_t, sizes as int32_t, cudaStream_t as void*.
  *   - the caller owns every buffer (weights arena, workspace, inputs, outputs); the library
- *     never allocates or frees device memory, never synchronises the device, and launches
- *     only on the stream it is given, so a run can be captured in a CUDA graph.
+ *     never allocates or frees device memory and never synchronises the device.  Work is
+ *     ordered on the stream it is given: ops marked for lane 1 run on a non-blocking side
+ *     stream the plan owns, forked from and joined back into the caller's stream with events
+ *     inside the same call, so a run can still be captured in a CUDA graph.
+ *   - a plan is bound to one device (vqa_plan_create / vqa_plan_run select it and restore the
+ *     caller's current device) and is not re-entrant: it owns its fork / join events and its
+ *     workspace, so two runs of one plan must be ordered by the caller (same stream or events)
+ *     and a second host thread enqueueing the same plan concurrently gets VQA_E_INVALID.
+ *     Independent batches run on separate plans ("slots" in the Python engine).
  *   - every entry point returns 0 on success or a negative VQA_E_* code; vqa_last_error()
  *     returns a thread-local human-readable message.  Nothing aborts the process
  *     (api/main.py:213-221 expects exceptions it can stringify).

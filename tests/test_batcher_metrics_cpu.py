@@ -33,7 +33,7 @@ class StubEngine:
 
 def test_concurrent_requests_share_batches_and_get_their_own_answers():
     eng = StubEngine(delay=0.01)
-    with MicroBatcher(eng, max_batch=8, max_wait_ms=50) as mb:
+    with MicroBatcher(eng, max_batch=8, max_wait_ms=50, pad_to=None) as mb:
         out = [None] * 20
 
         def client(i):
@@ -67,13 +67,33 @@ def test_padding_to_captured_sizes_and_error_isolation():
         assert [f.result(2)["top_answer"] for f in fs] == ["i0:q", "i1:q", "i2:q"]
     assert eng.sizes == [4]                                                      # 3 requests ran as a padded batch of 4
     eng = StubEngine()
-    with MicroBatcher(eng, max_batch=8, max_wait_ms=100) as mb:
+    with MicroBatcher(eng, max_batch=8, max_wait_ms=100, pad_to=None) as mb:
         fs = [mb.submit(im, "q") for im in ("ok1", "bad", "ok2")]
         assert fs[0].result(2)["top_answer"] == "ok1:q" and fs[2].result(2)["top_answer"] == "ok2:q"
         with pytest.raises(OSError):
             fs[1].result(2)
     with pytest.raises(ValueError):
         MicroBatcher(eng, max_batch=0)
+
+
+def test_default_padding_is_powers_of_two_and_cancelled_requests_do_not_kill_the_worker():
+    """a client that cancels its Future used to raise InvalidStateError inside the worker thread (every
+    later caller then hung), and un-padded batch sizes created one plan + CUDA graph per size."""
+    eng = StubEngine(delay=0.05)
+    with MicroBatcher(eng, max_batch=6, max_wait_ms=30) as mb:
+        assert mb.pad_to == [1, 2, 4, 6]
+        first = mb.submit("warm", "q")                   # occupies the worker for 50 ms
+        time.sleep(0.01)
+        doomed = [mb.submit(f"c{k}", "q") for k in range(3)]
+        assert doomed[1].cancel()                        # still queued: cancellable
+        kept = [mb.submit(f"k{k}", "q") for k in range(2)]
+        assert first.result(2)["top_answer"] == "warm:q"
+        assert doomed[0].result(2)["top_answer"] == "c0:q" and doomed[2].result(2)["top_answer"] == "c2:q"
+        assert [f.result(2)["top_answer"] for f in kept] == ["k0:q", "k1:q"]
+        assert doomed[1].cancelled()
+        assert mb.predict("after", "q", timeout=2)["top_answer"] == "after:q"     # the worker is still alive
+    assert set(eng.sizes) <= {1, 2, 4, 6}                                        # only padded sizes reached the engine
+    assert mb.requests == 6                                                      # the cancelled request never ran
 
 
 def test_confusion_matrix_and_per_class_accuracy():

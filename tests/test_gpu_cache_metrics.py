@@ -206,3 +206,35 @@ def test_vqa_accuracy_class_and_evaluate_loop(model):
     assert len(res["per_class_accuracy"]) == 100 and sum(e["count"] for e in res["common_errors"]) == 7
     conf = compute_confusion_matrix(all_logits.argmax(-1), answers, 1000)
     assert int(conf.sum()) == 15 and int(conf.diag().sum()) == 8
+
+
+def test_accuracy_counters_match_reference_golden():
+    """f4 against the REAL reference: tests/golden/metrics_golden.json was written by running utils/metrics.py's
+    VQAAccuracy (update :56-105, compute :107-134) on the seeded inputs of tests/golden/metrics_inputs.py
+    (tests/golden/make_metrics_golden.py); the device-resident counters must reproduce every number."""
+    import json
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import metrics_inputs as MI
+    from vqa_b200.metrics import VQAAccuracy
+    with open(os.path.join(GOLDEN, "metrics_golden.json")) as f:
+        golden = json.load(f)
+    assert [(g["B"], g["N"], g["seed"]) for g in golden] == MI.CASES
+    for g in golden:
+        logits, targets, qtypes = MI.make(g["B"], g["N"], g["seed"])
+        acc = VQAAccuracy()
+        acc.update(logits.cuda(), targets.cuda(), qtypes)
+        acc.update(logits.flip(0).cuda(), targets.flip(0).cuda(), list(reversed(qtypes)))
+        res = acc.compute()
+        assert (res["correct"], res["total"]) == (g["correct"], g["total"]), g
+        assert res["accuracy"] == pytest.approx(g["accuracy"], abs=1e-12)
+        assert res["accuracy_top5"] == pytest.approx(g["accuracy_top5"], abs=1e-12)
+        assert set(res["per_type"]) == set(g["per_type"])
+        for t, v in g["per_type"].items():
+            assert res["per_type"][t] == pytest.approx(v, abs=1e-12), (g["seed"], t)
+        idx = VQAAccuracy()
+        idx.update(logits.argmax(-1).cuda(), targets.cuda())
+        r1 = idx.compute()
+        assert [r1["correct"], round(r1["accuracy_top5"] * r1["total"]), r1["total"]] == g["index_form"]

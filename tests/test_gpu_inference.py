@@ -130,3 +130,57 @@ def test_predict_questions_shares_the_image(engine):
         np.testing.assert_allclose([a["probability"] for a in r["answers"]],
                                    [a["probability"] for a in single["answers"]], rtol=1e-5, atol=1e-7)
     assert engine.predict_questions(im, []) == []
+
+
+def test_micro_batcher_in_front_of_the_real_engine():
+    """SURVEY 8f row f3 on hardware (VERDICT r1): 20 concurrent clients through ``MicroBatcher`` in front of the real
+    ``VQAInference`` -- every client gets exactly what ``predict`` returns for its pair, the batches are padded to
+    [1, 2, 4, 8] so at most four CUDA graphs (and plan workspaces) exist afterwards (api/inference.py:255-323 behind
+    api/main.py:224-267's batch endpoint)."""
+    import threading
+    from vqa_b200.batcher import MicroBatcher
+    torch.manual_seed(0)
+    inf = VQAInference()
+    inf.load()
+    imgs = [Image.fromarray(synth_images_u8(1, 100 + i)[0].numpy(), "RGB") for i in range(20)]
+    imgs[3] = imgs[3].resize((300, 180))
+    qs = [("what is this", "how many are there", "where is what type", "what color is this")[i % 4] + " " * (i % 3)
+          for i in range(20)]
+    want = [inf.predict(im, q, top_k=3) for im, q in zip(imgs, qs)]
+    before = set(inf._graphs)
+    out = [None] * 20
+    with MicroBatcher(inf, max_batch=8, max_wait_ms=20, pad_to=[1, 2, 4, 8]) as mb:
+        def client(i):
+            out[i] = mb.predict(imgs[i], qs[i], top_k=3, timeout=60)
+        threads = [threading.Thread(target=client, args=(i,)) for i in range(20)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert mb.requests == 20 and mb.batches < 20
+    for o, w in zip(out, want):
+        assert o["question"] == w["question"] and [a["index"] for a in o["answers"]] == [a["index"] for a in w["answers"]]
+        np.testing.assert_allclose([a["probability"] for a in o["answers"]], [a["probability"] for a in w["answers"]],
+                                   rtol=1e-5, atol=1e-7)
+    new = set(inf._graphs) - before
+    assert {k[0] for k in new} <= {1, 2, 4, 8} and len(new) <= 4, new
+
+
+def test_plan_and_graph_caches_are_bounded():
+    """VERDICT r1 weak #10: predict_batch with varying batch sizes must not grow device memory without limit."""
+    torch.manual_seed(0)
+    inf = VQAInference(max_graphs=3)
+    inf.load()
+    inf.model.engine().max_plans = 3
+    img = Image.fromarray(synth_images_u8(1, 5)[0].numpy(), "RGB")
+    first = inf.predict_batch([img], ["what is this"], top_k=2)
+    for b in (2, 3, 5, 6, 7):
+        inf.predict_batch([img] * b, ["what is this"] * b, top_k=2)
+        assert len(inf._graphs) <= 3 and len(inf.model.engine()._plans) <= 3
+    torch.cuda.synchronize()
+    again = inf.predict_batch([img], ["what is this"], top_k=2)          # evicted shape: rebuilt, same answer
+    assert again[0]["answers"] == first[0]["answers"]
+    with pytest.raises(IndexError):                                       # tokenizer id beyond the model's vocabulary
+        inf.model.config["vocab_size"] = 5
+        try:
+            inf.preprocess_question("what color is this")
+        finally:
+            inf.model.config["vocab_size"] = 10000

@@ -52,10 +52,160 @@ def test_forward_matches_reference_golden(golden_meta, case):
     assert errs["logits"] <= LOGIT_REL_TOL, errs
     assert errs["image_features"] <= 5e-2, errs      # bf16 backbone, 17 conv layers deep
     assert errs["text_features"] <= 1e-2 and errs["fused"] <= 5e-2, errs
+    # every aux tensor of models/vqa_model.py:301-309 is gated, not only the ones the logits depend on most
+    assert errs["image_projected"] <= 5e-2 and errs["attended_pooled"] <= 5e-2 and errs["text_pooled"] <= 1e-2, errs
+    assert all(v <= 5e-2 for k, v in errs.items() if k.startswith("xattn")), errs
     top_idx, top_p = model.predict(img.cuda(), ids.cuda(), mask.cuda(), top_k=5)
     assert top_idx.dtype == torch.int64 and tuple(top_idx.shape) == (meta["batch"], 5)
     assert np.array_equal(top_idx[:, 0].cpu().numpy(), g["top_indices"][:, 0])
     np.testing.assert_allclose(top_p.cpu().numpy(), g["top_probs"], rtol=2e-2, atol=1e-4)
+
+
+def _grid_nchw(prog, name, H, W, C):
+    """A padded-flat NHWC workspace buffer (program.py, "HBM layout") as an NCHW fp32 tensor of the valid pixels."""
+    t = prog.tensor(name).float().cpu()
+    B = t.shape[0] // ((H + 1) * (W + 1))
+    return t.view(B, H + 1, W + 1, C)[:, :H, :W, :].permute(0, 3, 1, 2).contiguous()
+
+
+def _phases_nchw(prog, name, H, W, C):
+    """The 4-phase split a stage tail writes for the next stage's stride-2 convolution (phase (ph,pw) holds
+    x[2a+ph, 2b+pw] on the half-resolution padded grid) back to NCHW [B, C, H, W]."""
+    t = prog.tensor(name).float().cpu()
+    h2, w2 = H // 2, W // 2
+    rows = t.shape[0] // 4
+    B = rows // ((h2 + 1) * (w2 + 1))
+    out = torch.zeros(B, C, H, W)
+    for ph in range(2):
+        for pw in range(2):
+            q = t[(ph * 2 + pw) * rows: (ph * 2 + pw + 1) * rows].view(B, h2 + 1, w2 + 1, C)[:, :h2, :w2, :]
+            out[:, :, ph::2, pw::2] = q.permute(0, 3, 1, 2)
+    return out
+
+
+@pytest.mark.parametrize("case", ["default_b4", "plain_b2", "ablate_b3", "nospatial_b2"])
+def test_backbone_stage_taps_match_golden(golden_meta, case):
+    """logits barely see the image, so a backbone bug could hide behind the logit gate.  The
+    golden files hold strided samples of the reference's own stem / stage outputs (models/cnn_backbone.py:267-279,
+    349-354, taken through the reference modules by tests/golden/make_golden.py); the CUDA path's buffers after the
+    fused stem+pool, after every stage's residual blocks and after every stage's attention are checked against them."""
+    meta = golden_meta[case]
+    model, sd, u8, img, ids, mask = make(meta)
+    g = np.load(os.path.join(GOLDEN, f"{case}.npz"))
+    with torch.no_grad():
+        _, _, _, prog = model.engine().run(img.cuda(), ids.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    got = {"stem": _grid_nchw(prog, "s1.in", 56, 56, 64)}
+    for s, (hw, c) in enumerate(((56, 64), (28, 128), (14, 256), (7, 512)), start=1):
+        got[f"stage{s}.blocks"] = _grid_nchw(prog, f"s{s}.b1.out", hw, hw, c)
+        if s < 4:
+            got[f"stage{s}"] = _phases_nchw(prog, f"s{s + 1}.in", hw, hw, c)
+        else:
+            got[f"stage{s}"] = _grid_nchw(prog, prog.feat_name, hw, hw, c)
+    errs = {}
+    for k, v in got.items():
+        want = torch.from_numpy(g[f"tap.{k}.sample"])
+        sample = v.flatten()[::997]
+        assert sample.shape == want.shape, (k, sample.shape, want.shape)
+        errs[k] = float((sample - want).abs().max() / want.abs().max())
+    print(case, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["stem"] <= 1.5e-2, errs                       # one bf16 convolution + pool
+    assert all(v <= 5e-2 for v in errs.values()), errs        # up to 17 bf16 convolutions deep
+
+
+def test_batch256_fp32_nchw_matches_oracle():
+    """BASELINE configs[1] at its own size: 256 pairs, fp32 NCHW images, 20-token questions, against the fp32 oracle."""
+    torch.manual_seed(0)
+    model = VQAModel().eval()
+    sd = randomise_state(model.state_dict(), 1)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    _, img, ids, mask = synth_batch(256, 4242)
+    with torch.no_grad():
+        got, aux = model(img.cuda(), ids.cuda(), mask.cuda(), return_aux=True)
+    want, waux = O.vqa_forward(sd, img, ids, mask, return_aux=True)
+    got = got.cpu()
+    errs = {"logits": rel_err(got, want)}
+    for k in ("image_features", "text_features", "fused", "image_projected", "attended_pooled", "text_pooled"):
+        errs[k] = rel_err(aux[k].cpu(), waux[k])
+    agree = float((got.argmax(1) == want.argmax(1)).float().mean())
+    print("B=256", {k: f"{v:.2e}" for k, v in errs.items()}, f"top-1 agreement {agree:.4f}")
+    assert errs["logits"] <= LOGIT_REL_TOL and errs["image_features"] <= 5e-2 and errs["text_features"] <= 1e-2, errs
+    assert errs["fused"] <= 5e-2 and errs["image_projected"] <= 5e-2 and errs["attended_pooled"] <= 5e-2, errs
+    assert agree >= 0.98            # 256 pairs: the 99 % gate is checked on 10 000 pairs below
+    # every row of the big batch equals the same pair run in a small batch (tiles / CTAs do not leak between images)
+    with torch.no_grad():
+        small, _ = model(img[100:104].cuda(), ids[100:104].cuda(), mask[100:104].cuda())
+    assert torch.equal(small.cpu(), got[100:104])
+
+
+def test_batch1024_uint8_matches_oracle_sample():
+    """BASELINE configs[2] per GPU: 1024 uint8 HWC images + questions in one step, GPU preprocessing included; the
+    oracle (fp32 CPU) checks every 16th pair."""
+    torch.manual_seed(0)
+    model = VQAModel().eval()
+    sd = model.state_dict()
+    model = model.cuda()
+    u8, img, ids, mask = synth_batch(1024, 777)
+    with torch.no_grad():
+        got, _ = model(u8.cuda(), ids.cuda(), mask.cuda())
+        idx, probs = model.predict(u8.cuda(), ids.cuda(), mask.cuda(), top_k=5)
+    got = got.cpu()
+    pick = torch.arange(0, 1024, 16)
+    want, _ = O.vqa_forward(sd, O.preprocess_u8(u8[pick]), ids[pick], mask[pick])
+    err = rel_err(got[pick], want)
+    agree = float((got[pick].argmax(1) == want.argmax(1)).float().mean())
+    print(f"B=1024 u8: logits rel err {err:.2e}, top-1 agreement on the 64-pair sample {agree:.3f}")
+    assert err <= LOGIT_REL_TOL and agree >= 0.95
+    assert torch.equal(idx[:, 0].cpu(), got.argmax(1))
+    wi, wp = O.predict_topk(got, 5)
+    assert torch.equal(idx.cpu(), wi)
+    np.testing.assert_allclose(probs.cpu().numpy(), wp.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_fully_masked_row_and_weighted_float_mask():
+    """ADVICE r1.  (1) An all-zero mask row makes the reference's self-attention softmax NaN (models/text_encoder.py:244)
+    and its logits NaN; predict(top_k=5) must return that (NaN probabilities) without faulting -- the top-k kernel used
+    to index shared memory with 0x7fffffff on a NaN row -- also under CUDA-graph replay, and the other rows stay right.
+    (2) The masked mean pools weigh tokens with attention_mask.float() (models/fusion.py:303-313): a float mask with
+    weights other than 0 / 1 must match the oracle, not a binarised mask."""
+    torch.manual_seed(0)
+    model = VQAModel().eval()
+    sd = model.state_dict()
+    model = model.cuda()
+    _, img, ids, mask = synth_batch(6, 31)
+    dead = mask.clone()
+    dead[2] = 0
+    x, t, m = img.cuda(), ids.cuda(), dead.cuda()
+    idx, probs = model.predict(x, t, m, top_k=5)
+    torch.cuda.synchronize()
+    want, _ = O.vqa_forward(sd, img, ids, dead)
+    assert bool(torch.isnan(want[2]).all()) and bool(torch.isnan(probs[2]).all())
+    assert bool(((idx[2] >= 0) & (idx[2] < 1000)).all()) and len(set(idx[2].tolist())) == 5
+    live = [0, 1, 3, 4, 5]
+    assert torch.equal(idx[live, 0].cpu(), want[live].argmax(1))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        gi, gp = model.predict(x, t, m, top_k=5)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(gi.cpu(), idx.cpu()) and bool(torch.isnan(gp[2]).all())
+    with torch.no_grad():
+        ok, _ = model(x, t, mask.cuda())                      # the context survived: a normal forward still works
+    assert rel_err(ok.cpu(), O.vqa_forward(sd, img, ids, mask)[0]) <= LOGIT_REL_TOL
+    # (2) weighted float mask
+    wmask = mask.float() * (0.25 + 0.5 * (torch.arange(mask.shape[1]) % 3).float()).view(1, -1)   # per-token weights
+    with torch.no_grad():
+        got, aux = model(x, t, wmask.cuda(), return_aux=True)
+    want, waux = O.vqa_forward(sd, img, ids, wmask, return_aux=True)
+    assert rel_err(got.cpu(), want) <= LOGIT_REL_TOL
+    assert rel_err(aux["text_pooled"].cpu(), waux["text_pooled"]) <= 1e-2
+    binar, _ = O.vqa_forward(sd, img, ids, mask)
+    assert rel_err(want, binar) > 1e-3                        # the weights do matter in the reference
+    with pytest.raises(ValueError):
+        model.predict(x, t, m, top_k=0)
+    with pytest.raises(ValueError):
+        model.predict(x, t, m, top_k=1001)
 
 
 @pytest.mark.parametrize("case", ["default_b4", "plain_b2", "ablate_b3", "nospatial_b2"])
@@ -142,16 +292,16 @@ def test_mask_variants_and_padding_invariance(golden_meta):
     assert rel_err(full.cpu(), want_full) <= LOGIT_REL_TOL
 
 
-def test_top1_agreement_2000_pairs():
-    """BASELINE.json: >= 99 % top-1 agreement with the fp32 reference (plain seeded random init).
-    2000 pairs here to keep the suite short; bench.py --agreement runs the full 10 000."""
+def test_top1_agreement_10000_pairs():
+    """BASELINE.json: >= 99 % top-1 agreement with the fp32 reference over 10 000 pairs (plain seeded random init;
+    SURVEY 8d: 40 batches of 250 with seeds 1234 + i).  The fp32 oracle runs on the host cores (about a minute)."""
     torch.manual_seed(0)
     model = VQAModel().eval()
     sd = model.state_dict()
     model = model.cuda()
     agree = n = 0
     worst = 0.0
-    for b in range(8):
+    for b in range(40):
         _, img, ids, mask = synth_batch(250, 1234 + b)
         with torch.no_grad():
             got, _ = model(img.cuda(), ids.cuda(), mask.cuda())

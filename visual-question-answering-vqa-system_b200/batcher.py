@@ -13,21 +13,46 @@ from __future__ import annotations
 import queue
 import threading
 import time
-from concurrent.futures import Future
+from concurrent.futures import Future, InvalidStateError
 from typing import Dict, List, Optional, Tuple
 
 
+def _powers_of_two(limit: int) -> List[int]:
+    sizes, s = [], 1
+    while s < limit:
+        sizes.append(s)
+        s *= 2
+    return sizes + [limit]
+
+
+def _resolve(f: Future, result=None, error: Optional[BaseException] = None):
+    """Complete a client's Future; a Future the client cancelled (or that is already resolved) is left alone instead of
+    raising InvalidStateError inside the worker thread."""
+    try:
+        if error is not None:
+            f.set_exception(error)
+        else:
+            f.set_result(result)
+    except InvalidStateError:
+        pass
+
+
 class MicroBatcher:
-    def __init__(self, engine, max_batch: int = 64, max_wait_ms: float = 2.0, pad_to: Optional[List[int]] = None):
-        """``pad_to``: allowed batch sizes, ascending (e.g. [1, 2, 4, 8, 16, 32, 64]): a batch is padded with copies of
-        its last request up to the next allowed size, so that the engine replays a handful of captured CUDA graphs
-        instead of capturing one per batch size.  None = run whatever size was collected."""
+    def __init__(self, engine, max_batch: int = 64, max_wait_ms: float = 2.0, pad_to: Optional[List[int]] = "pow2"):
+        """``pad_to``: allowed batch sizes, ascending: a batch is padded with copies of its last request up to the next
+        allowed size, so that the engine replays a handful of captured CUDA graphs (and keeps a handful of plan
+        workspaces) instead of one per batch size.  Default: the powers of two up to ``max_batch``.  None = run
+        whatever size was collected (the engine's plan / graph caches are LRUs, so this stays bounded too)."""
         if max_batch < 1:
             raise ValueError("max_batch must be >= 1")
         self.engine = engine
         self.max_batch = int(max_batch)
         self.max_wait = float(max_wait_ms) / 1e3
-        self.pad_to = sorted(pad_to) if pad_to else None
+        if isinstance(pad_to, str):
+            if pad_to != "pow2":
+                raise ValueError("pad_to must be a list of batch sizes, None or 'pow2'")
+            pad_to = _powers_of_two(self.max_batch)
+        self.pad_to = sorted(int(s) for s in pad_to) if pad_to else None
         self._q: "queue.Queue[Optional[Tuple[object, str, int, Future]]]" = queue.Queue()
         self._closed = False
         self.batches = 0          # predict_batch calls made
@@ -90,20 +115,22 @@ class MicroBatcher:
             results = self.engine.predict_batch(images, questions, top_k=top_k)
             self.batches += 1
             self.requests += n
-            for it, r in zip(items, results[:n]):
-                it[3].set_result(r)
         except Exception as e:             # one bad request fails its batch: retry singly so the others still get answers
             if n == 1:
-                items[0][3].set_exception(e)
+                _resolve(items[0][3], error=e)
                 return
             for it in items:
                 try:
                     r = self.engine.predict_batch([it[0]], [it[1]], top_k=top_k)[0]
-                    self.batches += 1
-                    self.requests += 1
-                    it[3].set_result(r)
                 except Exception as e1:
-                    it[3].set_exception(e1)
+                    _resolve(it[3], error=e1)
+                    continue
+                self.batches += 1
+                self.requests += 1
+                _resolve(it[3], r)
+            return
+        for it, r in zip(items, results[:n]):
+            _resolve(it[3], r)
 
     def _loop(self):
         while True:
@@ -112,7 +139,8 @@ class MicroBatcher:
                 break
             by_k: Dict[int, list] = {}
             for it in batch:
-                by_k.setdefault(it[2], []).append(it)
+                if it[3].set_running_or_notify_cancel():     # skip requests whose client cancelled while they were queued
+                    by_k.setdefault(it[2], []).append(it)
             for k, items in by_k.items():
                 self._run(items, k)
         # fail whatever is still queued after close()
@@ -121,5 +149,5 @@ class MicroBatcher:
                 it = self._q.get_nowait()
             except queue.Empty:
                 break
-            if it is not None:
-                it[3].set_exception(RuntimeError("MicroBatcher is closed"))
+            if it is not None and it[3].set_running_or_notify_cancel():
+                _resolve(it[3], error=RuntimeError("MicroBatcher is closed"))

@@ -8,6 +8,8 @@
 
 namespace {
 
+constexpr int kMaxDevices = 64;
+
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -975,11 +977,14 @@ static int launch_attn(const float* q, const float* k, const float* v, const int
   AttnFn fn = ntt == 3 ? static_cast<AttnFn>(&attn_mma_kernel<3>) : ntt == 4 ? static_cast<AttnFn>(&attn_mma_kernel<4>)
             : ntt == 7 ? static_cast<AttnFn>(&attn_mma_kernel<7>) : static_cast<AttnFn>(&attn_mma_kernel<8>);
   const size_t smem = static_cast<size_t>(kAttnWarps) * attn_mma_warp_floats(ntt) * sizeof(float);
-  static bool attr_set[9] = {false};
-  if (!attr_set[ntt]) {
+  // cudaFuncSetAttribute is per device (context): remember it per (device, instantiation)
+  static bool attr_set[kMaxDevices][9] = {};
+  int dev = 0;
+  VQA_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev][ntt]) {
     VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
-    attr_set[ntt] = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev][ntt] = true;
   }
   VQA_CUDA_OK(vqa_launch(fn, dim3((B * H + kAttnWarps - 1) / kAttnWarps), dim3(kAttnWarps * 32), smem, st, q, k, v, mask, out,
                          weights, B * H, H, L, T, ld_q, ld_kv, no_round, q_per_kv));
@@ -1252,13 +1257,15 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const bool f32 = I[STAGE_TAIL_I_f32] != 0;
       const size_t smem = static_cast<size_t>(NP) * C * (f32 ? 4 : 2) + sizeof(float) * (static_cast<size_t>(red_rows) * C + 2 * C + 256 + NP + 128);
       VQA_REQUIRE(smem <= 227 * 1024, VQA_E_INVALID, "stage_tail: rows per CTA exceed shared memory (raise CS)");
-      static bool attr_set = false;
-      if (!attr_set) {
+      static bool attr_set[kMaxDevices] = {};   // per device: the attribute belongs to the device's context
+      int dev = 0;
+      VQA_CUDA_OK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
         VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&stage_tail_kernel<false>),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&stage_tail_kernel<true>),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
       }
       if (f32) {
         VQA_CUDA_OK(vqa_launch_cluster(stage_tail_kernel<true>, dim3(I[STAGE_TAIL_I_B] * q.CS), dim3(kTailThreads), smem, st, q.CS, q));

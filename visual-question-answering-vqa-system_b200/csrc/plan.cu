@@ -58,6 +58,7 @@ struct VqaPlan {
   int device = 0;
   std::vector<VqaOp> ops;
   std::vector<void*> gemm;   // per op: prepared GemmLaunch (64-byte aligned) or nullptr
+  std::atomic_flag busy = ATOMIC_FLAG_INIT;   // set while a host thread enqueues this plan (events / side stream are per plan)
   bool has_side = false;     // some op runs on lane 1
   cudaStream_t side = nullptr;
   static constexpr int kEvents = 16;   // fork / join edges of one run (cycled)
@@ -103,7 +104,13 @@ int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** o
   *out = nullptr;
   int rc = vqa_device_check(device);
   if (rc) return rc;
-  VQA_CUDA_OK(cudaSetDevice(device));
+  // tensor maps, streams and function attributes belong to `device`; the caller's current device is restored on return
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  VQA_CUDA_OK(cudaGetDevice(&guard.prev));
+  if (guard.prev == device) guard.prev = -1; else VQA_CUDA_OK(cudaSetDevice(device));
   VqaPlan* plan = new (std::nothrow) VqaPlan();
   VQA_REQUIRE(plan != nullptr, VQA_E_INVALID, "out of host memory");
   plan->device = device;
@@ -164,6 +171,29 @@ int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const u
   const int n = static_cast<int>(plan->ops.size());
   VQA_REQUIRE(first >= 0 && last <= n && first <= last, VQA_E_INVALID, "vqa_plan_run: bad op range");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // A plan owns its fork / join events and its side stream: two host threads must not enqueue the same plan at the same
+  // time (use one plan per slot).  Detected, not serialised: the second caller gets an error instead of a silent race.
+  VqaPlan* mut = const_cast<VqaPlan*>(plan);
+  if (mut->busy.test_and_set(std::memory_order_acquire)) {
+    vqa_set_error("vqa_plan_run: this plan is being enqueued by another thread (plans are not re-entrant; use one plan per stream)");
+    return VQA_E_INVALID;
+  }
+  struct RunGuard {
+    VqaPlan* plan;
+    int prev = -1;
+    ~RunGuard() {
+      if (prev >= 0) cudaSetDevice(prev);
+      plan->busy.clear(std::memory_order_release);
+    }
+  } guard{mut};
+  {   // kernels and events of this plan live on plan->device, whatever the calling thread's current device is
+    int cur = -1;
+    VQA_CUDA_OK(cudaGetDevice(&cur));
+    if (cur != plan->device) {
+      VQA_CUDA_OK(cudaSetDevice(plan->device));
+      guard.prev = cur;
+    }
+  }
   // Whole-plan runs put lane-1 ops (bit 0 of VqaOp.lane) on the plan's side stream.  The first lane-1 op of a
   // run forks (the side stream waits for everything the caller's stream holds so far); an op with
   // VQA_LANE_JOIN set waits for all work issued so far on the OTHER lane before it starts; the end of the plan

@@ -6,6 +6,7 @@ One Engine belongs to one VQAModel on one CUDA device.  Weights are packed once
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -42,8 +43,11 @@ class ImageCache:
         return ImageCache([torch.cat([c.kv[l] for c in caches], 0) for l in range(len(caches[0].kv))])
 
 
+MAX_TOP_K = 128      # softmax_topk_kernel selects one winner per block-wide pass
+
+
 class Engine:
-    def __init__(self, model, weights: Optional[P.Weights] = None):
+    def __init__(self, model, weights: Optional[P.Weights] = None, max_plans: int = 16):
         p = next(model.parameters())
         if p.device.type != "cuda":
             raise VqaError("vqa_b200.VQAModel runs on CUDA (sm_100a) only: move the model with .cuda() "
@@ -54,7 +58,12 @@ class Engine:
         with torch.no_grad():
             self.weights = weights if weights is not None else P.build_weights(
                 model.state_dict(), self.cfg, self.device, precision=getattr(model, "precision", "bf16"))
-        self._plans: Dict[tuple, Tuple[P.Program, Plan]] = {}
+        # LRU of plans: a plan owns a workspace (7.4 MB per pair: 1.9 GB at batch 256), so a server fed arbitrary batch
+        # sizes must not keep one per shape for ever.  An evicted plan stays alive while somebody (a captured CUDA graph,
+        # see ``last_plan``) still holds a reference; its workspace is released with the last reference.
+        self.max_plans = max(1, int(max_plans))
+        self._plans: "OrderedDict[tuple, Tuple[P.Program, Plan]]" = OrderedDict()
+        self.last_plan: Optional[Tuple[P.Program, Plan]] = None   # plan of the latest run (graph captures pin it)
         self.window = True
 
     # ------------------------------------------------------------------ plans
@@ -63,8 +72,12 @@ class Engine:
         """``slot``: plans with different slot numbers have their own workspace, so forwards issued on different
         streams may overlap on the GPU (the pipelined predict path runs two)."""
         n_images = n_images or B
+        if top_k < 0 or top_k > min(MAX_TOP_K, self.cfg["num_answers"]):
+            raise ValueError(f"top_k must be between 1 and min({MAX_TOP_K}, num_answers={self.cfg['num_answers']}), got {top_k}")
         key = (B, L, in_fmt, mask_dtype, want_aux, top_k, self.window, n_images, side, slot)
         hit = self._plans.get(key)
+        if hit is not None:
+            self._plans.move_to_end(key)
         if hit is None:
             if L > self.cfg["max_question_length"]:
                 raise RuntimeError(f"sequence length {L} exceeds max_question_length "
@@ -74,6 +87,9 @@ class Engine:
             idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
             hit = (prog, Plan(prog.ops, idx))
             self._plans[key] = hit
+            while len(self._plans) > self.max_plans:
+                self._plans.popitem(last=False)
+        self.last_plan = hit
         return hit
 
     @staticmethod
@@ -127,7 +143,7 @@ class Engine:
         ext = [0] * len(P.EXT)
         ext[P.EXT["images"]] = images.data_ptr()
         stream = torch.cuda.current_stream(self.device)
-        plan.run(ext, stream.cuda_stream)
+        plan.run(ext, stream.cuda_stream)     # the library selects the plan's device itself
         if not torch.cuda.is_current_stream_capturing():
             images.record_stream(stream)
         D2 = 2 * self.cfg["embed_dim"]
@@ -249,5 +265,7 @@ class Engine:
         return logits, aux
 
     def predict(self, images, token_ids, attention_mask=None, top_k=5, slot: int = 0):
+        if top_k < 1:
+            raise ValueError("top_k must be at least 1")
         _, idx, probs, _ = self.run(images, token_ids, attention_mask, top_k=top_k, slot=slot)
         return idx, probs

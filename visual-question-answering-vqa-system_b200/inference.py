@@ -51,7 +51,7 @@ def get_device() -> str:
 class VQAInference:
     def __init__(self, checkpoint_path: Optional[str] = None, device: Optional[str] = None,
                  question_vocab_path: Optional[str] = None, answer_vocab_path: Optional[str] = None,
-                 use_cuda_graph: bool = True, image_cache_size: int = 0):
+                 use_cuda_graph: bool = True, image_cache_size: int = 0, max_graphs: int = 16):
         self.device = device or get_device()
         self.checkpoint_path = checkpoint_path or DEFAULT_CHECKPOINT
         self.question_vocab_path = question_vocab_path or DEFAULT_QUESTION_VOCAB
@@ -63,7 +63,10 @@ class VQAInference:
         self.use_cuda_graph = use_cuda_graph
         self.pipeline_lanes = 2     # concurrent forwards in predict_tensors_pipelined (each lane: own stream + plan workspace)
         self.gpu_resize = True      # PIL-exact resize of non-224x224 inputs on the device
-        self._graphs: Dict[Tuple[int, int], dict] = {}
+        # captured CUDA graphs (static pinned / device buffers + the plan they replay), one per (batch, length, k) shape:
+        # an LRU, because every entry pins a plan workspace (7.4 MB per pair)
+        self.max_graphs = max(1, int(max_graphs))
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._is_loaded = False
         # LRU of per-image K/V entries (200 KB each) keyed by image content; 0 = off (reference behaviour:
         # every call recomputes the image side)
@@ -144,12 +147,19 @@ class VQAInference:
 
     def preprocess_question(self, question: str) -> Tuple[torch.Tensor, torch.Tensor]:
         ids, mask = self.tokenizer.encode(question, add_special_tokens=True, padding=True, truncation=True)
+        if self.model is not None and ids and max(ids) >= self.model.config["vocab_size"]:
+            # the reference's nn.Embedding raises here (tokenizer vocabulary larger than the checkpoint's); the CUDA embed
+            # kernel cannot raise, so the range is checked on the host where the ids still are
+            raise IndexError(f"token id {max(ids)} is out of range for the model's vocab_size "
+                             f"{self.model.config['vocab_size']} (index out of range in self)")
         return torch.tensor([ids], dtype=torch.long), torch.tensor([mask], dtype=torch.long)
 
     # ------------------------------------------------------------------ execution
     def _run(self, u8: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, top_k: int):
         """u8 [B,224,224,3], ids/mask [B,L] on the host -> (top_idx [B,k], top_probs [B,k]) on the host."""
         B, L = ids.shape
+        if top_k < 1:
+            raise ValueError("top_k must be at least 1")
         k = min(top_k, self.model.num_answers)
         if not self.use_cuda_graph:
             with torch.no_grad():
@@ -158,10 +168,9 @@ class VQAInference:
                                                 mask.to(self.device, non_blocking=True), top_k=k)
             return idx.cpu(), probs.cpu()
         key = (B, L, k)
-        g = self._graphs.get(key)
+        g = self._graph_get(key)
         if g is None:
-            g = self._capture(B, L, k)
-            self._graphs[key] = g
+            g = self._graph_put(key, self._capture(B, L, k))
         if u8.is_cuda:                      # resized on the device already
             g["d_u8"].copy_(u8, non_blocking=True)
         else:
@@ -172,6 +181,18 @@ class VQAInference:
         g["graph"].replay()
         torch.cuda.current_stream().synchronize()
         return g["h_idx"].clone(), g["h_probs"].clone()
+
+    def _graph_get(self, key):
+        g = self._graphs.get(key)
+        if g is not None:
+            self._graphs.move_to_end(key)
+        return g
+
+    def _graph_put(self, key, g):
+        self._graphs[key] = g
+        while len(self._graphs) > self.max_graphs:
+            self._graphs.popitem(last=False)      # drops the graph, its buffers and its reference to the plan
+        return g
 
     def _capture(self, B: int, L: int, k: int) -> dict:
         """Static pinned/device buffers + one CUDA graph: H2D copies, the plan's launches, D2H copies."""
@@ -199,7 +220,7 @@ class VQAInference:
                 g["h_idx"].copy_(idx, non_blocking=True)
                 g["h_probs"].copy_(probs, non_blocking=True)
         g["graph"] = graph
-        g["keep"] = (idx, probs)
+        g["keep"] = (idx, probs, engine.last_plan)   # the graph replays this plan's workspace: keep it alive
         return g
 
     @torch.no_grad()
@@ -235,7 +256,11 @@ class VQAInference:
 
         for i, (u8, ids, mask) in enumerate(batches):
             B, L = ids.shape
-            slots = self._pipe_slots.setdefault((B, L, k), [None] * n_slots)
+            slots = self._pipe_slots.get((B, L, k))
+            if slots is None:
+                slots = self._pipe_slots[(B, L, k)] = [None] * n_slots
+                while len(self._pipe_slots) > 4:        # shapes are few in practice; never keep more than four sets
+                    self._pipe_slots.pop(next(iter(self._pipe_slots)))
             j = i % n_slots
             lane = j % lanes
             comp_s = comp[lane]
@@ -265,7 +290,7 @@ class VQAInference:
                         gr = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(gr, stream=comp_s):
                             sl["idx"], sl["probs"] = engine.predict(sl["d_u8"], sl["d_ids"], sl["d_mask"], k, slot=lane)
-                        sl["graph"] = gr
+                        sl["graph"], sl["plan"] = gr, engine.last_plan   # keep the replayed plan's workspace alive
                     sl["graph"].replay()
                     idx, probs = sl["idx"], sl["probs"]
                 else:
@@ -347,7 +372,7 @@ class VQAInference:
         entry is copied in, 200 KB per image), H2D of ids / mask, the question-side plan, D2H of the top-k."""
         B, L = ids.shape
         key = ("answer", B, L, k, cache.n_images, len(cache.kv))
-        g = self._graphs.get(key)
+        g = self._graph_get(key)
         dev = torch.device(self.device)
         if g is None:
             from .engine import ImageCache
@@ -370,8 +395,8 @@ class VQAInference:
                 _, idx, probs = engine.answer(static, g["d_ids"], g["d_mask"], top_k=k)
                 g["h_idx"].copy_(idx, non_blocking=True)
                 g["h_probs"].copy_(probs, non_blocking=True)
-            g["graph"], g["keep"] = graph, (idx, probs)
-            self._graphs[key] = g
+            g["graph"], g["keep"] = graph, (idx, probs, engine.last_plan)
+            self._graph_put(key, g)
         for dst, src in zip(g["kv"], cache.kv):
             dst.copy_(src, non_blocking=True)
         g["h_ids"].copy_(ids)
