@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 7
+#define VQA_ABI_VERSION 8
 
 #define VQA_OK            0
 #define VQA_E_INVALID    -1   /* bad argument / unsupported shape */
@@ -77,7 +77,9 @@ enum VqaOpKind {
   VQA_OP_COPY_ROWS     = 16, /* fp32 [rows, cols] copy between leading dimensions (logits whose num_answers is not a multiple of 4) */
   VQA_OP_STAGE_TAIL    = 17, /* fused stage tail: SE squeeze+excite, spatial attention, scale, relayout (attention_modules.py:91-136,198-243) */
   VQA_OP_SPLIT_TF32    = 18, /* fp32 -> [tf32 hi | tf32 lo] A operand of the 3xTF32 Linears of the tf32 precision mode */
-  VQA_OP_KIND_MAX      = 19
+  VQA_OP_STEM_POOL     = 19, /* fused stem: conv7x7/2 + BN + ReLU + MaxPool2d 3x3/2 (models/cnn_backbone.py:349-354), two conv rows
+                                per N = 128 MMA, vertical max carried in registers along runs of pooled rows */
+  VQA_OP_KIND_MAX      = 20
 };
 
 typedef struct VqaOp {

@@ -141,6 +141,34 @@ class Emulator:
         out = torch.as_strided(_t(op.p["out"], odt, ext), (M, N), (i["ldo"], 1))
         out.copy_(acc.to(odt))
 
+    def op_stem_pool(self, op, ext):
+        """Two-row fused stem: acc[m, :64] = conv at flat position m, acc[m, 64:] = conv at m + P (same A window)."""
+        i = op.i
+        B, H, W_, Pp, rpi = i["B"], i["H"], i["W"], i["P"], i["RPI"]
+        rows = i["a_rows"]
+        A = _t(op.p["a"], torch.bfloat16, ext)[: rows * 16].view(rows, 16).float()
+        Wt = _t(op.p["w"], torch.bfloat16, ext)[: 128 * 320].view(128, 320).float()
+        m = torch.arange(B * rpi)
+        acc = torch.zeros(B * rpi, 128)
+        for ia in range(5):
+            for ib in range(4):
+                idx = m + (ia - 2) * Pp + (ib - 2)
+                ok = (idx >= 0) & (idx < rows)
+                a = torch.zeros(B * rpi, 16)
+                a[ok] = A[idx[ok]]
+                t = ia * 4 + ib
+                acc += a @ Wt[:, t * 16:(t + 1) * 16].t()
+        gi = _grid_index(B, H, W_, Pp, rpi)
+        conv = acc[:, :64].clamp_min(0).to(torch.bfloat16)
+        nxt = acc[:, 64:].clamp_min(0).to(torch.bfloat16)
+        inner = _grid_index(B, H - 1, W_, Pp, rpi)          # block 1 of row h is block 0 of row h + 1
+        assert torch.equal(nxt[inner], conv[inner + Pp]), "two-row stem weight blocks disagree"
+        y = F.max_pool2d(conv[gi].float().view(B, H, W_, 64).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).reshape(-1, 64)
+        rows_o = B * i["RPIo"]
+        dst = _t(op.p["out"], torch.bfloat16, ext)[: rows_o * 64].view(rows_o, 64)
+        dst.zero_()
+        dst[_grid_index(B, i["Ho"], i["Wo"], i["Po"], i["RPIo"])] = y.to(torch.bfloat16)
+
     def op_maxpool(self, op, ext):
         i = op.i
         B, C = i["B"], i["C"]

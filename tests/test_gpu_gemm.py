@@ -224,6 +224,31 @@ def test_stem_window_fused_maxpool(B, HW, max_ctas):
              atol=2e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("max_ctas", [0, 3])
+@pytest.mark.parametrize("B,HW,run_len", [(2, 20, 5), (2, 20, 1), (3, 112, 14), (1, 112, 2), (2, 56, None)])
+def test_stem_two_row_fused_maxpool(B, HW, run_len, max_ctas):
+    """stem_pool op: one N = 128 MMA set per conv-row pair (block 1 = the same window one vertical tap lower), vertical
+    max carried in registers along runs of pooled rows, horizontal max through shared memory."""
+    g0, g1 = P.Grid(B, HW, HW, pad=2), P.Grid(B, HW // 2, HW // 2)
+    def build(device):
+        g = torch.Generator().manual_seed(41)
+        w = torch.randn(64, 256, generator=g) * (1.0 / 147 ** 0.5)
+        W = P.Weights(device)
+        W.add("w2", P._stem_two_row_matrix(w), torch.bfloat16)
+        W.finalize()
+        ol = P.OpList(W, device)
+        a = ol._buf("a", torch.bfloat16, g0.rows, 16)
+        o = ol._buf("o", torch.bfloat16, g1.rows, 64)
+        ol.stem_pool("stem", a, g0, "w2", o, g1, run_len=run_len, max_ctas=max_ctas)
+        ol.commit()
+        G.named(ol, "a").copy_(_fill(ol, "a", 42))
+        G.named(ol, "o").fill_(7.0)      # pad rows/columns must be overwritten with zeros
+        return ol
+    cpu, gpu, _, _ = G.run_pair(build)
+    G.report(f"two-row stem + max-pool B{B} {HW}x{HW} run_len={run_len} max_ctas={max_ctas}", G.named(gpu, "o"),
+             G.named(cpu, "o"), atol=2e-2, rtol=1e-2)
+
+
 def _conv_sf_case(device, B, H, Wd, residual, max_ctas, pair):
     """Shift-fused 64 -> 64 3x3 convolution (N = 192 MMAs, horizontal taps added in the epilogue)."""
     g = P.Grid(B, H, Wd)

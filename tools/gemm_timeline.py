@@ -19,7 +19,7 @@ P.OpList.__init__(prog, W, "cuda", True)
 prog.cfg, prog.B, prog.L, prog.in_fmt, prog.mask_dtype, prog.want_aux, prog.top_k = model.config, B, 20, "nchw_f32", P.MASK_I64, False, 0
 prog.Bi, prog.side = B, "both"
 prog._build()
-gemms = [k for k, op in enumerate(prog.ops) if op.kind == "gemm"]
+gemms = [k for k, op in enumerate(prog.ops) if op.kind in ("gemm", "stem_pool")]
 for k in gemms:
     prog.ops[k].p["dbg"] = prog._buf(f"dbg{k}", torch.int64, 32)
 prog.commit()
@@ -40,7 +40,10 @@ for k in gemms:
     t = prog.tensor(f"dbg{k}").cpu().tolist()
     d = [x - t[0] for x in t]
     oi = prog.ops[k].i
-    tiles = oi["tiles_per_img"] * oi["n_imgs"] if oi.get("tiles_per_img") else (oi["M"] + 128 * oi["MT"] - 1) // (128 * oi["MT"])
+    if prog.ops[k].kind == "stem_pool":
+        tiles = oi["B"] * (oi["Ho"] + oi["Ho"] // oi["run_len"] - 1)
+    else:
+        tiles = oi["tiles_per_img"] * oi["n_imgs"] if oi.get("tiles_per_img") else (oi["M"] + 128 * oi["MT"] - 1) // (128 * oi["MT"])
     print(f"{k:3d} {prog.ops[k].name:14s} setup {d[1]:5d} tma0 {d[2]:5d} a_full0 {d[3]:6d} mma0_issued {d[4]:6d} acc_seen0 {d[5]:6d} "
           f"epi0_done {d[6]:6d} last_mma {d[9]:7d} last_epi {d[7]:7d} exit {d[8]:7d} | waits: prod a_empty {t[16]:7d} b_empty {t[17]:7d} "
           f"| mma acc_empty {t[18]:7d} a_full {t[19]:7d} b_full {t[20]:7d} | epi(w2) acc_full {t[21]:7d} | m_tiles {tiles} "

@@ -969,6 +969,14 @@ int num_sms(int device) {
 
 }  // namespace
 
+// shared with stem_tcgen05.cu
+int vqa_encode_2d(CUtensorMap* map, bool tf32, uint64_t base, int rows, int cols, int ld, int box_rows, int row_bytes,
+                  const char* what) {
+  return encode_2d(map, tf32, base, rows, cols, ld, box_rows, row_bytes, what);
+}
+int vqa_num_sms(int device) { return num_sms(device); }
+uint32_t vqa_make_idesc(bool tf32, bool f16, int n, int m) { return make_idesc(tf32, f16, n, m); }
+
 typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const CUtensorMap, const CUtensorMap, const GemmParams);
 

@@ -13,6 +13,9 @@ int gemm_launch_bytes();
 int gemm_prepare(const VqaOp& op, void* storage, int device);
 int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t stream);
 const char* gemm_kernel_name(const void* storage);
+int stem_launch_bytes();
+int stem_prepare(const VqaOp& op, void* storage, int device);
+int stem_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t stream);
 int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st);
 const char* misc_kernel_name(int kind);
 
@@ -41,6 +44,7 @@ const FieldCount kFields[VQA_OP_KIND_MAX] = {
     {COPY_ROWS_NI, COPY_ROWS_NP, COPY_ROWS_NF},
     {STAGE_TAIL_NI, STAGE_TAIL_NP, STAGE_TAIL_NF},
     {SPLIT_TF32_NI, SPLIT_TF32_NP, SPLIT_TF32_NF},
+    {STEM_POOL_NI, STEM_POOL_NP, STEM_POOL_NF},
 };
 static_assert(GEMM_NI <= VQA_OP_NI, "VqaOp.i too small for the gemm op");
 static_assert(POOL_GATE_LN_NP <= VQA_OP_NP, "VqaOp.p too small");
@@ -57,7 +61,7 @@ void vqa_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 struct VqaPlan {
   int device = 0;
   std::vector<VqaOp> ops;
-  std::vector<void*> gemm;   // per op: prepared GemmLaunch (64-byte aligned) or nullptr
+  std::vector<void*> gemm;   // per op: prepared GemmLaunch / StemLaunch (64-byte aligned) or nullptr
   std::atomic_flag busy = ATOMIC_FLAG_INIT;   // set while a host thread enqueues this plan (events / side stream are per plan)
   bool has_side = false;     // some op runs on lane 1
   cudaStream_t side = nullptr;
@@ -123,9 +127,10 @@ int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** o
       delete plan;
       return VQA_E_INVALID;
     }
-    if (op.kind == VQA_OP_GEMM) {
+    if (op.kind == VQA_OP_GEMM || op.kind == VQA_OP_STEM_POOL) {   // ops with prepared launches (tensor maps encoded once)
+      const bool is_gemm = op.kind == VQA_OP_GEMM;
       void* st = nullptr;
-      const size_t bytes = (static_cast<size_t>(gemm_launch_bytes()) + 63) / 64 * 64;
+      const size_t bytes = (static_cast<size_t>(is_gemm ? gemm_launch_bytes() : stem_launch_bytes()) + 63) / 64 * 64;
       if (posix_memalign(&st, 64, bytes) != 0) {
         vqa_set_error("out of host memory");
         delete plan;
@@ -133,7 +138,7 @@ int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** o
       }
       std::memset(st, 0, bytes);
       plan->gemm[k] = st;
-      rc = gemm_prepare(op, st, device);
+      rc = is_gemm ? gemm_prepare(op, st, device) : stem_prepare(op, st, device);
       if (rc) {
         vqa_set_error("op " + std::to_string(k) + ": " + g_error);
         delete plan;
@@ -222,7 +227,8 @@ int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const u
       }
       if (side) s = plan->side;
     }
-    int rc = (op.kind == VQA_OP_GEMM) ? gemm_run(plan->gemm[k], ext, n_ext, s) : run_misc_op(op, ext, n_ext, s);
+    int rc = (op.kind == VQA_OP_GEMM) ? gemm_run(plan->gemm[k], ext, n_ext, s)
+             : (op.kind == VQA_OP_STEM_POOL) ? stem_run(plan->gemm[k], ext, n_ext, s) : run_misc_op(op, ext, n_ext, s);
     if (rc) {
       vqa_set_error("op " + std::to_string(k) + ": " + g_error);
       return rc;
@@ -245,7 +251,7 @@ int vqa_plan_op_kernel_name(const VqaPlan* plan, int32_t op, char* buf, int32_t 
   VQA_REQUIRE(plan != nullptr && buf != nullptr && buflen > 0, VQA_E_INVALID, "null argument");
   VQA_REQUIRE(op >= 0 && op < static_cast<int32_t>(plan->ops.size()), VQA_E_INVALID, "op index out of range");
   const char* name = plan->ops[op].kind == VQA_OP_GEMM ? gemm_kernel_name(plan->gemm[op])
-                                                        : misc_kernel_name(plan->ops[op].kind);
+                     : plan->ops[op].kind == VQA_OP_STEM_POOL ? "stem_pool_kernel" : misc_kernel_name(plan->ops[op].kind);
   std::strncpy(buf, name, static_cast<size_t>(buflen) - 1);
   buf[buflen - 1] = 0;
   return VQA_OK;

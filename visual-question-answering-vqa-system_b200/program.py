@@ -36,7 +36,7 @@ KINDS = {
     "ingest": 1, "gemm": 2, "maxpool": 3, "se_squeeze": 4, "se_excite": 5, "spatial_map": 6,
     "scale_relayout": 7, "embed": 8, "layernorm": 9, "self_attn": 10, "cross_attn": 11,
     "pool_gate_ln": 12, "softmax_topk": 13, "mask_prep": 14, "grid_to_nchw": 15,
-    "copy_rows": 16, "stage_tail": 17, "split_tf32": 18,
+    "copy_rows": 16, "stage_tail": 17, "split_tf32": 18, "stem_pool": 19,
 }
 
 _GROUPS = [f"g_{k}{g}" for k in ("map", "delta", "acol", "chunks", "ntaps", "kbase", "tap0")
@@ -76,6 +76,8 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
     "split_tf32": {"i": ["M", "K", "ld_src"], "p": ["src", "dst"], "f": []},
     "stage_tail": {"i": ["B", "C", "H", "W", "P", "RPI", "R", "ks", "mode", "Po", "RPIo", "phase_rows", "CS", "f32"],
                    "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att"], "f": []},
+    "stem_pool": {"i": ["B", "H", "W", "P", "RPI", "Ho", "Wo", "Po", "RPIo", "run_len", "a_rows", "max_ctas"],
+                  "p": ["a", "w", "out", "dbg"], "f": []},
 }
 
 DT_BF16, DT_TF32, DT_F16 = 0, 1, 2      # gemm operand dtype
@@ -206,6 +208,17 @@ def _ohwi_phase_order(w):
     return torch.cat([w[:, :, kh, kw] for kh, kw in PHASE_TAP_ORDER], dim=1).contiguous()
 
 
+def _stem_two_row_matrix(m):
+    """[64, 256] stem matrix (4 vertical x 4 horizontal phase-pixel taps x 16) -> [128, 320] for the two-row form of the
+    fused stem (csrc/stem_tcgen05.cu): 5 vertical tap positions ia' = 0..4 against ONE A window; rows 0..63 produce conv
+    row r with W[ia'] (nothing at ia' = 4), rows 64..127 produce conv row r+1 with W[ia' - 1] (nothing at ia' = 0)."""
+    m = m.reshape(64, 4, 4, 16)
+    out = torch.zeros(128, 5, 4, 16, dtype=m.dtype, device=m.device)
+    out[:64, 0:4] = m
+    out[64:, 1:5] = m
+    return out.reshape(128, 320)
+
+
 def _ohwi_shift_fused(w):
     """[Cout,Cin,3,3] -> [3*Cout, 3*Cin] for the shift-fused form of a 3x3 convolution: row kw*Cout + co holds the
     weights of horizontal tap kw, K index = kh*Cin + c.  One N = 3*Cout MMA per vertical tap then produces the three
@@ -328,6 +341,7 @@ def build_weights(sd: Dict[str, torch.Tensor], cfg: dict, device, precision: str
     mb[:, 2, 2, 0, 1, 3] = (b - hi).to(bf).float()
     if not tf:
         W.add("stem.wb", mb.reshape(-1, 256), bf)
+        W.add("stem.w2", _stem_two_row_matrix(mb.reshape(-1, 256)), bf)
     for s in (1, 2, 3, 4):
         p = f"image_encoder.stage{s}"
         blk = 0
@@ -437,6 +451,8 @@ class OpList:
         self.out_mode = 1 if self.tf32 else 2       # producers of Linear operands: 1 = unrounded fp32 (3xTF32), 2 = fp16
         self.tdt = torch.float16 if self.half_tail else torch.float32   # storage of their A operands
         self.fuse_pool = window and not self.tf32
+        # fused stem: two conv rows per N = 128 MMA, vertical max in registers (stem_pool op); "0" = the 3-row gemm form
+        self.stem_two_row = os.environ.get("VQA_STEM_TWO_ROW", "1") != "0"
         self.fused_tail = window or self.tf32
         self.pair = window and not self.tf32
         self.phase_windows = os.environ.get("VQA_PHASE_WINDOWS", "1") != "0"   # A/B switch for the stride-2 block entries
@@ -574,6 +590,19 @@ class OpList:
                   w=w, bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F32, res=res,
                   res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=rnd)
 
+    def stem_pool(self, name, a, g0: Grid, w, out, g: Grid, run_len: Optional[int] = None, max_ctas: int = 0):
+        """Fused conv7x7/2 + ReLU + max-pool 3x3/2 over the phase-packed input ``a`` on grid ``g0`` (pad = 2) into the
+        pooled grid ``g`` (csrc/stem_tcgen05.cu).  A CTA walks runs of ``run_len`` consecutive pooled rows of one image
+        (the previous conv row is carried in registers); the default keeps every SM busy for small batches and costs one
+        primer tile per 14 rows for large ones."""
+        assert g0.pad == 2 and g0.P <= 128 and g.H * 2 == g0.H and g.W * 2 == g0.W and g.B == g0.B
+        if run_len is None:
+            run_len = next((r for r in (14, 8, 7, 4, 2, 1) if g.H % r == 0 and g0.B * (g.H // r) >= 148), 1)
+        assert g.H % run_len == 0
+        self._op("stem_pool", name, dict(B=g0.B, H=g0.H, W=g0.W, P=g0.P, RPI=g0.rpi, Ho=g.H, Wo=g.W, Po=g.P, RPIo=g.rpi,
+                                         run_len=run_len, a_rows=g0.rows, max_ctas=max_ctas),
+                 dict(a=a, w=self.W.buf(w), out=out))
+
     def _conv3x3_groups(self, g: Grid, nchunks: int, cout: int, residual: bool = False):
         """Stride-1 3x3 conv on a padded-flat grid -> (groups, halo, MT).
 
@@ -670,6 +699,8 @@ class Program(OpList):
                       w="stem.w", bias="stem.b", out=s1, ldo=64, out_dtype=OUT_F32, relu=True, rnd=True, grid=g0)
             self._op("maxpool", "stem.pool", dict(B=B, C=64, Hin=112, Win=112, Pin=g0.P, RPIin=g0.rpi,
                                                   Hout=56, Wout=56, Pout=g.P, RPIout=g.rpi, f32=1), dict(src=s1, dst=x))
+        elif fused and self.stem_two_row:
+            self.stem_pool("stem.conv+pool", s0, g0, "stem.w2", x, g)
         elif fused:
             lo, hi = 2 * g0.P + 2, g0.P + 1
             rels = [lo + (ia - 2) * g0.P + (ib - 2) for ia in range(4) for ib in range(4)]
