@@ -140,6 +140,11 @@ class Emulator:
             return
         out = torch.as_strided(_t(op.p["out"], odt, ext), (M, N), (i["ldo"], 1))
         out.copy_(acc.to(odt))
+        if op.p.get("sums") is not None:   # column sums of every 32-row slab (fp32, before the 16-bit rounding)
+            ns = (M + 31) // 32
+            padded = torch.zeros(ns * 32, N)
+            padded[:M] = acc
+            _t(op.p["sums"], torch.float32, ext)[: ns * N].view(ns, N).copy_(padded.view(ns, 32, N).sum(dim=1))
 
     def op_stem_pool(self, op, ext):
         """Two-row fused stem: acc[m, :64] = conv at flat position m, acc[m, 64:] = conv at m + P (same A window)."""

@@ -73,7 +73,7 @@ def test_tf32_linear_with_residual(M, K, N, ldo, max_ctas):
     G.report(f"tf32 M{M} K{K} N{N}", G.named(gpu, "o"), G.named(cpu, "o"), atol=2e-3, rtol=2e-3)
 
 
-def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, max_ctas=0, extra_ds=False):
+def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, max_ctas=0, extra_ds=False, sums=False, tail=None):
     g = P.Grid(B, H, Wd)
     gen = torch.Generator().manual_seed(7)
     k = 9 * cin + (cin if extra_ds else 0)
@@ -92,8 +92,30 @@ def _conv_case(device, window, B, H, Wd, cin, cout, residual, mt=None, max_ctas=
             a1=x1 if extra_ds else None, a1_shape=(g.rows, cin, cin) if extra_ds else None,
             w="c.w", bias="c.b", out=o, ldo=cout, out_dtype=P.OUT_BF16, relu=True,
             res=x if residual else None, res_dtype=P.OUT_BF16 if residual else -1, ldr=cin, grid=g,
-            halo=halo, MT=mt or mt_auto)
+            halo=halo, MT=mt or mt_auto, sums=ol._buf("sums", torch.float32, (g.rows + 31) // 32, cout) if sums else None)
     ol.ops[-1].i["max_ctas"] = max_ctas
+    if tail is not None:   # SE (+ spatial attention) stage tail fed by the slab sums: "stream" | "staged"
+        r = max(cout // 16, 1)
+        gen2 = torch.Generator().manual_seed(8)
+        W2 = P.Weights(device)
+        W2.add("se.w1", torch.randn(r, cout, generator=gen2) * 0.2, torch.float32)
+        W2.add("se.w2", torch.randn(r, cout, generator=gen2) * 0.5, torch.float32)
+        W2.add("sp.w", torch.randn(2, 49, generator=gen2) * 0.1, torch.float32)
+        W2.finalize()
+        ol._w2 = W2
+        mode = 1 if tail == "stream" else 0
+        gn = P.Grid(B, H // 2, Wd // 2) if mode else g
+        dst = ol._buf("dst", torch.bfloat16, (4 if mode else 1) * gn.rows, cout)
+        sc = ol._buf("scale", torch.float32, B, cout)
+        att = ol._buf("att", torch.float32, B, H * Wd) if tail == "staged" else None
+        split = 0
+        if tail == "stream":
+            split = 2 if H % 4 == 0 else 1
+        ol._op("stage_tail", "tail",
+               dict(B=B, C=cout, H=H, W=Wd, P=g.P, RPI=g.rpi, R=r, ks=7 if tail == "staged" else 0, mode=mode, Po=gn.P,
+                    RPIo=gn.rpi, phase_rows=gn.rows if mode else g.rows, CS=1, f32=0, split=split),
+               dict(src=o, w1=W2.buf("se.w1"), w2=W2.buf("se.w2"), wconv=W2.buf("sp.w") if tail == "staged" else None,
+                    dst=dst, scale=sc, att=att, sums=ol.named["sums"][0]))
     ol.commit()
     # valid pixels random, shared pads zero (the layout invariant every producer keeps)
     xv = torch.randn(g.rows, cin, generator=gen)
@@ -168,6 +190,24 @@ def test_conv3x3_window(B, H, W, cin, cout, mt, max_ctas):
                                                      max_ctas=max_ctas))
     G.report(f"conv window max_ctas={max_ctas} {B}x{H}x{W} {cin}->{cout} MT{mt}", G.named(gpu, "o"),
              G.named(cpu, "o"), atol=3e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("B,H,W,c,mt,tail", [(3, 56, 56, 64, 1, "stream"), (2, 28, 28, 128, 2, "stream"), (5, 14, 14, 256, 2, "staged"),
+                                            (4, 7, 7, 512, 2, "staged"), (3, 8, 12, 64, 1, "stream")])
+@pytest.mark.parametrize("max_ctas", [0, 3])
+def test_conv3x3_slab_sums_feed_the_stage_tail(B, H, W, c, mt, tail, max_ctas):
+    """The last convolution of a stage also writes the column sums of every 32-row slab of its output (SE squeeze
+    partial sums); the stage tail derives the SE scale from them -- streaming form without spatial attention, staged
+    form with it.  The emulator computes the mean from the stored bf16 data instead: both must agree."""
+    cpu, gpu, _, _ = G.run_pair(lambda d: _conv_case(d, True, B, H, W, c, c, True, mt=mt, max_ctas=max_ctas, sums=True, tail=tail))
+    G.report("conv out", G.named(gpu, "o"), G.named(cpu, "o"), atol=3e-2, rtol=2e-2)
+    g = P.Grid(B, H, W)
+    full = slice((g.rpi + 31) // 32, (g.rows // 32))     # slabs of the middle images (never partial at the end of the tensor)
+    G.report("slab sums", G.named(gpu, "sums")[full], G.named(cpu, "sums")[full], atol=2e-2, rtol=1e-3)
+    G.report("SE scale", G.named(gpu, "scale"), G.named(cpu, "scale"), atol=2e-3, rtol=2e-3)
+    if tail == "staged":
+        G.report("spatial attention", G.named(gpu, "att"), G.named(cpu, "att"), atol=2e-3, rtol=2e-3)
+    G.report("tail dst", G.named(gpu, "dst"), G.named(cpu, "dst"), atol=2e-2, rtol=1.6e-2)
 
 
 def test_conv3x3_window_with_shortcut_group():

@@ -16,7 +16,7 @@ from vqa_b200.runtime import Plan  # noqa: E402
 from vqa_b200.synth import randomise_state, synth_batch  # noqa: E402
 
 OUTPUTS = {
-    "ingest": [("dst", torch.bfloat16)], "gemm": [("out", None)], "maxpool": [("dst", torch.bfloat16)],
+    "ingest": [("dst", torch.bfloat16)], "gemm": [("out", None), ("sums", torch.float32)], "stem_pool": [("out", torch.bfloat16)], "maxpool": [("dst", torch.bfloat16)],
     "se_squeeze": [("sums", torch.float32)], "se_excite": [("scale", torch.float32)],
     "spatial_map": [("att", torch.float32)], "scale_relayout": [("dst", torch.bfloat16)],
     "embed": [("dst", torch.float32)], "layernorm": [("dst", torch.float32)],
@@ -116,3 +116,38 @@ def test_each_op_against_emulator(ctor, B, L, in_fmt, mask_kind, window, precisi
                 failures.append(msg)
                 print("FAIL", msg)
     assert not failures, "\n".join(failures[:20])
+
+
+@pytest.mark.parametrize("B,H,C,CS", [(40, 56, 64, 4), (77, 28, 128, 2), (150, 56, 64, 4)])
+def test_stage_tail_se_only_many_images(B, H, C, CS):
+    """SE-only stage tail (two-pass kernel: sums streamed through registers, rows re-read from L2) with more clusters than
+    fit the GPU at once, against the emulator."""
+    import gpu_util as G
+    g, gn = P.Grid(B, H, H), P.Grid(B, H // 2, H // 2)
+    R = C // 16
+
+    def build(device):
+        gen = torch.Generator().manual_seed(5)
+        W = P.Weights(device)
+        W.add("w1", torch.randn(R, C, generator=gen) * 0.2, torch.float32)
+        W.add("w2", torch.randn(R, C, generator=gen) * 0.5, torch.float32)
+        W.finalize()
+        ol = P.OpList(W, device)
+        x = ol._buf("x", torch.bfloat16, g.rows, C)
+        dst = ol._buf("dst", torch.bfloat16, 4 * gn.rows, C)
+        sc = ol._buf("scale", torch.float32, B, C)
+        ol._op("stage_tail", "tail",
+               dict(B=B, C=C, H=H, W=H, P=g.P, RPI=g.rpi, R=R, ks=0, mode=1, Po=gn.P, RPIo=gn.rpi, phase_rows=gn.rows,
+                    CS=CS, f32=0, split=0),
+               dict(src=x, w1=W.buf("w1"), w2=W.buf("w2"), wconv=None, dst=dst, scale=sc, att=None, sums=None))
+        ol.commit()
+        xv = torch.randn(g.rows, C, generator=gen).clamp_min(0)
+        r = torch.arange(g.rows) % g.rpi
+        xv[~(((r // g.P) < g.H) & ((r % g.P) < g.W))] = 0
+        G.named(ol, "x").copy_(xv.to(torch.bfloat16))
+        G.named(ol, "dst").fill_(3.0)           # pads must be rewritten with zeros
+        return ol
+
+    cpu, gpu, _, _ = G.run_pair(build)
+    G.report("SE scale", G.named(gpu, "scale"), G.named(cpu, "scale"), atol=1e-5, rtol=1e-4)
+    G.report("tail dst", G.named(gpu, "dst"), G.named(cpu, "dst"), atol=1e-2, rtol=1.6e-2)

@@ -81,8 +81,29 @@ struct GemmParams {
   int sf_step;
   // pad mask without integer division: n / d = umulhi(n, magic) >> shift for every n < 2^31 (checked on the host)
   uint32_t rpi_magic, rpi_shift, mp_magic, mp_shift;
+  // optional per-slab column sums of the stored values (SE squeeze partial sums, models/attention_modules.py:116):
+  // sums[(row / 32) * ld_sums + n] = sum over the 32 rows of that slab of out[row, n] (fp32, before the 16-bit rounding)
+  float* sums;
+  int ld_sums;
   long long* dbg;    // optional: 16 clock64() timestamps of CTA 0 (profiling aid, nullptr in production)
 };
+
+// Column sums of a 32 x 32 block held one row per lane: after 31 shuffles lane l holds sum over lanes of s[l] (fixed
+// order, so the result is deterministic).  Step with offset o: the half of the warp with bit o set keeps the upper o
+// columns and receives the partner's upper o columns, the other half the lower ones.  Destroys s.
+__device__ __forceinline__ float warp_colsum32(float (&s)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < o; ++k) {
+      const float send = up ? s[k] : s[k + o];
+      const float keep = up ? s[k + o] : s[k];
+      s[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return s[0];
+}
 
 __device__ __forceinline__ int tile_m0(const GemmParams& p, int tile_m, int mt) {
   if (p.tiles_per_img == 0) return tile_m * 128 * mt;
@@ -692,6 +713,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const bool relu = p.relu != 0, rnd = p.round_tf32 != 0, mask_en = p.mask_en != 0, out_f16 = p.out_f16 != 0;
     const int m_tiles = p.m_tiles, acc_stages = p.acc_stages;
     const bool has_bias = p.bias != nullptr;
+    float* const sums = p.sums;
+    const int ld_sums = p.ld_sums;
     {   // bias of all N tiles -> shared memory (zero beyond N), read back as warp-wide broadcasts
       const int nb = min(p.n_tiles * BN, kBiasTable);
       for (int i = threadIdx.x - 64; i < nb; i += 32 * kEpiWarps) s_bias[i] = (has_bias && i < N) ? __ldg(p.bias + i) : 0.f;
@@ -818,6 +841,13 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
             for (int u = 0; u < kUnits; ++u)
               *reinterpret_cast<uint4*>(out_row + ((u ^ swz) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+            if (sums != nullptr) {                      // SE squeeze partial sums of this 32-row slab (warp-uniform branch)
+              const bool live = pix[sub] && row0 + lane < p.M;     // rows past M exist only in the accumulator
+#pragma unroll
+              for (int k = 0; k < 32; ++k) x[k] = live ? (relu ? fmaxf(x[k], 0.f) : x[k]) : 0.f;
+              const float tot = warp_colsum32(x, lane);
+              if (row0 < p.M && col0 + lane < N) sums[static_cast<size_t>(row0 >> 5) * ld_sums + col0 + lane] = tot;
+            }
           } else {
             if (relu) {
 #pragma unroll
@@ -1226,6 +1256,10 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   VQA_REQUIRE(p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0, VQA_E_ALIGN,
               "gemm: bias must be 16-byte aligned");
   p.dbg = reinterpret_cast<long long*>(op.p[GEMM_P_dbg]);
+  p.sums = reinterpret_cast<float*>(op.p[GEMM_P_sums]);
+  p.ld_sums = p.N;
+  VQA_REQUIRE(p.sums == nullptr || (!(op.p[GEMM_P_sums] & VQA_EXT_TAG) && p.out_dtype != 1 && sf == 1 && !pool && p.tiles_per_img == 0),
+              VQA_E_INVALID, "gemm: slab column sums need a 16-bit output and the linear M tiling");
   L->out_raw = op.p[GEMM_P_out];
   L->res_raw = op.p[GEMM_P_res];
   VQA_REQUIRE(L->out_raw != 0, VQA_E_INVALID, "gemm: null output");

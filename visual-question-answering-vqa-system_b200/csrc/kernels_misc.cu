@@ -322,7 +322,146 @@ struct StageTailParams {
   uint4* dst;
   float *scale_out, *att_out;
   int C8, H, W, P, RPI, R, ks, mode, Po, RPIo, phase_rows, CS;
+  const float* sums;   // optional: per-32-row-slab channel sums written by the producing convolution's epilogue
 };
+
+// Channel sums of image n from the slab sums of the producing GEMM (sums[s*C + c] = sum over flat rows 32s..32s+31,
+// pad positions are zero there) plus, for the at most two slabs the image shares with its neighbours, the image's own
+// rows read directly (bf16).  Every thread accumulates a fixed subset in a fixed order and the partial rows of
+// part[] are added in index order by the caller: deterministic.  part = [parts][C] floats in shared memory.
+__device__ __forceinline__ void se_slab_sums(const float* __restrict__ sums, const __nv_bfloat16* __restrict__ src, int n,
+                                             int RPI, int C, float* part, int parts, int tid, int nthreads) {
+  const long long r_lo = static_cast<long long>(n) * RPI, r_hi = r_lo + RPI;
+  long long s_lo = (r_lo + 31) >> 5, s_hi = r_hi >> 5;
+  long long head_hi = s_lo * 32, tail_lo = s_hi * 32;
+  if (s_hi < s_lo) { s_hi = s_lo; head_hi = r_hi; tail_lo = r_hi; }     // the image lies inside one slab
+  for (int idx = tid; idx < C * parts; idx += nthreads) {
+    const int c = idx % C, pt = idx / C;
+    float a = 0.f;
+    for (long long sl = s_lo + pt; sl < s_hi; sl += parts) a += __ldg(sums + sl * C + c);
+    for (long long r = r_lo + pt; r < head_hi; r += parts) a += __bfloat162float(src[r * C + c]);
+    for (long long r = tail_lo + pt; r < r_hi; r += parts) a += __bfloat162float(src[r * C + c]);
+    part[pt * C + c] = a;
+  }
+}
+
+// Streaming form of the stage tail for stages WITHOUT spatial attention whose producer wrote slab sums: no staging in
+// shared memory, no cluster, nothing waits on a reduction over the data -- every CTA (image n, row slice j of `split`)
+// derives the image's SE scale from ~RPI/32 slab sums (a few KB from L2) and then streams its rows once:
+// read 16 B, scale, write 16 B at the (phase-split) destination.  bf16 only.
+constexpr int kStreamThreads = 256;
+constexpr int kStreamMaxC = 512;
+struct SeStreamParams {
+  const uint4* src;
+  uint4* dst;
+  const float *sums, *w1, *w2;
+  float* scale_out;
+  int B, C8, H, W, P, RPI, R, mode, Po, RPIo, phase_rows, split;
+};
+
+__global__ void __launch_bounds__(kStreamThreads)
+se_stream_kernel(const SeStreamParams p) {
+  __shared__ float part[kStreamMaxC];      // [parts][C], parts * C <= 512
+  __shared__ float mean[kStreamMaxC];
+  __shared__ float sc[kStreamMaxC];
+  __shared__ float hid[64];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C8 = p.C8, C = C8 * 8, W = p.W, split = p.split;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // images in DESCENDING order: the producer wrote them ascending, so the last images are still in L2
+  const int n = p.B - 1 - static_cast<int>(blockIdx.x) / split;
+  const int j = static_cast<int>(blockIdx.x) % split;
+  const int rows_l = p.H / split, h0 = j * rows_l;
+  const int NV = rows_l * W * C8;                              // 16-byte vectors of this CTA
+  const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8;
+  const int cg = tid % C8;                                     // 256 % C8 == 0: a thread keeps its channel group
+  // first loads of the stream in flight while the scale is being computed
+  constexpr int U = 4;
+  uint4 v[U];
+  auto src_of = [&](int t) -> const uint4* {
+    const int q = t / C8, hl = q / W, w = q - hl * W;
+    return img + (static_cast<size_t>(h0 + hl) * p.P + w) * C8 + cg;
+  };
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int t = tid + u * kStreamThreads;
+    v[u] = t < NV ? __ldg(src_of(t)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  // ---- SE scale of image n
+  const int parts = C <= kStreamMaxC / 2 ? kStreamMaxC / 2 / C * 1 : 1;   // C=64: 4, C=128: 2, C>=256: 1
+  se_slab_sums(p.sums, reinterpret_cast<const __nv_bfloat16*>(p.src), n, p.RPI, C, part, parts, tid, kStreamThreads);
+  __syncthreads();
+  const float inv_hw = 1.f / static_cast<float>(p.H * W);
+  for (int c = tid; c < C; c += kStreamThreads) {
+    float t = 0.f;
+    for (int l = 0; l < parts; ++l) t += part[l * C + c];
+    mean[c] = t * inv_hw;
+  }
+  __syncthreads();
+  for (int r = warp; r < p.R; r += kStreamThreads / 32) {
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t += __ldg(p.w1 + static_cast<size_t>(r) * C + c) * mean[c];
+    t = warp_sum(t);
+    if (lane == 0) hid[r] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kStreamThreads) {             // w2 is stored transposed [R][C]
+    float t = 0.f;
+    for (int r = 0; r < p.R; ++r) t += __ldg(p.w2 + static_cast<size_t>(r) * C + c) * hid[r];
+    const float sg = 1.f / (1.f + expf(-t));
+    sc[c] = sg;
+    if (p.scale_out && j == 0) p.scale_out[static_cast<size_t>(n) * C + c] = sg;
+  }
+  __syncthreads();
+  float k[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k[i] = sc[cg * 8 + i];
+  // ---- stream: x * scale -> bf16 at the destination (same grid, or the 4-phase split of the next stage)
+  const int Po = p.Po;
+  auto emit = [&](int t, const uint4& q4) {
+    const int q = t / C8, hl = q / W, w = q - hl * W, h = h0 + hl;
+    const uint32_t in[4] = {q4.x, q4.y, q4.z, q4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = pack_bf16x2(bf16lo(in[i]) * k[2 * i], bf16hi(in[i]) * k[2 * i + 1]);
+    size_t row;
+    if (p.mode) row = static_cast<size_t>((h & 1) * 2 + (w & 1)) * p.phase_rows + static_cast<size_t>(n) * p.RPIo + (h >> 1) * Po + (w >> 1);
+    else row = static_cast<size_t>(n) * p.RPIo + h * Po + w;
+    p.dst[row * C8 + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  for (int t0 = tid; t0 < NV; t0 += U * kStreamThreads) {
+    uint4 nx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                               // next batch in flight before this one is written
+      const int t = t0 + (U + u) * kStreamThreads;
+      nx[u] = t < NV ? __ldg(src_of(t)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * kStreamThreads;
+      if (t < NV) emit(t, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = nx[u];
+  }
+  // ---- the destination grid's zero padding that belongs to these rows
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const int rows_o = p.RPIo / Po;
+  const int Ho = p.mode ? p.H / 2 : p.H, Wo = p.mode ? W / 2 : W, nph = p.mode ? 4 : 1;
+  const int i0 = p.mode ? h0 / 2 : h0, i1 = p.mode ? (h0 + rows_l) / 2 : h0 + rows_l;
+  const int padw = Po - Wo;
+  for (int ph = 0; ph < nph; ++ph) {
+    uint4* base = p.dst + (static_cast<size_t>(ph) * p.phase_rows + static_cast<size_t>(n) * p.RPIo) * C8;
+    for (int t = tid; t < (i1 - i0) * padw * C8; t += kStreamThreads) {
+      const int c = t % C8, e = t / C8, i = i0 + e / padw, jj = Wo + e % padw;
+      base[(static_cast<size_t>(i) * Po + jj) * C8 + c] = z;
+    }
+    if (j == split - 1) {
+      for (int t = tid; t < (rows_o - Ho) * Po * C8; t += kStreamThreads) base[static_cast<size_t>(Ho) * Po * C8 + t] = z;
+    }
+  }
+}
 
 // One group of 8 channels of one pixel: one uint4 of bf16, or (F32, the tf32 precision mode) two uint4 of fp32.
 template <bool F32>
@@ -357,6 +496,153 @@ struct TailVec {
     for (int i = 0; i < N; ++i) base[group * N + i] = q[i];
   }
 };
+
+// Two-pass form of the tail for SE-only stages (no spatial attention, bf16).  The staged kernel below is bound by the
+// latency of its chain (load -> reduce -> cluster exchange -> excite -> apply; ncu: 26 % of the warp samples wait at a
+// barrier, 2.3-2.9 TB/s at 56x56) and its ~100 KB of staged rows allow only two CTAs per SM to overlap their chains.
+// Here nothing is staged: pass 1 streams the CTA's rows through registers for the channel sums, the cluster exchanges
+// them, every CTA runs the excite MLP, and pass 2 reads the same rows AGAIN -- from L2, which holds the ~100 KB a CTA
+// read a few microseconds earlier -- scales and writes them.  DRAM traffic stays one read + one write, but a CTA needs
+// 2 KB of shared memory, so six to eight CTAs per SM (every cluster of a 256-image batch at once) overlap their chains.
+// Same summation order per CTA as the staged kernel's 256-thread form; images are independent (batch-invariant).
+constexpr int kTwoPassThreads = 256;
+__global__ void __launch_bounds__(kTwoPassThreads, 4)
+se_two_pass_kernel(const StageTailParams p) {
+  __shared__ float red[2048];             // [part_rows][C]: 8 x 64, 8 x 128, 8 x 256 or 4 x 512
+  __shared__ float part[512], mean[512], sc[512], hid[64];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C8 = p.C8, C = C8 * 8, W = p.W, CS = p.CS, R = p.R;
+  const int rows_l = p.H / CS, NP = rows_l * W;
+  const int n = static_cast<int>(gridDim.x / CS) - 1 - static_cast<int>(blockIdx.x) / CS;   // descending: the last images are still in L2
+  const int rank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int h0 = rank * rows_l;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lanes = kTwoPassThreads / C8;
+  const int cg = tid % C8, pl = tid / C8;
+  const int lpw = C8 < 32 ? 32 / C8 : 1;
+  const int part_rows = lanes / lpw;
+  const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8;
+  // pixel q of this CTA -> source vector; q advances by `lanes` per step, (hl, w) are kept incrementally
+  const int dq_h = lanes / W, dq_w = lanes - dq_h * W;
+  // ---- pass 1: channel sums
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  {
+    int hl = pl / W, w = pl - hl * W;
+    constexpr int U = 4;
+    for (int q0 = pl; q0 < NP; q0 += U * lanes) {
+      uint4 v[U];
+      int hh = hl, ww = w;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u] = (q0 + u * lanes < NP) ? __ldg(img + (static_cast<size_t>(h0 + hh) * p.P + ww) * C8 + cg) : make_uint4(0u, 0u, 0u, 0u);
+        hh += dq_h; ww += dq_w;
+        if (ww >= W) { ww -= W; ++hh; }
+      }
+      hl = hh; w = ww;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x); acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
+        acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z); acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
+      }
+    }
+  }
+  for (int off = C8; off < 32; off <<= 1) {             // C8 < 32: the warp's pixel lanes first (fixed order)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+  }
+  if (pl % lpw == 0) {
+    const int prow = pl / lpw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[prow * C + cg * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kTwoPassThreads) {
+    float t = 0.f;
+    for (int l = 0; l < part_rows; ++l) t += red[l * C + c];
+    part[c] = t;
+  }
+  if (CS > 1) cluster_sync_all(); else __syncthreads();
+  const float inv_hw = 1.f / static_cast<float>(p.H * W);
+  for (int c = tid; c < C; c += kTwoPassThreads) {
+    float t = 0.f;
+    if (CS > 1) {
+      for (int r = 0; r < CS; ++r) t += ld_dsmem_f32(part + c, static_cast<uint32_t>(r));
+    } else {
+      t = part[c];
+    }
+    mean[c] = t * inv_hw;
+  }
+  __syncthreads();
+  // ---- excite: one warp per hidden unit, then one thread per channel
+  for (int r = warp; r < R; r += kTwoPassThreads / 32) {
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t += __ldg(p.w1 + static_cast<size_t>(r) * C + c) * mean[c];
+    t = warp_sum(t);
+    if (lane == 0) hid[r] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kTwoPassThreads) {      // w2 is stored transposed [R][C]
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += __ldg(p.w2 + static_cast<size_t>(r) * C + c) * hid[r];
+    const float sg = 1.f / (1.f + expf(-t));
+    sc[c] = sg;
+    if (p.scale_out && rank == 0) p.scale_out[static_cast<size_t>(n) * C + c] = sg;
+  }
+  __syncthreads();
+  // ---- pass 2: the same rows again (L2), scaled, to the destination grid
+  float kk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) kk[j] = sc[cg * 8 + j];
+  const int Po = p.Po;
+  {
+    int hl = pl / W, w = pl - hl * W;
+    constexpr int U = 4;
+    for (int q0 = pl; q0 < NP; q0 += U * lanes) {
+      uint4 v[U];
+      int hh = hl, ww = w;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u] = (q0 + u * lanes < NP) ? __ldg(img + (static_cast<size_t>(h0 + hh) * p.P + ww) * C8 + cg) : make_uint4(0u, 0u, 0u, 0u);
+        hh += dq_h; ww += dq_w;
+        if (ww >= W) { ww -= W; ++hh; }
+      }
+      hh = hl; ww = w;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (q0 + u * lanes < NP) {
+          const int h = h0 + hh;
+          const uint4 o = make_uint4(pack_bf16x2(bf16lo(v[u].x) * kk[0], bf16hi(v[u].x) * kk[1]), pack_bf16x2(bf16lo(v[u].y) * kk[2], bf16hi(v[u].y) * kk[3]),
+                                     pack_bf16x2(bf16lo(v[u].z) * kk[4], bf16hi(v[u].z) * kk[5]), pack_bf16x2(bf16lo(v[u].w) * kk[6], bf16hi(v[u].w) * kk[7]));
+          size_t row;
+          if (p.mode) row = static_cast<size_t>((h & 1) * 2 + (ww & 1)) * p.phase_rows + static_cast<size_t>(n) * p.RPIo + (h >> 1) * Po + (ww >> 1);
+          else row = static_cast<size_t>(n) * p.RPIo + h * Po + ww;
+          p.dst[row * C8 + cg] = o;
+        }
+        hh += dq_h; ww += dq_w;
+        if (ww >= W) { ww -= W; ++hh; }
+      }
+      hl = hh; w = ww;
+    }
+  }
+  // ---- the destination grid's zero padding that belongs to these rows
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const int rows_o = p.RPIo / Po;
+  const int Ho = p.mode ? p.H / 2 : p.H, Wo = p.mode ? W / 2 : W, nph = p.mode ? 4 : 1;
+  const int i0 = p.mode ? h0 / 2 : h0, i1 = p.mode ? (h0 + rows_l) / 2 : h0 + rows_l;
+  const int padw = Po - Wo;
+  for (int ph = 0; ph < nph; ++ph) {
+    uint4* base = p.dst + (static_cast<size_t>(ph) * p.phase_rows + static_cast<size_t>(n) * p.RPIo) * C8;
+    for (int t = tid; t < (i1 - i0) * padw * C8; t += kTwoPassThreads) {
+      const int c = t % C8, e = t / C8, i = i0 + e / padw, j = Wo + e % padw;
+      base[(static_cast<size_t>(i) * Po + j) * C8 + c] = z;
+    }
+    if (rank == CS - 1) {
+      for (int t = tid; t < (rows_o - Ho) * Po * C8; t += kTwoPassThreads) base[static_cast<size_t>(Ho) * Po * C8 + t] = z;
+    }
+  }
+  if (CS > 1) cluster_sync_all();                       // peers may still be reading this CTA's partial sums
+}
 
 template <bool F32>
 __global__ void __launch_bounds__(kTailThreads)
@@ -400,10 +686,21 @@ stage_tail_kernel(const StageTailParams p) {
                    "l"(g + i) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  const bool slab = use_se && p.sums != nullptr && !F32 && CS == 1;   // channel sums come from the producer's epilogue
+  if (slab) {   // (while the rows are in flight)
+    const int parts = red_rows < 4 ? red_rows : 4;
+    se_slab_sums(p.sums, reinterpret_cast<const __nv_bfloat16*>(p.src), n, p.RPI, C, red, parts, tid, kTailThreads);
+    __syncthreads();
+    for (int c = tid; c < C; c += kTailThreads) {
+      float t = 0.f;
+      for (int l = 0; l < parts; ++l) t += red[l * C + c];
+      part[c] = t;
+    }
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (use_se) {
+  if (use_se && !slab) {
     for (int q = pl; q < NP; q += lanes) {
       Vec v;
       v.load(tile, static_cast<size_t>(q) * C8 + cg);
@@ -413,7 +710,7 @@ stage_tail_kernel(const StageTailParams p) {
       for (int k = 0; k < 8; ++k) acc[k] += x[k];
     }
   }
-  if (use_se) {
+  if (use_se && !slab) {
     for (int off = C8; off < 32; off <<= 1) {           // C8 < 32: the warp's pixel lanes first (fixed order)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
@@ -441,6 +738,8 @@ stage_tail_kernel(const StageTailParams p) {
       for (int l = 0; l < red_rows; ++l) t += red[l * C + c];
       part[c] = t;
     }
+  }
+  if (use_se) {
     // ---- 2. cluster-wide channel sums (rank order) -> mean
     if (CS > 1) cluster_sync_all(); else __syncthreads();
     const float inv_hw = 1.f / static_cast<float>(p.H * W);
@@ -1255,6 +1554,29 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       VQA_REQUIRE(q.wconv == nullptr || 2 * NP <= red_rows * C, VQA_E_INVALID, "stage_tail: spatial maps do not fit the scratch area");
       VQA_REQUIRE(q.ks >= 0 && 2 * q.ks * q.ks <= 128, VQA_E_INVALID, "stage_tail: spatial kernel too large");
       const bool f32 = I[STAGE_TAIL_I_f32] != 0;
+      q.sums = PTR(const float*, STAGE_TAIL_P_sums);
+      if (I[STAGE_TAIL_I_split] > 0) {   // streaming form: slab sums from the producer, no spatial attention, bf16
+        SeStreamParams sp;
+        sp.src = q.src; sp.dst = q.dst; sp.sums = q.sums; sp.w1 = q.w1; sp.w2 = q.w2; sp.scale_out = q.scale_out;
+        sp.B = I[STAGE_TAIL_I_B]; sp.C8 = q.C8; sp.H = q.H; sp.W = q.W; sp.P = q.P; sp.RPI = q.RPI; sp.R = q.R; sp.mode = q.mode;
+        sp.Po = q.Po; sp.RPIo = q.RPIo; sp.phase_rows = q.phase_rows; sp.split = I[STAGE_TAIL_I_split];
+        VQA_REQUIRE(!f32 && q.wconv == nullptr && q.sums != nullptr && q.w1 != nullptr, VQA_E_INVALID,
+                    "stage_tail: the streaming form needs slab sums, SE weights, bf16 data and no spatial attention");
+        VQA_REQUIRE(kStreamThreads % q.C8 == 0 && C <= kStreamMaxC && q.R <= 64, VQA_E_INVALID, "stage_tail: streaming form: C/8 must divide 256, C <= 512");
+        VQA_REQUIRE(sp.split >= 1 && q.H % sp.split == 0 && (!q.mode || ((q.H / sp.split) % 2 == 0 && q.W % 2 == 0)), VQA_E_INVALID,
+                    "stage_tail: rows per CTA must be whole (and even for the phase split)");
+        VQA_CUDA_OK(vqa_launch(se_stream_kernel, dim3(sp.B * sp.split), dim3(kStreamThreads), 0, st, sp));
+        VQA_LAUNCH_OK("se_stream_kernel");
+        return VQA_OK;
+      }
+      {   // two-pass form: SE-only stages in bf16 (rows re-read from L2 instead of staged in shared memory)
+        static const bool two_pass_on = std::getenv("VQA_TAIL_TWO_PASS") == nullptr || std::atoi(std::getenv("VQA_TAIL_TWO_PASS")) != 0;
+        if (two_pass_on && !f32 && q.wconv == nullptr && q.w1 != nullptr && kTwoPassThreads % q.C8 == 0 && C <= 512 && q.R <= 64) {
+          VQA_CUDA_OK(vqa_launch_cluster(se_two_pass_kernel, dim3(I[STAGE_TAIL_I_B] * q.CS), dim3(kTwoPassThreads), 0, st, q.CS, q));
+          VQA_LAUNCH_OK("se_two_pass_kernel");
+          return VQA_OK;
+        }
+      }
       const size_t smem = static_cast<size_t>(NP) * C * (f32 ? 4 : 2) + sizeof(float) * (static_cast<size_t>(red_rows) * C + 2 * C + 256 + NP + 128);
       VQA_REQUIRE(smem <= 227 * 1024, VQA_E_INVALID, "stage_tail: rows per CTA exceed shared memory (raise CS)");
       static bool attr_set[kMaxDevices] = {};   // per device: the attribute belongs to the device's context

@@ -51,7 +51,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "halo_hi", "tiles_per_img", "tile_stride", "tile_row0", "img_rows", "n_imgs", "pool", "pool_P",
                    "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio", "pair", "sf", "sf_step"]
                   + _GROUPS + _TAPS,
-             "p": ["a0", "a1", "b", "out", "bias", "res", "dbg"], "f": []},
+             "p": ["a0", "a1", "b", "out", "bias", "res", "dbg", "sums"], "f": []},
     "maxpool": {"i": ["B", "C", "Hin", "Win", "Pin", "RPIin", "Hout", "Wout", "Pout", "RPIout", "f32"],
                 "p": ["src", "dst"], "f": []},
     "se_squeeze": {"i": ["B", "C", "H", "W", "P", "RPI", "S"], "p": ["src", "sums"], "f": []},
@@ -74,8 +74,8 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
     "grid_to_nchw": {"i": ["B", "C", "H", "W", "P", "RPI", "f32"], "p": ["src", "dst"], "f": []},
     "copy_rows": {"i": ["rows", "cols", "ld_src", "ld_dst"], "p": ["src", "dst"], "f": []},
     "split_tf32": {"i": ["M", "K", "ld_src"], "p": ["src", "dst"], "f": []},
-    "stage_tail": {"i": ["B", "C", "H", "W", "P", "RPI", "R", "ks", "mode", "Po", "RPIo", "phase_rows", "CS", "f32"],
-                   "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att"], "f": []},
+    "stage_tail": {"i": ["B", "C", "H", "W", "P", "RPI", "R", "ks", "mode", "Po", "RPIo", "phase_rows", "CS", "f32", "split"],
+                   "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att", "sums"], "f": []},
     "stem_pool": {"i": ["B", "H", "W", "P", "RPI", "Ho", "Wo", "Po", "RPIo", "run_len", "a_rows", "max_ctas"],
                   "p": ["a", "w", "out", "dbg"], "f": []},
 }
@@ -451,6 +451,11 @@ class OpList:
         self.out_mode = 1 if self.tf32 else 2       # producers of Linear operands: 1 = unrounded fp32 (3xTF32), 2 = fp16
         self.tdt = torch.float16 if self.half_tail else torch.float32   # storage of their A operands
         self.fuse_pool = window and not self.tf32
+        # SE squeeze partial sums in the epilogue of each stage's last convolution + streaming stage tail.  Correct and
+        # tested, but measured slower on B200 (the 31-shuffle column-sum butterfly costs the stage-1 convolution 14 us and
+        # the per-CTA scale chain of the streaming tail does not beat the staged one), so it is opt-in.  It also makes the
+        # SE mean depend on where an image's rows fall in the 32-row slab grid, i.e. on its position in the batch.
+        self.se_epilogue = window and os.environ.get("VQA_SE_EPILOGUE", "0") != "0"
         # fused stem: two conv rows per N = 128 MMA, vertical max in registers (stem_pool op); "0" = the 3-row gemm form
         self.stem_two_row = os.environ.get("VQA_STEM_TWO_ROW", "1") != "0"
         self.fused_tail = window or self.tf32
@@ -492,7 +497,7 @@ class OpList:
              a1=None, a1_shape=None, res=None, res_dtype=-1, ldr=0, relu=False, rnd=False,
              grid: Optional[Grid] = None, halo: int = 0, MT: int = 1, row_bytes: int = 128,
              halo_hi: Optional[int] = None, pool_to: Optional[Grid] = None, pair: Optional[bool] = None,
-             sf: int = 1, sf_step: int = 1):
+             sf: int = 1, sf_step: int = 1, sums=None):
         """Tap-shifted GEMM.  ``groups``: list of (map, row_delta, a_col, n_chunks, [tap_rel...]).
 
         For K-chunk c of group g the kernel loads ONE window of A rows
@@ -561,8 +566,9 @@ class OpList:
         assert kbase == ktot, (name, kbase, ktot)
         assert tap0 <= MAX_TAPS
         i["ntaps"] = tap0
+        # ``sums``: fp32 [ceil(M/32), N] -- the epilogue also writes the column sums of every 32-row slab of the output
         self._op("gemm", name, i, dict(a0=a0, a1=a1, b=wbuf, out=out,
-                                        bias=self.W.buf(bias) if bias else None, res=res))
+                                        bias=self.W.buf(bias) if bias else None, res=res, sums=sums))
 
     def linear(self, name, a, M, K, w, bias, out, N, ldo=None, res=None, relu=False, rnd=False, lda=None):
         """fp32/TF32 dense layer: out[M,N] = a[M,K] @ W^T (+bias)(+res)(relu).
@@ -735,8 +741,11 @@ class Program(OpList):
         self._op("maxpool", "stem.pool", dict(B=B, C=64, Hin=112, Win=112, Pin=g0.P, RPIin=g0.rpi,
                                               Hout=56, Wout=56, Pout=g.P, RPIout=g.rpi), dict(src=s1, dst=x))
 
-    def _stage_tail(self, s, x, g, cout, has_se, has_sp):
-        """One fused kernel per stage: SE squeeze/excite, spatial attention, scaling and the relayout."""
+    def _stage_tail(self, s, x, g, cout, has_se, has_sp, sums=None):
+        """One fused kernel per stage: SE squeeze/excite, spatial attention, scaling and the relayout.  ``sums``: per-slab
+        channel sums written by the epilogue of the stage's last convolution (SE squeeze for free); without spatial
+        attention the tail is then a pure streaming pass (``split`` CTAs per image), with it the staged kernel skips
+        its own reduction."""
         B, W = self.Bi, self.W
         bf, f32 = torch.bfloat16, torch.float32
         scale = self._buf(f"s{s}.se.scale", f32, B, cout) if has_se else None
@@ -757,11 +766,19 @@ class Program(OpList):
             esz = 4 if self.tf32 else 2
             while (g.H // cs) * g.W * cout * esz > lim and cs < 8 and (g.H // (2 * cs)) % 2 == 0 and g.H % (2 * cs) == 0:
                 cs *= 2
+        split = 0
+        if sums is not None and not has_sp:
+            # streaming form: ~6k 16-byte vectors per CTA, rows per CTA even for the phase split
+            split = 1
+            while ((g.H // split) * g.W * cout // 8 > 8192 and g.H % (2 * split) == 0
+                   and (mode == 0 or (g.H // (2 * split)) % 2 == 0)):
+                split *= 2
+            cs = 1
         self._op("stage_tail", f"s{s}.tail",
                  dict(B=B, C=cout, H=g.H, W=g.W, P=g.P, RPI=g.rpi, R=r, ks=ks, mode=mode, Po=Po, RPIo=RPIo,
-                      phase_rows=prow, CS=cs, f32=int(self.tf32)),
+                      phase_rows=prow, CS=cs, f32=int(self.tf32), split=split),
                  dict(src=x, w1=W.buf(f"s{s}.se.w1") if has_se else None, w2=W.buf(f"s{s}.se.w2") if has_se else None,
-                      wconv=W.buf(f"s{s}.spatial.w") if has_sp else None, dst=nxt, scale=scale, att=att))
+                      wconv=W.buf(f"s{s}.spatial.w") if has_sp else None, dst=nxt, scale=scale, att=att, sums=sums))
         return out
 
     def _build_rest(self, g, x):
@@ -810,6 +827,11 @@ class Program(OpList):
                           groups=taps, w=w1name, bias=f"s{s}.b{blk}.conv1.b", out=y, ldo=cout,
                           out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo1, halo_hi=halo1_hi, MT=mt1, sf=sf)
                 has_ds = W.items[f"s{s}.b{blk}.conv2.w"][2][1] > 9 * cout
+                # the stage's last convolution also writes the SE squeeze partial sums (one row per 32-row slab)
+                se_sums = None
+                if (blk == nblk - 1 and self.se_epilogue and self.fused_tail and not self.tf32 and sf == 1
+                        and f"s{s}.se.w1" in W):
+                    se_sums = self._buf(f"s{s}.se.slabs", f32, (g.rows + 31) // 32, cout)
                 taps2, halo2, mt2 = self._conv3x3_groups(g, cout // self.cchunk, cout, residual=not has_ds)
                 halo2_hi, w2name = None, f"s{s}.b{blk}.conv2.w"
                 if sf > 1:
@@ -823,18 +845,19 @@ class Program(OpList):
                               a0_shape=(g.rows, cout, cout), a1=x,
                               a1_shape=(phase_rows if x_is_phase else g.rows, cin, cin), groups=taps2,
                               w=f"s{s}.b{blk}.conv2.w", bias=f"s{s}.b{blk}.conv2.b", out=o, ldo=cout,
-                              out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo2, MT=mt2)
+                              out_dtype=codt, relu=True, rnd=rnd, grid=g, halo=halo2, MT=mt2, sums=se_sums)
                 else:
                     assert not x_is_phase
                     self.gemm(f"s{s}.b{blk}.conv2", dtype=cdt, M=g.rows, N=cout, a0=y,
                               a0_shape=(g.rows, cout, cout), groups=taps2, w=w2name,
                               bias=f"s{s}.b{blk}.conv2.b", out=o, ldo=cout, out_dtype=codt, relu=True, rnd=rnd,
-                              res=x, res_dtype=codt, ldr=cin, grid=g, halo=halo2, halo_hi=halo2_hi, MT=mt2, sf=sf)
+                              res=x, res_dtype=codt, ldr=cin, grid=g, halo=halo2, halo_hi=halo2_hi, MT=mt2, sf=sf,
+                              sums=se_sums)
                 x, cin, x_is_phase = o, cout, False
             # ---- stage attention + relayout for the next stage
             has_se, has_sp = f"s{s}.se.w1" in W, f"s{s}.spatial.w" in W
             if self.fused_tail and (s < 4 or has_se or has_sp):
-                x, x_is_phase, phase_rows = self._stage_tail(s, x, g, cout, has_se, has_sp)
+                x, x_is_phase, phase_rows = self._stage_tail(s, x, g, cout, has_se, has_sp, sums=se_sums if nblk else None)
                 continue
             scale = att = None
             if has_se:
