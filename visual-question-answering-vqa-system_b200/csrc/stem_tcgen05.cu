@@ -330,7 +330,12 @@ int stem_prepare(const VqaOp& op, void* storage, int device) {
   p.dbg = reinterpret_cast<long long*>(op.p[STEM_POOL_P_dbg]);
   int sms = vqa_num_sms(device);
   if (I[STEM_POOL_I_max_ctas] > 0 && I[STEM_POOL_I_max_ctas] < sms) sms = I[STEM_POOL_I_max_ctas];
-  L->grid = dim3(p.n_runs < sms ? p.n_runs : sms, 1, 1);
+  int ctas = p.n_runs < sms ? p.n_runs : sms;
+  if (p.n_runs > sms) {   // the fewest CTAs that finish in the same number of rounds
+    const int rounds = (p.n_runs + sms - 1) / sms;
+    ctas = (p.n_runs + rounds - 1) / rounds;
+  }
+  L->grid = dim3(ctas, 1, 1);
   VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&stem_pool_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024));
   return VQA_OK;
