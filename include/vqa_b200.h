@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 8
+#define VQA_ABI_VERSION 9
 
 #define VQA_OK            0
 #define VQA_E_INVALID    -1   /* bad argument / unsupported shape */
@@ -50,7 +50,7 @@ extern "C" {
 #define VQA_MAX_GROUPS 12
 #define VQA_LANE_JOIN  4
 #define VQA_OP_NI      160
-#define VQA_OP_NP     12
+#define VQA_OP_NP     16
 #define VQA_OP_NF     4
 
 /* Op kinds.  Field layouts (indices into VqaOp.i / .p / .f) are listed in program.py
@@ -79,7 +79,9 @@ enum VqaOpKind {
   VQA_OP_SPLIT_TF32    = 18, /* fp32 -> [tf32 hi | tf32 lo] A operand of the 3xTF32 Linears of the tf32 precision mode */
   VQA_OP_STEM_POOL     = 19, /* fused stem: conv7x7/2 + BN + ReLU + MaxPool2d 3x3/2 (models/cnn_backbone.py:349-354), two conv rows
                                 per N = 128 MMA, vertical max carried in registers along runs of pooled rows */
-  VQA_OP_KIND_MAX      = 20
+  VQA_OP_MLP_CHAIN     = 20, /* fused post-attention chain of a transformer layer: W_o + residual, LayerNorm, FFN, residual and the next
+                                block's LayerNorm + projection (models/text_encoder.py:373-399, models/cross_attention.py:265-299) */
+  VQA_OP_KIND_MAX      = 21
 };
 
 typedef struct VqaOp {

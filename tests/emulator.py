@@ -174,6 +174,28 @@ class Emulator:
         dst.zero_()
         dst[_grid_index(B, i["Ho"], i["Wo"], i["Po"], i["RPIo"])] = y.to(torch.bfloat16)
 
+    def op_mlp_chain(self, op, ext):
+        """x1 = xres + ctx Wo^T; x2 = x1 + relu(LN(x1) W1^T + b1) W2^T + b2; y = LN'(x2) Wn^T (fp16 operands, fp32 accumulate)."""
+        i = op.i
+        T, D, Fh, Nn = i["T"], i["D"], i["F"], i["Nn"]
+        f16, f32 = torch.float16, torch.float32
+        ctx = _t(op.p["ctx"], f16, ext)[: T * D].view(T, D).float()
+        xres = _t(op.p["xres"], f32, ext)[: T * D].view(T, D).clone()
+        wo = _t(op.p["wo"], f16, ext)[: D * D].view(D, D).float()
+        w1 = _t(op.p["w1"], f16, ext)[: Fh * D].view(Fh, D).float()
+        w2 = _t(op.p["w2"], f16, ext)[: D * Fh].view(D, Fh).float()
+        b1 = _t(op.p["b1"], f32, ext)[:Fh]
+        b2 = _t(op.p["b2"], f32, ext)[:D]
+        x1 = xres + ctx @ wo.t()
+        xn = F.layer_norm(x1, (D,), _t(op.p["ln_g"], f32, ext)[:D], _t(op.p["ln_b"], f32, ext)[:D], op.f["eps"]).half().float()
+        h = F.relu(xn @ w1.t() + b1).half().float()
+        x2 = x1 + h @ w2.t() + b2
+        if Nn:
+            wn = _t(op.p["wn"], f16, ext)[: Nn * D].view(Nn, D).float()
+            xn2 = F.layer_norm(x2, (D,), _t(op.p["n_g"], f32, ext)[:D], _t(op.p["n_b"], f32, ext)[:D], op.f["eps_n"]).half().float()
+            _t(op.p["y"], f32, ext)[: T * Nn].view(T, Nn).copy_(xn2 @ wn.t())
+        _t(op.p["xout"], f32, ext)[: T * D].view(T, D).copy_(x2)
+
     def op_maxpool(self, op, ext):
         i = op.i
         B, C = i["B"], i["C"]

@@ -337,3 +337,42 @@ def test_conv3x3_shift_fused(B, H, W, residual, max_ctas, pair):
     pads = torch.ones(g.rows, dtype=torch.bool)
     pads[idx] = False
     assert G.named(gpu, "o").cpu()[pads].abs().max() == 0   # shared zero padding is rewritten as zeros
+
+
+@pytest.mark.parametrize("T,F,Nn,max_ctas", [(128, 1024, 0, 0), (300, 1024, 768, 0), (1000, 1024, 256, 3), (700, 256, 768, 2),
+                                             (5120, 1024, 768, 0)])
+def test_mlp_chain(T, F, Nn, max_ctas):
+    """Fused post-attention chain (W_o + residual, LayerNorm, FFN in 128-column hidden chunks, residual, the next block's
+    LayerNorm + projection) against the emulator; max_ctas forces several 128-row tiles per CTA (barrier phases, TMEM and
+    operand-buffer reuse across tiles), T = 300 / 700 / 1000 a ragged last tile."""
+    D = 256
+    def build(device):
+        g = torch.Generator().manual_seed(61)
+        W = P.Weights(device)
+        rnd = lambda *s: torch.randn(*s, generator=g)
+        W.add("l.o.w.h", rnd(D, D) / 16, torch.float16)
+        W.add("l.fc1.w.h", rnd(F, D) / 16, torch.float16)
+        W.add("l.fc1.b", rnd(F) * 0.1, torch.float32)
+        W.add("l.fc2.w.h", rnd(D, F) / F ** 0.5, torch.float16)
+        W.add("l.fc2.b", rnd(D) * 0.1, torch.float32)
+        W.add("l.ln.g", 1 + 0.1 * rnd(D), torch.float32)
+        W.add("l.ln.b", 0.1 * rnd(D), torch.float32)
+        W.add("n.ln.g", 1 + 0.1 * rnd(D), torch.float32)
+        W.add("n.ln.b", 0.1 * rnd(D), torch.float32)
+        W.add("n.w.h", rnd(max(Nn, 128), D) / 16, torch.float16)
+        W.finalize()
+        ol = P.OpList(W, device)
+        ctx = ol._buf("ctx", torch.float16, T, D)
+        x = ol._buf("x", torch.float32, T, D)
+        xo = ol._buf("xo", torch.float32, T, D)
+        y = ol._buf("y", torch.float32, T, max(Nn, 4))
+        ol.mlp_chain("chain", ctx=ctx, xres=x, xout=xo, T=T, prefix="l", ln="l.ln",
+                     nxt=("n.ln", "n.w.h", y, Nn) if Nn else None, max_ctas=max_ctas)
+        ol.commit()
+        G.named(ol, "ctx").copy_(_fill(ol, "ctx", 62))
+        G.named(ol, "x").copy_(_fill(ol, "x", 63, scale=2.0))
+        return ol
+    cpu, gpu, _, _ = G.run_pair(build)
+    G.report(f"chain xout T{T} F{F}", G.named(gpu, "xo"), G.named(cpu, "xo"), atol=4e-3, rtol=2e-3)
+    if Nn:
+        G.report(f"chain y T{T} Nn{Nn}", G.named(gpu, "y"), G.named(cpu, "y"), atol=6e-3, rtol=4e-3)

@@ -16,7 +16,7 @@ from vqa_b200.runtime import Plan  # noqa: E402
 from vqa_b200.synth import randomise_state, synth_batch  # noqa: E402
 
 OUTPUTS = {
-    "ingest": [("dst", torch.bfloat16)], "gemm": [("out", None), ("sums", torch.float32)], "stem_pool": [("out", torch.bfloat16)], "maxpool": [("dst", torch.bfloat16)],
+    "ingest": [("dst", torch.bfloat16)], "gemm": [("out", None), ("sums", torch.float32)], "stem_pool": [("out", torch.bfloat16)], "mlp_chain": [("xout", torch.float32), ("y", torch.float32)], "maxpool": [("dst", torch.bfloat16)],
     "se_squeeze": [("sums", torch.float32)], "se_excite": [("scale", torch.float32)],
     "spatial_map": [("att", torch.float32)], "scale_relayout": [("dst", torch.bfloat16)],
     "embed": [("dst", torch.float32)], "layernorm": [("dst", torch.float32)],

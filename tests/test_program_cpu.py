@@ -36,7 +36,7 @@ def test_program_matches_oracle(ctor, B, L, fmt, mk, window):
     assert float((feat - aux["image_features"]).abs().max() / aux["image_features"].abs().max()) < 3e-2
     assert torch.equal(ext[P.EXT["top_idx"]][:, 0], want.argmax(1))
     kinds = [op.kind for op in prog.ops]
-    assert kinds.count("gemm") + kinds.count("stem_pool") >= 30 and kinds[0] == "ingest"
+    assert kinds.count("gemm") + kinds.count("stem_pool") + 6 * kinds.count("mlp_chain") >= 30 and kinds[0] == "ingest"
     assert all((op.lane & ~P.LANE_JOIN) in (0, 1) for op in prog.ops) and any(op.lane & 1 for op in prog.ops)
     assert any(op.lane & P.LANE_JOIN for op in prog.ops)
 

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvqa_b200.so")
-SOURCES = ["plan.cu", "gemm_tcgen05.cu", "stem_tcgen05.cu", "kernels_misc.cu", "resize.cu", "metrics.cu"]
+SOURCES = ["plan.cu", "gemm_tcgen05.cu", "stem_tcgen05.cu", "chain_tcgen05.cu", "kernels_misc.cu", "resize.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 

@@ -1004,6 +1004,9 @@ int vqa_encode_2d(CUtensorMap* map, bool tf32, uint64_t base, int rows, int cols
                   const char* what) {
   return encode_2d(map, tf32, base, rows, cols, ld, box_rows, row_bytes, what);
 }
+int vqa_encode_box32f(CUtensorMap* map, uint64_t base, int rows, int cols, int ld, const char* what) {
+  return encode_box32(map, true, base, rows, cols, ld, what);
+}
 int vqa_num_sms(int device) { return num_sms(device); }
 uint32_t vqa_make_idesc(bool tf32, bool f16, int n, int m) { return make_idesc(tf32, f16, n, m); }
 

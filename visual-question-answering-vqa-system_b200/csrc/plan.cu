@@ -16,6 +16,9 @@ const char* gemm_kernel_name(const void* storage);
 int stem_launch_bytes();
 int stem_prepare(const VqaOp& op, void* storage, int device);
 int stem_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t stream);
+int chain_launch_bytes();
+int chain_prepare(const VqaOp& op, void* storage, int device);
+int chain_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t stream);
 int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st);
 const char* misc_kernel_name(int kind);
 
@@ -45,7 +48,9 @@ const FieldCount kFields[VQA_OP_KIND_MAX] = {
     {STAGE_TAIL_NI, STAGE_TAIL_NP, STAGE_TAIL_NF},
     {SPLIT_TF32_NI, SPLIT_TF32_NP, SPLIT_TF32_NF},
     {STEM_POOL_NI, STEM_POOL_NP, STEM_POOL_NF},
+    {MLP_CHAIN_NI, MLP_CHAIN_NP, MLP_CHAIN_NF},
 };
+static_assert(MLP_CHAIN_NP <= VQA_OP_NP, "VqaOp.p too small for the chain op");
 static_assert(GEMM_NI <= VQA_OP_NI, "VqaOp.i too small for the gemm op");
 static_assert(POOL_GATE_LN_NP <= VQA_OP_NP, "VqaOp.p too small");
 }  // namespace
@@ -127,10 +132,10 @@ int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** o
       delete plan;
       return VQA_E_INVALID;
     }
-    if (op.kind == VQA_OP_GEMM || op.kind == VQA_OP_STEM_POOL) {   // ops with prepared launches (tensor maps encoded once)
-      const bool is_gemm = op.kind == VQA_OP_GEMM;
+    if (op.kind == VQA_OP_GEMM || op.kind == VQA_OP_STEM_POOL || op.kind == VQA_OP_MLP_CHAIN) {   // ops with prepared launches (tensor maps encoded once)
+      const bool is_gemm = op.kind == VQA_OP_GEMM, is_stem = op.kind == VQA_OP_STEM_POOL;
       void* st = nullptr;
-      const size_t bytes = (static_cast<size_t>(is_gemm ? gemm_launch_bytes() : stem_launch_bytes()) + 63) / 64 * 64;
+      const size_t bytes = (static_cast<size_t>(is_gemm ? gemm_launch_bytes() : is_stem ? stem_launch_bytes() : chain_launch_bytes()) + 63) / 64 * 64;
       if (posix_memalign(&st, 64, bytes) != 0) {
         vqa_set_error("out of host memory");
         delete plan;
@@ -138,7 +143,7 @@ int vqa_plan_create(const VqaOp* ops, int32_t n_ops, int32_t device, VqaPlan** o
       }
       std::memset(st, 0, bytes);
       plan->gemm[k] = st;
-      rc = is_gemm ? gemm_prepare(op, st, device) : stem_prepare(op, st, device);
+      rc = is_gemm ? gemm_prepare(op, st, device) : is_stem ? stem_prepare(op, st, device) : chain_prepare(op, st, device);
       if (rc) {
         vqa_set_error("op " + std::to_string(k) + ": " + g_error);
         delete plan;
@@ -228,7 +233,8 @@ int vqa_plan_run_range(const VqaPlan* plan, int32_t first, int32_t last, const u
       if (side) s = plan->side;
     }
     int rc = (op.kind == VQA_OP_GEMM) ? gemm_run(plan->gemm[k], ext, n_ext, s)
-             : (op.kind == VQA_OP_STEM_POOL) ? stem_run(plan->gemm[k], ext, n_ext, s) : run_misc_op(op, ext, n_ext, s);
+             : (op.kind == VQA_OP_STEM_POOL) ? stem_run(plan->gemm[k], ext, n_ext, s)
+             : (op.kind == VQA_OP_MLP_CHAIN) ? chain_run(plan->gemm[k], ext, n_ext, s) : run_misc_op(op, ext, n_ext, s);
     if (rc) {
       vqa_set_error("op " + std::to_string(k) + ": " + g_error);
       return rc;
@@ -251,7 +257,8 @@ int vqa_plan_op_kernel_name(const VqaPlan* plan, int32_t op, char* buf, int32_t 
   VQA_REQUIRE(plan != nullptr && buf != nullptr && buflen > 0, VQA_E_INVALID, "null argument");
   VQA_REQUIRE(op >= 0 && op < static_cast<int32_t>(plan->ops.size()), VQA_E_INVALID, "op index out of range");
   const char* name = plan->ops[op].kind == VQA_OP_GEMM ? gemm_kernel_name(plan->gemm[op])
-                     : plan->ops[op].kind == VQA_OP_STEM_POOL ? "stem_pool_kernel" : misc_kernel_name(plan->ops[op].kind);
+                     : plan->ops[op].kind == VQA_OP_STEM_POOL ? "stem_pool_kernel"
+                     : plan->ops[op].kind == VQA_OP_MLP_CHAIN ? "mlp_chain_kernel" : misc_kernel_name(plan->ops[op].kind);
   std::strncpy(buf, name, static_cast<size_t>(buflen) - 1);
   buf[buflen - 1] = 0;
   return VQA_OK;

@@ -36,7 +36,7 @@ KINDS = {
     "ingest": 1, "gemm": 2, "maxpool": 3, "se_squeeze": 4, "se_excite": 5, "spatial_map": 6,
     "scale_relayout": 7, "embed": 8, "layernorm": 9, "self_attn": 10, "cross_attn": 11,
     "pool_gate_ln": 12, "softmax_topk": 13, "mask_prep": 14, "grid_to_nchw": 15,
-    "copy_rows": 16, "stage_tail": 17, "split_tf32": 18, "stem_pool": 19,
+    "copy_rows": 16, "stage_tail": 17, "split_tf32": 18, "stem_pool": 19, "mlp_chain": 20,
 }
 
 _GROUPS = [f"g_{k}{g}" for k in ("map", "delta", "acol", "chunks", "ntaps", "kbase", "tap0")
@@ -78,6 +78,9 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att", "sums"], "f": []},
     "stem_pool": {"i": ["B", "H", "W", "P", "RPI", "Ho", "Wo", "Po", "RPIo", "run_len", "a_rows", "max_ctas"],
                   "p": ["a", "w", "out", "dbg"], "f": []},
+    "mlp_chain": {"i": ["T", "D", "F", "Nn", "Nn_pad", "max_ctas"],
+                  "p": ["ctx", "xres", "xout", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b", "n_g", "n_b", "wn", "y"],
+                  "f": ["eps", "eps_n"]},
 }
 
 DT_BF16, DT_TF32, DT_F16 = 0, 1, 2      # gemm operand dtype
@@ -456,6 +459,9 @@ class OpList:
         # the per-CTA scale chain of the streaming tail does not beat the staged one), so it is opt-in.  It also makes the
         # SE mean depend on where an image's rows fall in the 32-row slab grid, i.e. on its position in the batch.
         self.se_epilogue = window and os.environ.get("VQA_SE_EPILOGUE", "0") != "0"
+        # fused post-attention chains (W_o + residual + LayerNorm + FFN + residual + next block's LayerNorm + projection
+        # in one kernel, csrc/chain_tcgen05.cu) for the fp16-operand text / fusion path; "0" = one launch per Linear / LayerNorm
+        self.chain = self.half_tail and os.environ.get("VQA_CHAIN", "1") != "0"
         # fused stem: two conv rows per N = 128 MMA, vertical max in registers (stem_pool op); "0" = the 3-row gemm form
         self.stem_two_row = os.environ.get("VQA_STEM_TWO_ROW", "1") != "0"
         self.fused_tail = window or self.tf32
@@ -608,6 +614,23 @@ class OpList:
         self._op("stem_pool", name, dict(B=g0.B, H=g0.H, W=g0.W, P=g0.P, RPI=g0.rpi, Ho=g.H, Wo=g.W, Po=g.P, RPIo=g.rpi,
                                          run_len=run_len, a_rows=g0.rows, max_ctas=max_ctas),
                  dict(a=a, w=self.W.buf(w), out=out))
+
+    def mlp_chain(self, name, *, ctx, xres, xout, T, prefix, ln, nxt=None, max_ctas: int = 0):
+        """One kernel for xout = x1 + FFN(LN(x1)), x1 = xres + ctx W_o^T, and optionally y = LN'(xout) W_n^T.
+
+        ``prefix``: weight name prefix with ``.o.w.h / .fc1.w.h / .fc1.b / .fc2.w.h / .fc2.b``; ``ln``: name prefix of the
+        LayerNorm between W_o and the FFN (``.g / .b``); ``nxt`` = (LayerNorm prefix, weight name, y buffer, Nn)."""
+        W = self.W
+        F = W.items[prefix + ".fc1.w.h"][2][0]
+        p = dict(ctx=ctx, xres=xres, xout=xout, wo=W.buf(prefix + ".o.w.h"), w1=W.buf(prefix + ".fc1.w.h"),
+                 b1=W.buf(prefix + ".fc1.b"), w2=W.buf(prefix + ".fc2.w.h"), b2=W.buf(prefix + ".fc2.b"),
+                 ln_g=W.buf(ln + ".g"), ln_b=W.buf(ln + ".b"), n_g=None, n_b=None, wn=None, y=None)
+        Nn = npad = 0
+        if nxt is not None:
+            nln, wn, y, Nn = nxt
+            npad = W.items[wn][2][0]
+            p.update(n_g=W.buf(nln + ".g"), n_b=W.buf(nln + ".b"), wn=W.buf(wn), y=y)
+        self._op("mlp_chain", name, dict(T=T, D=256, F=F, Nn=Nn, Nn_pad=npad, max_ctas=max_ctas), p, dict(eps=1e-5, eps_n=1e-5))
 
     def _conv3x3_groups(self, g: Grid, nchunks: int, cout: int, residual: bool = False):
         """Stride-1 3x3 conv on a padded-flat grid -> (groups, halo, MT).
@@ -946,12 +969,20 @@ class Program(OpList):
         self._op("embed", "text.embed", dict(B=B, L=L, D=D, V=V),
                  dict(ids=ExtRef(EXT["ids"]), table=W.buf("text.emb"), pe=W.buf("text.pe"), dst=xt))
         layer = 0
+        chain = self.chain and D == 256 and F % 128 == 0 and F <= 1024
         while f"text.{layer}.qkv.w" in W:
             p = f"text.{layer}"
-            self.layernorm(p + ".ln1", xt, p + ".ln1.g", p + ".ln1.b", xn, T, rnd=True)
-            self.linear(p + ".qkv", xn, T, D, p + ".qkv.w", None, qkv, 3 * D)
+            if not (chain and layer > 0):         # chains: the previous layer's kernel already produced this layer's q, k, v
+                self.layernorm(p + ".ln1", xt, p + ".ln1.g", p + ".ln1.b", xn, T, rnd=True)
+                self.linear(p + ".qkv", xn, T, D, p + ".qkv.w", None, qkv, 3 * D)
             self._op("self_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, ld_qkv=3 * D, no_round=self.out_mode),
                      dict(qkv=qkv, mask=mask, out=ctx))
+            if chain:
+                q1 = f"text.{layer + 1}"
+                nxt = (q1 + ".ln1", q1 + ".qkv.w.h", qkv, 3 * D) if (q1 + ".qkv.w") in W else None
+                self.mlp_chain(p + ".chain", ctx=ctx, xres=xt, xout=xt, T=T, prefix=p, ln=p + ".ln2", nxt=nxt)
+                layer += 1
+                continue
             self.linear(p + ".o", ctx, T, D, p + ".o.w", None, xt, D, res=xt)
             self.layernorm(p + ".ln2", xt, p + ".ln2.g", p + ".ln2.b", xn, T, rnd=True)
             self.linear(p + ".fc1", xn, T, D, p + ".fc1.w", p + ".fc1.b", hid, F, relu=True, rnd=True)
@@ -999,7 +1030,7 @@ class Program(OpList):
         self.xattn_weights = []
         for layer in range(n_layers):
             p = f"x.{layer}"
-            if layer > 0:
+            if layer > 0 and not chain:           # chains: the previous layer's kernel already produced this layer's query
                 self.layernorm(p + ".lnq", src_q, p + ".lnq.g", p + ".lnq.b", qn, T, rnd=True)
                 self.linear(p + ".q", qn, T, D, p + ".q.w", None, qp, D)
             wts = None
@@ -1018,6 +1049,12 @@ class Program(OpList):
                     kv_proj(l)
                 self.ops[first].lane |= LANE_JOIN  # needs image_projected from the main lane
                 self.lane = 0
+            if chain:
+                q1 = f"x.{layer + 1}"
+                nxt = (q1 + ".lnq", q1 + ".q.w.h", qp, D) if layer + 1 < n_layers else None
+                self.mlp_chain(p + ".chain", ctx=cx, xres=src_q, xout=q, T=T, prefix=p, ln=p + ".lnf", nxt=nxt)
+                src_q = q
+                continue
             # q = src_q + W_o ctx   (first layer reads the text features as residual, writes the stream buffer)
             self.linear(p + ".o", cx, T, D, p + ".o.w", None, q, D, res=src_q)
             self.layernorm(p + ".lnf", q, p + ".lnf.g", p + ".lnf.b", qn, T, rnd=True)

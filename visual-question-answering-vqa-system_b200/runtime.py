@@ -13,8 +13,8 @@ from . import program as P
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvqa_b200.so")
 
-OP_NI, OP_NP, OP_NF = 160, 12, 4
-ABI_VERSION = 8
+OP_NI, OP_NP, OP_NF = 160, 16, 4
+ABI_VERSION = 9
 
 
 class VqaOp(C.Structure):
