@@ -469,6 +469,17 @@ def run_b200(args):
     c1.record()
     torch.cuda.synchronize()
     h2d_gbps = 5 * h_u8.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    # the same copies with every rank copying AT THE SAME TIME: the box's aggregate pinned H2D ceiling (host DRAM / PCIe
+    # root complexes shared by the GPUs), which bounds the end-to-end number at N > 1
+    barrier()
+    c0.record()
+    for _ in range(10):
+        d_probe.copy_(h_u8, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    ms_conc = reduce_max(c0.elapsed_time(c1))
+    barrier()
+    h2d_conc_gbps = 10 * h_u8.numel() / (ms_conc * 1e-3) / 1e9          # per rank, slowest rank
     del d_probe
     def e2e_run(lanes):
         inf.pipeline_lanes = lanes
@@ -700,6 +711,13 @@ def run_b200(args):
                 "cached_image_side": cached_leg,
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K, "h2d_pinned_copy_gbps": h2d_gbps,
+                        "h2d_ceiling": {
+                            "per_rank_gbps_all_ranks_copying": h2d_conc_gbps, "aggregate_gbps": world * h2d_conc_gbps,
+                            "pairs_per_sec": world * h2d_conc_gbps * 1e9 / (h2d / B),
+                            "e2e_fraction": e2e_value / (world * h2d_conc_gbps * 1e9 / (h2d / B)),
+                            "note": "copies only, every rank at once (barrier on both sides, slowest rank): what the "
+                                    "host side of this box delivers when all GPUs pull their pixels; the e2e step also "
+                                    "has to compute"},
                         "single_lane_value": world * B * K / (ms_e2e_1 * 1e-3), "compute_lanes": 2,
                         "path": "VQAInference.predict_tensors_pipelined: pinned uint8 HWC + ids + mask -> H2D (copy "
                                 "stream, 4 device slots) -> normalise+forward+top-5 (two compute lanes: the forwards of "

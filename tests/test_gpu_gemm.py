@@ -339,12 +339,13 @@ def test_conv3x3_shift_fused(B, H, W, residual, max_ctas, pair):
     assert G.named(gpu, "o").cpu()[pads].abs().max() == 0   # shared zero padding is rewritten as zeros
 
 
-@pytest.mark.parametrize("T,F,Nn,max_ctas", [(128, 1024, 0, 0), (300, 1024, 768, 0), (1000, 1024, 256, 3), (700, 256, 768, 2),
-                                             (5120, 1024, 768, 0)])
-def test_mlp_chain(T, F, Nn, max_ctas):
+@pytest.mark.parametrize("T,F,Nn,max_ctas,cs", [(128, 1024, 0, 0, 0), (300, 1024, 768, 0, 0), (1000, 1024, 256, 3, 1), (700, 256, 768, 2, 2),
+                                                (5120, 1024, 768, 0, 0), (1100, 1024, 768, 4, 4), (2000, 512, 256, 0, 1)])
+def test_mlp_chain(T, F, Nn, max_ctas, cs):
     """Fused post-attention chain (W_o + residual, LayerNorm, FFN in 128-column hidden chunks, residual, the next block's
     LayerNorm + projection) against the emulator; max_ctas forces several 128-row tiles per CTA (barrier phases, TMEM and
-    operand-buffer reuse across tiles), T = 300 / 700 / 1000 a ragged last tile."""
+    operand-buffer reuse across tiles), T = 300 / 700 / 1000 a ragged last tile, cs the cluster size that shares the
+    multicast weight stream (0 = automatic; phantom tiles pad the last cluster)."""
     D = 256
     def build(device):
         g = torch.Generator().manual_seed(61)
@@ -367,7 +368,7 @@ def test_mlp_chain(T, F, Nn, max_ctas):
         xo = ol._buf("xo", torch.float32, T, D)
         y = ol._buf("y", torch.float32, T, max(Nn, 4))
         ol.mlp_chain("chain", ctx=ctx, xres=x, xout=xo, T=T, prefix="l", ln="l.ln",
-                     nxt=("n.ln", "n.w.h", y, Nn) if Nn else None, max_ctas=max_ctas)
+                     nxt=("n.ln", "n.w.h", y, Nn) if Nn else None, max_ctas=max_ctas, cs=cs)
         ol.commit()
         G.named(ol, "ctx").copy_(_fill(ol, "ctx", 62))
         G.named(ol, "x").copy_(_fill(ol, "x", 63, scale=2.0))

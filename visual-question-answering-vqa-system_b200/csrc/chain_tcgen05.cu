@@ -17,7 +17,11 @@
 //     memory (fp16, fence.proxy.async) -- the 1024-wide hidden activation never leaves the SM: it is produced in
 //     128-column chunks (acc1, double-buffered) and consumed chunk by chunk as K slices of the second GEMM;
 //   * all weights (1.5 MB per layer) stream through one TMA ring in the order the MMA thread consumes them; they
-//     are constants, so the ring fills before griddepcontrol.wait.
+//     are constants, so the ring fills before griddepcontrol.wait.  Every CTA needs the SAME tiles in the same order and
+//     an SM pulls only 40-48 B/clk out of L2, so the CTAs of a cluster (CS = 2 or 4 row tiles) share the stream: each
+//     loads 1/CS of every tile and multicasts it into all CS rings (cp.async.bulk.tensor ... .multicast::cluster); a ring
+//     slot is free when all CS MMA threads have consumed it (tcgen05.commit ... .multicast::cluster onto every CTA's
+//     empty barrier).
 // Operands are fp16 with fp32 accumulation, like the unfused Linears of the throughput mode (program.py::linear).
 //
 // CTA = 10 warps: warp 0 weight producer, warp 1 MMA issuer (one elected thread; also loads the ctx tile),
@@ -56,7 +60,8 @@ static_assert(kSmemBytes <= 227 * 1024, "chain kernel: shared memory budget");
 static_assert(8 * 2 * kSlot <= 2 * kHBytes, "epilogue slots must fit the hidden-activation buffers");
 
 struct ChainParams {
-  int T, m_tiles, F, Nn;               // rows, 128-row tiles, hidden width, width of the follow-up projection (0 = none)
+  int T, m_tiles, F, Nn;               // rows, 128-row tiles (padded to the cluster size), hidden width, follow-up projection width (0 = none)
+  int CS;                              // cluster size: CTAs that share the weight stream
   const float *b1, *b2, *ln_g, *ln_b, *n_g, *n_b;
   float eps, eps_n;
   uint32_t idesc;
@@ -73,6 +78,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// one part of a weight tile into the same ring slot of every CTA in `mask`; each CTA's barrier at this offset gets the bytes
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t x, int32_t y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+// the barrier at this offset in every CTA of `mask` receives one arrival when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_chain_kernel(const __grid_constant__ CUtensorMap mapCtx, const __grid_constant__ CUtensorMap mapWo,
@@ -114,6 +133,10 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap mapCtx, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nF = p.F / 128, nN = p.Nn / 128;
+  const int CS = p.CS;
+  const uint32_t rank = CS > 1 ? cluster_rank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << CS) - 1u);
+  const int part_rows = 128 / CS;      // weight-tile rows this CTA fetches for the whole cluster
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapCtx); tma_prefetch_desc(&mapWo); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
@@ -121,7 +144,7 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap mapCtx, const __grid_consta
     tma_prefetch_desc(&mapXres); tma_prefetch_desc(&mapXout);
   }
   if (warp == 1) {
-    if (lane < kRing) { mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], 1); }
+    if (lane < kRing) { mbar_init(&b_full[lane], 1); mbar_init(&b_empty[lane], static_cast<uint32_t>(CS)); }
     if (lane == 8) {
       mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(acc0_ready, 1); mbar_init(xn_ready, 8);
       mbar_init(acc0_final, 1); mbar_init(xn2_ready, 8); mbar_init(acc0_free, 8);
@@ -142,7 +165,7 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap mapCtx, const __grid_consta
     s_ng[i] = nN ? __ldg(p.n_g + i) : 0.f; s_nb[i] = nN ? __ldg(p.n_b + i) : 0.f;
   }
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync(); else __syncthreads();   // peers multicast into this CTA's ring and signal its barriers
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 1) pdl_launch_dependents();
@@ -154,10 +177,11 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap mapCtx, const __grid_consta
     int ring = 0;
     uint32_t rph = 0;
     auto put = [&](const CUtensorMap* m, int n0, int k0) {
-      mbar_wait(&b_empty[ring], rph ^ 1u);
+      mbar_wait(&b_empty[ring], rph ^ 1u);               // every CTA of the cluster has consumed this slot
       if (elect_one()) {
-        mbar_expect_tx(&b_full[ring], kTile);
-        tma_load_2d(s_ring + ring * kTile, m, &b_full[ring], k0, n0);
+        mbar_expect_tx(&b_full[ring], kTile);             // the whole tile: this CTA's part plus the peers' multicasts
+        if (CS > 1) tma_load_2d_mc(s_ring + ring * kTile + rank * part_rows * 128, m, &b_full[ring], k0, n0 + rank * part_rows, cmask);
+        else tma_load_2d(s_ring + ring * kTile, m, &b_full[ring], k0, n0);
       }
       __syncwarp();
       if (++ring == kRing) { ring = 0; rph ^= 1u; }
@@ -189,7 +213,7 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap mapCtx, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(d, kDescHi | (a + 2 * k), kDescHi | (b + 2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
-        umma_commit(&b_empty[ring]);
+        if (CS > 1) umma_commit_mc(&b_empty[ring], cmask); else umma_commit(&b_empty[ring]);
         if (++ring == kRing) { ring = 0; rph ^= 1u; }
       };
       auto g2 = [&](int j) {     // acc1[j & 1] = LN(x1) W_1[j]^T
@@ -448,7 +472,7 @@ mlp_chain_kernel(const __grid_constant__ CUtensorMap mapCtx, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync(); else __syncthreads();     // peers' last multicasts / commits land in this CTA
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -473,6 +497,13 @@ int chain_prepare(const VqaOp& op, void* storage, int device) {
   VQA_REQUIRE(p.F >= 128 && p.F % 128 == 0 && p.F <= kMaxF, VQA_E_INVALID, "mlp_chain: hidden width must be a multiple of 128, <= 1024");
   VQA_REQUIRE(p.Nn >= 0 && p.Nn % 128 == 0, VQA_E_INVALID, "mlp_chain: follow-up width must be a multiple of 128");
   p.m_tiles = (p.T + 127) / 128;
+  // measured on B200 (256 pairs, 40 row tiles): clusters of 1 / 2 / 4 give the same step time within noise -- the chain is
+  // bound by the shared-memory port (N = 128 MMAs read 8 KB per 64 cycles while the ring is being filled), not by L2 --
+  // so the default is no cluster; VQA_CHAIN_CS / the op's CS field select the multicast form
+  p.CS = I[MLP_CHAIN_I_CS] > 0 ? I[MLP_CHAIN_I_CS] : 1;
+  VQA_REQUIRE(p.CS == 1 || p.CS == 2 || p.CS == 4, VQA_E_INVALID, "mlp_chain: cluster size must be 1, 2 or 4");
+  p.m_tiles = (p.m_tiles + p.CS - 1) / p.CS * p.CS;   // phantom tiles keep the cluster's weight stream in lockstep (loads read
+                                                       // zeros past T, stores are clipped)
   for (int k = 0; k < MLP_CHAIN_NP; ++k)
     VQA_REQUIRE(!(op.p[k] & VQA_EXT_TAG) && (op.p[k] & 15) == 0, VQA_E_INVALID, "mlp_chain: operands must be 16-byte aligned arena buffers");
   auto P = [&](int k) { return op.p[k]; };
@@ -492,16 +523,17 @@ int chain_prepare(const VqaOp& op, void* storage, int device) {
   p.idesc = vqa_make_idesc(false, true, 128, 128);
   int rc = vqa_encode_2d(&L->mapCtx, false, P(MLP_CHAIN_P_ctx), p.T, kD, kD, 128, 128, "mlp_chain ctx");
   if (rc) return rc;
-  rc = vqa_encode_2d(&L->mapWo, false, P(MLP_CHAIN_P_wo), kD, kD, kD, 128, 128, "mlp_chain W_o");
+  const int wbox = 128 / p.CS;     // each CTA of a cluster fetches 1/CS of every weight tile
+  rc = vqa_encode_2d(&L->mapWo, false, P(MLP_CHAIN_P_wo), kD, kD, kD, wbox, 128, "mlp_chain W_o");
   if (rc) return rc;
-  rc = vqa_encode_2d(&L->mapW1, false, P(MLP_CHAIN_P_w1), p.F, kD, kD, 128, 128, "mlp_chain W_1");
+  rc = vqa_encode_2d(&L->mapW1, false, P(MLP_CHAIN_P_w1), p.F, kD, kD, wbox, 128, "mlp_chain W_1");
   if (rc) return rc;
-  rc = vqa_encode_2d(&L->mapW2, false, P(MLP_CHAIN_P_w2), kD, p.F, p.F, 128, 128, "mlp_chain W_2");
+  rc = vqa_encode_2d(&L->mapW2, false, P(MLP_CHAIN_P_w2), kD, p.F, p.F, wbox, 128, "mlp_chain W_2");
   if (rc) return rc;
   L->mapWn = L->mapWo;
   L->mapY = L->mapCtx;
   if (p.Nn) {
-    rc = vqa_encode_2d(&L->mapWn, false, P(MLP_CHAIN_P_wn), I[MLP_CHAIN_I_Nn_pad], kD, kD, 128, 128, "mlp_chain W_n");
+    rc = vqa_encode_2d(&L->mapWn, false, P(MLP_CHAIN_P_wn), I[MLP_CHAIN_I_Nn_pad], kD, kD, wbox, 128, "mlp_chain W_n");
     if (rc) return rc;
     rc = vqa_encode_box32f(&L->mapY, P(MLP_CHAIN_P_y), p.T, p.Nn, p.Nn, "mlp_chain y");
     if (rc) return rc;
@@ -513,7 +545,8 @@ int chain_prepare(const VqaOp& op, void* storage, int device) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (I[MLP_CHAIN_I_max_ctas] > 0 && I[MLP_CHAIN_I_max_ctas] < sms) sms = I[MLP_CHAIN_I_max_ctas];
-  L->grid = dim3(p.m_tiles < sms ? p.m_tiles : sms, 1, 1);
+  sms = sms / p.CS * p.CS;
+  L->grid = dim3(p.m_tiles < sms ? p.m_tiles : (sms > 0 ? sms : p.CS), 1, 1);
   VQA_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&mlp_chain_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kSmemBytes));
   return VQA_OK;
@@ -521,8 +554,8 @@ int chain_prepare(const VqaOp& op, void* storage, int device) {
 
 int chain_run(const void* storage, const uint64_t*, int, cudaStream_t stream) {
   const ChainLaunch* L = reinterpret_cast<const ChainLaunch*>(storage);
-  VQA_CUDA_OK(vqa_launch(mlp_chain_kernel, L->grid, dim3(kThreads), kSmemBytes, stream, L->mapCtx, L->mapWo, L->mapW1, L->mapW2,
-                         L->mapWn, L->mapXres, L->mapXout, L->mapY, L->prm));
+  VQA_CUDA_OK(vqa_launch_cluster(mlp_chain_kernel, L->grid, dim3(kThreads), kSmemBytes, stream, L->prm.CS, L->mapCtx, L->mapWo,
+                                 L->mapW1, L->mapW2, L->mapWn, L->mapXres, L->mapXout, L->mapY, L->prm));
   VQA_LAUNCH_OK("mlp_chain_kernel");
   return VQA_OK;
 }

@@ -78,7 +78,7 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "p": ["src", "w1", "w2", "wconv", "dst", "scale", "att", "sums"], "f": []},
     "stem_pool": {"i": ["B", "H", "W", "P", "RPI", "Ho", "Wo", "Po", "RPIo", "run_len", "a_rows", "max_ctas"],
                   "p": ["a", "w", "out", "dbg"], "f": []},
-    "mlp_chain": {"i": ["T", "D", "F", "Nn", "Nn_pad", "max_ctas"],
+    "mlp_chain": {"i": ["T", "D", "F", "Nn", "Nn_pad", "max_ctas", "CS"],
                   "p": ["ctx", "xres", "xout", "wo", "w1", "b1", "w2", "b2", "ln_g", "ln_b", "n_g", "n_b", "wn", "y"],
                   "f": ["eps", "eps_n"]},
 }
@@ -615,7 +615,7 @@ class OpList:
                                          run_len=run_len, a_rows=g0.rows, max_ctas=max_ctas),
                  dict(a=a, w=self.W.buf(w), out=out))
 
-    def mlp_chain(self, name, *, ctx, xres, xout, T, prefix, ln, nxt=None, max_ctas: int = 0):
+    def mlp_chain(self, name, *, ctx, xres, xout, T, prefix, ln, nxt=None, max_ctas: int = 0, cs: int = 0):
         """One kernel for xout = x1 + FFN(LN(x1)), x1 = xres + ctx W_o^T, and optionally y = LN'(xout) W_n^T.
 
         ``prefix``: weight name prefix with ``.o.w.h / .fc1.w.h / .fc1.b / .fc2.w.h / .fc2.b``; ``ln``: name prefix of the
@@ -630,7 +630,9 @@ class OpList:
             nln, wn, y, Nn = nxt
             npad = W.items[wn][2][0]
             p.update(n_g=W.buf(nln + ".g"), n_b=W.buf(nln + ".b"), wn=W.buf(wn), y=y)
-        self._op("mlp_chain", name, dict(T=T, D=256, F=F, Nn=Nn, Nn_pad=npad, max_ctas=max_ctas), p, dict(eps=1e-5, eps_n=1e-5))
+        # cs: CTAs per cluster that share the multicast weight stream (0 = by the number of 128-row tiles)
+        cs = cs or int(os.environ.get("VQA_CHAIN_CS", "0"))
+        self._op("mlp_chain", name, dict(T=T, D=256, F=F, Nn=Nn, Nn_pad=npad, max_ctas=max_ctas, CS=cs), p, dict(eps=1e-5, eps_n=1e-5))
 
     def _conv3x3_groups(self, g: Grid, nchunks: int, cout: int, residual: bool = False):
         """Stride-1 3x3 conv on a padded-flat grid -> (groups, halo, MT).
