@@ -118,7 +118,7 @@ def test_each_op_against_emulator(ctor, B, L, in_fmt, mask_kind, window, precisi
     assert not failures, "\n".join(failures[:20])
 
 
-@pytest.mark.parametrize("B,H,C,CS", [(40, 56, 64, 4), (77, 28, 128, 2), (150, 56, 64, 4)])
+@pytest.mark.parametrize("B,H,C,CS", [(40, 56, 64, 4), (77, 28, 128, 2), (150, 56, 64, 4), (3, 12, 256, 1)])
 def test_stage_tail_se_only_many_images(B, H, C, CS):
     """SE-only stage tail (two-pass kernel: sums streamed through registers, rows re-read from L2) with more clusters than
     fit the GPU at once, against the emulator."""

@@ -505,7 +505,7 @@ struct TailVec {
 // read a few microseconds earlier -- scales and writes them.  DRAM traffic stays one read + one write, but a CTA needs
 // 2 KB of shared memory, so six to eight CTAs per SM (every cluster of a 256-image batch at once) overlap their chains.
 // Same summation order per CTA as the staged kernel's 256-thread form; images are independent (batch-invariant).
-constexpr int kTwoPassThreads = 256;
+constexpr int kTwoPassThreads = 256;   // four CTAs per SM; 128-thread CTAs (eight per SM) measured 64 -> 68 us at 56x56
 __global__ void __launch_bounds__(kTwoPassThreads, 4)
 se_two_pass_kernel(const StageTailParams p) {
   __shared__ float red[2048];             // [part_rows][C]: 8 x 64, 8 x 128, 8 x 256 or 4 x 512
@@ -523,28 +523,31 @@ se_two_pass_kernel(const StageTailParams p) {
   const int lpw = C8 < 32 ? 32 / C8 : 1;
   const int part_rows = lanes / lpw;
   const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8;
-  // pixel q of this CTA -> source vector; q advances by `lanes` per step, (hl, w) are kept incrementally
-  const int dq_h = lanes / W, dq_w = lanes - dq_h * W;
-  // ---- pass 1: channel sums
+  // ---- pass 1: channel sums.  The CTA's rows are ONE contiguous run of rows_l * P pixels when the pad pixel that ends
+  // every grid row is included; pads are zero by the layout's invariant (every producer masks them), so they add nothing.
+  // Thread t walks vectors t, t + T, ... of that run: T is a multiple of C8, so its channel group never changes and the
+  // loop is a load, 16 unpack / add instructions and a pointer bump (the kernel is issue-bound, not bandwidth-bound:
+  // ncu showed 150 warp instructions per 16-byte vector over the two passes of the first version).
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   {
-    int hl = pl / W, w = pl - hl * W;
-    constexpr int U = 4;
-    for (int q0 = pl; q0 < NP; q0 += U * lanes) {
-      uint4 v[U];
-      int hh = hl, ww = w;
+    const uint4* run = img + static_cast<size_t>(h0) * p.P * C8;
+    const int NV = rows_l * p.P * C8;
+    constexpr int U = 8;
+    int v = tid;
+    for (; v + (U - 1) * kTwoPassThreads < NV; v += U * kTwoPassThreads) {
+      uint4 x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) x[u] = __ldg(run + v + u * kTwoPassThreads);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        v[u] = (q0 + u * lanes < NP) ? __ldg(img + (static_cast<size_t>(h0 + hh) * p.P + ww) * C8 + cg) : make_uint4(0u, 0u, 0u, 0u);
-        hh += dq_h; ww += dq_w;
-        if (ww >= W) { ww -= W; ++hh; }
+        acc[0] += bf16lo(x[u].x); acc[1] += bf16hi(x[u].x); acc[2] += bf16lo(x[u].y); acc[3] += bf16hi(x[u].y);
+        acc[4] += bf16lo(x[u].z); acc[5] += bf16hi(x[u].z); acc[6] += bf16lo(x[u].w); acc[7] += bf16hi(x[u].w);
       }
-      hl = hh; w = ww;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        acc[0] += bf16lo(v[u].x); acc[1] += bf16hi(v[u].x); acc[2] += bf16lo(v[u].y); acc[3] += bf16hi(v[u].y);
-        acc[4] += bf16lo(v[u].z); acc[5] += bf16hi(v[u].z); acc[6] += bf16lo(v[u].w); acc[7] += bf16hi(v[u].w);
-      }
+    }
+    for (; v < NV; v += kTwoPassThreads) {
+      const uint4 x = __ldg(run + v);
+      acc[0] += bf16lo(x.x); acc[1] += bf16hi(x.x); acc[2] += bf16lo(x.y); acc[3] += bf16hi(x.y);
+      acc[4] += bf16lo(x.z); acc[5] += bf16hi(x.z); acc[6] += bf16lo(x.w); acc[7] += bf16hi(x.w);
     }
   }
   for (int off = C8; off < 32; off <<= 1) {             // C8 < 32: the warp's pixel lanes first (fixed order)
@@ -590,39 +593,50 @@ se_two_pass_kernel(const StageTailParams p) {
     if (p.scale_out && rank == 0) p.scale_out[static_cast<size_t>(n) * C + c] = sg;
   }
   __syncthreads();
-  // ---- pass 2: the same rows again (L2), scaled, to the destination grid
+  // ---- pass 2: the same rows again (L2), scaled, to the destination grid.  A thread keeps its pixel column w and walks
+  // down the rows four at a time: the source advances by one grid row, the destination alternates between the two
+  // phases of the row parity (mode 1: rows come in even / odd pairs because h0 and rows_l are even) -- pointer bumps only.
   float kk[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) kk[j] = sc[cg * 8 + j];
   const int Po = p.Po;
-  {
-    int hl = pl / W, w = pl - hl * W;
-    constexpr int U = 4;
-    for (int q0 = pl; q0 < NP; q0 += U * lanes) {
-      uint4 v[U];
-      int hh = hl, ww = w;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        v[u] = (q0 + u * lanes < NP) ? __ldg(img + (static_cast<size_t>(h0 + hh) * p.P + ww) * C8 + cg) : make_uint4(0u, 0u, 0u, 0u);
-        hh += dq_h; ww += dq_w;
-        if (ww >= W) { ww -= W; ++hh; }
+  auto scaled = [&](const uint4& x) {
+    return make_uint4(pack_bf16x2(bf16lo(x.x) * kk[0], bf16hi(x.x) * kk[1]), pack_bf16x2(bf16lo(x.y) * kk[2], bf16hi(x.y) * kk[3]),
+                      pack_bf16x2(bf16lo(x.z) * kk[4], bf16hi(x.z) * kk[5]), pack_bf16x2(bf16lo(x.w) * kk[6], bf16hi(x.w) * kk[7]));
+  };
+  const size_t srow = static_cast<size_t>(p.P) * C8;            // source vectors per grid row
+  for (int w = pl; w < W; w += lanes) {
+    const uint4* s = img + (static_cast<size_t>(h0) * p.P + w) * C8 + cg;
+    if (p.mode) {
+      // even rows -> phase (0, w & 1), odd rows -> phase (1, w & 1); both at position (h >> 1, w >> 1)
+      uint4* dE = p.dst + (static_cast<size_t>(w & 1) * p.phase_rows + static_cast<size_t>(n) * p.RPIo +
+                           static_cast<size_t>(h0 >> 1) * Po + (w >> 1)) * C8 + cg;
+      uint4* dO = dE + 2 * static_cast<size_t>(p.phase_rows) * C8;
+      const size_t dstep = static_cast<size_t>(Po) * C8;
+      int hl = 0;
+      for (; hl + 4 <= rows_l; hl += 4) {
+        const uint4 x0 = __ldg(s), x1 = __ldg(s + srow), x2 = __ldg(s + 2 * srow), x3 = __ldg(s + 3 * srow);
+        dE[0] = scaled(x0); dO[0] = scaled(x1); dE[dstep] = scaled(x2); dO[dstep] = scaled(x3);
+        s += 4 * srow; dE += 2 * dstep; dO += 2 * dstep;
       }
-      hh = hl; ww = w;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (q0 + u * lanes < NP) {
-          const int h = h0 + hh;
-          const uint4 o = make_uint4(pack_bf16x2(bf16lo(v[u].x) * kk[0], bf16hi(v[u].x) * kk[1]), pack_bf16x2(bf16lo(v[u].y) * kk[2], bf16hi(v[u].y) * kk[3]),
-                                     pack_bf16x2(bf16lo(v[u].z) * kk[4], bf16hi(v[u].z) * kk[5]), pack_bf16x2(bf16lo(v[u].w) * kk[6], bf16hi(v[u].w) * kk[7]));
-          size_t row;
-          if (p.mode) row = static_cast<size_t>((h & 1) * 2 + (ww & 1)) * p.phase_rows + static_cast<size_t>(n) * p.RPIo + (h >> 1) * Po + (ww >> 1);
-          else row = static_cast<size_t>(n) * p.RPIo + h * Po + ww;
-          p.dst[row * C8 + cg] = o;
-        }
-        hh += dq_h; ww += dq_w;
-        if (ww >= W) { ww -= W; ++hh; }
+      for (; hl < rows_l; hl += 2) {
+        const uint4 x0 = __ldg(s), x1 = __ldg(s + srow);
+        dE[0] = scaled(x0); dO[0] = scaled(x1);
+        s += 2 * srow; dE += dstep; dO += dstep;
       }
-      hl = hh; w = ww;
+    } else {
+      uint4* d = p.dst + (static_cast<size_t>(n) * p.RPIo + static_cast<size_t>(h0) * Po + w) * C8 + cg;
+      const size_t dstep = static_cast<size_t>(Po) * C8;
+      int hl = 0;
+      for (; hl + 4 <= rows_l; hl += 4) {
+        const uint4 x0 = __ldg(s), x1 = __ldg(s + srow), x2 = __ldg(s + 2 * srow), x3 = __ldg(s + 3 * srow);
+        d[0] = scaled(x0); d[dstep] = scaled(x1); d[2 * dstep] = scaled(x2); d[3 * dstep] = scaled(x3);
+        s += 4 * srow; d += 4 * dstep;
+      }
+      for (; hl < rows_l; ++hl) {
+        d[0] = scaled(__ldg(s));
+        s += srow; d += dstep;
+      }
     }
   }
   // ---- the destination grid's zero padding that belongs to these rows

@@ -532,6 +532,11 @@ class OpList:
         # (measured: stage 3 conv 66 -> 57 us; the 256-column tile fills TMEM with one stage)
         if bn == 256 and dtype == DT_BF16 and out_dtype == OUT_BF16 and MT == 2 and self.pair and halo > 0:
             bn = 128
+        # experiment switch: "MT,BN,pair" for the window convolutions with >= 256 output channels (stages 3 and 4)
+        wide = os.environ.get("VQA_WIDE_CONV", "")
+        if wide and N >= 256 and dtype == DT_BF16 and out_dtype == OUT_BF16 and halo > 0 and sf == 1 and grid is not None:
+            MT, bn, pair = (int(v) for v in wide.split(","))
+            pair = bool(pair) and self.pair
         assert npad % bn == 0 and npad >= N, (name, npad, bn)
         assert len(groups) <= MAX_GROUPS and MT * bn * sf <= 512
         assert sf == 1 or (1 < sf <= 3 and npad == sf * bn and MT == 1 and pool_to is None and (sf - 1) * sf_step <= 4)
