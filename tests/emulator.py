@@ -145,6 +145,11 @@ class Emulator:
             padded = torch.zeros(ns * 32, N)
             padded[:M] = acc
             _t(op.p["sums"], torch.float32, ext)[: ns * N].view(ns, N).copy_(padded.view(ns, 32, N).sum(dim=1))
+        if i.get("topk"):                  # fused softmax + top-k of the stored rows (the answer head's last Linear)
+            k = i["topk"]
+            probs, idx = F.softmax(acc, dim=-1).topk(k, dim=-1)
+            ext[op.p["topk_idx"].slot].view(M, k).copy_(idx)
+            ext[op.p["topk_probs"].slot].view(M, k).copy_(probs)
 
     def op_stem_pool(self, op, ext):
         """Two-row fused stem: acc[m, :64] = conv at flat position m, acc[m, 64:] = conv at m + P (same A window)."""

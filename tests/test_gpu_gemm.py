@@ -4,6 +4,8 @@ Ordered from the plainest configuration to the ones that rely on less-documented
 behaviour (row-shifted UMMA descriptors inside a SWIZZLE_128B window, overlapping-row tensor
 maps), so that a failure in the latter does not hide the former.
 """
+import os
+
 import pytest
 import torch
 
@@ -377,3 +379,70 @@ def test_mlp_chain(T, F, Nn, max_ctas, cs):
     G.report(f"chain xout T{T} F{F}", G.named(gpu, "xo"), G.named(cpu, "xo"), atol=4e-3, rtol=2e-3)
     if Nn:
         G.report(f"chain y T{T} Nn{Nn}", G.named(gpu, "y"), G.named(cpu, "y"), atol=6e-3, rtol=4e-3)
+
+
+@pytest.mark.parametrize("M,N,k", [(256, 1000, 5), (1, 1000, 5), (300, 1000, 8), (130, 136, 1), (1024, 1000, 5), (64, 3128, 3)])
+def test_linear_with_fused_softmax_topk(M, N, k):
+    """The answer head's last Linear with softmax + top-k in its epilogue (models/vqa_model.py:336-337,
+    api/inference.py:231-234) against softmax().topk() of the SAME logits: winners bit-exact (ties go to the lower index,
+    NaN ranks first like torch.topk), probabilities to fp32 rounding; rows with -inf, duplicated maxima and NaN; the
+    launch is repeated so the arrival counters must have been reset by the merging CTA."""
+    import gpu_util as G
+    K = 256
+
+    def build(device):
+        gen = torch.Generator().manual_seed(11)
+        W = P.Weights(device)
+        npad = (N + 127) // 128 * 128
+        w = torch.zeros(npad, K)
+        w[:N] = torch.randn(N, K, generator=gen) * 0.2
+        if N > 40:
+            w[7] = w[3]                       # two identical logit columns: a tie in every row
+            w[N - 1] = w[N - 2]
+        W.add("w.h", w, torch.float16)
+        bias = torch.zeros(npad)
+        bias[:N] = torch.randn(N, generator=gen)
+        if N > 40:
+            bias[7], bias[N - 1] = bias[3], bias[N - 2]
+            bias[11] = float("-inf")          # a column nobody may pick before the finite ones
+        W.add("b", bias, torch.float32)
+        W.finalize()
+        ol = P.OpList(W, device)
+        ol.half_tail, ol.tf32 = True, False
+        a = ol._buf("a", torch.float16, M, K)
+        ol.linear("head2", a, M, K, "w", "b", P.ExtRef(P.EXT["logits"]), N, ldo=N,
+                  topk=(k, P.ExtRef(P.EXT["top_idx"]), P.ExtRef(P.EXT["top_probs"])))
+        ol.commit()
+        av = torch.randn(M, K, generator=gen)
+        if M > 2:
+            av[2] = float("nan")              # an all-NaN row (a fully masked question in the reference)
+        G.named(ol, "a").copy_(av.to(torch.float16))
+        return ol
+
+    ext = [None, None, None, torch.zeros(M, N), torch.zeros(M, k, dtype=torch.int64), torch.zeros(M, k)]
+    cpu, gpu, ext_c, ext_g = G.run_pair(build, ext)
+    logits = ext_g[3].cpu()
+    G.report("logits", logits, ext_c[3], atol=2e-3, rtol=2e-3) if M <= 2 else None
+    rows = [r for r in range(M) if r != 2] if M > 2 else list(range(M))
+    want_p, want_i = torch.softmax(logits[rows], dim=-1).topk(k, dim=-1)
+    got_i, got_p = ext_g[4].cpu(), ext_g[5].cpu()
+    # torch.topk does not promise an order among equal values: compare the VALUES picked, and the index rule separately
+    assert torch.equal(torch.gather(logits[rows], 1, got_i[rows]), torch.gather(logits[rows], 1, want_i))
+    torch.testing.assert_close(got_p[rows], want_p, rtol=1e-5, atol=1e-9)
+    key = logits[rows].clone()
+    order = torch.argsort(torch.stack([-key[:, j] for j in range(N)], 1), dim=1, stable=True)[:, :k]   # value desc, index asc
+    if not os.environ.get("VQA_DRY"):          # (the emulator's torch.topk promises no order among equal values)
+        assert torch.equal(got_i[rows], order)
+    if M > 2:                                 # the NaN row: first k indices, NaN probabilities, no fault
+        assert torch.equal(got_i[2], torch.arange(k)) and bool(torch.isnan(got_p[2]).all())
+    if os.environ.get("VQA_DRY"):
+        return
+    # replay on the same plan: counters were reset
+    from vqa_b200.runtime import Plan
+    plan = Plan(gpu.ops, 0)
+    ext_g[4].fill_(-1)
+    ptrs = [0 if t is None else t.data_ptr() for t in ext_g]
+    for _ in range(3):
+        plan.run(ptrs, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(ext_g[4].cpu()[rows], order)

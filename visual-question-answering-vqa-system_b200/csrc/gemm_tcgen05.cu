@@ -85,6 +85,14 @@ struct GemmParams {
   // sums[(row / 32) * ld_sums + n] = sum over the 32 rows of that slab of out[row, n] (fp32, before the 16-bit rounding)
   float* sums;
   int ld_sums;
+  // fused softmax + top-k of the output rows (EPI 6: the answer head's last Linear, models/vqa_model.py:336-337):
+  // every epilogue thread keeps the running max / exp-sum / k best of its row over the columns it drains and writes them as
+  // partial (row, n_tile, column half); the CTA that finishes the last N tile of an M tile (atomic counter) merges them
+  long long* topk_idx;   // [M, topk_k] winners, best first (ties to the lower index, NaN ranks first like torch.topk)
+  float* topk_probs;     // [M, topk_k] softmax probabilities of the winners
+  float* topk_part;      // [M, 2 * n_tiles, 2 + 2 * kTopKMax] scratch
+  int* topk_cnt;         // [m_tiles] arrival counters (zero between launches: the merging CTA resets its counter)
+  int topk_k;
   long long* dbg;    // optional: 16 clock64() timestamps of CTA 0 (profiling aid, nullptr in production)
 };
 
@@ -117,6 +125,22 @@ __device__ __forceinline__ bool grid_pixel(const GemmParams& p, int row) {
   const uint32_t rem = n - (__umulhi(n, p.rpi_magic) >> p.rpi_shift) * static_cast<uint32_t>(p.mRPI);
   const uint32_t h = __umulhi(rem, p.mp_magic) >> p.mp_shift;
   return h < static_cast<uint32_t>(p.mH) && rem - h * static_cast<uint32_t>(p.mP) < static_cast<uint32_t>(p.mW);
+}
+
+constexpr int kTopKMax = 8;             // fused top-k epilogue: winners kept per thread (larger k: softmax_topk_kernel)
+constexpr int kTopKRec = 2 + 2 * kTopKMax;   // floats per partial record: max, exp-sum, keys, indices
+// (key, index) beats (key', index') when key > key', or on a tie when the index is lower; the list stays sorted best first
+__device__ __forceinline__ void topk_insert(float (&tv)[kTopKMax], int (&ti)[kTopKMax], float key, int idx) {
+  if (!(key > tv[kTopKMax - 1] || (key == tv[kTopKMax - 1] && idx < ti[kTopKMax - 1]))) return;
+#pragma unroll
+  for (int j = kTopKMax - 1; j >= 0; --j) {
+    const bool better = key > tv[j] || (key == tv[j] && idx < ti[j]);
+    if (better) {
+      if (j + 1 < kTopKMax) { tv[j + 1] = tv[j]; ti[j + 1] = ti[j]; }
+      tv[j] = key;
+      ti[j] = idx;
+    }
+  }
 }
 
 #define VQA_DBG(slot)                                                         \
@@ -693,6 +717,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     // ===================== epilogue warps =====================
     constexpr bool kOutBf16 = EPI < 2;
     constexpr bool kRes = (EPI & 1) != 0;
+    constexpr bool kTopK = EPI == 6;    // fp32 output + fused softmax / top-k of the rows (MT = 1)
+    static_assert(!kTopK || MT == 1, "the top-k epilogue is instantiated for MT = 1");
     constexpr int kCols = BN / 2;       // columns per epilogue warp (two warps share a lane quadrant)
     constexpr int kChunks = kCols / 32; // 32-column chunks per warp per sub-tile (1, 2 or 4)
     constexpr int kRowB = kOutBf16 ? 64 : 128;          // bytes of one chunk row in the staging slot
@@ -753,6 +779,14 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const bool has_ntile = ntile < total_tiles;
       const int n_row0 = tile_m0(p, cta_mtile(ntile), MT) + quad * 32;
       const int n_col0 = (ntile / m_tiles) * BN + half * kCols;
+
+      // fused softmax / top-k (EPI 6): this thread's row over the columns this warp drains
+      float tk_m = -INFINITY, tk_s = 0.f;
+      bool tk_nan = false;
+      float tk_v[kTopKMax];
+      int tk_i[kTopKMax];
+#pragma unroll
+      for (int j = 0; j < kTopKMax; ++j) { tk_v[j] = -INFINITY; tk_i[j] = 0x7fffffff; }
 
       mbar_wait_t(&acc_full[acc], accph, timed, w_accfull);
       tc_fence_after();
@@ -861,6 +895,29 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 32; ++k) x[k] = round_tf32_rna(x[k]);
             }
+            if constexpr (kTopK) {
+              // online softmax statistics (max ignores NaN like fmaxf, the sum turns NaN like the reference's) and the
+              // k best of the stored values; selection key: NaN ranks above everything (torch.topk's order)
+              float cm = -INFINITY;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                if (col0 + k < N) { if (x[k] != x[k]) tk_nan = true; else cm = fmaxf(cm, x[k]); }
+              }
+              const float m_new = fmaxf(tk_m, cm);
+              if (m_new > -INFINITY) {
+                float add = 0.f;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                  if (col0 + k < N && x[k] == x[k]) add += expf(x[k] - m_new);
+                }
+                tk_s = tk_s * expf(tk_m - m_new) + add;
+                tk_m = m_new;
+              }
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                if (col0 + k < N) topk_insert(tk_v, tk_i, (x[k] != x[k]) ? INFINITY : x[k], col0 + k);
+              }
+            }
 #pragma unroll
             for (int u = 0; u < kUnits; ++u)
               *reinterpret_cast<float4*>(out_row + ((u ^ swz) << 4)) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
@@ -880,6 +937,56 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       __syncwarp();
       if (lane == 0) {
         if (PAIR) mbar_arrive_leader(&acc_empty[acc]); else mbar_arrive(&acc_empty[acc]);
+      }
+      if constexpr (kTopK) {
+        // ---- publish this thread's partial; the CTA that completes the M tile's last N tile merges the row
+        const int nparts = 2 * p.n_tiles, mt_idx = tile % m_tiles;
+        const int row = m0 + quad * 32 + lane;
+        if (row < p.M) {
+          float* rec = p.topk_part + (static_cast<size_t>(row) * nparts + (tile / m_tiles) * 2 + half) * kTopKRec;
+          rec[0] = tk_m;
+          rec[1] = tk_nan ? __int_as_float(0x7fc00000) : tk_s;
+#pragma unroll
+          for (int j = 0; j < kTopKMax; ++j) { rec[2 + j] = tk_v[j]; rec[2 + kTopKMax + j] = __int_as_float(tk_i[j]); }
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        volatile uint32_t* last_flag = tmem_slot + 1;
+        if (threadIdx.x == 64) *last_flag = (atomicAdd(p.topk_cnt + mt_idx, 1) == p.n_tiles - 1) ? 1u : 0u;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*last_flag != 0u) {
+          __threadfence();
+          if (half == 0 && row < p.M) {
+            const float* rec = p.topk_part + static_cast<size_t>(row) * nparts * kTopKRec;
+            float gm = -INFINITY;
+            for (int q = 0; q < nparts; ++q) gm = fmaxf(gm, __ldcg(rec + q * kTopKRec));
+            float gs = 0.f;
+            float bv[kTopKMax];
+            int bi[kTopKMax];
+#pragma unroll
+            for (int j = 0; j < kTopKMax; ++j) { bv[j] = -INFINITY; bi[j] = 0x7fffffff; }
+            for (int q = 0; q < nparts; ++q) {
+              const float* r = rec + q * kTopKRec;
+              const float pm = __ldcg(r), ps = __ldcg(r + 1);
+              if (ps != ps) gs = ps;                          // a NaN anywhere in the row: the softmax denominator is NaN
+              else if (pm > -INFINITY) gs += ps * expf(pm - gm);
+#pragma unroll
+              for (int j = 0; j < kTopKMax; ++j)
+                topk_insert(bv, bi, __ldcg(r + 2 + j), __float_as_int(__ldcg(r + 2 + kTopKMax + j)));
+            }
+            const int kk = p.topk_k;
+#pragma unroll
+            for (int t = 0; t < kTopKMax; ++t) {
+              if (t < kk) {
+                int ii = bi[t];
+                if (ii < 0 || ii >= N) ii = t < N ? t : N - 1;      // cannot happen with k <= N; never an out-of-row index
+                p.topk_idx[static_cast<size_t>(row) * kk + t] = ii;
+                p.topk_probs[static_cast<size_t>(row) * kk + t] = expf(bv[t] - gm) / gs;
+              }
+            }
+          }
+          if (threadIdx.x == 64) p.topk_cnt[mt_idx] = 0;          // ready for the next launch (CUDA-graph replay)
+        }
       }
       if (warp == 2 && tile == walker) VQA_DBG(6);
       if (warp == 2 && tile + tstep >= total_tiles) VQA_DBG(7);
@@ -1043,6 +1150,7 @@ static GemmKernelFn pick_kernel(int bn, int mt, bool tf32, int epi, int row_byte
   VQA_PICK(BN_, MT_, false, 2, false) VQA_PICK(BN_, MT_, false, 0, true) VQA_PICK(BN_, MT_, false, 1, true)
 #define VQA_PICK_F16RES(BN_) VQA_PICK(BN_, 1, false, 3, false)   /* 16-bit operands, fp32 out + fp32 residual (fp16 tail) */
 #define VQA_PICK_TF32(BN_) VQA_PICK(BN_, 1, true, 2, false) VQA_PICK(BN_, 1, true, 3, false)
+  VQA_PICK(128, 1, false, 6, false)   /* 16-bit operands, fp32 out + fused softmax / top-k (answer head) */
   VQA_PICK_BF16(64, 1) VQA_PICK_BF16(64, 2) VQA_PICK_BF16(128, 1) VQA_PICK_BF16(128, 2)
   VQA_PICK_BF16(256, 1) VQA_PICK_BF16(256, 2)
   VQA_PICK_TF32(64) VQA_PICK_TF32(128) VQA_PICK_TF32(256)
@@ -1066,7 +1174,7 @@ struct GemmLaunch {
   int bn;
   int threads;          // CTA size: 10 warps, 18 for the shift-fused kernels
   size_t smem;
-  uint64_t out_raw, res_raw;
+  uint64_t out_raw, res_raw, topk_idx_raw, topk_probs_raw;
 };
 
 int gemm_launch_bytes() { return static_cast<int>(sizeof(GemmLaunch)); }
@@ -1181,6 +1289,21 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   VQA_REQUIRE(p.out_dtype >= 0 && p.out_dtype <= 2, VQA_E_INVALID, "gemm: out_dtype must be 0 (bf16), 1 (fp32) or 2 (fp16)");
   p.out_f16 = p.out_dtype == 2 ? 1 : 0;
   L->epi = pool ? 4 : (p.out_dtype != 1 ? 0 : 2) + (has_res ? 1 : 0);
+  p.topk_k = I[GEMM_I_topk];
+  L->topk_idx_raw = op.p[GEMM_P_topk_idx];
+  L->topk_probs_raw = op.p[GEMM_P_topk_probs];
+  p.topk_part = reinterpret_cast<float*>(op.p[GEMM_P_topk_part]);
+  p.topk_cnt = reinterpret_cast<int*>(op.p[GEMM_P_topk_cnt]);
+  p.topk_idx = nullptr;
+  p.topk_probs = nullptr;
+  if (p.topk_k > 0) {
+    VQA_REQUIRE(L->epi == 2 && !tf32 && bn == 128 && p.MT == 1 && p.topk_k <= kTopKMax && p.topk_k <= p.N && !I[GEMM_I_relu] &&
+                    L->topk_idx_raw != 0 && L->topk_probs_raw != 0 && p.topk_part != nullptr && p.topk_cnt != nullptr &&
+                    !(op.p[GEMM_P_topk_part] & VQA_EXT_TAG) && !(op.p[GEMM_P_topk_cnt] & VQA_EXT_TAG),
+                VQA_E_INVALID, "gemm: the fused top-k epilogue needs 16-bit operands, an fp32 output without residual, BN = 128, "
+                               "MT = 1, k <= 8 and its scratch buffers");
+    L->epi = 6;
+  }
 
   // shared-memory plan: one CTA per SM (persistent): rings + epilogue staging + bias table + barriers <= 227 KB
   const int stage_bytes = epi_stage_bytes(L->epi, sf);
@@ -1325,6 +1448,11 @@ int gemm_run(const void* storage, const uint64_t* ext, int n_ext, cudaStream_t s
   p.out = reinterpret_cast<void*>(vqa_resolve(L->out_raw, ext, n_ext));
   p.res = reinterpret_cast<const void*>(vqa_resolve(L->res_raw, ext, n_ext));
   VQA_REQUIRE(p.out != nullptr, VQA_E_INVALID, "gemm: unresolved external output");
+  if (p.topk_k > 0) {
+    p.topk_idx = reinterpret_cast<long long*>(vqa_resolve(L->topk_idx_raw, ext, n_ext));
+    p.topk_probs = reinterpret_cast<float*>(vqa_resolve(L->topk_probs_raw, ext, n_ext));
+    VQA_REQUIRE(p.topk_idx != nullptr && p.topk_probs != nullptr, VQA_E_INVALID, "gemm: unresolved top-k outputs");
+  }
   if (L->out_external) {   // caller-owned output: encode its store map for this call (host-only work, graph-capturable)
     CUtensorMap mo;
     int rc = encode_box32(&mo, p.out_dtype == 1, reinterpret_cast<uint64_t>(p.out), p.M, p.N, p.ldo, "gemm output");

@@ -513,7 +513,7 @@ se_two_pass_kernel(const StageTailParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const int C8 = p.C8, C = C8 * 8, W = p.W, CS = p.CS, R = p.R;
-  const int rows_l = p.H / CS, NP = rows_l * W;
+  const int rows_l = p.H / CS;
   const int n = static_cast<int>(gridDim.x / CS) - 1 - static_cast<int>(blockIdx.x) / CS;   // descending: the last images are still in L2
   const int rank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int h0 = rank * rows_l;

@@ -49,9 +49,9 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                    "a1_rows", "a1_cols", "a1_ld", "ngroups", "ntaps", "out_dtype", "ldo", "res_dtype", "ldr",
                    "relu", "round_tf32", "mask_en", "mP", "mRPI", "mH", "mW", "smem_budget", "max_ctas", "row_bytes",
                    "halo_hi", "tiles_per_img", "tile_stride", "tile_row0", "img_rows", "n_imgs", "pool", "pool_P",
-                   "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio", "pair", "sf", "sf_step"]
+                   "pool_W", "pool_Wo", "pool_Ho", "pool_Po", "pool_rpio", "pair", "sf", "sf_step", "topk"]
                   + _GROUPS + _TAPS,
-             "p": ["a0", "a1", "b", "out", "bias", "res", "dbg", "sums"], "f": []},
+             "p": ["a0", "a1", "b", "out", "bias", "res", "dbg", "sums", "topk_idx", "topk_probs", "topk_part", "topk_cnt"], "f": []},
     "maxpool": {"i": ["B", "C", "Hin", "Win", "Pin", "RPIin", "Hout", "Wout", "Pout", "RPIout", "f32"],
                 "p": ["src", "dst"], "f": []},
     "se_squeeze": {"i": ["B", "C", "H", "W", "P", "RPI", "S"], "p": ["src", "sums"], "f": []},
@@ -90,6 +90,7 @@ MASK_NONE, MASK_I64, MASK_F32, MASK_I32, MASK_U8 = 0, 1, 2, 3, 4
 # external slots (order of the ext[] array given to vqa_plan_run)
 EXT = {"images": 0, "ids": 1, "mask": 2, "logits": 3, "top_idx": 4, "top_probs": 5}
 MAX_CACHED_LAYERS = 8
+TOPK_FUSED_MAX = 8   # kTopKMax in csrc/gemm_tcgen05.cu: winners an epilogue thread keeps; larger k uses softmax_topk_kernel
 # K/V of a cached image side (question-side programs): one slot per cross-attention layer
 EXT.update({f"kv{l}": 6 + l for l in range(MAX_CACHED_LAYERS)})
 
@@ -503,7 +504,7 @@ class OpList:
              a1=None, a1_shape=None, res=None, res_dtype=-1, ldr=0, relu=False, rnd=False,
              grid: Optional[Grid] = None, halo: int = 0, MT: int = 1, row_bytes: int = 128,
              halo_hi: Optional[int] = None, pool_to: Optional[Grid] = None, pair: Optional[bool] = None,
-             sf: int = 1, sf_step: int = 1, sums=None):
+             sf: int = 1, sf_step: int = 1, sums=None, topk=None):
         """Tap-shifted GEMM.  ``groups``: list of (map, row_delta, a_col, n_chunks, [tap_rel...]).
 
         For K-chunk c of group g the kernel loads ONE window of A rows
@@ -517,6 +518,9 @@ class OpList:
         ``sf`` > 1 (shift-fused form, N <= 64): the weight matrix has ``sf`` row blocks of BN rows and every MMA is
         sf*BN columns wide; the epilogue forms out[m] = sum_j acc[m + j*sf_step, j*BN + n].  A 128-row tile then
         yields 128 - (sf-1)*sf_step output rows (the M tiling is strided accordingly).
+
+        ``topk`` = (k, idx, probs): fused softmax + top-k of the fp32 output rows in the epilogue (k <= TOPK_FUSED_MAX,
+        16-bit operands, 128-column tiles): winners and their probabilities go to ``idx`` [M, k] int64 / ``probs`` [M, k].
         """
         wbuf, _, wshape = self.W.items[w]
         npad, ktot = wshape
@@ -537,6 +541,10 @@ class OpList:
         if wide and N >= 256 and dtype == DT_BF16 and out_dtype == OUT_BF16 and halo > 0 and sf == 1 and grid is not None:
             MT, bn, pair = (int(v) for v in wide.split(","))
             pair = bool(pair) and self.pair
+        if topk is not None:
+            assert dtype != DT_TF32 and out_dtype == OUT_F32 and res is None and not relu and MT == 1 and npad % 128 == 0
+            assert 0 < topk[0] <= min(TOPK_FUSED_MAX, N)
+            bn = 128
         assert npad % bn == 0 and npad >= N, (name, npad, bn)
         assert len(groups) <= MAX_GROUPS and MT * bn * sf <= 512
         assert sf == 1 or (1 < sf <= 3 and npad == sf * bn and MT == 1 and pool_to is None and (sf - 1) * sf_step <= 4)
@@ -547,7 +555,7 @@ class OpList:
                  res_dtype=res_dtype, ldr=ldr, relu=int(relu), round_tf32=int(rnd),
                  mask_en=int(grid is not None), mP=grid.P if grid else 1, mRPI=grid.rpi if grid else 1,
                  mH=grid.H if grid else 1, mW=grid.W if grid else 1, smem_budget=0, max_ctas=0,
-                 row_bytes=row_bytes, halo_hi=halo_hi, sf=sf, sf_step=sf_step)
+                 row_bytes=row_bytes, halo_hi=halo_hi, sf=sf, sf_step=sf_step, topk=topk[0] if topk else 0)
         if sf > 1:   # strided M tiling: tile t covers accumulator rows [t*stride, t*stride + 128), outputs the first `stride`
             stride = 128 * MT - (sf - 1) * sf_step
             i.update(tiles_per_img=(M + stride - 1) // stride, tile_stride=stride, tile_row0=0, img_rows=M, n_imgs=1)
@@ -578,10 +586,15 @@ class OpList:
         assert tap0 <= MAX_TAPS
         i["ntaps"] = tap0
         # ``sums``: fp32 [ceil(M/32), N] -- the epilogue also writes the column sums of every 32-row slab of the output
-        self._op("gemm", name, i, dict(a0=a0, a1=a1, b=wbuf, out=out,
-                                        bias=self.W.buf(bias) if bias else None, res=res, sums=sums))
+        p = dict(a0=a0, a1=a1, b=wbuf, out=out, bias=self.W.buf(bias) if bias else None, res=res, sums=sums)
+        if topk is not None:
+            n_tiles = npad // bn
+            p.update(topk_idx=topk[1], topk_probs=topk[2],
+                     topk_part=self._buf(name + ".topk_part", torch.float32, M, 2 * n_tiles, 2 + 2 * TOPK_FUSED_MAX),
+                     topk_cnt=self._buf(name + ".topk_cnt", torch.int32, (M + 127) // 128))
+        self._op("gemm", name, i, p)
 
-    def linear(self, name, a, M, K, w, bias, out, N, ldo=None, res=None, relu=False, rnd=False, lda=None):
+    def linear(self, name, a, M, K, w, bias, out, N, ldo=None, res=None, relu=False, rnd=False, lda=None, topk=None):
         """fp32/TF32 dense layer: out[M,N] = a[M,K] @ W^T (+bias)(+res)(relu).
 
         tf32 precision mode: 3xTF32.  ``a`` (unrounded fp32) is split into [a_hi | a_lo] by a small kernel and the
@@ -601,8 +614,9 @@ class OpList:
             assert not (rnd and res is not None)
             self.gemm(name, dtype=DT_F16, M=M, N=N, a0=a, a0_shape=(M, K, lda or K), groups=[(0, 0, 0, K // 64, [0])],
                       w=w + ".h", bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F16 if rnd else OUT_F32, res=res,
-                      res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=False)
+                      res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=False, topk=topk)
             return
+        assert topk is None, "the fused top-k epilogue exists for the fp16-operand Linears only"
         self.gemm(name, dtype=DT_TF32, M=M, N=N, a0=a, a0_shape=(M, K, lda or K), groups=[(0, 0, 0, K // 32, [0])],
                   w=w, bias=bias, out=out, ldo=ldo or N, out_dtype=OUT_F32, res=res,
                   res_dtype=OUT_F32 if res is not None else -1, ldr=(ldo or N), relu=relu, rnd=rnd)
@@ -1095,8 +1109,14 @@ class Program(OpList):
         h1 = self._buf("head.h1", self.tdt, B, D)
         self.linear("head0", fused_h if self.half_tail else fused, B, D, "head0.w", "head0.b", h0, 2 * D, relu=True, rnd=True)
         self.linear("head1", h0, B, 2 * D, "head1.w", "head1.b", h1, D, relu=True, rnd=True)
+        # softmax + top-k fused into the last Linear's epilogue (models/vqa_model.py:336-337, api/inference.py:231-234):
+        # per-thread running max / exp-sum / k best while the logits are drained from TMEM, merged by the CTA that finishes
+        # an M tile's last N tile; larger k, odd num_answers and the tf32 mode keep the separate softmax_topk kernel
+        fuse_topk = (0 < self.top_k <= TOPK_FUSED_MAX and NA % 4 == 0 and self.half_tail and "head2.w.h" in W
+                     and W.items["head2.w.h"][2][0] % 128 == 0 and os.environ.get("VQA_FUSED_TOPK", "1") != "0")
         if NA % 4 == 0:
-            self.linear("head2", h1, B, D, "head2.w", "head2.b", ExtRef(EXT["logits"]), NA, ldo=NA)
+            self.linear("head2", h1, B, D, "head2.w", "head2.b", ExtRef(EXT["logits"]), NA, ldo=NA,
+                        topk=(self.top_k, ExtRef(EXT["top_idx"]), ExtRef(EXT["top_probs"])) if fuse_topk else None)
         else:
             # the GEMM epilogue stores through TMA (16-byte row pitch and N granules): an odd num_answers goes
             # through a padded scratch matrix (the padded weight rows / bias entries are zero)
@@ -1105,6 +1125,6 @@ class Program(OpList):
             self.linear("head2", h1, B, D, "head2.w", "head2.b", lg, nap, ldo=nap)
             self._op("copy_rows", "head2.unpad", dict(rows=B, cols=NA, ld_src=nap, ld_dst=NA),
                      dict(src=lg, dst=ExtRef(EXT["logits"])))
-        if self.top_k:
+        if self.top_k and not fuse_topk:
             self._op("softmax_topk", "topk", dict(B=B, N=NA, k=self.top_k, ld=NA),
                      dict(logits=ExtRef(EXT["logits"]), idx=ExtRef(EXT["top_idx"]), probs=ExtRef(EXT["top_probs"])))
