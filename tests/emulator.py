@@ -344,6 +344,23 @@ class Emulator:
         pe = _t(op.p["pe"], torch.float32, ext)
         x = table[ids] + pe[: L * D].view(1, L, D)
         _t(op.p["dst"], torch.float32, ext)[: B * L * D].view(B, L, D).copy_(x)
+        if op.p.get("gamma") is not None:     # + the first encoder layer's LayerNorm (+ mask normalisation), same launch
+            y = F.layer_norm(x.view(B * L, D), (D,), _t(op.p["gamma"], torch.float32, ext)[:D],
+                             _t(op.p["beta"], torch.float32, ext)[:D], op.f["eps"])
+            self._ln_store(op.p["ln_dst"], i.get("round_tf32", 0), y, ext)
+            if op.p.get("mask_dst") is not None:
+                src = ext[op.p["mask_src"].slot]
+                _t(op.p["mask_dst"], torch.int32, ext)[: B * L].view(B, L).copy_((src != 0).to(torch.int32))
+                if op.p.get("mask_dstf") is not None:
+                    _t(op.p["mask_dstf"], torch.float32, ext)[: B * L].view(B, L).copy_(src.to(torch.float32))
+
+    @staticmethod
+    def _ln_store(ref, rnd, y, ext):
+        rows, D = y.shape
+        if rnd == 2:                          # fp16 operand of the next Linear
+            _t(ref, torch.float16, ext)[: rows * D].view(rows, D).copy_(y.half())
+        else:
+            _t(ref, torch.float32, ext)[: rows * D].view(rows, D).copy_(P.round_tf32(y) if rnd else y)
 
     def op_layernorm(self, op, ext):
         i = op.i
@@ -363,12 +380,12 @@ class Emulator:
             S = i["S"]
             pos = _t(op.p["pos"], torch.float32, ext)[: S * S * D].view(1, S * S, D)
             y = (y.view(-1, S * S, D) + pos).view(rows, D)
-        if i["round_tf32"] == 2:          # fp16 operand of the next Linear
-            _t(op.p["dst"], torch.float16, ext)[: rows * D].view(rows, D).copy_(y.half())
-            return
-        if i["round_tf32"]:
-            y = P.round_tf32(y)
-        _t(op.p["dst"], torch.float32, ext)[: rows * D].view(rows, D).copy_(y)
+        for k in (2, 3):                      # chained LayerNorms of the unrounded first output
+            if op.p.get(f"gamma{k}") is not None:
+                z = F.layer_norm(y, (D,), _t(op.p[f"gamma{k}"], torch.float32, ext)[:D],
+                                 _t(op.p[f"beta{k}"], torch.float32, ext)[:D], op.f["eps"])
+                self._ln_store(op.p[f"dst{k}"], i.get(f"rnd{k}", 0), z, ext)
+        self._ln_store(op.p["dst"], i["round_tf32"], y, ext)
 
     @staticmethod
     def _attend(q, k, v, hd, key_mask=None):

@@ -19,7 +19,8 @@ OUTPUTS = {
     "ingest": [("dst", torch.bfloat16)], "gemm": [("out", None), ("sums", torch.float32)], "stem_pool": [("out", torch.bfloat16)], "mlp_chain": [("xout", torch.float32), ("y", torch.float32)], "maxpool": [("dst", torch.bfloat16)],
     "se_squeeze": [("sums", torch.float32)], "se_excite": [("scale", torch.float32)],
     "spatial_map": [("att", torch.float32)], "scale_relayout": [("dst", torch.bfloat16)],
-    "embed": [("dst", torch.float32)], "layernorm": [("dst", torch.float32)],
+    "embed": [("dst", torch.float32), ("ln_dst", torch.float32), ("mask_dst", torch.int32)],
+    "layernorm": [("dst", torch.float32), ("dst2", torch.float32), ("dst3", torch.float32)],
     "self_attn": [("out", torch.float32)], "cross_attn": [("out", torch.float32), ("weights", torch.float32)],
     "pool_gate_ln": [("fused", torch.float32), ("att_pooled", torch.float32), ("txt_pooled", torch.float32),
                      ("cat", torch.float32)],
@@ -89,7 +90,8 @@ def test_each_op_against_emulator(ctor, B, L, in_fmt, mask_kind, window, precisi
                 dtype = torch.float32          # tf32 precision mode: fp32 activation grids
             # operands of the fp16 tail Linears are stored as fp16 by their producers
             if (op.kind in ("self_attn", "cross_attn") and field == "out" and op.i.get("no_round") == 2) or \
-               (op.kind == "layernorm" and op.i.get("round_tf32") == 2) or \
+               (op.kind == "layernorm" and op.i.get({"dst": "round_tf32", "dst2": "rnd2", "dst3": "rnd3"}[field]) == 2) or \
+               (op.kind == "embed" and field == "ln_dst" and op.i.get("round_tf32") == 2) or \
                (op.kind == "pool_gate_ln" and field == "cat" and op.i.get("no_round") == 2):
                 dtype = torch.float16
             want = _view(ref_c, dtype, ext)

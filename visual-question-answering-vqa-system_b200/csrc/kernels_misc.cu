@@ -1020,10 +1020,53 @@ __global__ void embed_kernel(const long long* __restrict__ ids, const float4* __
 // LayerNorm over D = 256, one warp per row (biased variance, eps inside the sqrt).  mode 1 is the
 // image projector's variant: source rows are the valid pixels of the 7x7 (+pad) grid and the
 // learned position embedding is added after the affine (models/fusion.py:98-112).
+// One LayerNorm-256 row held by a warp (8 values per lane: columns 4*lane.. and 128 + 4*lane..): statistics, affine.
+__device__ __forceinline__ void ln256_apply(const float (&x)[8], const float4& g0, const float4& g1, const float4& b0,
+                                            const float4& b1, float eps, float (&y)[8]) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  const float mean = warp_sum(s) * (1.f / 256.f);
+  float v[8], q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] = x[k] - mean; q += v[k] * v[k]; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = v[k] * rstd * g[k] + bb[k];
+}
+// Store a row: rnd 0 = fp32, 1 = tf32-rounded fp32, 2 = fp16 (operand of an fp16 Linear).
+__device__ __forceinline__ void ln256_store(float* dst, int row, int lane, int rnd, float (&y)[8]) {
+  if (rnd == 2) {   // 8 bytes per float4
+    uint2* o2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dst) + static_cast<size_t>(row) * 256);
+    o2[lane] = make_uint2(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]));
+    o2[32 + lane] = make_uint2(pack_f16x2(y[4], y[5]), pack_f16x2(y[6], y[7]));
+    return;
+  }
+  float4* o4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(row) * 256);
+  if (rnd) {
+    o4[lane] = make_float4(round_tf32_rna(y[0]), round_tf32_rna(y[1]), round_tf32_rna(y[2]), round_tf32_rna(y[3]));
+    o4[32 + lane] = make_float4(round_tf32_rna(y[4]), round_tf32_rna(y[5]), round_tf32_rna(y[6]), round_tf32_rna(y[7]));
+  } else {
+    o4[lane] = make_float4(y[0], y[1], y[2], y[3]);
+    o4[32 + lane] = make_float4(y[4], y[5], y[6], y[7]);
+  }
+}
+
+// Up to two further LayerNorms of the (unrounded) first output in the same launch: the final text norm + the first
+// cross-attention layer's query norm (text_encoder.py:522, cross_attention.py:265), the projector norm + the key/value
+// norms of the cross-attention layers (fusion.py:98-112, cross_attention.py:266).
+struct LnExtra {
+  const float *gamma2, *beta2, *gamma3, *beta3;
+  float *dst2, *dst3;
+  int rnd2, rnd3;
+};
+
 __global__ void layernorm256_kernel(const float* __restrict__ src, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, float* __restrict__ dst,
                                     const float* __restrict__ pos, int rows, int ld, int mode, int rnd, int S, int Pg,
-                                    int RPIg, float eps) {
+                                    int RPIg, float eps, const LnExtra ex) {
   pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -1041,39 +1084,66 @@ __global__ void layernorm256_kernel(const float* __restrict__ src, const float* 
   }
   const float4* x4 = reinterpret_cast<const float4*>(src + srow * ld);
   const float4 a = x4[lane], b = x4[32 + lane];
-  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s += v[k];
-  const float mean = warp_sum(s) * (1.f / 256.f);
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { v[k] -= mean; q += v[k] * v[k]; }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
-  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   float y[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) y[k] = v[k] * rstd * g[k] + bb[k];
+  ln256_apply(v, g0, g1, b0, b1, eps, y);
   if (mode == 1 && pos) {
     const float4 p0 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(pix) * 256)[lane];
     const float4 p1 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(pix) * 256)[32 + lane];
     y[0] += p0.x; y[1] += p0.y; y[2] += p0.z; y[3] += p0.w;
     y[4] += p1.x; y[5] += p1.y; y[6] += p1.z; y[7] += p1.w;
   }
-  if (rnd == 2) {   // fp16 operand of the next GEMM: 8 bytes per float4
-    uint2* o2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dst) + static_cast<size_t>(row) * 256);
-    o2[lane] = make_uint2(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]));
-    o2[32 + lane] = make_uint2(pack_f16x2(y[4], y[5]), pack_f16x2(y[6], y[7]));
-    return;
+  if (ex.gamma2 != nullptr) {
+    float z[8];
+    ln256_apply(y, __ldg(reinterpret_cast<const float4*>(ex.gamma2) + lane), __ldg(reinterpret_cast<const float4*>(ex.gamma2) + 32 + lane),
+                __ldg(reinterpret_cast<const float4*>(ex.beta2) + lane), __ldg(reinterpret_cast<const float4*>(ex.beta2) + 32 + lane), eps, z);
+    ln256_store(ex.dst2, row, lane, ex.rnd2, z);
   }
-  if (rnd) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) y[k] = round_tf32_rna(y[k]);
+  if (ex.gamma3 != nullptr) {
+    float z[8];
+    ln256_apply(y, __ldg(reinterpret_cast<const float4*>(ex.gamma3) + lane), __ldg(reinterpret_cast<const float4*>(ex.gamma3) + 32 + lane),
+                __ldg(reinterpret_cast<const float4*>(ex.beta3) + lane), __ldg(reinterpret_cast<const float4*>(ex.beta3) + 32 + lane), eps, z);
+    ln256_store(ex.dst3, row, lane, ex.rnd3, z);
   }
-  float4* o4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(row) * 256);
-  o4[lane] = make_float4(y[0], y[1], y[2], y[3]);
-  o4[32 + lane] = make_float4(y[4], y[5], y[6], y[7]);
+  ln256_store(dst, row, lane, rnd, y);
+}
+
+// EMBED with the first encoder layer's LayerNorm and the mask normalisation in the same launch (warp per token):
+// x = table[id] + pe[position] -> dst (the fp32 residual stream); LN(x) -> ln_dst; the token's mask element -> int32 key mask
+// + float pooling weight (text_encoder.py:504-512, :373; fusion.py:299-312).
+__global__ void embed_ln_kernel(const long long* __restrict__ ids, const float* __restrict__ table, const float* __restrict__ pe,
+                                float* __restrict__ dst, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float* __restrict__ ln_dst, int T, int L, int V, int rnd, float eps,
+                                const void* __restrict__ mask_src, int* __restrict__ mask_dst, float* __restrict__ mask_dstf,
+                                int mask_dtype) {
+  pdl_launch_dependents();
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + lane), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 32 + lane);
+  pdl_wait();
+  if (tok >= T) return;
+  if (lane == 0 && mask_dst != nullptr) {
+    float m = 1.f;
+    if (mask_dtype == 1) m = static_cast<float>(reinterpret_cast<const long long*>(mask_src)[tok]);
+    else if (mask_dtype == 2) m = reinterpret_cast<const float*>(mask_src)[tok];
+    else if (mask_dtype == 3) m = static_cast<float>(reinterpret_cast<const int*>(mask_src)[tok]);
+    else if (mask_dtype == 4) m = static_cast<float>(reinterpret_cast<const unsigned char*>(mask_src)[tok]);
+    mask_dst[tok] = m != 0.f;
+    if (mask_dstf) mask_dstf[tok] = m;
+  }
+  long long id = ids[tok];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const float4* e4 = reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * 256);
+  const float4* p4 = reinterpret_cast<const float4*>(pe + static_cast<size_t>(tok % L) * 256);
+  const float4 e0 = __ldg(e4 + lane), e1 = __ldg(e4 + 32 + lane), p0 = __ldg(p4 + lane), p1 = __ldg(p4 + 32 + lane);
+  const float x[8] = {e0.x + p0.x, e0.y + p0.y, e0.z + p0.z, e0.w + p0.w, e1.x + p1.x, e1.y + p1.y, e1.z + p1.z, e1.w + p1.w};
+  float4* o4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(tok) * 256);
+  o4[lane] = make_float4(x[0], x[1], x[2], x[3]);
+  o4[32 + lane] = make_float4(x[4], x[5], x[6], x[7]);
+  float y[8];
+  ln256_apply(x, g0, g1, b0, b1, eps, y);
+  ln256_store(ln_dst, tok, lane, rnd, y);
 }
 
 constexpr int kHd = 32;
@@ -1642,6 +1712,20 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
       const int T = I[EMBED_I_B] * I[EMBED_I_L], D4 = I[EMBED_I_D] / 4;
       const long long* ids = PTR(const long long*, EMBED_P_ids);
       VQA_REQUIRE(ids != nullptr, VQA_E_INVALID, "embed: null token ids");
+      if (op.p[EMBED_P_gamma] != 0) {   // + first LayerNorm (+ mask normalisation) in the same launch
+        VQA_REQUIRE(I[EMBED_I_D] == 256 && op.p[EMBED_P_beta] != 0 && op.p[EMBED_P_ln_dst] != 0, VQA_E_INVALID,
+                    "embed: the fused LayerNorm needs D = 256, beta and an output");
+        const void* msrc = PTR(const void*, EMBED_P_mask_src);
+        int* mdst = PTR(int*, EMBED_P_mask_dst);
+        VQA_REQUIRE(mdst == nullptr || msrc != nullptr || I[EMBED_I_mask_dtype] == 0, VQA_E_INVALID, "embed: null mask");
+        VQA_CUDA_OK(vqa_launch(embed_ln_kernel, dim3(blocks_for(T, 8)), dim3(256), 0, st, ids, PTR(const float*, EMBED_P_table),
+                               PTR(const float*, EMBED_P_pe), PTR(float*, EMBED_P_dst), PTR(const float*, EMBED_P_gamma),
+                               PTR(const float*, EMBED_P_beta), PTR(float*, EMBED_P_ln_dst), T, I[EMBED_I_L], I[EMBED_I_V],
+                               I[EMBED_I_round_tf32], op.f[EMBED_F_eps], msrc, mdst, PTR(float*, EMBED_P_mask_dstf),
+                               I[EMBED_I_mask_dtype]));
+        VQA_LAUNCH_OK("embed_ln_kernel");
+        return VQA_OK;
+      }
       VQA_CUDA_OK(vqa_launch(embed_kernel, dim3(blocks_for(static_cast<long long>(T) * D4, 256)), dim3(256), 0, st, 
           ids, PTR(const float4*, EMBED_P_table), PTR(const float4*, EMBED_P_pe), PTR(float4*, EMBED_P_dst), T,
           I[EMBED_I_L], D4, I[EMBED_I_V]));
@@ -1651,11 +1735,19 @@ int run_misc_op(const VqaOp& op, const uint64_t* ext, int n_ext, cudaStream_t st
     case VQA_OP_LAYERNORM: {
       VQA_REQUIRE(I[LAYERNORM_I_D] == 256, VQA_E_INVALID, "layernorm: D must be 256");
       const int rows = I[LAYERNORM_I_rows];
+      LnExtra ex;
+      ex.gamma2 = PTR(const float*, LAYERNORM_P_gamma2); ex.beta2 = PTR(const float*, LAYERNORM_P_beta2);
+      ex.dst2 = PTR(float*, LAYERNORM_P_dst2); ex.rnd2 = I[LAYERNORM_I_rnd2];
+      ex.gamma3 = PTR(const float*, LAYERNORM_P_gamma3); ex.beta3 = PTR(const float*, LAYERNORM_P_beta3);
+      ex.dst3 = PTR(float*, LAYERNORM_P_dst3); ex.rnd3 = I[LAYERNORM_I_rnd3];
+      VQA_REQUIRE((ex.gamma2 == nullptr || (ex.beta2 != nullptr && ex.dst2 != nullptr)) &&
+                      (ex.gamma3 == nullptr || (ex.beta3 != nullptr && ex.dst3 != nullptr)),
+                  VQA_E_INVALID, "layernorm: a chained LayerNorm needs gamma, beta and an output");
       VQA_CUDA_OK(vqa_launch(layernorm256_kernel, dim3(blocks_for(rows, 8)), dim3(256), 0, st, 
           PTR(const float*, LAYERNORM_P_src), PTR(const float*, LAYERNORM_P_gamma), PTR(const float*, LAYERNORM_P_beta),
           PTR(float*, LAYERNORM_P_dst), PTR(const float*, LAYERNORM_P_pos), rows, I[LAYERNORM_I_ld_src],
           I[LAYERNORM_I_mode], I[LAYERNORM_I_round_tf32], I[LAYERNORM_I_S], I[LAYERNORM_I_Pg], I[LAYERNORM_I_RPIg],
-          op.f[LAYERNORM_F_eps]));
+          op.f[LAYERNORM_F_eps], ex));
       VQA_LAUNCH_OK("layernorm256_kernel");
       return VQA_OK;
     }

@@ -60,9 +60,10 @@ FIELDS: Dict[str, Dict[str, List[str]]] = {
                     "p": ["src", "scale", "wconv", "att"], "f": []},
     "scale_relayout": {"i": ["B", "C", "H", "W", "P", "RPI", "mode", "Po", "RPIo", "phase_rows"],
                        "p": ["src", "scale", "att", "dst"], "f": []},
-    "embed": {"i": ["B", "L", "D", "V"], "p": ["ids", "table", "pe", "dst"], "f": []},
-    "layernorm": {"i": ["rows", "D", "ld_src", "mode", "round_tf32", "S", "Pg", "RPIg"],
-                  "p": ["src", "gamma", "beta", "dst", "pos"], "f": ["eps"]},
+    "embed": {"i": ["B", "L", "D", "V", "round_tf32", "mask_dtype"],
+              "p": ["ids", "table", "pe", "dst", "gamma", "beta", "ln_dst", "mask_src", "mask_dst", "mask_dstf"], "f": ["eps"]},
+    "layernorm": {"i": ["rows", "D", "ld_src", "mode", "round_tf32", "S", "Pg", "RPIg", "rnd2", "rnd3"],
+                  "p": ["src", "gamma", "beta", "dst", "pos", "gamma2", "beta2", "dst2", "gamma3", "beta3", "dst3"], "f": ["eps"]},
     "self_attn": {"i": ["B", "L", "H", "hd", "ld_qkv", "no_round"], "p": ["qkv", "mask", "out"], "f": []},
     "cross_attn": {"i": ["B", "L", "H", "hd", "T", "ld_q", "ld_kv", "k_off", "v_off", "no_round", "q_per_kv"],
                    "p": ["q", "kv", "out", "weights"], "f": []},
@@ -465,6 +466,9 @@ class OpList:
         self.chain = self.half_tail and os.environ.get("VQA_CHAIN", "1") != "0"
         # fused stem: two conv rows per N = 128 MMA, vertical max in registers (stem_pool op); "0" = the 3-row gemm form
         self.stem_two_row = os.environ.get("VQA_STEM_TWO_ROW", "1") != "0"
+        # LayerNorms that follow each other (or the embedding) share a launch: embedding + first encoder norm + mask
+        # normalisation, final text norm + first query norm, projector norm + key/value norms; "0" = one launch each
+        self.fuse_ln = os.environ.get("VQA_FUSE_LN", "1") != "0"
         self.fused_tail = window or self.tf32
         self.pair = window and not self.tf32
         self.phase_windows = os.environ.get("VQA_PHASE_WINDOWS", "1") != "0"   # A/B switch for the stride-2 block entries
@@ -677,12 +681,24 @@ class OpList:
         rels = [halo + (kh - 1) * g.P - 1 for kh in range(3)]
         return [(0, 0, 0, nchunks, rels)], halo, g.P - 1
 
-    def layernorm(self, name, src, g, b, dst, rows, rnd=False, ld=256):
+    def _ln_mode(self, rnd):
         # output mode: 0 = fp32, 1 = tf32-rounded fp32, 2 = fp16 (operand of an fp16 Linear); tf32 precision mode:
         # consumers split the unrounded value into hi + lo
-        mode = 0 if (not rnd or self.tf32) else (2 if self.half_tail else 1)
-        self._op("layernorm", name, dict(rows=rows, D=256, ld_src=ld, mode=0, round_tf32=mode, S=0, Pg=0, RPIg=0),
-                 dict(src=src, gamma=self.W.buf(g), beta=self.W.buf(b), dst=dst, pos=None), dict(eps=1e-5))
+        return 0 if (not rnd or self.tf32) else (2 if self.half_tail else 1)
+
+    def _ln_extra(self, extra):
+        """``extra``: up to two (gamma, beta, dst, rnd) -- further LayerNorms of the first one's unrounded output, same launch."""
+        i, p = {}, {}
+        assert len(extra) <= 2
+        for k, (g2, b2, dst2, rnd2) in enumerate(extra, start=2):
+            i[f"rnd{k}"] = self._ln_mode(rnd2)
+            p.update({f"gamma{k}": self.W.buf(g2), f"beta{k}": self.W.buf(b2), f"dst{k}": dst2})
+        return i, p
+
+    def layernorm(self, name, src, g, b, dst, rows, rnd=False, ld=256, extra=()):
+        xi, xp = self._ln_extra(extra)
+        self._op("layernorm", name, dict(rows=rows, D=256, ld_src=ld, mode=0, round_tf32=self._ln_mode(rnd), S=0, Pg=0, RPIg=0, **xi),
+                 dict(src=src, gamma=self.W.buf(g), beta=self.W.buf(b), dst=dst, pos=None, **xp), dict(eps=1e-5))
 
 
 class Program(OpList):
@@ -958,14 +974,17 @@ class Program(OpList):
             self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
                       groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
             img = self._buf("image_projected", f32, TI, D)
-            self._op("layernorm", "proj.ln", dict(rows=TI, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
-                     dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos")),
+            imns = [self._buf(f"x.{l}.imgn", self.tdt, TI, D) for l in range(n_layers)]
+            n_fused = min(n_layers, 2) if self.fuse_ln else 0   # key/value norms that ride in the projector norm's launch
+            xi, xp = self._ln_extra([(f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imns[l], True) for l in range(n_fused)])
+            self._op("layernorm", "proj.ln", dict(rows=TI, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi, **xi),
+                     dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos"), **xp),
                      dict(eps=1e-5))
             for l in range(n_layers):
-                imn = self._buf(f"x.{l}.imgn", self.tdt, TI, D)
                 kv = self._buf(f"x.{l}.kv", f32, TI, 2 * D)
-                self.layernorm(f"x.{l}.lnkv", img, f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imn, TI, rnd=True)
-                self.linear(f"x.{l}.kv", imn, TI, D, f"x.{l}.kv.w", None, kv, 2 * D)
+                if l >= n_fused:
+                    self.layernorm(f"x.{l}.lnkv", img, f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imns[l], TI, rnd=True)
+                self.linear(f"x.{l}.kv", imns[l], TI, D, f"x.{l}.kv.w", None, kv, 2 * D)
             return
         cached = self.side == "question"
         if cached and n_layers > MAX_CACHED_LAYERS:
@@ -976,25 +995,35 @@ class Program(OpList):
         # the key mask of the self-attention is binary (mask == 0 -> -inf, models/text_encoder.py:244); the masked mean
         # pools weigh every token with attention_mask.float() (models/fusion.py:299-312): both forms are kept
         mask = maskw = None
+        fuse_embed = self.fuse_ln and D == 256 and "text.0.ln1.g" in W
         if self.mask_dtype != MASK_NONE:
             mask = self._buf("mask_i32", i32, B, L)
             maskw = self._buf("mask_f32", f32, B, L)
-            self._op("mask_prep", "mask", dict(B=B, L=L, dtype=self.mask_dtype),
-                     dict(src=ExtRef(EXT["mask"]), dst=mask, dstf=maskw))
+            if not fuse_embed:
+                self._op("mask_prep", "mask", dict(B=B, L=L, dtype=self.mask_dtype),
+                         dict(src=ExtRef(EXT["mask"]), dst=mask, dstf=maskw))
         xt = self._buf("text.x", f32, T, D)
         xn = self._buf("text.xn", self.tdt, T, D)
         qkv = self._buf("text.qkv", f32, T, 3 * D)
         ctx = self._buf("text.ctx", self.tdt, T, D)
         hid = self._buf("text.hid", self.tdt, T, F)
         V = W.items["text.emb"][2][0]
-        self._op("embed", "text.embed", dict(B=B, L=L, D=D, V=V),
-                 dict(ids=ExtRef(EXT["ids"]), table=W.buf("text.emb"), pe=W.buf("text.pe"), dst=xt))
+        if fuse_embed:   # embedding + position, the first layer's LayerNorm and the mask normalisation in one launch
+            self._op("embed", "text.embed", dict(B=B, L=L, D=D, V=V, round_tf32=self._ln_mode(True), mask_dtype=self.mask_dtype),
+                     dict(ids=ExtRef(EXT["ids"]), table=W.buf("text.emb"), pe=W.buf("text.pe"), dst=xt,
+                          gamma=W.buf("text.0.ln1.g"), beta=W.buf("text.0.ln1.b"), ln_dst=xn,
+                          mask_src=ExtRef(EXT["mask"]) if mask is not None else None, mask_dst=mask, mask_dstf=maskw),
+                     dict(eps=1e-5))
+        else:
+            self._op("embed", "text.embed", dict(B=B, L=L, D=D, V=V),
+                     dict(ids=ExtRef(EXT["ids"]), table=W.buf("text.emb"), pe=W.buf("text.pe"), dst=xt))
         layer = 0
         chain = self.chain and D == 256 and F % 128 == 0 and F <= 1024
         while f"text.{layer}.qkv.w" in W:
             p = f"text.{layer}"
             if not (chain and layer > 0):         # chains: the previous layer's kernel already produced this layer's q, k, v
-                self.layernorm(p + ".ln1", xt, p + ".ln1.g", p + ".ln1.b", xn, T, rnd=True)
+                if not (fuse_embed and layer == 0):
+                    self.layernorm(p + ".ln1", xt, p + ".ln1.g", p + ".ln1.b", xn, T, rnd=True)
                 self.linear(p + ".qkv", xn, T, D, p + ".qkv.w", None, qkv, 3 * D)
             self._op("self_attn", p + ".attn", dict(B=B, L=L, H=H, hd=D // H, ld_qkv=3 * D, no_round=self.out_mode),
                      dict(qkv=qkv, mask=mask, out=ctx))
@@ -1010,7 +1039,10 @@ class Program(OpList):
             self.linear(p + ".fc2", hid, T, F, p + ".fc2.w", p + ".fc2.b", xt, D, res=xt)
             layer += 1
         text = self._buf("text_features", f32, T, D)
-        self.layernorm("text.lnf", xt, "text.lnf.g", "text.lnf.b", text, T)
+        qn0 = self._buf("x.0.qn", self.tdt, T, D) if n_layers else None
+        fuse_lnq = self.fuse_ln and n_layers > 0
+        self.layernorm("text.lnf", xt, "text.lnf.g", "text.lnf.b", text, T,
+                       extra=[("x.0.lnq.g", "x.0.lnq.b", qn0, True)] if fuse_lnq else ())
 
         # ================= fusion =================
         # Two lanes stay busy: the side lane (which just finished the text encoder) goes on with the first layer's
@@ -1028,8 +1060,8 @@ class Program(OpList):
             imns = [self._buf(f"x.{l}.imgn", self.tdt, TI, D) for l in range(n_layers)]
             kvs = [self._buf(f"x.{l}.kv", f32, TI, 2 * D) for l in range(n_layers)]
         if n_layers:                              # side lane: LN_q + W_q of layer 0
-            qn0 = self._buf("x.0.qn", self.tdt, T, D)
-            self.layernorm("x.0.lnq", text, "x.0.lnq.g", "x.0.lnq.b", qn0, T, rnd=True)
+            if not fuse_lnq:
+                self.layernorm("x.0.lnq", text, "x.0.lnq.g", "x.0.lnq.b", qn0, T, rnd=True)
             self.linear("x.0.q", qn0, T, D, "x.0.q.w", None, qp, D)
         self.lane = 0
         if not cached:
@@ -1037,12 +1069,15 @@ class Program(OpList):
             self.gemm("proj", dtype=self.cdt, M=gf.rows, N=D, a0=feat, a0_shape=(gf.rows, 512, 512),
                       groups=[(0, 0, 0, 512 // self.cchunk, [0])], w="proj.w", bias="proj.b", out=praw, ldo=D, out_dtype=OUT_F32)
             img = self._buf("image_projected", f32, Bi * S * S, D)
-            self._op("layernorm", "proj.ln", dict(rows=Bi * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi),
-                     dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos")),
+            n_fused = min(n_layers, 2) if self.fuse_ln else 0   # key/value norms that ride in the projector norm's launch
+            xi, xp = self._ln_extra([(f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imns[l], True) for l in range(n_fused)])
+            self._op("layernorm", "proj.ln", dict(rows=Bi * S * S, D=D, ld_src=D, mode=1, round_tf32=0, S=S, Pg=gf.P, RPIg=gf.rpi, **xi),
+                     dict(src=praw, gamma=W.buf("proj.ln.g"), beta=W.buf("proj.ln.b"), dst=img, pos=W.buf("proj.pos"), **xp),
                      dict(eps=1e-5))
 
         def kv_proj(l):
-            self.layernorm(f"x.{l}.lnkv", img, f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imns[l], TI, rnd=True)
+            if l >= n_fused:
+                self.layernorm(f"x.{l}.lnkv", img, f"x.{l}.lnkv.g", f"x.{l}.lnkv.b", imns[l], TI, rnd=True)
             self.linear(f"x.{l}.kv", imns[l], TI, D, f"x.{l}.kv.w", None, kvs[l], 2 * D)
 
         if n_layers and not cached:
