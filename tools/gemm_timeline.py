@@ -32,6 +32,10 @@ st = torch.cuda.current_stream().cuda_stream
 for _ in range(3):
     plan.run(ext, st)
 torch.cuda.synchronize()
+if os.environ.get("VQA_TIMELINE_ISOLATED"):   # every GEMM launched alone: no PDL overlap with its neighbours in the numbers
+    for k in gemms:
+        plan.run(ext, st, k, k + 1)
+        torch.cuda.synchronize()
 print("op name: setup | first_tma | first_a_full | tile0_mma_issued | tile0_acc_full_seen | tile0_epi_done | last_mma_issued | last_epi_done | exit   (cycles from kernel entry)")
 only = os.environ.get("VQA_TIMELINE_ONLY", "")
 for k in gemms:
