@@ -128,7 +128,7 @@ __device__ __forceinline__ bool grid_pixel(const GemmParams& p, int row) {
 }
 
 constexpr int kTopKMax = 8;             // fused top-k epilogue: winners kept per thread (larger k: softmax_topk_kernel)
-constexpr int kTopKRec = 2 + 2 * kTopKMax;   // floats per partial record: max, exp-sum, keys, indices
+constexpr int kTopKRec = 4 + 2 * kTopKMax;   // floats per partial record (80 bytes): max, exp-sum, 2 pad, keys, indices
 // (key, index) beats (key', index') when key > key', or on a tie when the index is lower; the list stays sorted best first
 __device__ __forceinline__ void topk_insert(float (&tv)[kTopKMax], int (&ti)[kTopKMax], float key, int idx) {
   if (!(key > tv[kTopKMax - 1] || (key == tv[kTopKMax - 1] && idx < ti[kTopKMax - 1]))) return;
@@ -939,15 +939,18 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (PAIR) mbar_arrive_leader(&acc_empty[acc]); else mbar_arrive(&acc_empty[acc]);
       }
       if constexpr (kTopK) {
-        // ---- publish this thread's partial; the CTA that completes the M tile's last N tile merges the row
+        // ---- publish this thread's partial (one 80-byte record: max, exp-sum, pad, pad, 8 keys, 8 indices); the CTA that
+        // completes the M tile's last N tile merges the row: thread (row, half) folds the records of every other slot
+        // (vector loads, the next record in flight while the current one is inserted), the two halves meet in shared memory
         const int nparts = 2 * p.n_tiles, mt_idx = tile % m_tiles;
         const int row = m0 + quad * 32 + lane;
         if (row < p.M) {
-          float* rec = p.topk_part + (static_cast<size_t>(row) * nparts + (tile / m_tiles) * 2 + half) * kTopKRec;
-          rec[0] = tk_m;
-          rec[1] = tk_nan ? __int_as_float(0x7fc00000) : tk_s;
-#pragma unroll
-          for (int j = 0; j < kTopKMax; ++j) { rec[2 + j] = tk_v[j]; rec[2 + kTopKMax + j] = __int_as_float(tk_i[j]); }
+          float4* rec = reinterpret_cast<float4*>(p.topk_part + (static_cast<size_t>(row) * nparts + (tile / m_tiles) * 2 + half) * kTopKRec);
+          rec[0] = make_float4(tk_m, tk_nan ? __int_as_float(0x7fc00000) : tk_s, 0.f, 0.f);
+          rec[1] = make_float4(tk_v[0], tk_v[1], tk_v[2], tk_v[3]);
+          rec[2] = make_float4(tk_v[4], tk_v[5], tk_v[6], tk_v[7]);
+          rec[3] = make_float4(__int_as_float(tk_i[0]), __int_as_float(tk_i[1]), __int_as_float(tk_i[2]), __int_as_float(tk_i[3]));
+          rec[4] = make_float4(__int_as_float(tk_i[4]), __int_as_float(tk_i[5]), __int_as_float(tk_i[6]), __int_as_float(tk_i[7]));
         }
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -956,24 +959,51 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (*last_flag != 0u) {
           __threadfence();
-          if (half == 0 && row < p.M) {
-            const float* rec = p.topk_part + static_cast<size_t>(row) * nparts * kTopKRec;
-            float gm = -INFINITY;
-            for (int q = 0; q < nparts; ++q) gm = fmaxf(gm, __ldcg(rec + q * kTopKRec));
-            float gs = 0.f;
-            float bv[kTopKMax];
-            int bi[kTopKMax];
+          float gm = -INFINITY, gs = 0.f;
+          float bv[kTopKMax];
+          int bi[kTopKMax];
 #pragma unroll
-            for (int j = 0; j < kTopKMax; ++j) { bv[j] = -INFINITY; bi[j] = 0x7fffffff; }
-            for (int q = 0; q < nparts; ++q) {
-              const float* r = rec + q * kTopKRec;
-              const float pm = __ldcg(r), ps = __ldcg(r + 1);
-              if (ps != ps) gs = ps;                          // a NaN anywhere in the row: the softmax denominator is NaN
-              else if (pm > -INFINITY) gs += ps * expf(pm - gm);
+          for (int j = 0; j < kTopKMax; ++j) { bv[j] = -INFINITY; bi[j] = 0x7fffffff; }
+          auto fold = [&](const float4 (&r)[5]) {            // online merge of one record into (gm, gs, bv, bi)
+            const float pm = r[0].x, ps = r[0].y;
+            const float nm = fmaxf(gm, pm);
+            if (ps != ps) gs = ps;                            // a NaN anywhere in the row: the softmax denominator is NaN
+            else if (nm > -INFINITY && gs == gs) gs = gs * expf(gm - nm) + ps * expf(pm - nm);
+            gm = nm;
+            const float kv[8] = {r[1].x, r[1].y, r[1].z, r[1].w, r[2].x, r[2].y, r[2].z, r[2].w};
+            const float ki[8] = {r[3].x, r[3].y, r[3].z, r[3].w, r[4].x, r[4].y, r[4].z, r[4].w};
 #pragma unroll
-              for (int j = 0; j < kTopKMax; ++j)
-                topk_insert(bv, bi, __ldcg(r + 2 + j), __float_as_int(__ldcg(r + 2 + kTopKMax + j)));
+            for (int j = 0; j < kTopKMax; ++j) topk_insert(bv, bi, kv[j], __float_as_int(ki[j]));
+          };
+          if (row < p.M) {
+            const float4* rec = reinterpret_cast<const float4*>(p.topk_part + static_cast<size_t>(row) * nparts * kTopKRec);
+            float4 cur[5], nxt[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) cur[u] = __ldcg(rec + half * 5 + u);
+            for (int q = half; q < nparts; q += 2) {
+              const bool more = q + 2 < nparts;
+#pragma unroll
+              for (int u = 0; u < 5; ++u) nxt[u] = more ? __ldcg(rec + (q + 2) * 5 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+              fold(cur);
+#pragma unroll
+              for (int u = 0; u < 5; ++u) cur[u] = nxt[u];
             }
+          }
+          // the half-1 thread hands its merged record to the half-0 thread of the same row through its staging slot
+          if (lane == 0) bulk_wait_read0();                   // this warp's last TMA store has drained the slot
+          __syncwarp();
+          float4* xrow = reinterpret_cast<float4*>(smem_stage + (ew | 4) * kSlotBytes + lane * kRowB);   // the half-1 warp's slot
+          if (half == 1) {
+            xrow[0] = make_float4(gm, gs, 0.f, 0.f);
+            xrow[1] = make_float4(bv[0], bv[1], bv[2], bv[3]);
+            xrow[2] = make_float4(bv[4], bv[5], bv[6], bv[7]);
+            xrow[3] = make_float4(__int_as_float(bi[0]), __int_as_float(bi[1]), __int_as_float(bi[2]), __int_as_float(bi[3]));
+            xrow[4] = make_float4(__int_as_float(bi[4]), __int_as_float(bi[5]), __int_as_float(bi[6]), __int_as_float(bi[7]));
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (half == 0 && row < p.M) {
+            const float4 r[5] = {xrow[0], xrow[1], xrow[2], xrow[3], xrow[4]};
+            fold(r);
             const int kk = p.topk_k;
 #pragma unroll
             for (int t = 0; t < kTopKMax; ++t) {
@@ -986,6 +1016,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             }
           }
           if (threadIdx.x == 64) p.topk_cnt[mt_idx] = 0;          // ready for the next launch (CUDA-graph replay)
+          asm volatile("bar.sync 1, 256;" ::: "memory");           // the staging slots are free again for the next tile
         }
       }
       if (warp == 2 && tile == walker) VQA_DBG(6);

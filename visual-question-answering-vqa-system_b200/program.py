@@ -594,7 +594,7 @@ class OpList:
         if topk is not None:
             n_tiles = npad // bn
             p.update(topk_idx=topk[1], topk_probs=topk[2],
-                     topk_part=self._buf(name + ".topk_part", torch.float32, M, 2 * n_tiles, 2 + 2 * TOPK_FUSED_MAX),
+                     topk_part=self._buf(name + ".topk_part", torch.float32, M, 2 * n_tiles, 4 + 2 * TOPK_FUSED_MAX),
                      topk_cnt=self._buf(name + ".topk_cnt", torch.int32, (M + 127) // 128))
         self._op("gemm", name, i, p)
 
@@ -1146,9 +1146,11 @@ class Program(OpList):
         self.linear("head1", h0, B, 2 * D, "head1.w", "head1.b", h1, D, relu=True, rnd=True)
         # softmax + top-k fused into the last Linear's epilogue (models/vqa_model.py:336-337, api/inference.py:231-234):
         # per-thread running max / exp-sum / k best while the logits are drained from TMEM, merged by the CTA that finishes
-        # an M tile's last N tile; larger k, odd num_answers and the tf32 mode keep the separate softmax_topk kernel
+        # an M tile's last N tile.  Correct and tested (tests/test_gpu_gemm.py), but OPT-IN (VQA_FUSED_TOPK=1): one thread
+        # per row and partial selects among its 64 columns, against 256 threads per row in softmax_topk_kernel, and this
+        # GEMM (K = 256) has no MMA time to hide that behind -- measured 55.6 us against 14.2 + 14.2 us at 256 rows.
         fuse_topk = (0 < self.top_k <= TOPK_FUSED_MAX and NA % 4 == 0 and self.half_tail and "head2.w.h" in W
-                     and W.items["head2.w.h"][2][0] % 128 == 0 and os.environ.get("VQA_FUSED_TOPK", "1") != "0")
+                     and W.items["head2.w.h"][2][0] % 128 == 0 and os.environ.get("VQA_FUSED_TOPK", "0") != "0")
         if NA % 4 == 0:
             self.linear("head2", h1, B, D, "head2.w", "head2.b", ExtRef(EXT["logits"]), NA, ldo=NA,
                         topk=(self.top_k, ExtRef(EXT["top_idx"]), ExtRef(EXT["top_probs"])) if fuse_topk else None)
