@@ -138,3 +138,30 @@ def test_image_side_and_question_side_programs_compose():
     # matrix shape, so a bf16 rounding may flip (the CUDA kernels are batch-invariant: tests/test_gpu_cache_metrics.py
     # checks this composition bit for bit)
     torch.testing.assert_close(got4, want4, atol=5e-3, rtol=0)
+
+
+def test_fused_and_unfused_program_forms_agree(monkeypatch):
+    """Launch fusions change the op list, never the arithmetic: the LayerNorms that share a launch (embedding + first encoder
+    norm + mask, final text norm + first query norm, projector norm + key/value norms) and the softmax / top-k in the head
+    GEMM's epilogue give bit-identical logits and winners on the emulator, with fewer ops."""
+    torch.manual_seed(0)
+    model = VQAModel().eval()
+    sd = randomise_state(model.state_dict(), 1)
+    u8, img, ids, mask = synth_batch(2, 99, max_len=20, vocab=model.config["vocab_size"])
+    W = P.build_weights(sd, model.config, "cpu")
+
+    def run(fuse_ln, fuse_topk):
+        monkeypatch.setenv("VQA_FUSE_LN", fuse_ln)
+        monkeypatch.setenv("VQA_FUSED_TOPK", fuse_topk)
+        prog = P.Program(W, model.config, 2, 20, "nchw_f32", P.MASK_I64, want_aux=False, top_k=5, device="cpu")
+        logits, ext = E.run_program(prog, img, ids, mask, top_k=5)
+        return logits.clone(), ext[P.EXT["top_idx"]].clone(), ext[P.EXT["top_probs"]].clone(), [op.kind for op in prog.ops]
+
+    base = run("0", "0")
+    ln = run("1", "0")
+    tk = run("1", "1")
+    assert torch.equal(base[0], ln[0]) and torch.equal(base[0], tk[0])
+    assert torch.equal(base[1], ln[1]) and torch.equal(base[1], tk[1])
+    torch.testing.assert_close(base[2], tk[2], rtol=1e-6, atol=0)
+    assert len(ln[3]) == len(base[3]) - 5 and "mask_prep" not in ln[3]          # 3 + 2 + 3 launches became 1 + 1 + 1
+    assert len(tk[3]) == len(ln[3]) - 1 and "softmax_topk" not in tk[3]
