@@ -210,7 +210,12 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const int walker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // tile-sequence id
   const int n_walkers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   // per-CTA m-tile index of a walked tile (pair mode: 2 * pair index + rank; may be a phantom tile >= m_tiles_cta)
-  auto cta_mtile = [&](int tile) { return PAIR ? 2 * (tile % p.m_tiles) + static_cast<int>(rank) : tile % p.m_tiles; };
+  // tile -> (m tile, n tile) without an integer division when there is one N tile (every 64- / 128-channel convolution):
+  // the divisions by a runtime value cost ~25 instructions each, several times per tile and warp
+  const bool one_ntile = p.n_tiles == 1;
+  auto tile_mt = [&](int tile) { return one_ntile ? tile : tile % p.m_tiles; };
+  auto tile_nt = [&](int tile) { return one_ntile ? 0 : tile / p.m_tiles; };
+  auto cta_mtile = [&](int tile) { return PAIR ? 2 * tile_mt(tile) + static_cast<int>(rank) : tile_mt(tile); };
   const int b_region_slots = p.b_resident ? p.k_chunks : p.b_slots;
 
   uint8_t* smem_a = smem;
@@ -287,7 +292,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     };
     for (int tile = walker; tile < total_tiles; tile += n_walkers) {
       const int m0 = tile_m0(p, cta_mtile(tile), MT);
-      const int n0 = (tile / p.m_tiles) * kAcc + (PAIR ? static_cast<int>(rank) * (kAcc / 2) : 0);   // pair: this CTA's half of the N tile
+      const int n0 = tile_nt(tile) * kAcc + (PAIR ? static_cast<int>(rank) * (kAcc / 2) : 0);   // pair: this CTA's half of the N tile
       if (p.b_resident && !b_loaded) {   // n_tiles == 1 in this mode: load every weight chunk once
         if (elect_one()) {
           if (expects) mbar_expect_tx(&b_full[0], static_cast<uint32_t>(p.k_chunks * p.b_slot_bytes) * kTxMul);
@@ -761,12 +766,12 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       tma_load_2d(res_slot, &mapRes, my_res_bar, col0, row0);
     };
     if (kRes && lane == 0 && walker < total_tiles) {
-      issue_res(tile_m0(p, cta_mtile(walker), MT) + quad * 32, (walker / m_tiles) * BN + half * kCols);
+      issue_res(tile_m0(p, cta_mtile(walker), MT) + quad * 32, tile_nt(walker) * BN + half * kCols);
     }
 
     for (int tile = walker; tile < total_tiles; tile += tstep) {
       const int m0 = tile_m0(p, cta_mtile(tile), MT);
-      const int n0 = (tile / m_tiles) * BN;
+      const int n0 = tile_nt(tile) * BN;
       const int colw = n0 + half * kCols;               // first column this warp owns
       // ---- work that does not need the accumulator: done while the MMAs are still running
       bool pix[MT];
@@ -778,7 +783,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const int ntile = tile + tstep;                   // the residual of its first chunk is prefetched at the end
       const bool has_ntile = ntile < total_tiles;
       const int n_row0 = tile_m0(p, cta_mtile(ntile), MT) + quad * 32;
-      const int n_col0 = (ntile / m_tiles) * BN + half * kCols;
+      const int n_col0 = tile_nt(ntile) * BN + half * kCols;
 
       // fused softmax / top-k (EPI 6): this thread's row over the columns this warp drains
       float tk_m = -INFINITY, tk_s = 0.f;
@@ -942,10 +947,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         // ---- publish this thread's partial (one 80-byte record: max, exp-sum, pad, pad, 8 keys, 8 indices); the CTA that
         // completes the M tile's last N tile merges the row: thread (row, half) folds the records of every other slot
         // (vector loads, the next record in flight while the current one is inserted), the two halves meet in shared memory
-        const int nparts = 2 * p.n_tiles, mt_idx = tile % m_tiles;
+        const int nparts = 2 * p.n_tiles, mt_idx = tile_mt(tile);
         const int row = m0 + quad * 32 + lane;
         if (row < p.M) {
-          float4* rec = reinterpret_cast<float4*>(p.topk_part + (static_cast<size_t>(row) * nparts + (tile / m_tiles) * 2 + half) * kTopKRec);
+          float4* rec = reinterpret_cast<float4*>(p.topk_part + (static_cast<size_t>(row) * nparts + tile_nt(tile) * 2 + half) * kTopKRec);
           rec[0] = make_float4(tk_m, tk_nan ? __int_as_float(0x7fc00000) : tk_s, 0.f, 0.f);
           rec[1] = make_float4(tk_v[0], tk_v[1], tk_v[2], tk_v[3]);
           rec[2] = make_float4(tk_v[4], tk_v[5], tk_v[6], tk_v[7]);
