@@ -690,8 +690,14 @@ stage_tail_kernel(const StageTailParams p) {
   // ---- 1. stage the rows with cp.async (every 16-byte piece of the CTA's rows in flight at once: one DRAM round
   // trip instead of a register-limited sequence of them), then accumulate the channel sums from shared memory
   const uint4* img = p.src + static_cast<size_t>(n) * p.RPI * C8 * Vec::N;
+  // pixel q = pl, pl + lanes, ...: (row, column) are kept incrementally (ncu: the two q / W divisions of this kernel were
+  // 12 % of its instructions, and the kernel is issue-bound)
+  const int dq_h = lanes / W, dq_w = lanes - dq_h * W;
+  int hl_s = pl / W, w_s = pl - hl_s * W;
   for (int q = pl; q < NP; q += lanes) {
-    const int hl = q / W, w = q - hl * W;
+    const int hl = hl_s, w = w_s;
+    hl_s += dq_h; w_s += dq_w;
+    if (w_s >= W) { w_s -= W; ++hl_s; }
     const uint4* g = img + ((static_cast<size_t>(h0 + hl) * p.P + w) * C8 + cg) * Vec::N;
     uint4* d = tile + (static_cast<size_t>(q) * C8 + cg) * Vec::N;
 #pragma unroll
@@ -866,8 +872,11 @@ stage_tail_kernel(const StageTailParams p) {
   for (int j = 0; j < 8; ++j) k[j] = sc[cg * 8 + j];
   const int Po = p.Po;
   const int rows_o = p.RPIo / Po;                       // destination rows per image incl. padding
+  int hl_a = pl / W, w_a = pl - hl_a * W;
   for (int q = pl; q < NP; q += lanes) {
-    const int hl = q / W, w = q - hl * W, h = h0 + hl;
+    const int w = w_a, h = h0 + hl_a;
+    hl_a += dq_h; w_a += dq_w;
+    if (w_a >= W) { w_a -= W; ++hl_a; }
     Vec v, o;
     v.load(tile, static_cast<size_t>(q) * C8 + cg);
     const float a = use_sp ? att[q] : 1.f;
