@@ -549,6 +549,30 @@ class OpList:
             assert dtype != DT_TF32 and out_dtype == OUT_F32 and res is None and not relu and MT == 1 and npad % 128 == 0
             assert 0 < topk[0] <= min(TOPK_FUSED_MAX, N)
             bn = 128
+        # CTA pairs (cta_group::2): bf16 convolutions with a bf16 output; each CTA loads half of every weight tile
+        if pair is None:
+            pair_bns = [int(v) for v in os.environ.get("VQA_PAIR_BN", "128").split(",") if v]
+            pair = (self.pair and dtype == DT_BF16 and out_dtype == OUT_BF16 and bn in pair_bns
+                    and not (row_bytes == 32 and MT == 1))
+            if sf > 1:
+                pair = self.pair and os.environ.get("VQA_SF_PAIR", "0") != "0"
+        # Small batches (batch-1 `predict`, BASELINE configs[3]): the big tiles leave most SMs without a tile -- one image at
+        # 7x7 is ONE 512-row pair tile per 128 output channels, 8 CTAs each walking K = 4608 alone.  While fewer than half the
+        # SMs would get a tile, shrink it: 128-row sub-tiles, single CTAs instead of pairs, then 64-column tiles, so that more
+        # CTAs share the weight stream and the serial MMA chain of each gets shorter.  Large batches never take this path.
+        if (dtype == DT_BF16 and out_dtype == OUT_BF16 and grid is not None and sf == 1 and pool_to is None and topk is None
+                and sums is None and row_bytes == 128 and os.environ.get("VQA_SMALL_M", "1") != "0"):
+            def n_tiles_of(mt_, bn_, pair_):
+                return -(-M // (128 * mt_ * (2 if pair_ else 1))) * -(-N // bn_)
+            for step in ("mt", "pair", "bn"):
+                if n_tiles_of(MT, bn, pair) >= 74:
+                    break
+                if step == "mt" and MT == 2:
+                    MT = 1
+                elif step == "pair" and pair:
+                    pair = False
+                elif step == "bn" and bn > 64 and npad % 64 == 0:
+                    bn = 64
         assert npad % bn == 0 and npad >= N, (name, npad, bn)
         assert len(groups) <= MAX_GROUPS and MT * bn * sf <= 512
         assert sf == 1 or (1 < sf <= 3 and npad == sf * bn and MT == 1 and pool_to is None and (sf - 1) * sf_step <= 4)
@@ -563,13 +587,6 @@ class OpList:
         if sf > 1:   # strided M tiling: tile t covers accumulator rows [t*stride, t*stride + 128), outputs the first `stride`
             stride = 128 * MT - (sf - 1) * sf_step
             i.update(tiles_per_img=(M + stride - 1) // stride, tile_stride=stride, tile_row0=0, img_rows=M, n_imgs=1)
-        # CTA pairs (cta_group::2): bf16 convolutions with a bf16 output; each CTA loads half of every weight tile
-        if pair is None:
-            pair_bns = [int(v) for v in os.environ.get("VQA_PAIR_BN", "128").split(",") if v]
-            pair = (self.pair and dtype == DT_BF16 and out_dtype == OUT_BF16 and bn in pair_bns
-                    and not (row_bytes == 32 and MT == 1))
-            if sf > 1:
-                pair = self.pair and os.environ.get("VQA_SF_PAIR", "0") != "0"
         i["pair"] = int(bool(pair))
         if pool_to is not None:
             # fused 3x3/2 max-pool epilogue: tile t = (image, pooled row i') covers conv rows 2i'-1 .. 2i'+1
