@@ -557,15 +557,15 @@ class OpList:
             if sf > 1:
                 pair = self.pair and os.environ.get("VQA_SF_PAIR", "0") != "0"
         # Small batches (batch-1 `predict`, BASELINE configs[3]): the big tiles leave most SMs without a tile -- one image at
-        # 7x7 is ONE 512-row pair tile per 128 output channels, 8 CTAs each walking K = 4608 alone.  While fewer than half the
-        # SMs would get a tile, shrink it: 128-row sub-tiles, single CTAs instead of pairs, then 64-column tiles, so that more
+        # 7x7 is ONE 512-row pair tile per 128 output channels, 8 CTAs each walking K = 4608 alone.  While fewer than a third of
+        # the SMs would get a tile, shrink it: 128-row sub-tiles, single CTAs instead of pairs, then 64-column tiles, so that more
         # CTAs share the weight stream and the serial MMA chain of each gets shorter.  Large batches never take this path.
         if (dtype == DT_BF16 and out_dtype == OUT_BF16 and grid is not None and sf == 1 and pool_to is None and topk is None
                 and sums is None and row_bytes == 128 and os.environ.get("VQA_SMALL_M", "1") != "0"):
             def n_tiles_of(mt_, bn_, pair_):
                 return -(-M // (128 * mt_ * (2 if pair_ else 1))) * -(-N // bn_)
             for step in ("mt", "pair", "bn"):
-                if n_tiles_of(MT, bn, pair) >= 74:
+                if n_tiles_of(MT, bn, pair) >= 48:      # measured: 64 big tiles (batch 128 at 7x7) beat 128 small ones
                     break
                 if step == "mt" and MT == 2:
                     MT = 1
