@@ -80,7 +80,7 @@ def test_pipelined_throughput_path_matches_single_calls(engine, lanes, graph):
     assert len(outs) == 11
     outs2 = list(engine.predict_tensors_pipelined(batches[::-1], top_k=4))      # second call reuses the captured slots
     assert all(torch.equal(a[0], b[0]) for a, b in zip(outs, outs2[::-1]))
-    engine.pipeline_lanes = 2
+    engine.pipeline_lanes = 3
     engine.use_cuda_graph = False
     for (u8, ids, mask), (idx, probs) in zip(batches, outs):
         ridx, rprobs = engine._run(u8, ids, mask, 4)

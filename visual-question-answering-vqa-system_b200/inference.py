@@ -61,7 +61,7 @@ class VQAInference:
         self.answer_vocab: Optional[AnswerVocabulary] = None
         self.transform = None
         self.use_cuda_graph = use_cuda_graph
-        self.pipeline_lanes = 2     # concurrent forwards in predict_tensors_pipelined (each lane: own stream + plan workspace)
+        self.pipeline_lanes = 3     # concurrent forwards in predict_tensors_pipelined (each lane: own stream + plan workspace)
         self.gpu_resize = True      # PIL-exact resize of non-224x224 inputs on the device
         # captured CUDA graphs (static pinned / device buffers + the plan they replay), one per (batch, length, k) shape:
         # an LRU, because every entry pins a plan workspace (7.4 MB per pair)
@@ -228,7 +228,7 @@ class VQAInference:
         """Throughput path: iterate over host batches ``(u8 [B,224,224,3], ids [B,L], mask [B,L])`` (ideally
         pinned) and yield ``(top_idx, top_probs)`` host tensors in order.
 
-        ``pipeline_lanes`` compute lanes (default 2) run on their own streams with their own plan workspace, so the
+        ``pipeline_lanes`` compute lanes (default 3) run on their own streams with their own plan workspace, so the
         forward of batch i+1 overlaps the forward of batch i on the GPU: the small launch-latency-bound kernels of one
         batch's text / fusion / head path and the last, partially filled wave of each persistent convolution leave SMs
         idle that the other batch's kernels fill.  Inputs go through ``2 * lanes`` device slots filled by a copy stream
@@ -237,7 +237,7 @@ class VQAInference:
         if not self._is_loaded:
             self.load()
         dev = torch.device(self.device)
-        lanes = max(1, int(getattr(self, "pipeline_lanes", 2)))
+        lanes = max(1, int(getattr(self, "pipeline_lanes", 3)))
         n_slots = max(lanes, int(getattr(self, "pipeline_slots", 0) or 2 * lanes))
         if not hasattr(self, "_pipe_streams") or len(self._pipe_streams[1]) != lanes or self._pipe_nslots != n_slots:
             self._pipe_streams = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev) for _ in range(lanes)])
