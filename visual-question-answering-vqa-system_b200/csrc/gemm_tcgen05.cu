@@ -72,6 +72,10 @@ struct GemmParams {
   int ldo, ldr, out_dtype, res_dtype;
   int relu, round_tf32, mask_en, mP, mRPI, mH, mW;
   int out_f16;       // 16-bit outputs are fp16 instead of bf16 (operands of the fp16 tail GEMMs)
+  // programmatic dependent launch trigger: 0 = right after the prologue, 1 = when this CTA's producer starts its LAST tile
+  // (dependents' CTAs spin at griddepcontrol.wait on the SMs they get: triggering late leaves the SMs that finish early to
+  // the other compute lanes' kernels instead)
+  int pdl_late;
   // strided M tiling (fused stem + max-pool): tile t starts at (t / tiles_per_img) * img_rows +
   // (t % tiles_per_img) * tile_stride + tile_row0 instead of t * 128 * MT  (tiles_per_img = 0: linear)
   int tiles_per_img, tile_stride, tile_row0, img_rows;
@@ -275,7 +279,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   if (warp == 0) VQA_DBG(1);
   // Programmatic dependent launch: the next kernel of the stream may start its own prologue now; this one
   // has done everything that does not depend on its predecessors (barriers, TMEM, descriptor prefetch).
-  if (warp == 1) pdl_launch_dependents();
+  if (warp == 1 && (!p.pdl_late || walker >= total_tiles)) pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -291,6 +295,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       if (PAIR) tma_load_2d_pair(dst, map, bar, x, y); else tma_load_2d(dst, map, bar, x, y);
     };
     for (int tile = walker; tile < total_tiles; tile += n_walkers) {
+      if (p.pdl_late && tile + n_walkers >= total_tiles) pdl_launch_dependents();
       const int m0 = tile_m0(p, cta_mtile(tile), MT);
       const int n0 = tile_nt(tile) * kAcc + (PAIR ? static_cast<int>(rank) * (kAcc / 2) : 0);   // pair: this CTA's half of the N tile
       if (p.b_resident && !b_loaded) {   // n_tiles == 1 in this mode: load every weight chunk once
@@ -1325,6 +1330,10 @@ int gemm_prepare(const VqaOp& op, void* storage, int device) {
   VQA_REQUIRE(p.out_dtype >= 0 && p.out_dtype <= 2, VQA_E_INVALID, "gemm: out_dtype must be 0 (bf16), 1 (fp32) or 2 (fp16)");
   p.out_f16 = p.out_dtype == 2 ? 1 : 0;
   L->epi = pool ? 4 : (p.out_dtype != 1 ? 0 : 2) + (has_res ? 1 : 0);
+  {
+    static const int pdl_late = std::getenv("VQA_PDL_LATE") ? std::atoi(std::getenv("VQA_PDL_LATE")) : 0;
+    p.pdl_late = pdl_late;
+  }
   p.topk_k = I[GEMM_I_topk];
   L->topk_idx_raw = op.p[GEMM_P_topk_idx];
   L->topk_probs_raw = op.p[GEMM_P_topk_probs];
