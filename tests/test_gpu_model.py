@@ -353,3 +353,24 @@ def test_api_surface_and_errors(tmp_path):
     assert tuple(maps["cross_attention_spatial"].shape) == (2, 20, 7, 7)
     with pytest.raises(NotImplementedError):
         VQAModel(embed_dim=32, num_attention_heads=4).cuda().eval()(img.cuda(), ids.cuda())
+
+
+def test_batch_invariance_across_tile_shapes():
+    """A pair's logits do not depend on the batch it arrives in: small batches pick smaller convolution tiles (128-row
+    sub-tiles, single CTAs, 64-column tiles; program.py::gemm) and every batch size lands on a different mix of tile
+    shapes and persistent-grid sizes, but none of that may change the order in which K is accumulated.  Bit-exact."""
+    torch.manual_seed(0)
+    model = VQAModel().eval()
+    sd = randomise_state(model.state_dict(), 1)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    _, img, ids, mask = synth_batch(130, 31337)
+    img, ids, mask = img.cuda(), ids.cuda(), mask.cuda()
+    with torch.no_grad():
+        full, _ = model(img, ids, mask)
+        for b in (1, 2, 3, 5, 8, 13, 24, 33, 48, 65, 96):
+            part, _ = model(img[:b], ids[:b], mask[:b])
+            assert torch.equal(part, full[:b]), f"batch {b}: max diff {float((part - full[:b]).abs().max()):.3e}"
+            if b < 60:                                         # the same pairs at the END of a batch of their own
+                tail, _ = model(img[130 - b:], ids[130 - b:], mask[130 - b:])
+                assert torch.equal(tail, full[130 - b:]), f"tail batch {b}"
