@@ -531,13 +531,16 @@ def run_b200(args):
     barrier()
     h2d_conc_gbps = 10 * h_u8.numel() / (ms_conc * 1e-3) / 1e9          # per rank, slowest rank
     del d_probe
-    def e2e_run(lanes):
+    def e2e_run(lanes, idle_s=0.0):
         inf.pipeline_lanes = lanes
         inf.pipeline_slots = int(os.environ.get("VQA_PIPE_SLOTS", "0"))
         with torch.no_grad():
             for _ in inf.predict_tensors_pipelined([(h_u8, h_ids, h_mask)] * (4 * lanes + 4), 5):   # captures every slot's graph
                 pass
             barrier()
+            if idle_s > 0:                            # informational leg: start from an idle GPU (see e2e.from_idle_value)
+                time.sleep(idle_s)
+                barrier()
             t0 = time.perf_counter()                  # host clock: copies and compute run on the API's own streams
             n_out = 0
             for top_idx, top_probs in inf.predict_tensors_pipelined([(h_u8, h_ids, h_mask)] * K, 5):
@@ -553,6 +556,7 @@ def run_b200(args):
     assert torch.equal(idx_1, idx_2)
     ms_e2e, idx_3 = e2e_run(3)                       # the API's default: three lanes, like the device-resident leg
     assert torch.equal(idx_1, idx_3)
+    ms_e2e_idle, _ = e2e_run(3, idle_s=0.5)           # the same K steps started from an idle GPU
     inf.pipeline_lanes = 3
     e2e_value = world * B * K / (ms_e2e * 1e-3)
     h2d = h_u8.numel() + h_ids.numel() * 8 + h_mask.numel() * 8
@@ -793,6 +797,12 @@ def run_b200(args):
                                     "has to compute"},
                         "single_lane_value": world * B * K / (ms_e2e_1 * 1e-3), "compute_lanes": 3,
                         "two_lane_value": world * B * K / (ms_e2e_2 * 1e-3),
+                        "from_idle_value": world * B * K / (ms_e2e_idle * 1e-3),
+                        "from_idle_note": "the same K steps after 0.5 s of idle: `value` above is taken right after ~150 ms of "
+                                          "continuous load (the one- and two-lane A/B runs and this leg's own warm-up), i.e. in the "
+                                          "power-capped regime the `sustained` leg reports, while the device-resident `value` of "
+                                          "this line starts from an idle GPU; the captured graphs themselves run at the same speed "
+                                          "(tools/lane_probe.py)",
                         "path": "VQAInference.predict_tensors_pipelined: pinned uint8 HWC + ids + mask -> H2D (copy "
                                 "stream, 6 device slots) -> normalise+forward+top-5 (three compute lanes: the forwards of "
                                 "consecutive batches overlap on the GPU) -> D2H; every step copies its own "

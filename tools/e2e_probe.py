@@ -20,10 +20,12 @@ model = VQAModel().eval().cuda()
 inf = VQAInference(device="cuda:0")
 inf.model, inf._is_loaded = model, True
 inf.pipeline_lanes = lanes
+inf.pipeline_slots = int(os.environ.get("VQA_PIPE_SLOTS", "0"))
 u8, _, ids, mask = synth_batch(256, 1234, full_length=True)
 host = (u8.pin_memory(), ids.pin_memory(), mask.pin_memory())
 dev = (u8.cuda(), ids.cuda(), mask.cuda())
-K = 40
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+IDLE = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
 
 
 def run(src, name):
@@ -31,6 +33,7 @@ def run(src, name):
         for _ in inf.predict_tensors_pipelined([src] * (4 * lanes + 4), 5):
             pass
         torch.cuda.synchronize()
+        time.sleep(IDLE)
         t0 = time.perf_counter()
         for _ in inf.predict_tensors_pipelined([src] * K, 5):
             pass
@@ -46,18 +49,21 @@ run(dev, "device inputs (D2D every step)   ")
 slots = next(iter(inf._pipe_slots.values()))
 streams = inf._pipe_streams[1]
 torch.cuda.synchronize()
-for rep in range(2):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    cur = torch.cuda.current_stream()
-    a.record(cur)
-    for st in streams:
-        st.wait_stream(cur)
-    for i in range(K):
-        sl = slots[i % len(slots)]
-        with torch.cuda.stream(streams[(i % len(slots)) % lanes]):
-            sl["graph"].replay()
-    for st in streams:
-        cur.wait_stream(st)
-    b.record(cur)
-    torch.cuda.synchronize()
-print(f"graphs only, no copies / events: {a.elapsed_time(b) / K:.4f} ms/step, {256 * K / a.elapsed_time(b) * 1e3:.0f} pairs/s")
+for nuse in (len(slots), lanes):
+    for rep in range(2):
+        torch.cuda.synchronize()
+        time.sleep(IDLE)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        a.record(cur)
+        for st in streams:
+            st.wait_stream(cur)
+        for i in range(K):
+            sl = slots[i % nuse]
+            with torch.cuda.stream(streams[(i % nuse) % lanes]):
+                sl["graph"].replay()
+        for st in streams:
+            cur.wait_stream(st)
+        b.record(cur)
+        torch.cuda.synchronize()
+    print(f"graphs only ({nuse} of {len(slots)} slots), no copies / events: {a.elapsed_time(b) / K:.4f} ms/step, {256 * K / a.elapsed_time(b) * 1e3:.0f} pairs/s")

@@ -19,7 +19,7 @@ eng = model.engine()
 u8, img, ids, mask = synth_batch(256, 1234, full_length=True)
 u8, img, ids, mask = u8.cuda(), img.cuda(), ids.cuda(), mask.cuda()
 streams = [torch.cuda.Stream() for _ in range(lanes)]
-K = 40
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 
 
 def measure(name, fn):
@@ -35,7 +35,10 @@ def measure(name, fn):
                 out = fn(l)
             graphs.append((g, out))
     cur = torch.cuda.current_stream()
+    import time
     for rep in range(2):
+        torch.cuda.synchronize()
+        time.sleep(0.5)                       # let the power-averaging window drain: every repetition is a burst measurement
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(cur)
         for st in streams:
@@ -50,6 +53,10 @@ def measure(name, fn):
     print(f"{name}: {a.elapsed_time(b) / K:.4f} ms/step, {256 * K / a.elapsed_time(b) * 1e3:.0f} pairs/s ({lanes} lanes)")
 
 
+u8s = [u8.clone() for _ in range(lanes)]
+imgs = [img.clone() for _ in range(lanes)]
 measure("fp32 NCHW forward        ", lambda l: eng.run(img, ids, mask, slot=l)[0])
+measure("fp32, own input per lane ", lambda l: eng.run(imgs[l], ids, mask, slot=l)[0])
+measure("uint8 predict, own input ", lambda l: eng.predict(u8s[l], ids, mask, 5, slot=l))
 measure("uint8 HWC forward        ", lambda l: eng.run(u8, ids, mask, slot=l)[0])
 measure("uint8 HWC predict (top-5)", lambda l: eng.predict(u8, ids, mask, 5, slot=l))
